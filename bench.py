@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- PED k-mer hot path on B200: read bases -> edges per second.
+
+Workload (BASELINE.json configs[1]): C. elegans-scale synthetic target +
+control, 100 Mb random genome, 30x of 150 bp reads (20 M reads per sample),
+0.2 % substitution errors, 0.1 % reads with an N, planted SNPs (1e-3) and
+indels (1e-4), k = 20.  One step = the whole hot path over both
+samples: FASTQ text -> strand-closed de-duplicated reads -> canonical 20-mers
+-> radix sort -> count tables -> merged strand rows -> edge list.
+
+  value  bases/s with the FASTQ text already resident in HBM (device-timed)
+  e2e    the same through the C-ABI call with HOST (pinned) FASTQ buffers:
+         H2D of the text and D2H of the edge list inside the timed region
+  roofline      the dominant kernel (k_radix_pass on the k-mer instance stream):
+                16 B per key per launch / mean launch time, vs measured HBM copy peak
+  cpu_baseline  the oracle (CPU restatement of ped.pl) on a bounded sample, host cores
+
+`--impl reference` times the CPU arm alone (the oracle port with all host
+threads; the Perl reference itself cannot travel to the GPU box -- DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "read bases -> edges per second (k=20, target+control)"
+UNIT = "bases/s"
+K = 20
+L = 150
+
+
+def workload(scale: float):
+    """configs[1] scaled by `scale` (1.0 = the full configuration)."""
+    G = int(100_000_000 * scale)
+    N = int(20_000_000 * scale)
+    return dict(name="configs[1]: C. elegans-scale 100 Mb, 30x 150 bp, target+control, k=20", genome=G, reads=N,
+                read_len=L, k=K, scale=scale, cfg=2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(wl, sample_reads: int, threads: int):
+    """Oracle (CPU restatement of ped.pl) on the first `sample_reads` reads of each sample."""
+    from oracle import oracle
+    from ped_b200 import api
+
+    if threads > 0:
+        oracle.set_threads(threads)
+    cores = oracle.get_threads()
+    cfg = wl["cfg"]
+    g = api.synth_genome(1000 + cfg, wl["genome"])
+    t = api.synth_mutate(g, 2000 + cfg, 1000, 100)
+    fc = api.synth_fastq(g, 3000 + cfg, sample_reads, read_len=L)
+    ft = api.synth_fastq(t, 4000 + cfg, sample_reads, read_len=L)
+    t0 = time.perf_counter()
+    _, _, snp = oracle.run(fc, ft, K)
+    dt = time.perf_counter() - t0
+    bases = 2 * sample_reads * L
+    return dict(value=bases / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"first {sample_reads} reads of each sample of the workload ({bases} bases, {dt:.1f} s, "
+                       f"{snp.count(chr(10).encode())} edges); oracle/ped_oracle.c, OpenMP over ped.pl's 64 buckets"), dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    wl = workload(args.scale)
+    n = max(10_000, min(args.cpu_sample_reads, wl["reads"]))
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, dt = cpu_arm(wl, n, 0)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    value = 2 * n * L / (ms / 1000.0)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["name"], "genome": wl["genome"], "reads_per_sample": wl["reads"],
+                       "read_len": L, "k": K, "step": f"bounded sample: first {n} reads of each sample on the host CPU"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pedk", choices=["pedk", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of configs[1] (1.0 = 100 Mb genome, 20 M reads/sample)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        from ped_b200 import build
+        build.build_oracle()
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ped_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = api.Context(local_rank)
+    wl = workload(args.scale)
+    cfg = wl["cfg"]
+    # weak scaling over independent sample pairs: rank r works on its own pair (seeds offset by rank)
+    N = wl["reads"]
+    G = wl["genome"]
+    g = api.synth_genome(1000 + cfg + 100 * rank, G)
+    t = api.synth_mutate(g, 2000 + cfg + 100 * rank, 1000, 100)
+    gd, td = torch.from_numpy(g).cuda(), torch.from_numpy(t).cuda()
+    nb = api.synth_fastq_bytes(0, N, L)
+    dev_c = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    dev_t = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.synth_fastq_device(api.SynthParams(3000 + cfg + 100 * rank, len(g), L, 2000, 1000, 0), gd, 0, N, dev_c)
+    ctx.synth_fastq_device(api.SynthParams(4000 + cfg + 100 * rank, len(t), L, 2000, 1000, 0), td, 0, N, dev_t)
+    del gd, td
+    bases_per_step = 2 * N * L
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        edges = None
+        for _ in range(warmup):
+            r = fn()
+            edges = r.num_edges
+            r.destroy()
+        barrier()
+        ctx.reset_stats()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            r = fn()
+            edges = r.num_edges
+            r.destroy()
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - w0) * 1000.0
+        dev_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        st = ctx.stats()
+        ms = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms[0].item() / steps, ms[1].item() / steps, st, clocks, edges
+
+    # ---- resident leg: FASTQ text already in HBM ----
+    dev_ms, wall_ms, st, clocks, edges = timed(
+        lambda: ctx.kmer_edges(dev_c, nb, dev_t, nb, device_buffers=True, k=K), args.steps, args.warmup)
+    value = world * bases_per_step / (dev_ms / 1000.0)
+    launches = st["kernel_launches"]
+
+    peak, peak_src = peaks()
+    n_launch = max(1, st["sort_pass_launches"])
+    sort_bytes = 16.0 * st["sort_pass_keys"]
+    achieved = sort_bytes / (st["sort_pass_ms"] / 1000.0) / 1e9 if st["sort_pass_ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_radix_pass<false> (8-bit onesweep pass over the canonical 20-mer stream)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": sort_bytes / n_launch,
+                "launches_in_timed_region": st["sort_pass_launches"],
+                "mean_launch_ms": st["sort_pass_ms"] / n_launch,
+                "sort_share_of_step": st["sort_pass_ms"] / args.steps / dev_ms}
+    stage_ms = {k: v / args.steps for k, v in st["stage_ms"].items()}
+
+    # ---- e2e leg: host (pinned) FASTQ -> edge list on the host ----
+    e2e = None
+    if not args.no_e2e:
+        host_c = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        host_t = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        host_c.copy_(dev_c)
+        host_t.copy_(dev_t)
+        torch.cuda.synchronize()
+        del dev_c, dev_t
+        torch.cuda.empty_cache()
+
+        def step_e2e():
+            r = ctx.kmer_edges(host_c, nb, host_t, nb, device_buffers=False, k=K)
+            r.text()  # the edge list is host memory here
+            return r
+
+        e_dev_ms, e_wall_ms, e_st, _, _ = timed(step_e2e, max(1, args.steps), min(args.warmup, 3))
+        steps_e = max(1, args.steps)
+        e2e = {"value": world * bases_per_step / (e_wall_ms / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": e_st["h2d_bytes"] / steps_e, "d2h_bytes_per_step": e_st["d2h_bytes"] / steps_e,
+               "ms_per_step": e_wall_ms, "timing": "wall clock around the C-ABI call, synchronised on both sides"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from ped_b200 import build
+        build.build_oracle()
+        cpu, _ = cpu_arm(wl, max(10_000, min(args.cpu_sample_reads, N)), 0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": wl["name"], "genome": G, "reads_per_sample": N, "read_len": L, "k": K,
+                           "bases_per_step_per_gpu": bases_per_step, "edges": edges,
+                           "l2": "inputs larger than L2 (FASTQ text and k-mer stream are GBs)",
+                           "parallelism": f"{world} independent target/control pairs, one per GPU" if world > 1 else "1 GPU"},
+                "wall_ms_per_step": wall_ms, "stage_ms_per_step": stage_ms, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "peak_device_bytes": st["peak_device_bytes"]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+/*
+ * pedk.h -- C ABI of libpedk.so, the B200-native k-mer hot path of PED
+ * (Polymorphic Edge Detection, akiomiyao/ped).
+ *
+ * The reference has no library API: its boundary is the ped.pl command line
+ * and the files its subs hand to each other.  Every entry point
+ * below names the ped.pl sub (file:line in the reference tree) whose work it
+ * replaces; perl/PedK.xs binds exactly these symbols and INTEGRATION.md shows
+ * the edit a ped.pl maintainer makes.
+ *
+ * Conventions: plain C types only; the caller owns every pointer it passes and
+ * every output buffer; strings are copied before return.  Functions return 0 on
+ * success or a negative PEDK_E_* code; pedk_last_error() gives the message.  No
+ * exceptions and no exit() cross this boundary.  A context drives ONE CUDA
+ * device from one host thread at a time; multi-GPU jobs run one context per
+ * process/rank and connect them with pedk_comm_* (NCCL).  There is no CPU
+ * fallback: without a usable sm_100 device pedk_open fails.
+ *
+ * 2-bit code A=0 C=1 G=2 T=3 (byte order of LANG=C, ped.pl:91).  A k-mer is a
+ * right-aligned 2k-bit integer, first base most significant, so ascending
+ * integers are ascending strings.
+ */
+#ifndef PEDK_H
+#define PEDK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEDK_OK 0
+#define PEDK_E_INVAL (-1)       /* bad argument */
+#define PEDK_E_CUDA (-2)        /* CUDA runtime error (sticky for the context) */
+#define PEDK_E_NOMEM (-3)
+#define PEDK_E_IO (-4)
+#define PEDK_E_ALPHABET (-5)    /* a kept read holds a byte outside ACGTN */
+#define PEDK_E_UNSUPPORTED (-6)
+#define PEDK_E_NCCL (-7)
+#define PEDK_E_INTERNAL (-8)
+#define PEDK_E_NODEVICE (-9)    /* no CUDA device / not sm_100 */
+
+typedef struct pedk_ctx pedk_ctx;
+typedef struct pedk_sample pedk_sample;
+typedef struct pedk_result pedk_result;
+
+/* ---- context ---------------------------------------------------------- */
+
+/* devices/ndev: CUDA ordinals this context may use; ndev must be 1 (one rank
+ * per GPU).  Replaces the process pool of ped.pl:244-255, 3504-3543. */
+int pedk_open(pedk_ctx **ctx, const int *devices, int ndev);
+int pedk_close(pedk_ctx *ctx);
+const char *pedk_last_error(pedk_ctx *ctx);
+const char *pedk_strerror(int code);
+int pedk_abi_version(void);
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so a
+ * caller can bracket calls with its own CUDA events. */
+void *pedk_stream(pedk_ctx *ctx);
+
+/* ---- one sample (target or control) ---------------------------------- */
+
+typedef struct pedk_ingest_info {
+    uint64_t fastq_bytes;
+    uint64_t records;         /* FASTQ records seen */
+    uint64_t reads_kept;      /* sequence lines without 'N' (ped.pl:1436) */
+    uint64_t strand_reads;    /* lines ped.pl writes to the TAG.tmp files (reads + reverse complements) */
+    uint64_t unique_reads;    /* U: lines in sort_uniq/ after `sort | uniq` (ped.pl:1416) */
+    uint64_t palindromes;     /* unique reads equal to their own reverse complement */
+    int32_t clipping_used;    /* the "clipping : N" line of <s>.log (ped.pl:1495, 1526) */
+    int32_t auto_clipped;     /* 1 if mixed lengths triggered ped.pl:1478-1524 */
+    int32_t n_groups;         /* read-length groups held (1, or 2 after auto clipping) */
+    int32_t pad;
+} pedk_ingest_info;
+
+typedef struct pedk_count_info {
+    int32_t k;
+    int32_t sort_passes;
+    uint64_t instances;       /* canonical k-mer instances sorted (half of the reference's M) */
+    uint64_t canonical_kmers; /* rows of the canonical table */
+    uint64_t correction_rows; /* windows of palindromic reads (usually 0) */
+} pedk_count_info;
+
+int pedk_sample_create(pedk_ctx *ctx, pedk_sample **s);
+int pedk_sample_destroy(pedk_sample *s);
+/* Optional size hint for the FASTQ text buffer in HBM. */
+int pedk_sample_reserve(pedk_sample *s, uint64_t fastq_bytes);
+/* Append FASTQ text.  Chunks may split anywhere; the bytes of successive calls
+ * are concatenated exactly like `cat file1 file2 |` (ped.pl:1383-1398).
+ * _add_fastq: HOST memory (pinned gives full PCIe speed), copied asynchronously.
+ * _add_fastq_device: memory already in HBM. */
+int pedk_sample_add_fastq(pedk_sample *s, const void *host_bytes, uint64_t n);
+int pedk_sample_add_fastq_device(pedk_sample *s, const void *device_bytes, uint64_t n);
+/* S0+S1 = mkSortUniq/sortUniqSub/complement/sortUniqSort (ped.pl:1365-1530,
+ * 3464-3484): 4-line state machine, drop reads with N, clipping (0 = not
+ * given -> fixed length, or ped.pl's automatic choice for mixed lengths),
+ * strand closure, exact de-duplication.  Frees the FASTQ text. */
+int pedk_sample_ingest(pedk_sample *s, int clipping, pedk_ingest_info *info);
+/* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer
+ * of every unique read, sorted and counted.  4 <= k <= 32 (the reference
+ * hard-codes 20, ped.pl:912-913).  Leaves the canonical table in HBM. */
+int pedk_sample_count(pedk_sample *s, int k, pedk_count_info *info);
+/* The count table as ped.pl's count/<s>.count.*.gz hold it (both strands,
+ * ascending; bucket TAG = the rows whose first three bases are TAG).  Call
+ * with kmers == NULL to get *n only. */
+int pedk_sample_table(pedk_sample *s, uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n);
+/* Unique reads of length group g as packed canonical representatives
+ * (words_per_read u64 each, first base in the top bits of word 0) plus the
+ * palindrome flag; the sort_uniq/ lines are these and their reverse
+ * complements.  words == NULL: sizes only. */
+int pedk_sample_reads(pedk_sample *s, int group, uint64_t *words, uint8_t *pal, uint64_t cap_reads,
+                      uint64_t *n_reads, int32_t *read_len, int32_t *words_per_read);
+/* Drop device state that later stages do not need (packed reads). */
+int pedk_sample_release_reads(pedk_sample *s);
+
+/* ---- target x control ------------------------------------------------- */
+
+typedef struct pedk_edge {
+    uint64_t prefix;       /* the (k-1)-mer */
+    uint32_t control[4];   /* counts of prefix+A,C,G,T in the control (columns 4-7 of <t>.kmer.snp) */
+    uint32_t target[4];    /* same for the target (columns 8-11) */
+    uint8_t cont_mask;     /* bit b: base b is a control allele (column 2) */
+    uint8_t alt_mask;      /* bit b: base b is a target allele (column 3) */
+    uint8_t quirk;         /* 1: row went through ped.pl's first-row text path;
+                              its exact bytes are only in pedk_result_text */
+    uint8_t pad[5];
+} pedk_edge;
+
+/* S5+S6 = lbcKmerSub + joinKmerSub + the no-ref `cat` (ped.pl:833-860, 703-782,
+ * 374-378).  Both samples must have been counted with the same k. */
+int pedk_join(pedk_ctx *ctx, pedk_sample *control, pedk_sample *target, pedk_result **out);
+uint64_t pedk_result_num_edges(const pedk_result *r);
+/* The exact bytes of <target>/<target>.kmer.snp (no-ref mode, ped.pl:375). */
+int pedk_result_text(const pedk_result *r, const char **text, uint64_t *len);
+int pedk_result_edges(const pedk_result *r, pedk_edge *out, uint64_t cap, uint64_t *n);
+/* The lbc table of one sample as text (`zcat <s>/lbc/<s>.lbc.TAG.gz`, with the
+ * F7 first row), tag in [0,64).  Caller frees with pedk_free. */
+int pedk_sample_lbc_text(pedk_sample *s, int tag, char **text, uint64_t *len);
+int pedk_sample_count_text(pedk_sample *s, int tag, char **text, uint64_t *len);
+int pedk_sample_sort_uniq_text(pedk_sample *s, int tag, char **text, uint64_t *len);
+void pedk_free(void *p);
+int pedk_result_destroy(pedk_result *r);
+
+/* Whole hot path in one call: FASTQ text of both samples -> edge list.
+ * where = 0: buffers are HOST memory; 1: DEVICE memory. */
+int pedk_kmer_edges(pedk_ctx *ctx, const void *control_fastq, uint64_t control_bytes, const void *target_fastq,
+                    uint64_t target_bytes, int where, int k, int clipping, pedk_result **out);
+
+/* ---- file level: what ped.pl calls ------------------- */
+
+/* mkSortUniq (ped.pl:1365-1410): reads <wd>/<subject>/read/ (gz, bz2, xz and
+ * *q files, grouped and ordered like ped.pl), writes
+ * <wd>/<subject>/sort_uniq/<subject>.sort_uniq.TAG.gz. */
+int pedk_mk_sort_uniq(pedk_ctx *ctx, const char *wd, const char *subject, int clipping, int *clipping_used);
+/* countKmer (ped.pl:784-815): writes <wd>/<subject>/count/<subject>.count.TAG.gz */
+int pedk_count_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
+/* lbcKmer (ped.pl:817-831): writes <wd>/<subject>/lbc/<subject>.lbc.TAG.gz */
+int pedk_lbc_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
+/* joinKmer (ped.pl:687-701) + ped.pl:374-378: writes <tmpdir>/<target>.snp.TAG when
+ * have_ref != 0, else <wd>/<target>/<target>.kmer.snp */
+int pedk_join_kmer(pedk_ctx *ctx, const char *wd, const char *target, const char *control, int k,
+                   const char *tmpdir, int have_ref);
+
+/* ---- statistics -------------------------------------------------------- */
+
+enum {
+    PEDK_ST_INGEST = 0,   /* newline scan, record index, pack */
+    PEDK_ST_DEDUP = 1,
+    PEDK_ST_EXTRACT = 2,
+    PEDK_ST_SORT = 3,     /* radix passes over the instance stream */
+    PEDK_ST_COUNT = 4,    /* run-length count */
+    PEDK_ST_EXPAND = 5,
+    PEDK_ST_ROWSORT = 6,  /* radix passes over the merged strand rows */
+    PEDK_ST_EDGES = 7,
+    PEDK_ST_COPY = 8,     /* host<->device copies issued by the library */
+    PEDK_ST_EXCHANGE = 9, /* multi-GPU all-to-all */
+    PEDK_N_STAGES = 10
+};
+typedef struct pedk_stats {
+    double stage_ms[PEDK_N_STAGES];       /* CUDA-event time on the context stream */
+    uint64_t stage_launches[PEDK_N_STAGES];
+    uint64_t kernel_launches;             /* all kernels of this library */
+    uint64_t sort_pass_launches;          /* k_radix_pass launches on the instance stream */
+    uint64_t sort_pass_keys;              /* keys moved by them (sum over launches) */
+    double sort_pass_ms;                  /* their summed duration */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t peak_device_bytes;
+} pedk_stats;
+int pedk_get_stats(pedk_ctx *ctx, pedk_stats *out);   /* synchronises the stream */
+int pedk_reset_stats(pedk_ctx *ctx);
+
+/* ---- multi-GPU (one rank per process) ---------------------------------- */
+
+#define PEDK_COMM_ID_BYTES 128
+/* rank 0 makes the id, the launcher (torchrun store, MPI, a file) hands it to
+ * the other ranks, every rank calls pedk_comm_init. */
+int pedk_comm_unique_id(pedk_ctx *ctx, void *id_bytes);
+int pedk_comm_init(pedk_ctx *ctx, const void *id_bytes, int rank, int nranks);
+
+/* ---- synthetic reads (tests and bench.py) ---------------- */
+
+typedef struct pedk_synth_params {
+    uint64_t seed;
+    uint64_t genome_len;
+    uint32_t read_len;
+    uint32_t err_ppm;   /* substitution errors per million bases */
+    uint32_t n_ppm;     /* reads with one N per million reads */
+    uint32_t dup_ppm;   /* reads re-using the placement of the previous read, per million */
+} pedk_synth_params;
+
+/* host-only helpers (no CUDA call) */
+int pedk_synth_genome(uint64_t seed, uint64_t genome_len, char *out);
+int pedk_synth_mutate(const char *genome, uint64_t genome_len, uint64_t seed, uint32_t snp_ppm, uint32_t indel_ppm,
+                      char *out, uint64_t cap, uint64_t *out_len);
+uint64_t pedk_synth_fastq_bytes(uint64_t first_read, uint64_t n_reads, uint32_t read_len);
+int pedk_synth_fastq_host(const pedk_synth_params *p, const char *genome, uint64_t first_read, uint64_t n_reads,
+                          char *out);
+/* same bytes, generated in HBM: genome_dev and out_dev are device pointers */
+int pedk_synth_fastq_device(pedk_ctx *ctx, const pedk_synth_params *p, const char *genome_dev,
+                            uint64_t first_read, uint64_t n_reads, char *out_dev);
+
+/* ---- raw kernels, exposed for unit tests (device pointers) ------------- */
+int pedk_test_sort_u64(pedk_ctx *ctx, uint64_t *keys_dev, uint64_t n, int key_bits);
+int pedk_test_sort_pairs(pedk_ctx *ctx, uint64_t *keys_dev, uint32_t *vals_dev, uint64_t n, int key_bits);
+int pedk_test_rle(pedk_ctx *ctx, const uint64_t *sorted_dev, uint64_t n, uint64_t *ukey_dev, uint32_t *count_dev,
+                  uint64_t *n_runs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEDK_H */

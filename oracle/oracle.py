@@ -1,0 +1,180 @@
+"""ctypes wrapper of oracle/ped_oracle.c -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module; the product (ped_b200/, perl/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libped_oracle.so")
+SRC_PATH = os.path.join(_HERE, "ped_oracle.c")
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(SRC_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libped_oracle.so"])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        P = C.c_void_p
+        L.oracle_sample_new.restype = P
+        L.oracle_sample_free.argtypes = [P]
+        L.oracle_error.restype = C.c_char_p
+        L.oracle_error.argtypes = [P]
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_get_threads.restype = C.c_int
+        L.oracle_ingest.argtypes = [P, C.c_char_p, C.c_size_t, C.c_int]
+        L.oracle_clipping_used.argtypes = [P]
+        L.oracle_auto_clipped.argtypes = [P]
+        L.oracle_dedup.argtypes = [P]
+        L.oracle_num_reads.restype = C.c_size_t
+        L.oracle_num_reads.argtypes = [P]
+        L.oracle_reads_kept.restype = C.c_uint64
+        L.oracle_reads_kept.argtypes = [P]
+        L.oracle_read.restype = C.c_size_t
+        L.oracle_read.argtypes = [P, C.c_size_t, C.POINTER(C.c_char_p)]
+        L.oracle_count.argtypes = [P, C.c_int]
+        L.oracle_num_kmers.restype = C.c_size_t
+        L.oracle_num_kmers.argtypes = [P]
+        L.oracle_num_instances.restype = C.c_uint64
+        L.oracle_num_instances.argtypes = [P]
+        L.oracle_kmers.restype = C.POINTER(C.c_uint64)
+        L.oracle_kmers.argtypes = [P]
+        L.oracle_counts.restype = C.POINTER(C.c_uint32)
+        L.oracle_counts.argtypes = [P]
+        for fn in (L.oracle_sort_uniq_text, L.oracle_count_text, L.oracle_lbc_text):
+            fn.restype = P
+            fn.argtypes = [P, C.c_int, C.POINTER(C.c_size_t)]
+        L.oracle_join_text.restype = P
+        L.oracle_join_text.argtypes = [P, P, C.POINTER(C.c_size_t)]
+        L.oracle_free.argtypes = [P]
+        _lib = L
+    return _lib
+
+
+TAGS = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT"]
+
+
+class OracleSample:
+    """CPU restatement of ped.pl's per-sample stages (see ped_oracle.c header)."""
+
+    def __init__(self, fastq: bytes = b"", clipping: int = 0):
+        self.L = lib()
+        self.h = self.L.oracle_sample_new()
+        self.k = 0
+        if fastq:
+            self.ingest(fastq, clipping)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.oracle_sample_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def ingest(self, fastq: bytes, clipping: int = 0) -> None:
+        rc = self.L.oracle_ingest(self.h, fastq, len(fastq), clipping)
+        if rc:
+            raise RuntimeError(self.L.oracle_error(self.h).decode())
+        self.L.oracle_dedup(self.h)
+
+    @property
+    def clipping_used(self) -> int:
+        return self.L.oracle_clipping_used(self.h)
+
+    @property
+    def auto_clipped(self) -> bool:
+        return bool(self.L.oracle_auto_clipped(self.h))
+
+    @property
+    def num_reads(self) -> int:
+        return self.L.oracle_num_reads(self.h)
+
+    @property
+    def reads_kept(self) -> int:
+        return self.L.oracle_reads_kept(self.h)
+
+    def reads(self) -> List[bytes]:
+        out = []
+        p = C.c_char_p()
+        for i in range(self.num_reads):
+            n = self.L.oracle_read(self.h, i, C.byref(p))
+            out.append(C.string_at(p, n))
+        return out
+
+    def count(self, k: int = 20) -> None:
+        rc = self.L.oracle_count(self.h, k)
+        if rc:
+            raise RuntimeError(self.L.oracle_error(self.h).decode())
+        self.k = k
+
+    @property
+    def num_instances(self) -> int:
+        return self.L.oracle_num_instances(self.h)
+
+    def table(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = self.L.oracle_num_kmers(self.h)
+        if n == 0:
+            return np.empty(0, np.uint64), np.empty(0, np.uint32)
+        km = np.ctypeslib.as_array(self.L.oracle_kmers(self.h), shape=(n,)).copy()
+        ct = np.ctypeslib.as_array(self.L.oracle_counts(self.h), shape=(n,)).copy()
+        return km, ct
+
+    def _text(self, fn, tag: int) -> bytes:
+        n = C.c_size_t()
+        p = fn(self.h, tag, C.byref(n))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            self.L.oracle_free(p)
+
+    def sort_uniq_text(self, tag: int) -> bytes:
+        return self._text(self.L.oracle_sort_uniq_text, tag)
+
+    def count_text(self, tag: int) -> bytes:
+        return self._text(self.L.oracle_count_text, tag)
+
+    def lbc_text(self, tag: int) -> bytes:
+        return self._text(self.L.oracle_lbc_text, tag)
+
+
+def join_text(control: OracleSample, target: OracleSample) -> bytes:
+    """`<target>.kmer.snp` of the no-ref k-mer mode (ped.pl:703-782, 374-378)."""
+    L = lib()
+    n = C.c_size_t()
+    p = L.oracle_join_text(control.h, target.h, C.byref(n))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        L.oracle_free(p)
+
+
+def run(control_fastq: bytes, target_fastq: bytes, k: int = 20, clipping: int = 0):
+    c = OracleSample(control_fastq, clipping)
+    t = OracleSample(target_fastq, clipping)
+    c.count(k)
+    t.count(k)
+    return c, t, join_text(c, t)
+
+
+def set_threads(n: int) -> None:
+    lib().oracle_set_threads(n)
+
+
+def get_threads() -> int:
+    return lib().oracle_get_threads()

@@ -1,0 +1,387 @@
+"""ctypes mirror of include/pedk.h.
+
+The host-side interface of the k-mer hot path follows ped.pl's own subs
+(reference: ped.pl mkSortUniq 1365-1410, countKmer 784-815, lbcKmer 817-831,
+joinKmer 687-701, kmer 368-378): a `Sample` is ingested (sort_uniq), counted
+(count), and two samples are joined into the edge list (`<target>.kmer.snp`).
+Everything is computed by libpedk.so on a B200; importing this module without
+the built library, or opening a context without a GPU, raises -- there is no
+CPU path in the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpedk.so")
+
+PEDK_N_STAGES = 10
+STAGES = ["ingest", "dedup", "extract", "sort", "count", "expand", "rowsort", "edges", "copy", "exchange"]
+COMM_ID_BYTES = 128
+
+
+class PedkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pedk error {code}: {msg}")
+        self.code = code
+
+
+class IngestInfo(C.Structure):
+    _fields_ = [("fastq_bytes", C.c_uint64), ("records", C.c_uint64), ("reads_kept", C.c_uint64),
+                ("strand_reads", C.c_uint64), ("unique_reads", C.c_uint64), ("palindromes", C.c_uint64),
+                ("clipping_used", C.c_int32), ("auto_clipped", C.c_int32), ("n_groups", C.c_int32),
+                ("pad", C.c_int32)]
+
+
+class CountInfo(C.Structure):
+    _fields_ = [("k", C.c_int32), ("sort_passes", C.c_int32), ("instances", C.c_uint64),
+                ("canonical_kmers", C.c_uint64), ("correction_rows", C.c_uint64)]
+
+
+class Edge(C.Structure):
+    _fields_ = [("prefix", C.c_uint64), ("control", C.c_uint32 * 4), ("target", C.c_uint32 * 4),
+                ("cont_mask", C.c_uint8), ("alt_mask", C.c_uint8), ("quirk", C.c_uint8), ("pad", C.c_uint8 * 5)]
+
+
+EDGE_DTYPE = np.dtype([("prefix", "<u8"), ("control", "<u4", (4,)), ("target", "<u4", (4,)), ("cont_mask", "u1"),
+                       ("alt_mask", "u1"), ("quirk", "u1"), ("pad", "u1", (5,))])
+
+
+class Stats(C.Structure):
+    _fields_ = [("stage_ms", C.c_double * PEDK_N_STAGES), ("stage_launches", C.c_uint64 * PEDK_N_STAGES),
+                ("kernel_launches", C.c_uint64), ("sort_pass_launches", C.c_uint64), ("sort_pass_keys", C.c_uint64),
+                ("sort_pass_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("peak_device_bytes", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        return {
+            "stage_ms": {STAGES[i]: self.stage_ms[i] for i in range(PEDK_N_STAGES)},
+            "stage_launches": {STAGES[i]: int(self.stage_launches[i]) for i in range(PEDK_N_STAGES)},
+            "kernel_launches": int(self.kernel_launches),
+            "sort_pass_launches": int(self.sort_pass_launches),
+            "sort_pass_keys": int(self.sort_pass_keys),
+            "sort_pass_ms": float(self.sort_pass_ms),
+            "h2d_bytes": int(self.h2d_bytes),
+            "d2h_bytes": int(self.d2h_bytes),
+            "peak_device_bytes": int(self.peak_device_bytes),
+        }
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32), ("err_ppm", C.c_uint32),
+                ("n_ppm", C.c_uint32), ("dup_ppm", C.c_uint32)]
+
+
+# every symbol include/pedk.h declares: (restype, argtypes)
+_P = C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+_U64P = C.POINTER(C.c_uint64)
+SIGNATURES = {
+    "pedk_open": (C.c_int, [_PP, C.POINTER(C.c_int), C.c_int]),
+    "pedk_close": (C.c_int, [_P]),
+    "pedk_last_error": (C.c_char_p, [_P]),
+    "pedk_strerror": (C.c_char_p, [C.c_int]),
+    "pedk_abi_version": (C.c_int, []),
+    "pedk_stream": (C.c_void_p, [_P]),
+    "pedk_sample_create": (C.c_int, [_P, _PP]),
+    "pedk_sample_destroy": (C.c_int, [_P]),
+    "pedk_sample_reserve": (C.c_int, [_P, C.c_uint64]),
+    "pedk_sample_add_fastq": (C.c_int, [_P, _P, C.c_uint64]),
+    "pedk_sample_add_fastq_device": (C.c_int, [_P, _P, C.c_uint64]),
+    "pedk_sample_ingest": (C.c_int, [_P, C.c_int, C.POINTER(IngestInfo)]),
+    "pedk_sample_count": (C.c_int, [_P, C.c_int, C.POINTER(CountInfo)]),
+    "pedk_sample_table": (C.c_int, [_P, _P, _P, C.c_uint64, _U64P]),
+    "pedk_sample_reads": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint64, _U64P, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32)]),
+    "pedk_sample_release_reads": (C.c_int, [_P]),
+    "pedk_join": (C.c_int, [_P, _P, _P, _PP]),
+    "pedk_result_num_edges": (C.c_uint64, [_P]),
+    "pedk_result_text": (C.c_int, [_P, C.POINTER(C.c_char_p), _U64P]),
+    "pedk_result_edges": (C.c_int, [_P, _P, C.c_uint64, _U64P]),
+    "pedk_sample_lbc_text": (C.c_int, [_P, C.c_int, _PP, _U64P]),
+    "pedk_sample_count_text": (C.c_int, [_P, C.c_int, _PP, _U64P]),
+    "pedk_sample_sort_uniq_text": (C.c_int, [_P, C.c_int, _PP, _U64P]),
+    "pedk_free": (None, [_P]),
+    "pedk_result_destroy": (C.c_int, [_P]),
+    "pedk_kmer_edges": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _PP]),
+    "pedk_mk_sort_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
+    "pedk_count_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
+    "pedk_lbc_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
+    "pedk_join_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
+    "pedk_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "pedk_reset_stats": (C.c_int, [_P]),
+    "pedk_comm_unique_id": (C.c_int, [_P, _P]),
+    "pedk_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "pedk_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
+    "pedk_synth_mutate": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _U64P]),
+    "pedk_synth_fastq_bytes": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint32]),
+    "pedk_synth_fastq_host": (C.c_int, [C.POINTER(SynthParams), _P, C.c_uint64, C.c_uint64, _P]),
+    "pedk_synth_fastq_device": (C.c_int, [_P, C.POINTER(SynthParams), _P, C.c_uint64, C.c_uint64, _P]),
+    "pedk_test_sort_u64": (C.c_int, [_P, _P, C.c_uint64, C.c_int]),
+    "pedk_test_sort_pairs": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
+    "pedk_test_rle": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _U64P]),
+}
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Load libpedk.so (built by `python -m ped_b200.build`).  Fails loudly."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(f"{p} is missing: build it with `python -m ped_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(x) -> C.c_void_p:
+    """Raw address of a numpy array, bytes object, int or torch tensor."""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)) if isinstance(x, bytearray) else C.c_char_p(x), C.c_void_p)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(type(x))
+
+
+class Context:
+    """One CUDA device.  Replaces ped.pl's process pool (ped.pl:244-255, 3504-3543)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        dev = (C.c_int * 1)(device)
+        rc = self.lib.pedk_open(C.byref(self.h), dev, 1)
+        if rc != 0:
+            msg = self.lib.pedk_last_error(None).decode()
+            raise PedkError(rc, msg)
+        self.device = device
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            raise PedkError(rc, self.lib.pedk_last_error(self.h).decode())
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.pedk_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the context (wrap with torch.cuda.ExternalStream to time it)."""
+        return int(self.lib.pedk_stream(self.h) or 0)
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.check(self.lib.pedk_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def reset_stats(self) -> None:
+        self.check(self.lib.pedk_reset_stats(self.h))
+
+    # ---- whole path ----
+    def kmer_edges(self, control_fastq, control_bytes: int, target_fastq, target_bytes: int, *, device_buffers: bool,
+                   k: int = 20, clipping: int = 0) -> "Result":
+        r = C.c_void_p()
+        self.check(self.lib.pedk_kmer_edges(self.h, _ptr(control_fastq), control_bytes, _ptr(target_fastq),
+                                            target_bytes, 1 if device_buffers else 0, k, clipping, C.byref(r)))
+        return Result(self, r)
+
+    def join(self, control: "Sample", target: "Sample") -> "Result":
+        r = C.c_void_p()
+        self.check(self.lib.pedk_join(self.h, control.h, target.h, C.byref(r)))
+        return Result(self, r)
+
+    # ---- raw kernels (unit tests) ----
+    def test_sort_u64(self, keys_dev, n: int, key_bits: int) -> None:
+        self.check(self.lib.pedk_test_sort_u64(self.h, _ptr(keys_dev), n, key_bits))
+
+    def test_sort_pairs(self, keys_dev, vals_dev, n: int, key_bits: int) -> None:
+        self.check(self.lib.pedk_test_sort_pairs(self.h, _ptr(keys_dev), _ptr(vals_dev), n, key_bits))
+
+    def test_rle(self, sorted_dev, n: int, ukey_dev, count_dev) -> int:
+        d = C.c_uint64()
+        self.check(self.lib.pedk_test_rle(self.h, _ptr(sorted_dev), n, _ptr(ukey_dev), _ptr(count_dev), C.byref(d)))
+        return int(d.value)
+
+    def synth_fastq_device(self, params: SynthParams, genome_dev, first: int, n: int, out_dev) -> None:
+        self.check(self.lib.pedk_synth_fastq_device(self.h, C.byref(params), _ptr(genome_dev), first, n,
+                                                    _ptr(out_dev)))
+
+
+class Sample:
+    """One sample (target or control): sort_uniq -> count, resident in HBM."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.pedk_sample_create(ctx.h, C.byref(self.h)))
+
+    def destroy(self) -> None:
+        if self.h:
+            self.ctx.lib.pedk_sample_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.destroy()
+
+    def add_fastq(self, data, nbytes: Optional[int] = None) -> None:
+        """Append FASTQ text held in HOST memory (bytes / numpy / pinned tensor)."""
+        n = nbytes if nbytes is not None else len(data)
+        self.ctx.check(self.ctx.lib.pedk_sample_add_fastq(self.h, _ptr(data), n))
+
+    def add_fastq_device(self, dev_ptr, nbytes: int) -> None:
+        self.ctx.check(self.ctx.lib.pedk_sample_add_fastq_device(self.h, _ptr(dev_ptr), nbytes))
+
+    def ingest(self, clipping: int = 0) -> IngestInfo:
+        """mkSortUniq (ped.pl:1365-1530)."""
+        info = IngestInfo()
+        self.ctx.check(self.ctx.lib.pedk_sample_ingest(self.h, clipping, C.byref(info)))
+        return info
+
+    def count(self, k: int = 20) -> CountInfo:
+        """countKmer (ped.pl:784-932)."""
+        info = CountInfo()
+        self.ctx.check(self.ctx.lib.pedk_sample_count(self.h, k, C.byref(info)))
+        return info
+
+    def table(self) -> Tuple[np.ndarray, np.ndarray]:
+        """The count table of count/<s>.count.*.gz: (kmers u64 ascending, counts u32), both strands."""
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_sample_table(self.h, None, None, 0, C.byref(n)))
+        km = np.empty(n.value, dtype=np.uint64)
+        ct = np.empty(n.value, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.pedk_sample_table(self.h, _ptr(km), _ptr(ct), n.value, C.byref(n)))
+        return km, ct
+
+    def reads(self, group: int = 0) -> Tuple[np.ndarray, np.ndarray, int]:
+        """Unique canonical packed reads of a length group: (words [n, W] u64, pal [n] u8, read_len)."""
+        n = C.c_uint64()
+        L = C.c_int32()
+        W = C.c_int32()
+        lib = self.ctx.lib
+        self.ctx.check(lib.pedk_sample_reads(self.h, group, None, None, 0, C.byref(n), C.byref(L), C.byref(W)))
+        words = np.empty((n.value, W.value), dtype=np.uint64)
+        pal = np.empty(n.value, dtype=np.uint8)
+        self.ctx.check(lib.pedk_sample_reads(self.h, group, _ptr(words), _ptr(pal), n.value, C.byref(n), C.byref(L),
+                                             C.byref(W)))
+        return words, pal, int(L.value)
+
+    def _text(self, fn, tag: int) -> bytes:
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self.ctx.check(fn(self.h, tag, C.byref(p), C.byref(n)))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            self.ctx.lib.pedk_free(p)
+
+    def count_text(self, tag: int) -> bytes:
+        return self._text(self.ctx.lib.pedk_sample_count_text, tag)
+
+    def lbc_text(self, tag: int) -> bytes:
+        return self._text(self.ctx.lib.pedk_sample_lbc_text, tag)
+
+    def sort_uniq_text(self, tag: int) -> bytes:
+        return self._text(self.ctx.lib.pedk_sample_sort_uniq_text, tag)
+
+
+class Result:
+    """The edge list: `<target>/<target>.kmer.snp` (ped.pl:374-378, 777)."""
+
+    def __init__(self, ctx: Context, h: C.c_void_p):
+        self.ctx = ctx
+        self.h = h
+
+    def destroy(self) -> None:
+        if self.h:
+            self.ctx.lib.pedk_result_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.destroy()
+
+    @property
+    def num_edges(self) -> int:
+        return int(self.ctx.lib.pedk_result_num_edges(self.h))
+
+    def text(self) -> bytes:
+        p = C.c_char_p()
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_result_text(self.h, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    def edges(self) -> np.ndarray:
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=EDGE_DTYPE)
+        self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+
+# ---- synthetic inputs (host side; no GPU needed) ----
+
+def synth_genome(seed: int, length: int) -> np.ndarray:
+    lib = load_library()
+    g = np.empty(length, dtype=np.uint8)
+    rc = lib.pedk_synth_genome(seed, length, _ptr(g))
+    if rc:
+        raise PedkError(rc, "pedk_synth_genome")
+    return g
+
+
+def synth_mutate(genome: np.ndarray, seed: int, snp_ppm: int = 1000, indel_ppm: int = 100) -> np.ndarray:
+    lib = load_library()
+    cap = len(genome) + len(genome) // 8 + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_uint64()
+    rc = lib.pedk_synth_mutate(_ptr(genome), len(genome), seed, snp_ppm, indel_ppm, _ptr(out), cap, C.byref(n))
+    if rc:
+        raise PedkError(rc, "pedk_synth_mutate")
+    return out[: n.value].copy()
+
+
+def synth_fastq_bytes(first: int, n_reads: int, read_len: int) -> int:
+    return int(load_library().pedk_synth_fastq_bytes(first, n_reads, read_len))
+
+
+def synth_fastq(genome: np.ndarray, seed: int, n_reads: int, read_len: int = 150, err_ppm: int = 2000,
+                n_ppm: int = 1000, dup_ppm: int = 0, first: int = 0) -> bytes:
+    lib = load_library()
+    p = SynthParams(seed, len(genome), read_len, err_ppm, n_ppm, dup_ppm)
+    nb = synth_fastq_bytes(first, n_reads, read_len)
+    out = np.empty(nb, dtype=np.uint8)
+    rc = lib.pedk_synth_fastq_host(C.byref(p), _ptr(genome), first, n_reads, _ptr(out))
+    if rc:
+        raise PedkError(rc, "pedk_synth_fastq_host")
+    return out.tobytes()

@@ -1,0 +1,340 @@
+// Context life cycle, stream-ordered device memory, stage timing, the radix
+// sort driver and the raw-kernel test entry points of libpedk.so.
+#include "ctx.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+using namespace pedk;
+
+namespace pedk {
+
+cudaStream_t ctx_stream(pedk_ctx* ctx) { return ctx->stream; }
+
+int ctx_fail(pedk_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char b[256];
+        snprintf(b, sizeof b, "device allocation of %zu bytes failed (%zu in use): %s", bytes, ctx->cur_bytes,
+                 cudaGetErrorString(e));
+        throw PedkError(PEDK_E_NOMEM, b);
+    }
+    ctx->cur_bytes += bytes;
+    if (ctx->cur_bytes > ctx->stats.peak_device_bytes) ctx->stats.peak_device_bytes = ctx->cur_bytes;
+    return p;
+}
+
+void dev_free(pedk_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    cudaFreeAsync(p, ctx->stream);
+    ctx->cur_bytes -= bytes;
+}
+
+static cudaEvent_t get_event(pedk_ctx* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    PEDK_CUDA_TRY(cudaEventCreate(&e));
+    return e;
+}
+
+StageScope::StageScope(pedk_ctx* c, int stage, uint64_t launches, uint64_t sort_keys, uint64_t sort_launches)
+    : ctx(c) {
+    pedk_ctx::Pending p;
+    p.a = get_event(c);
+    p.b = get_event(c);
+    p.stage = stage;
+    p.sort_keys = sort_keys;
+    p.sort_launches = sort_launches;
+    PEDK_CUDA_TRY(cudaEventRecord(p.a, c->stream));
+    idx = c->pending.size();
+    c->pending.push_back(p);
+    c->stats.stage_launches[stage] += launches;
+    c->stats.kernel_launches += launches;
+}
+
+StageScope::~StageScope() { cudaEventRecord(ctx->pending[idx].b, ctx->stream); }
+
+static void resolve_pending(pedk_ctx* ctx) {
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->stats.stage_ms[p.stage] += ms;
+            if (p.sort_keys) {
+                ctx->stats.sort_pass_ms += ms;
+                ctx->stats.sort_pass_keys += p.sort_keys;
+                ctx->stats.sort_pass_launches += p.sort_launches;
+            }
+        } else {
+            cudaGetLastError();
+        }
+        ctx->event_pool.push_back(p.a);
+        ctx->event_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+RadixWorkspace radix_workspace(pedk_ctx* ctx, size_t n_keys) {
+    size_t tiles = radix_tiles(n_keys);
+    size_t words = tiles * 256;
+    // the RLE look-back (one u64 per 4096-key tile) shares the buffer
+    size_t rle_words = rle_tiles(n_keys) * 2;
+    if (rle_words > words) words = rle_words;
+    if (words > ctx->lookback_words) {
+        if (ctx->lookback) dev_free(ctx, ctx->lookback, ctx->lookback_words * sizeof(uint32_t));
+        ctx->lookback = nullptr;
+        ctx->lookback_words = 0;
+        ctx->lookback = static_cast<uint32_t*>(dev_alloc(ctx, words * sizeof(uint32_t)));
+        ctx->lookback_words = words;
+    }
+    RadixWorkspace ws;
+    ws.lookback = reinterpret_cast<uint64_t*>(ctx->lookback);
+    ws.tile_ctr = ctx->tile_ctr;
+    ws.err = ctx->err_flag;
+    ws.tiles_cap = ctx->lookback_words / 256;
+    return ws;
+}
+
+int radix_sort(pedk_ctx* ctx, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* vb, size_t n, int n_pass,
+               unsigned long long* digit_hist, int stage) {
+    if (!n) return 0;
+    RadixWorkspace ws = radix_workspace(ctx, n);
+    {
+        StageScope sc(ctx, stage, 1);
+        launch_hist_to_base(digit_hist, n_pass, ctx->stream);
+    }
+    int cur = 0;
+    size_t portions = (n + ((size_t(1) << 30) - 1)) >> 30;  // upper bound, only for launch accounting
+    if (portions == 0) portions = 1;
+    for (int p = 0; p < n_pass; ++p) {
+        StageScope sc(ctx, stage, portions, stage == PEDK_ST_SORT ? n : 0, stage == PEDK_ST_SORT ? portions : 0);
+        if (cur == 0)
+            launch_radix_pass(a, b, va, vb, n, p, digit_hist, ws, ctx->stream);
+        else
+            launch_radix_pass(b, a, vb, va, n, p, digit_hist, ws, ctx->stream);
+        cur ^= 1;
+    }
+    return cur;
+}
+
+void check_err_flag(pedk_ctx* ctx, const char* what) {
+    int flag = 0;
+    PEDK_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        PEDK_CUDA_TRY(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), ctx->stream));
+        throw PedkError(PEDK_E_INTERNAL, std::string("chained scan timed out in ") + what);
+    }
+}
+
+}  // namespace pedk
+
+extern "C" int pedk_abi_version(void) { return 1; }
+
+extern "C" void* pedk_stream(pedk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" const char* pedk_strerror(int code) {
+    switch (code) {
+    case PEDK_OK: return "ok";
+    case PEDK_E_INVAL: return "invalid argument";
+    case PEDK_E_CUDA: return "CUDA error";
+    case PEDK_E_NOMEM: return "out of memory";
+    case PEDK_E_IO: return "I/O error";
+    case PEDK_E_ALPHABET: return "read with a byte outside ACGTN";
+    case PEDK_E_UNSUPPORTED: return "unsupported input";
+    case PEDK_E_NCCL: return "NCCL error";
+    case PEDK_E_INTERNAL: return "internal error";
+    case PEDK_E_NODEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+static thread_local std::string g_open_error;
+
+extern "C" const char* pedk_last_error(pedk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_open_error.c_str(); }
+
+extern "C" int pedk_open(pedk_ctx** out, const int* devices, int ndev) {
+    if (!out) return PEDK_E_INVAL;
+    *out = nullptr;
+    if (ndev > 1) {
+        g_open_error = "pedk_open: one device per context (run one rank per GPU and connect with pedk_comm_init)";
+        return PEDK_E_INVAL;
+    }
+    int dev = (devices && ndev == 1) ? devices[0] : 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_open_error = std::string("pedk_open: no CUDA device (") + cudaGetErrorString(e) +
+                       "); libpedk has no CPU fallback";
+        return PEDK_E_NODEVICE;
+    }
+    if (dev < 0 || dev >= count) {
+        g_open_error = "pedk_open: device ordinal out of range";
+        return PEDK_E_INVAL;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        cudaGetLastError();
+        g_open_error = "pedk_open: device is not sm_100 (kernels are built for sm_100a only)";
+        return PEDK_E_NODEVICE;
+    }
+    pedk_ctx* ctx = new pedk_ctx();
+    ctx->device = dev;
+    try {
+        PEDK_CUDA_TRY(cudaSetDevice(dev));
+        PEDK_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        PEDK_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        PEDK_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
+        // a private stream-ordered pool: freed blocks stay cached for the next stage and
+        // nothing is taken from (or left in) the pool other libraries in the process use
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        PEDK_CUDA_TRY(cudaMemPoolCreate(&ctx->pool, &props));
+        uint64_t thr = UINT64_MAX;
+        PEDK_CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        PEDK_CUDA_TRY(cudaMalloc(&ctx->tile_ctr, sizeof(unsigned)));
+        PEDK_CUDA_TRY(cudaMalloc(&ctx->err_flag, sizeof(int)));
+        PEDK_CUDA_TRY(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+        PEDK_CUDA_TRY(cudaMalloc(&ctx->scalars, 16 * sizeof(unsigned long long)));
+        PEDK_CUDA_TRY(cudaMallocHost(&ctx->h_scalars, 16 * sizeof(unsigned long long)));
+    } catch (const CudaError& err) {
+        g_open_error = err.msg;
+        delete ctx;
+        return PEDK_E_CUDA;
+    }
+    *out = ctx;
+    return PEDK_OK;
+}
+
+namespace pedk {
+void comm_destroy(pedk_ctx* ctx);
+}
+
+extern "C" int pedk_close(pedk_ctx* ctx) {
+    if (!ctx) return PEDK_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    comm_destroy(ctx);
+    for (auto& p : ctx->pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->lookback) cudaFreeAsync(ctx->lookback, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    cudaFree(ctx->tile_ctr);
+    cudaFree(ctx->err_flag);
+    cudaFree(ctx->scalars);
+    cudaFreeHost(ctx->h_scalars);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_alloc);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PEDK_OK;
+}
+
+extern "C" int pedk_get_stats(pedk_ctx* ctx, pedk_stats* out) {
+    if (!ctx || !out) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    resolve_pending(ctx);
+    *out = ctx->stats;
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_reset_stats(pedk_ctx* ctx) {
+    if (!ctx) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    resolve_pending(ctx);
+    ctx->stats = pedk_stats{};
+    ctx->stats.peak_device_bytes = ctx->cur_bytes;
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" void pedk_free(void* p) { free(p); }
+
+// ---------------- raw kernels for unit tests ----------------
+
+extern "C" int pedk_test_sort_u64(pedk_ctx* ctx, uint64_t* keys_dev, uint64_t n, int key_bits) {
+    if (!ctx || (!keys_dev && n) || key_bits < 1 || key_bits > 64) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    int n_pass = (key_bits + 7) / 8;
+    DBuf<uint64_t> tmp(ctx, n);
+    DBuf<unsigned long long> hist(ctx, 8 * 256);
+    PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), ctx->stream));
+    launch_digit_hist(keys_dev, n, hist.p, n_pass, ctx->stream);
+    int cur = radix_sort(ctx, keys_dev, tmp.p, nullptr, nullptr, n, n_pass, hist.p, PEDK_ST_SORT);
+    if (cur == 1)
+        PEDK_CUDA_TRY(cudaMemcpyAsync(keys_dev, tmp.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    check_err_flag(ctx, "radix sort");
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_test_sort_pairs(pedk_ctx* ctx, uint64_t* keys_dev, uint32_t* vals_dev, uint64_t n,
+                                    int key_bits) {
+    if (!ctx || ((!keys_dev || !vals_dev) && n) || key_bits < 1 || key_bits > 64) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    int n_pass = (key_bits + 7) / 8;
+    DBuf<uint64_t> tmp(ctx, n);
+    DBuf<uint32_t> vtmp(ctx, n);
+    DBuf<unsigned long long> hist(ctx, 8 * 256);
+    PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), ctx->stream));
+    launch_digit_hist(keys_dev, n, hist.p, n_pass, ctx->stream);
+    int cur = radix_sort(ctx, keys_dev, tmp.p, vals_dev, vtmp.p, n, n_pass, hist.p, PEDK_ST_ROWSORT);
+    if (cur == 1) {
+        PEDK_CUDA_TRY(cudaMemcpyAsync(keys_dev, tmp.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(vals_dev, vtmp.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    check_err_flag(ctx, "radix sort (pairs)");
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+namespace pedk {
+__global__ void k_start_to_count(const uint32_t* __restrict__ ustart, uint64_t D, uint32_t* __restrict__ cnt) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < D) cnt[r] = ustart[r + 1] - ustart[r];
+}
+}  // namespace pedk
+
+extern "C" int pedk_test_rle(pedk_ctx* ctx, const uint64_t* sorted_dev, uint64_t n, uint64_t* ukey_dev,
+                             uint32_t* count_dev, uint64_t* n_runs) {
+    if (!ctx || !n_runs) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    DBuf<uint32_t> ustart(ctx, n + 1);
+    RadixWorkspace ws = radix_workspace(ctx, n);
+    launch_rle(sorted_dev, n, ukey_dev, ustart.p, ws.lookback, ws.tile_ctr, ws.err, ctx->scalars, ctx->stream);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    check_err_flag(ctx, "run-length count");
+    uint64_t D = ctx->h_scalars[0];
+    *n_runs = D;
+    if (D) {
+        k_start_to_count<<<(unsigned)((D + 255) / 256), 256, 0, ctx->stream>>>(ustart.p, D, count_dev);
+        PEDK_CUDA_TRY(cudaGetLastError());
+    }
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}

@@ -1,0 +1,259 @@
+// S0: FASTQ text on the device -> packed canonical reads.
+//
+// Replaces the serial Perl loop of sortUniqSub (ped.pl:1420-1475) and the
+// char-by-char `complement` (ped.pl:3464-3484).  The raw file bytes are shipped
+// to HBM untouched; record structure is recovered with a newline count + scan,
+// then one warp per read packs 32 bases per 64-bit word with ballots.
+#include "kernels.h"
+#include "util.cuh"
+
+namespace pedk {
+
+namespace {
+
+constexpr int NL_THREADS = 256;
+constexpr int NL_BYTES_PER_THREAD = INGEST_TILE_BYTES / NL_THREADS;  // 64
+static_assert(NL_BYTES_PER_THREAD == 64, "tile layout");
+
+__device__ __forceinline__ unsigned count_nl16(uint4 v) {
+    // __vcmpeq4 gives 0xff per equal byte
+    return (__popc(__vcmpeq4(v.x, 0x0A0A0A0Au)) + __popc(__vcmpeq4(v.y, 0x0A0A0A0Au)) +
+            __popc(__vcmpeq4(v.z, 0x0A0A0A0Au)) + __popc(__vcmpeq4(v.w, 0x0A0A0A0Au))) >>
+           3;
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_newline_count(const uint4* __restrict__ fq, size_t n_tiles,
+                                                             uint32_t* __restrict__ tile_counts) {
+    __shared__ unsigned warp_sums[NL_THREADS / 32];
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint4* base = fq + tile * (INGEST_TILE_BYTES / 16);
+        unsigned c = 0;
+#pragma unroll
+        for (int j = 0; j < NL_BYTES_PER_THREAD / 16; ++j) c += count_nl16(__ldg(base + j * NL_THREADS + threadIdx.x));
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane_id() == 0) warp_sums[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned s = 0;
+#pragma unroll
+            for (int w = 0; w < NL_THREADS / 32; ++w) s += warp_sums[w];
+            tile_counts[tile] = s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NL_THREADS) k_line_index(const uint8_t* __restrict__ fq, size_t n, size_t n_tiles,
+                                                          const uint64_t* __restrict__ tile_prefix,
+                                                          uint64_t* __restrict__ seq_start,
+                                                          uint64_t* __restrict__ seq_end, uint64_t n_records) {
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // blocked: thread t owns bytes [64t, 64t+64) of the tile
+        size_t off = tile * INGEST_TILE_BYTES + (size_t)threadIdx.x * NL_BYTES_PER_THREAD;
+        const uint4* p = reinterpret_cast<const uint4*>(fq + off);
+        uint4 v[4];
+        unsigned c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = __ldg(p + j);
+            c += count_nl16(v[j]);
+        }
+        uint64_t line = block_exclusive_scan<NL_THREADS>(c, nullptr) + tile_prefix[tile];
+        if (c) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                uint32_t x = w[j];
+                if (__vcmpeq4(x, 0x0A0A0A0Au)) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        if (((x >> (8 * b)) & 0xffu) == 0x0Au) {
+                            size_t pos = off + 4 * j + b;
+                            if (pos < n) {
+                                uint64_t rec = line >> 2;
+                                unsigned phase = (unsigned)(line & 3);
+                                if (rec < n_records) {
+                                    if (phase == 0) seq_start[rec] = pos + 1;  // end of the header line
+                                    if (phase == 1) seq_end[rec] = pos;        // end of the sequence line
+                                }
+                            }
+                            ++line;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_read_scan(const uint8_t* __restrict__ fq,
+                                                  const uint64_t* __restrict__ seq_start,
+                                                  const uint64_t* __restrict__ seq_end, uint64_t n_records,
+                                                  uint32_t* __restrict__ rlen, uint8_t* __restrict__ rflag,
+                                                  unsigned long long* __restrict__ len_hist,
+                                                  unsigned long long* __restrict__ counters) {
+    unsigned lane = lane_id();
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    // each warp takes a contiguous span of reads so that equal lengths aggregate
+    uint64_t per = (n_records + n_warps - 1) / n_warps;
+    uint64_t lo = warp * per, hi = lo + per < n_records ? lo + per : n_records;
+    uint32_t run_len = 0;
+    unsigned long long run_cnt = 0, kept = 0, bad_reads = 0;
+    for (uint64_t r = lo; r < hi; ++r) {
+        uint64_t s = seq_start[r], e = seq_end[r];
+        uint32_t len = (uint32_t)(e - s);
+        bool has_n = false, bad = false;
+        for (uint32_t i = lane; i < len; i += 32) {
+            uint32_t c = fq[s + i];
+            has_n |= (c == 'N');
+            bad |= !(is_acgt(c) || c == 'N');
+        }
+        has_n = __any_sync(0xffffffffu, has_n);
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            rlen[r] = len;
+            rflag[r] = (uint8_t)((has_n ? 1 : 0) | (bad ? 2 : 0));
+            if (!has_n) {
+                ++kept;
+                if (bad) ++bad_reads;
+                uint32_t bin = len < LEN_HIST_BINS - 1 ? len : LEN_HIST_BINS - 1;
+                if (bin == run_len) {
+                    ++run_cnt;
+                } else {
+                    if (run_cnt) atomicAdd(&len_hist[run_len], run_cnt);
+                    run_len = bin;
+                    run_cnt = 1;
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        if (run_cnt) atomicAdd(&len_hist[run_len], run_cnt);
+        if (kept) atomicAdd(&counters[0], kept);
+        if (bad_reads) atomicAdd(&counters[1], bad_reads);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_chunk_count(const uint32_t* __restrict__ rlen,
+                                                    const uint8_t* __restrict__ rflag, uint64_t n_records,
+                                                    uint64_t r_limit, uint32_t clip, int whole,
+                                                    uint32_t* __restrict__ chunks) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records) return;
+    uint32_t c = 0;
+    if (r < r_limit && rflag[r] == 0) {
+        uint32_t len = rlen[r];
+        c = whole ? (len == clip ? 1u : 0u) : len / clip;
+    }
+    chunks[r] = c;
+}
+
+// spread the 32 bits of x to the even bit positions of a 64-bit word
+__device__ __forceinline__ uint64_t spread32(uint32_t x) {
+    uint64_t v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ fq, const uint64_t* __restrict__ seq_start,
+                                             const uint32_t* __restrict__ chunks,
+                                             const uint64_t* __restrict__ chunk_base, uint64_t n_records,
+                                             uint32_t clip, int W, uint64_t* __restrict__ words,
+                                             uint8_t* __restrict__ pal) {
+    unsigned lane = lane_id();
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int L = (int)clip;
+    for (uint64_t r = warp; r < n_records; r += n_warps) {
+        uint32_t nch = chunks[r];
+        if (nch == 0) continue;
+        uint64_t s0 = seq_start[r];
+        uint64_t slot0 = chunk_base[r];
+        for (uint32_t j = 0; j < nch; ++j) {
+            const uint8_t* src = fq + s0 + (uint64_t)j * clip;
+            // lane w ends up holding word w of the forward chunk
+            uint64_t mine = 0;
+            for (int w = 0; w < W; ++w) {
+                int i = 32 * w + (int)lane;
+                uint32_t code = i < L ? base_code(src[i]) : 0u;
+                // ballot bit t <-> base 32w+t; brev puts base 0 at bit 31
+                uint32_t m1 = __brev(__ballot_sync(0xffffffffu, code & 2u));
+                uint32_t m0 = __brev(__ballot_sync(0xffffffffu, code & 1u));
+                uint64_t word = (spread32(m1) << 1) | spread32(m0);
+                if ((int)lane == w) mine = word;
+            }
+            // reverse complement: lane w needs 32 bases starting at L-32w-32
+            int sbase = L - 32 * (int)lane - 32;
+            int wi = sbase >> 5, o = sbase & 31;
+            uint64_t hi = __shfl_sync(0xffffffffu, mine, wi & 31);
+            uint64_t lo = __shfl_sync(0xffffffffu, mine, (wi + 1) & 31);
+            if (wi < 0 || wi >= W) hi = 0;
+            if (wi + 1 < 0 || wi + 1 >= W) lo = 0;
+            uint64_t win = o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+            uint64_t rc = (int)lane < W ? (revcomp_groups64(win) & tail_mask(L, (int)lane)) : 0ull;
+            unsigned diff = __ballot_sync(0xffffffffu, mine != rc);
+            bool use_rc = false;
+            if (diff) {
+                int f = __ffs(diff) - 1;
+                use_rc = __shfl_sync(0xffffffffu, rc < mine ? 1 : 0, f) != 0;
+            }
+            uint64_t slot = slot0 + j;
+            if ((int)lane < W) words[slot * (uint64_t)W + lane] = use_rc ? rc : mine;
+            if (lane == 0) pal[slot] = diff == 0 ? 1 : 0;
+        }
+    }
+}
+
+}  // namespace
+
+void launch_newline_count(const uint8_t* fq, size_t n, uint32_t* tile_counts, cudaStream_t st) {
+    size_t n_tiles = (n + INGEST_TILE_BYTES - 1) / INGEST_TILE_BYTES;
+    if (!n_tiles) return;
+    unsigned grid = (unsigned)(n_tiles < (size_t)kNumSMs * 8 ? n_tiles : (size_t)kNumSMs * 8);
+    k_newline_count<<<grid, NL_THREADS, 0, st>>>(reinterpret_cast<const uint4*>(fq), n_tiles, tile_counts);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_line_index(const uint8_t* fq, size_t n, const uint64_t* tile_prefix, uint64_t* seq_start,
+                       uint64_t* seq_end, uint64_t n_records, cudaStream_t st) {
+    size_t n_tiles = (n + INGEST_TILE_BYTES - 1) / INGEST_TILE_BYTES;
+    if (!n_tiles) return;
+    unsigned grid = (unsigned)(n_tiles < (size_t)kNumSMs * 8 ? n_tiles : (size_t)kNumSMs * 8);
+    k_line_index<<<grid, NL_THREADS, 0, st>>>(fq, n, n_tiles, tile_prefix, seq_start, seq_end, n_records);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_read_scan(const uint8_t* fq, const uint64_t* seq_start, const uint64_t* seq_end, uint64_t n_records,
+                      uint32_t* rlen, uint8_t* rflag, unsigned long long* len_hist,
+                      unsigned long long* counters, cudaStream_t st) {
+    if (!n_records) return;
+    uint64_t warps_wanted = (n_records + 15) / 16;  // >= 16 reads per warp when there are many
+    uint64_t blocks = (warps_wanted + 7) / 8;
+    unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_read_scan<<<grid, 256, 0, st>>>(fq, seq_start, seq_end, n_records, rlen, rflag, len_hist, counters);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_chunk_count(const uint32_t* rlen, const uint8_t* rflag, uint64_t n_records, uint64_t r_limit,
+                        uint32_t clip, int whole, uint32_t* chunks, cudaStream_t st) {
+    if (!n_records) return;
+    unsigned grid = (unsigned)((n_records + 255) / 256);
+    k_chunk_count<<<grid, 256, 0, st>>>(rlen, rflag, n_records, r_limit, clip, whole, chunks);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_pack(const uint8_t* fq, const uint64_t* seq_start, const uint32_t* chunks, const uint64_t* chunk_base,
+                 uint64_t n_records, uint32_t clip, int W, uint64_t* words, uint8_t* pal, cudaStream_t st) {
+    if (!n_records) return;
+    uint64_t blocks = (n_records + 7) / 8;
+    unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_pack<<<grid, 256, 0, st>>>(fq, seq_start, chunks, chunk_base, n_records, clip, W, words, pal);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+}  // namespace pedk

@@ -1,0 +1,118 @@
+// Host-side launchers of the pedk kernels (one per stage of SURVEY.md 7.2).
+// Every launcher enqueues on `st` and returns; none of them synchronises.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace pedk {
+
+// ---------------- S0: ingest (ingest.cu) ----------------
+constexpr int INGEST_TILE_BYTES = 16384;
+constexpr int LEN_HIST_BINS = 1024;  // lengths >= LEN_HIST_BINS-1 land in the last bin
+
+// tile_counts[t] = number of '\n' in bytes [t*TILE, (t+1)*TILE); fq must be
+// readable (and newline-free) up to the next multiple of INGEST_TILE_BYTES.
+void launch_newline_count(const uint8_t* fq, size_t n, uint32_t* tile_counts, cudaStream_t st);
+// seq_start[r] / seq_end[r]: byte span of line 4r+1 (ped.pl:1435-1436 state machine)
+void launch_line_index(const uint8_t* fq, size_t n, const uint64_t* tile_prefix, uint64_t* seq_start,
+                       uint64_t* seq_end, uint64_t n_records, cudaStream_t st);
+// rlen[r], rflag[r] (bit0: contains 'N' -> dropped, ped.pl:1436; bit1: byte outside ACGTN);
+// len_hist over reads without N; counters[0] += reads without N, counters[1] += kept reads with bad bytes
+void launch_read_scan(const uint8_t* fq, const uint64_t* seq_start, const uint64_t* seq_end, uint64_t n_records,
+                      uint32_t* rlen, uint8_t* rflag, unsigned long long* len_hist,
+                      unsigned long long* counters, cudaStream_t st);
+// chunks[r] for r in [0, n_records): number of clip-length pieces read r contributes
+//   r >= r_limit -> 0;  flagged -> 0;  whole==1: (len == clip ? 1 : 0);  else len / clip
+void launch_chunk_count(const uint32_t* rlen, const uint8_t* rflag, uint64_t n_records, uint64_t r_limit,
+                        uint32_t clip, int whole, uint32_t* chunks, cudaStream_t st);
+// 2-bit pack every chunk, take min(read, revcomp(read)) (ped.pl:1460-1464 emits both;
+// we keep one representative), pal[i] = 1 iff the chunk equals its own reverse complement
+void launch_pack(const uint8_t* fq, const uint64_t* seq_start, const uint32_t* chunks, const uint64_t* chunk_base,
+                 uint64_t n_records, uint32_t clip, int W, uint64_t* words, uint8_t* pal, cudaStream_t st);
+
+// ---------------- S1: exact read dedup (dedup.cu) ----------------
+// table: capacity slots (power of two) preset to 0xFFFFFFFF; uniq[i] = 1 iff chunk i is
+// the representative of its value
+void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, uint8_t* uniq,
+                  cudaStream_t st);
+void launch_compact_reads(const uint64_t* words, const uint8_t* pal, const uint8_t* uniq, const uint64_t* pos,
+                          int W, uint32_t n, uint64_t* out_words, uint8_t* out_pal, cudaStream_t st);
+
+// *out += number of non-zero flags
+void launch_count_flags(const uint8_t* flags, uint64_t n, unsigned long long* out, cudaStream_t st);
+
+// ---------------- S2: k-mer extraction (kmer.cu) ----------------
+// out[r*nwin + i] = canonical k-mer of window i of unique read r; digit_hist[p*256 + d]
+// accumulates the 8-bit digit histograms for passes p < n_pass.  When lo < hi only
+// k-mers with lo <= canon < hi are wanted: others are written as ~0 (sorts last).
+void launch_extract(const uint64_t* words, int W, int L, int k, uint64_t n_reads, uint64_t* out,
+                    unsigned long long* digit_hist, int n_pass, cudaStream_t st);
+// canonical k-mers of every window of the palindromic reads only (count corrections)
+void launch_extract_pal(const uint64_t* words, const uint8_t* pal, int W, int L, int k, uint64_t n_reads,
+                        uint64_t* out, unsigned long long* cursor, cudaStream_t st);
+
+// ---------------- S3: LSD radix sort (radix.cu) ----------------
+struct RadixWorkspace {
+    uint64_t* lookback;      // tiles * 256 words
+    unsigned int* tile_ctr;  // 1 word
+    int* err;                // 1 word
+    size_t tiles_cap;
+};
+size_t radix_tiles(size_t n);
+// one onesweep pass on digit `pass` (bits [8*pass, 8*pass+8)); bin_base[256] = exclusive
+// scan of that digit's global histogram
+void launch_radix_pass(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t n, int pass,
+                       const unsigned long long* digit_hist, RadixWorkspace ws, cudaStream_t st);
+// digit histograms of an existing key array (pairs sort; the instance sort gets its
+// histograms from the extraction kernel)
+void launch_digit_hist(const uint64_t* keys, size_t n, unsigned long long* digit_hist, int n_pass,
+                       cudaStream_t st);
+void launch_hist_to_base(unsigned long long* digit_hist, int n_pass, cudaStream_t st);
+
+// ---------------- S4: run-length count (kmer.cu) ----------------
+size_t rle_tiles(size_t n);
+// ukey[r], ustart[r] (low 32 bits of the index where run r starts), ustart[D] = n; *n_runs = D.
+// Keys equal to ~0 (range-filtered placeholders) end the table.
+void launch_rle(const uint64_t* keys, size_t n, uint64_t* ukey, uint32_t* ustart, uint64_t* lookback,
+                unsigned int* tile_ctr, int* err, unsigned long long* n_runs, cudaStream_t st);
+
+// ---------------- S5/S6: strand expansion, lbc groups, edges (edges.cu) ----------------
+// rows (K, cnt | sample<<31) for K and revcomp(K) of every canonical row; corr = sorted
+// palindromic-read corrections (may be empty).  Forward rows go to rows [0, D), reverse
+// rows are appended through *cursor (preset to D).
+void launch_expand(const uint64_t* ukey, const uint32_t* ustart, uint64_t D, int k, int sample,
+                   const uint64_t* corr_key, const uint32_t* corr_start, uint64_t n_corr, uint64_t* row_key,
+                   uint32_t* row_val, unsigned long long* cursor, cudaStream_t st);
+// first[(sample*64 + tag)] = smallest key of that sample in 3-nt bucket `tag` (preset ~0)
+void launch_first_of_bucket(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
+                            unsigned long long* first, cudaStream_t st);
+
+struct EdgeRec {
+    uint64_t p;      // the (k-1)-mer
+    uint32_t c[4];   // control counts by last base (ped.pl:777 columns 4-7)
+    uint32_t t[4];   // target counts (columns 8-11)
+    uint8_t cont;    // bit x set: base x in the control allele set (>25 %)
+    uint8_t alt;     // same for the target
+    uint8_t pad[6];
+};
+// joinKmerSub (ped.pl:703-782) on every (k-1)-mer group of the merged table that is not the
+// first group of its bucket in either sample (those rows carry the F7 text quirk and are
+// evaluated on the host).  Edges are appended through *n_edges; at most cap are stored.
+void launch_edges(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
+                  const unsigned long long* first, EdgeRec* edges, uint64_t cap, unsigned long long* n_edges,
+                  cudaStream_t st);
+struct GroupRec {
+    uint64_t p;
+    uint32_t c[4], t[4];
+    uint8_t hasc[4], hast[4];  // row present in the table
+};
+// look up the groups of n_p given (k-1)-mers (host-side quirk rows)
+void launch_lookup_groups(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, const uint64_t* p_list,
+                          int n_p, GroupRec* out, cudaStream_t st);
+// ---------------- synthetic reads (synth.cu) ----------------
+struct SynthParams;
+void launch_synth_fastq(const SynthParams& p, const char* genome_dev, uint64_t first, uint64_t n, char* out_dev,
+                        cudaStream_t st);
+
+}  // namespace pedk

@@ -1,0 +1,258 @@
+// S3: least-significant-digit radix sort of 64-bit k-mer words (optionally with a
+// 32-bit payload), 8-bit digits, one "onesweep" pass per digit.
+//
+// Replaces `sort -S 1M` (ped.pl:928, 1416).  Per pass every key is read once
+// and written once (16 B/key of HBM traffic, 20 B/row with a payload):
+//   * the global digit histograms are produced upstream (by the k-mer
+//     extraction kernel, or launch_digit_hist for row tables), so a pass is a
+//     single kernel;
+//   * a tile (THREADS x ITEMS keys) ranks its keys with warp match_any +
+//     per-warp shared-memory counters, finds its global offsets with a
+//     decoupled look-back over 256 per-digit counters, stages the keys in
+//     shared memory in digit order and writes each digit run contiguously;
+//   * tiles take their index from an atomic ticket, so a tile only ever waits
+//     on tiles that are already running; the wait is bounded (err flag).
+// Look-back words are 32 bit (2 flag + 30 value bits); inputs longer than
+// PORTION keys are sorted in portions, the last tile of a portion folding its
+// inclusive digit counts into bin_base for the next portion.
+#include "kernels.h"
+#include "util.cuh"
+
+namespace pedk {
+
+namespace {
+
+constexpr int RS_THREADS = 384;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 6144 keys
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr size_t RS_PORTION = ((size_t(1) << 30) / RS_TILE - 1) * RS_TILE;
+
+constexpr uint32_t LB32_AGG = 1u << 30;
+constexpr uint32_t LB32_INC = 2u << 30;
+constexpr uint32_t LB32_MASK = (1u << 30) - 1;
+
+__device__ __forceinline__ void lb32_store(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lb32_load(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool PAIRS>
+struct RadixSmem {
+    uint64_t keys[RS_TILE];
+    uint32_t warp_hist[RS_WARPS][256];
+    uint32_t bin_start[256];
+    uint64_t gbase[256];
+    unsigned tile;
+};
+template <>
+struct RadixSmem<true> {
+    uint64_t keys[RS_TILE];
+    uint32_t vals[RS_TILE];
+    uint32_t warp_hist[RS_WARPS][256];
+    uint32_t bin_start[256];
+    uint64_t gbase[256];
+    unsigned tile;
+};
+
+template <bool PAIRS>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                          const uint32_t* __restrict__ vin,
+                                                          uint32_t* __restrict__ vout, size_t n, int shift,
+                                                          unsigned long long* __restrict__ bin_base,
+                                                          uint32_t* __restrict__ lookback,
+                                                          unsigned int* __restrict__ tile_ctr, unsigned n_tiles,
+                                                          int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RadixSmem<PAIRS>& sm = *reinterpret_cast<RadixSmem<PAIRS>*>(smem_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) sm.tile = atomicAdd(tile_ctr, 1u);
+#pragma unroll
+    for (int i = 0; i < 256 / 32; ++i) sm.warp_hist[warp][i * 32 + lane] = 0;
+    // read the global base before anything is published (see portion hand-over below)
+    unsigned long long my_base = tid < 256 ? bin_base[tid] : 0ull;
+    __syncthreads();
+    const unsigned tile = sm.tile;
+    const size_t tile_off = (size_t)tile * RS_TILE;
+    const unsigned tile_n = (unsigned)((n - tile_off) < (size_t)RS_TILE ? (n - tile_off) : (size_t)RS_TILE);
+
+    // ---- load (warp-striped: item j of lane l is key warp_off + 32j + l) ----
+    uint64_t key[RS_ITEMS];
+    uint32_t val[PAIRS ? RS_ITEMS : 1];
+    const unsigned warp_off = warp * (32 * RS_ITEMS);
+    if (tile_n == RS_TILE) {
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            key[j] = in[tile_off + warp_off + 32 * j + lane];
+            if constexpr (PAIRS) val[j] = vin[tile_off + warp_off + 32 * j + lane];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            unsigned i = warp_off + 32 * j + lane;
+            key[j] = i < tile_n ? in[tile_off + i] : ~0ull;  // padding ranks last in the last bin
+            if constexpr (PAIRS) val[j] = i < tile_n ? vin[tile_off + i] : 0u;
+        }
+    }
+
+    // ---- rank inside the warp ----
+    uint16_t rank[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        unsigned d = (unsigned)(key[j] >> shift) & 255u;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned leader = __ffs(peers) - 1;
+        unsigned before = 0;
+        if (lane == leader) before = atomicAdd(&sm.warp_hist[warp][d], __popc(peers));
+        before = __shfl_sync(0xffffffffu, before, leader);
+        rank[j] = (uint16_t)(before + __popc(peers & lanemask_lt()));
+    }
+    __syncthreads();
+
+    // ---- per-digit: warp offsets, tile histogram, look-back ----
+    unsigned dcount = 0;
+    if (tid < 256) {
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            unsigned c = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = dcount;
+            dcount += c;
+        }
+        lb32_store(lookback + (size_t)tile * 256 + tid, (tile == 0 ? LB32_INC : LB32_AGG) | dcount);
+    }
+    uint64_t ex = block_exclusive_scan<RS_THREADS>(dcount, nullptr);
+    if (tid < 256) {
+        sm.bin_start[tid] = (uint32_t)ex;
+        uint32_t excl = 0;
+        if (tile > 0) {
+            for (long long t = (long long)tile - 1; t >= 0; --t) {
+                uint32_t v;
+                unsigned spins = 0;
+                while (((v = lb32_load(lookback + (size_t)t * 256 + tid)) >> 30) == 0) {
+                    __nanosleep(32);
+                    if (++spins > (1u << 22)) {
+                        atomicExch(err, 1);
+                        v = LB32_INC;  // give up: the result is flagged invalid
+                        break;
+                    }
+                }
+                excl += v & LB32_MASK;
+                if (v & LB32_INC) break;
+            }
+            lb32_store(lookback + (size_t)tile * 256 + tid, LB32_INC | (excl + dcount));
+        }
+        sm.gbase[tid] = my_base + excl - ex;
+        // last tile of the portion: hand the running digit totals to the next portion
+        if (tile == n_tiles - 1) bin_base[tid] = my_base + excl + dcount;
+    }
+    __syncthreads();
+
+    // ---- stage in shared memory in digit order ----
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        unsigned d = (unsigned)(key[j] >> shift) & 255u;
+        unsigned pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[j];
+        sm.keys[pos] = key[j];
+        if constexpr (PAIRS) sm.vals[pos] = val[j];
+    }
+    __syncthreads();
+
+    // ---- write each digit run contiguously ----
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        unsigned i = j * RS_THREADS + tid;
+        if (i < tile_n) {
+            uint64_t k = sm.keys[i];
+            unsigned d = (unsigned)(k >> shift) & 255u;
+            size_t g = (size_t)(sm.gbase[d] + i);
+            out[g] = k;
+            if constexpr (PAIRS) vout[g] = sm.vals[i];
+        }
+    }
+}
+
+constexpr int DH_THREADS = 256;
+constexpr int DH_MAX_PASS = 8;
+
+__global__ void __launch_bounds__(DH_THREADS) k_digit_hist(const uint64_t* __restrict__ keys, size_t n,
+                                                          unsigned long long* __restrict__ digit_hist, int n_pass) {
+    __shared__ unsigned h[DH_MAX_PASS][256];
+    for (int i = threadIdx.x; i < DH_MAX_PASS * 256; i += DH_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    size_t stride = (size_t)gridDim.x * DH_THREADS;
+    for (size_t i = (size_t)blockIdx.x * DH_THREADS + threadIdx.x; i < n; i += stride) {
+        uint64_t k = keys[i];
+        for (int p = 0; p < n_pass; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pass * 256; i += DH_THREADS) {
+        unsigned c = (&h[0][0])[i];
+        if (c) atomicAdd(&digit_hist[i], (unsigned long long)c);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_hist_to_base(unsigned long long* __restrict__ digit_hist) {
+    unsigned long long* h = digit_hist + (size_t)blockIdx.x * 256;
+    uint64_t v = h[threadIdx.x];
+    uint64_t ex = block_exclusive_scan<256>(v, nullptr);
+    h[threadIdx.x] = ex;
+}
+
+}  // namespace
+
+size_t radix_tiles(size_t n) {
+    size_t p = n < RS_PORTION ? n : RS_PORTION;
+    return (p + RS_TILE - 1) / RS_TILE;
+}
+
+void launch_radix_pass(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t n, int pass,
+                       const unsigned long long* digit_hist, RadixWorkspace ws, cudaStream_t st) {
+    if (!n) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(RadixSmem<false>)));
+        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(RadixSmem<true>)));
+        attr_set = true;
+    }
+    unsigned long long* bin_base = const_cast<unsigned long long*>(digit_hist) + (size_t)pass * 256;
+    for (size_t off = 0; off < n; off += RS_PORTION) {
+        size_t pn = (n - off) < RS_PORTION ? (n - off) : RS_PORTION;
+        unsigned tiles = (unsigned)((pn + RS_TILE - 1) / RS_TILE);
+        if (tiles > ws.tiles_cap) throw PedkError(-8, "radix workspace too small");
+        PEDK_CUDA_TRY(cudaMemsetAsync(ws.lookback, 0, (size_t)tiles * 256 * sizeof(uint32_t), st));
+        PEDK_CUDA_TRY(cudaMemsetAsync(ws.tile_ctr, 0, sizeof(unsigned), st));
+        if (vin) {
+            k_radix_pass<true><<<tiles, RS_THREADS, sizeof(RadixSmem<true>), st>>>(
+                in + off, out, vin + off, vout, pn, 8 * pass, bin_base, reinterpret_cast<uint32_t*>(ws.lookback),
+                ws.tile_ctr, tiles, ws.err);
+        } else {
+            k_radix_pass<false><<<tiles, RS_THREADS, sizeof(RadixSmem<false>), st>>>(
+                in + off, out, nullptr, nullptr, pn, 8 * pass, bin_base, reinterpret_cast<uint32_t*>(ws.lookback),
+                ws.tile_ctr, tiles, ws.err);
+        }
+        PEDK_CUDA_TRY(cudaGetLastError());
+    }
+}
+
+void launch_digit_hist(const uint64_t* keys, size_t n, unsigned long long* digit_hist, int n_pass,
+                       cudaStream_t st) {
+    if (!n) return;
+    size_t blocks = (n + DH_THREADS * 16 - 1) / (DH_THREADS * 16);
+    unsigned grid = (unsigned)(blocks < (size_t)kNumSMs * 8 ? blocks : (size_t)kNumSMs * 8);
+    k_digit_hist<<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist, n_pass);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_hist_to_base(unsigned long long* digit_hist, int n_pass, cudaStream_t st) {
+    k_hist_to_base<<<n_pass, 256, 0, st>>>(digit_hist);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+}  // namespace pedk

@@ -1,0 +1,566 @@
+// One sample: FASTQ text in HBM -> unique packed reads (S0+S1) -> canonical
+// k-mer count table (S2-S4).  Host code here only sequences kernels and makes
+// the few decisions ped.pl makes from whole-file statistics (read-length mode).
+#include "sample.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+using namespace pedk;
+
+namespace {
+
+constexpr size_t FQ_ALIGN = INGEST_TILE_BYTES;
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void fq_reserve(pedk_sample* s, size_t want) {
+    size_t cap = round_up(want ? want : 1, FQ_ALIGN) + FQ_ALIGN;
+    if (s->fq.p && s->fq.n >= cap) return;
+    size_t grow = s->fq.n + s->fq.n / 2;
+    if (cap < grow) cap = round_up(grow, FQ_ALIGN);
+    DBuf<uint8_t> nb(s->ctx, cap);
+    if (s->fq_len) {
+        StageScope sc(s->ctx, PEDK_ST_COPY, 0);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(nb.p, s->fq.p, s->fq_len, cudaMemcpyDeviceToDevice, s->ctx->stream));
+    }
+    s->fq = std::move(nb);
+}
+
+uint64_t read_scalar(pedk_ctx* ctx, const unsigned long long* dev) {
+    PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += 8;
+    return ctx->h_scalars[0];
+}
+
+struct GroupPlan {
+    uint32_t clip;
+    int whole;
+    uint64_t r_limit;
+};
+
+// Build one read-length group: chunk -> pack -> dedup -> compact.
+void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_start, const uint32_t* rlen,
+                 const uint8_t* rflag, uint64_t R, uint64_t* strand_reads) {
+    pedk_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int L = (int)plan.clip;
+    const int W = (L + 31) / 32;
+    DBuf<uint32_t> chunks(ctx, R);
+    DBuf<uint64_t> base(ctx, R);
+    DBuf<uint64_t> ws(ctx, scan_workspace_words(R));
+    uint64_t n_c;
+    {
+        StageScope sc(ctx, PEDK_ST_INGEST, 4);
+        launch_chunk_count(rlen, rflag, R, plan.r_limit, plan.clip, plan.whole, chunks.p, st);
+        exclusive_scan_u32(chunks.p, base.p, R, ctx->scalars, ws.p, st);
+    }
+    n_c = read_scalar(ctx, ctx->scalars);
+    *strand_reads += 2 * n_c;
+    if (n_c == 0) return;
+    if (n_c >= 0xFFFFFFF0ull) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^32 reads in one sample on one GPU");
+    DBuf<uint64_t> words(ctx, n_c * W);
+    DBuf<uint8_t> pal(ctx, n_c);
+    {
+        StageScope sc(ctx, PEDK_ST_INGEST, 1);
+        launch_pack(s->fq.p, seq_start, chunks.p, base.p, R, plan.clip, W, words.p, pal.p, st);
+    }
+    chunks.reset();
+    base.reset();
+    ws.reset();
+    // exact dedup
+    uint32_t cap = 1024;
+    while ((uint64_t)cap < 2 * n_c) cap <<= 1;
+    DBuf<uint32_t> table(ctx, cap);
+    DBuf<uint8_t> uniq(ctx, n_c);
+    DBuf<uint64_t> pos(ctx, n_c);
+    DBuf<uint64_t> ws2(ctx, scan_workspace_words(n_c));
+    {
+        StageScope sc(ctx, PEDK_ST_DEDUP, 4);
+        PEDK_CUDA_TRY(cudaMemsetAsync(table.p, 0xFF, table.bytes(), st));
+        launch_dedup(words.p, W, (uint32_t)n_c, table.p, cap, uniq.p, st);
+        exclusive_scan_u8(uniq.p, pos.p, n_c, ctx->scalars, ws2.p, st);
+    }
+    uint64_t U = read_scalar(ctx, ctx->scalars);
+    table.reset();
+    ReadGroup g;
+    g.L = L;
+    g.W = W;
+    g.n = U;
+    g.words = DBuf<uint64_t>(ctx, U * W);
+    g.pal = DBuf<uint8_t>(ctx, U);
+    {
+        StageScope sc(ctx, PEDK_ST_DEDUP, 2);
+        launch_compact_reads(words.p, pal.p, uniq.p, pos.p, W, (uint32_t)n_c, g.words.p, g.pal.p, st);
+        PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 1, 0, sizeof(unsigned long long), st));
+        launch_count_flags(g.pal.p, U, ctx->scalars + 1, st);
+    }
+    g.n_pal = read_scalar(ctx, ctx->scalars + 1);
+    s->groups.push_back(std::move(g));
+}
+
+void do_ingest(pedk_sample* s, int clipping) {
+    pedk_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    s->groups.clear();
+    s->info = pedk_ingest_info{};
+    s->info.fastq_bytes = s->fq_len;
+    s->have_table = s->have_reads = false;
+    const size_t n = s->fq_len;
+    if (clipping < 0) throw PedkError(PEDK_E_INVAL, "clipping must be >= 0");
+    if (n == 0) {
+        s->ingested = true;
+        return;
+    }
+    if (s->copy_pending) {
+        StageScope sc(ctx, PEDK_ST_COPY, 0);  // time the kernels had to wait for the text
+        PEDK_CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copied, 0));
+        s->copy_pending = false;
+    }
+    fq_reserve(s, n);
+    const size_t padded = round_up(n, FQ_ALIGN);
+    PEDK_CUDA_TRY(cudaMemsetAsync(s->fq.p + n, 0, padded - n, st));
+    const size_t tiles = padded / FQ_ALIGN;
+
+    // ---- record structure: newline count, scan, line index ----
+    DBuf<uint32_t> tile_counts(ctx, tiles);
+    DBuf<uint64_t> tile_prefix(ctx, tiles);
+    DBuf<uint64_t> ws(ctx, scan_workspace_words(tiles));
+    {
+        StageScope sc(ctx, PEDK_ST_INGEST, 4);
+        launch_newline_count(s->fq.p, n, tile_counts.p, st);
+        exclusive_scan_u32(tile_counts.p, tile_prefix.p, tiles, ctx->scalars, ws.p, st);
+    }
+    uint8_t last_byte = 0;
+    PEDK_CUDA_TRY(cudaMemcpyAsync(&last_byte, s->fq.p + n - 1, 1, cudaMemcpyDeviceToHost, st));
+    uint64_t NL = read_scalar(ctx, ctx->scalars);
+    uint64_t TL = NL + (last_byte != '\n' ? 1 : 0);
+    uint64_t R = TL >= 2 ? (TL - 2) / 4 + 1 : 0;  // records that have a sequence line (line 4r+1)
+    s->info.records = R;
+    if (R == 0) {
+        s->fq.reset();
+        s->fq_len = 0;
+        s->ingested = true;
+        return;
+    }
+    DBuf<uint64_t> seq_start(ctx, R), seq_end(ctx, R);
+    DBuf<uint32_t> rlen(ctx, R);
+    DBuf<uint8_t> rflag(ctx, R);
+    DBuf<unsigned long long> hist(ctx, LEN_HIST_BINS + 4);
+    {
+        StageScope sc(ctx, PEDK_ST_INGEST, 2);
+        launch_line_index(s->fq.p, n, tile_prefix.p, seq_start.p, seq_end.p, R, st);
+        if (last_byte != '\n' && ((TL - 1) & 3) == 1) {
+            // the file ends inside a sequence line: it has no terminating newline
+            uint64_t end = n;
+            PEDK_CUDA_TRY(cudaMemcpyAsync(seq_end.p + (R - 1), &end, sizeof end, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        launch_read_scan(s->fq.p, seq_start.p, seq_end.p, R, rlen.p, rflag.p, hist.p, hist.p + LEN_HIST_BINS, st);
+    }
+    tile_counts.reset();
+    tile_prefix.reset();
+    ws.reset();
+    std::vector<unsigned long long> h_hist(LEN_HIST_BINS + 4);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(h_hist.data(), hist.p, hist.bytes(), cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->stats.d2h_bytes += hist.bytes();
+    const uint64_t kept = h_hist[LEN_HIST_BINS];
+    const uint64_t bad = h_hist[LEN_HIST_BINS + 1];
+    s->info.reads_kept = kept;
+    if (bad) {
+        char b[200];
+        snprintf(b, sizeof b, "%llu reads hold a byte outside ACGTN (ped.pl would carry them as text; not supported)",
+                 (unsigned long long)bad);
+        throw PedkError(PEDK_E_ALPHABET, b);
+    }
+    if (h_hist[LEN_HIST_BINS - 1]) throw PedkError(PEDK_E_UNSUPPORTED, "read longer than 1022 bases");
+    int n_lengths = 0;
+    uint32_t only_len = 0;
+    for (uint32_t l = 0; l < LEN_HIST_BINS - 1; ++l)
+        if (h_hist[l]) { ++n_lengths; only_len = l; }
+
+    // ---- the length mode ped.pl would end up in (ped.pl:1437-1464, 1478-1527) ----
+    std::vector<GroupPlan> plans;
+    if (clipping > 0) {
+        plans.push_back({(uint32_t)clipping, 0, R});
+        // ped.pl:1526 logs the length of the last kept read even then
+        std::vector<uint32_t> hl(R);
+        std::vector<uint8_t> hf(R);
+        size_t tail = R < 65536 ? R : 65536;
+        for (;;) {
+            PEDK_CUDA_TRY(cudaMemcpyAsync(hl.data(), rlen.p + (R - tail), tail * 4, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaMemcpyAsync(hf.data(), rflag.p + (R - tail), tail, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            bool found = false;
+            for (size_t i = tail; i-- > 0;)
+                if ((hf[i] & 1) == 0) { s->info.clipping_used = (int32_t)hl[i]; found = true; break; }
+            if (found || tail == R) break;
+            tail = R;
+        }
+    } else if (n_lengths <= 1) {
+        s->info.clipping_used = (int32_t)only_len;
+        if (kept) plans.push_back({only_len, 1, R});
+    } else {
+        // mixed lengths, no clipping=: reads before the first length change were already
+        // written unclipped (ped.pl:1440-1464), then everything is re-read and clipped
+        std::vector<uint32_t> hl(R);
+        std::vector<uint8_t> hf(R);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(hl.data(), rlen.p, R * 4, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(hf.data(), rflag.p, R, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += R * 5;
+        uint32_t L0 = 0;
+        uint64_t r_change = R;
+        bool have_first = false;
+        for (uint64_t r = 0; r < R; ++r) {
+            if (hf[r] & 1) continue;
+            // ped.pl:1440 `$readLength != $prev and $prev != 0`
+            if (have_first && L0 != 0 && hl[r] != L0) { r_change = r; break; }
+            if (!have_first || L0 == 0) { L0 = hl[r]; have_first = true; }
+        }
+        uint64_t sum = 0;
+        uint32_t clip = 0;
+        for (uint32_t l = LEN_HIST_BINS - 1; l-- > 0;) {
+            if (!h_hist[l]) continue;
+            sum += h_hist[l];
+            if (sum * 100 / kept >= 90) { clip = l; break; }
+        }
+        if (clip > 200) clip = clip / (clip / 100);
+        else if (clip < 75) clip = 75;
+        if (r_change == R) {
+            // the only other length is 0 and it came first: ped.pl never raises its flag
+            s->info.clipping_used = (int32_t)L0;
+            plans.push_back({L0, 1, R});
+        } else {
+            s->info.clipping_used = (int32_t)clip;
+            s->info.auto_clipped = 1;
+            if (L0 != clip && L0 != 0) plans.push_back({L0, 1, r_change});
+            plans.push_back({clip, 0, R});
+        }
+    }
+    hist.reset();
+
+    uint64_t strand_reads = 0;
+    for (const GroupPlan& p : plans) {
+        if (p.clip < 3) continue;  // ped.pl: no TAG handle is open for such lines, they go nowhere
+        if (p.clip > 32 * PEDK_MAX_WORDS) throw PedkError(PEDK_E_UNSUPPORTED, "reads longer than 512 bases");
+        build_group(s, p, seq_start.p, rlen.p, rflag.p, R, &strand_reads);
+    }
+    s->info.strand_reads = strand_reads;
+    s->info.n_groups = (int32_t)s->groups.size();
+    for (const ReadGroup& g : s->groups) {
+        s->info.unique_reads += 2 * g.n - g.n_pal;
+        s->info.palindromes += g.n_pal;
+    }
+    s->fq.reset();
+    s->fq_len = 0;
+    s->ingested = true;
+}
+
+void rle_into(pedk_ctx* ctx, const uint64_t* sorted, size_t n, uint64_t* ukey_big, DBuf<uint64_t>* ukey,
+              DBuf<uint32_t>* ustart, uint64_t* D_out) {
+    cudaStream_t st = ctx->stream;
+    DBuf<uint32_t> ustart_big(ctx, n + 1);
+    RadixWorkspace ws = radix_workspace(ctx, n);
+    {
+        StageScope sc(ctx, PEDK_ST_COUNT, 1);
+        launch_rle(sorted, n, ukey_big, ustart_big.p, ws.lookback, ws.tile_ctr, ws.err, ctx->scalars, st);
+    }
+    uint64_t D = read_scalar(ctx, ctx->scalars);
+    check_err_flag(ctx, "run-length count");
+    *ukey = DBuf<uint64_t>(ctx, D);
+    *ustart = DBuf<uint32_t>(ctx, D + 1);
+    {
+        StageScope sc(ctx, PEDK_ST_COUNT, 0);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ukey->p, ukey_big, D * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ustart->p, ustart_big.p, (D + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    *D_out = D;
+}
+
+void do_count(pedk_sample* s, int k) {
+    pedk_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!s->ingested) throw PedkError(PEDK_E_INVAL, "pedk_sample_count before pedk_sample_ingest");
+    if (k < 4 || k > 32) throw PedkError(PEDK_E_INVAL, "k must be in [4, 32]");
+    s->k = k;
+    s->D = 0;
+    s->n_corr = 0;
+    s->ukey.reset();
+    s->ustart.reset();
+    s->ckey.reset();
+    s->cstart.reset();
+    s->have_table = false;
+    s->cinfo = pedk_count_info{};
+    s->cinfo.k = k;
+    const int n_pass = (2 * k + 7) / 8;
+    s->cinfo.sort_passes = n_pass;
+    uint64_t M = 0, Mpal = 0;
+    for (const ReadGroup& g : s->groups)
+        if (g.L >= k) {
+            M += g.n * (uint64_t)(g.L - k + 1);
+            Mpal += g.n_pal * (uint64_t)(g.L - k + 1);
+        }
+    s->cinfo.instances = M;
+    s->cinfo.correction_rows = Mpal;
+    s->ukey = DBuf<uint64_t>(ctx, 0);
+    s->ustart = DBuf<uint32_t>(ctx, 1);
+    PEDK_CUDA_TRY(cudaMemsetAsync(s->ustart.p, 0, sizeof(uint32_t), st));
+    if (M == 0) return;
+
+    DBuf<unsigned long long> hist(ctx, 8 * 256);
+    {
+        DBuf<uint64_t> a(ctx, M), b(ctx, M);
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        uint64_t off = 0;
+        for (const ReadGroup& g : s->groups) {
+            if (g.L < k || !g.n) continue;
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            launch_extract(g.words.p, g.W, g.L, k, g.n, a.p + off, hist.p, n_pass, st);
+            off += g.n * (uint64_t)(g.L - k + 1);
+        }
+        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, M, n_pass, hist.p, PEDK_ST_SORT);
+        check_err_flag(ctx, "radix sort");
+        uint64_t* sorted = cur ? b.p : a.p;
+        uint64_t* spare = cur ? a.p : b.p;
+        rle_into(ctx, sorted, M, spare, &s->ukey, &s->ustart, &s->D);
+    }
+    s->cinfo.canonical_kmers = s->D;
+
+    if (Mpal) {
+        // windows of palindromic reads: each was emitted once but stands for one strand only
+        DBuf<uint64_t> a(ctx, Mpal), b(ctx, Mpal);
+        PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 2, 0, sizeof(unsigned long long), st));
+        for (const ReadGroup& g : s->groups) {
+            if (g.L < k || !g.n_pal) continue;
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            launch_extract_pal(g.words.p, g.pal.p, g.W, g.L, k, g.n, a.p, ctx->scalars + 2, st);
+        }
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        {
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            launch_digit_hist(a.p, Mpal, hist.p, n_pass, st);
+        }
+        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, Mpal, n_pass, hist.p, PEDK_ST_EXTRACT);
+        check_err_flag(ctx, "radix sort (corrections)");
+        rle_into(ctx, cur ? b.p : a.p, Mpal, cur ? a.p : b.p, &s->ckey, &s->cstart, &s->n_corr);
+    }
+}
+
+}  // namespace
+
+namespace pedk {
+
+std::string kmer_string(uint64_t v, int k) {
+    std::string r((size_t)k, 'A');
+    for (int j = 0; j < k; ++j) r[(size_t)j] = "ACGT"[(v >> (2 * (k - 1 - j))) & 3];
+    return r;
+}
+
+void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTable* out) {
+    cudaStream_t st = ctx->stream;
+    const int k = control->k;
+    const int n_pass = (2 * k + 7) / 8;
+    uint64_t cap = 2 * control->D + (target ? 2 * target->D : 0);
+    out->n = 0;
+    if (cap == 0) return;
+    DBuf<uint64_t> ka(ctx, cap), kb(ctx, cap);
+    DBuf<uint32_t> va(ctx, cap), vb(ctx, cap);
+    uint64_t rows = 0;
+    pedk_sample* ss[2] = {control, target};
+    for (int i = 0; i < 2; ++i) {
+        pedk_sample* s = ss[i];
+        if (!s || !s->D) continue;
+        unsigned long long preset = s->D;
+        {
+            StageScope sc(ctx, PEDK_ST_EXPAND, 1);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 3, &preset, sizeof preset, cudaMemcpyHostToDevice, st));
+            launch_expand(s->ukey.p, s->ustart.p, s->D, k, i, s->ckey.p, s->cstart.p, s->n_corr, ka.p + rows,
+                          va.p + rows, ctx->scalars + 3, st);
+        }
+        rows += read_scalar(ctx, ctx->scalars + 3);
+    }
+    DBuf<unsigned long long> hist(ctx, 8 * 256);
+    PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+    {
+        StageScope sc(ctx, PEDK_ST_ROWSORT, 1);
+        launch_digit_hist(ka.p, rows, hist.p, n_pass, st);
+    }
+    int cur = radix_sort(ctx, ka.p, kb.p, va.p, vb.p, rows, n_pass, hist.p, PEDK_ST_ROWSORT);
+    check_err_flag(ctx, "radix sort (rows)");
+    out->key = std::move(cur ? kb : ka);
+    out->val = std::move(cur ? vb : va);
+    out->n = rows;
+}
+
+void ensure_host_table(pedk_sample* s) {
+    if (s->have_table) return;
+    pedk_ctx* ctx = s->ctx;
+    if (!s->k) throw PedkError(PEDK_E_INVAL, "sample has not been counted");
+    RowTable t;
+    build_rows(ctx, s, nullptr, &t);
+    s->h_kmer.resize(t.n);
+    s->h_cnt.resize(t.n);
+    if (t.n) {
+        StageScope sc(ctx, PEDK_ST_COPY, 0);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(s->h_kmer.data(), t.key.p, t.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(s->h_cnt.data(), t.val.p, t.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += t.n * 12;
+    // bucket boundaries by the first three bases
+    const int shift = 2 * s->k - 6;
+    size_t i = 0;
+    for (int tag = 0; tag < 64; ++tag) {
+        while (i < s->h_kmer.size() && (int)(s->h_kmer[i] >> shift) < tag) ++i;
+        s->tag_start[tag] = i;
+    }
+    s->tag_start[64] = s->h_kmer.size();
+    s->have_table = true;
+}
+
+}  // namespace pedk
+
+// ---------------- C ABI ----------------
+
+extern "C" int pedk_sample_create(pedk_ctx* ctx, pedk_sample** out) {
+    if (!ctx || !out) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    pedk_sample* s = new pedk_sample();
+    s->ctx = ctx;
+    *out = s;
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_sample_destroy(pedk_sample* s) {
+    if (!s) return PEDK_OK;
+    cudaSetDevice(s->ctx->device);
+    if (s->copy_pending) cudaStreamSynchronize(s->ctx->copy_stream);
+    if (s->ev_copied) cudaEventDestroy(s->ev_copied);
+    delete s;
+    return PEDK_OK;
+}
+
+extern "C" int pedk_sample_reserve(pedk_sample* s, uint64_t fastq_bytes) {
+    if (!s) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    PEDK_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    fq_reserve(s, fastq_bytes);
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+static int add_fastq(pedk_sample* s, const void* bytes, uint64_t n, cudaMemcpyKind kind) {
+    if (!s || (!bytes && n)) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    if (!n) return PEDK_OK;
+    pedk_ctx* ctx = s->ctx;
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (s->ingested) {
+        s->ingested = false;
+        s->groups.clear();
+    }
+    if (s->copy_pending && !(s->fq.p && s->fq.n >= s->fq_len + n + 2 * INGEST_TILE_BYTES)) {
+        // the buffer is about to move: earlier chunks must have landed first
+        PEDK_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copied, 0));
+    }
+    fq_reserve(s, s->fq_len + n);
+    if (kind == cudaMemcpyHostToDevice) {
+        // host text goes through the copy stream so it overlaps kernels already queued
+        PEDK_CUDA_TRY(cudaEventRecord(ctx->ev_alloc, ctx->stream));
+        PEDK_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(s->fq.p + s->fq_len, bytes, n, kind, ctx->copy_stream));
+        if (!s->ev_copied) PEDK_CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+        PEDK_CUDA_TRY(cudaEventRecord(s->ev_copied, ctx->copy_stream));
+        s->copy_pending = true;
+        ctx->stats.h2d_bytes += n;
+    } else {
+        StageScope sc(ctx, PEDK_ST_COPY, 0);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(s->fq.p + s->fq_len, bytes, n, kind, ctx->stream));
+    }
+    s->fq_len += n;
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+extern "C" int pedk_sample_add_fastq(pedk_sample* s, const void* host_bytes, uint64_t n) {
+    return add_fastq(s, host_bytes, n, cudaMemcpyHostToDevice);
+}
+
+extern "C" int pedk_sample_add_fastq_device(pedk_sample* s, const void* device_bytes, uint64_t n) {
+    return add_fastq(s, device_bytes, n, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int pedk_sample_ingest(pedk_sample* s, int clipping, pedk_ingest_info* info) {
+    if (!s) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_ingest(s, clipping);
+    if (info) *info = s->info;
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+extern "C" int pedk_sample_count(pedk_sample* s, int k, pedk_count_info* info) {
+    if (!s) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_count(s, k);
+    if (info) *info = s->cinfo;
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+extern "C" int pedk_sample_table(pedk_sample* s, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n) {
+    if (!s || !n) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    PEDK_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    ensure_host_table(s);
+    *n = s->h_kmer.size();
+    if (kmers && counts) {
+        if (cap < *n) throw PedkError(PEDK_E_INVAL, "pedk_sample_table: buffer too small");
+        memcpy(kmers, s->h_kmer.data(), *n * 8);
+        memcpy(counts, s->h_cnt.data(), *n * 4);
+    }
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+extern "C" int pedk_sample_reads(pedk_sample* s, int group, uint64_t* words, uint8_t* pal, uint64_t cap_reads,
+                                 uint64_t* n_reads, int32_t* read_len, int32_t* words_per_read) {
+    if (!s || !n_reads) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    if (group < 0 || group >= (int)s->groups.size()) throw PedkError(PEDK_E_INVAL, "no such read group");
+    PEDK_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    const ReadGroup& g = s->groups[(size_t)group];
+    *n_reads = g.n;
+    if (read_len) *read_len = g.L;
+    if (words_per_read) *words_per_read = g.W;
+    if (words && pal) {
+        if (cap_reads < g.n) throw PedkError(PEDK_E_INVAL, "pedk_sample_reads: buffer too small");
+        PEDK_CUDA_TRY(cudaMemcpyAsync(words, g.words.p, g.n * g.W * 8, cudaMemcpyDeviceToHost, s->ctx->stream));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(pal, g.pal.p, g.n, cudaMemcpyDeviceToHost, s->ctx->stream));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+        s->ctx->stats.d2h_bytes += g.n * (g.W * 8 + 1);
+    }
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+extern "C" int pedk_sample_release_reads(pedk_sample* s) {
+    if (!s) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    PEDK_CUDA_TRY(cudaSetDevice(s->ctx->device));
+    for (ReadGroup& g : s->groups) {
+        g.words.reset();
+        g.pal.reset();
+    }
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}

@@ -1,0 +1,54 @@
+// Device-resident state of one sample (internal).
+#pragma once
+#include <vector>
+
+#include "ctx.h"
+
+struct ReadGroup {
+    int L = 0, W = 0;      // bases per read, 64-bit words per read
+    uint64_t n = 0;        // unique canonical representatives
+    uint64_t n_pal = 0;    // of which palindromic
+    pedk::DBuf<uint64_t> words;
+    pedk::DBuf<uint8_t> pal;
+};
+
+struct pedk_sample {
+    pedk_ctx* ctx = nullptr;
+    // FASTQ text in HBM
+    pedk::DBuf<uint8_t> fq;
+    size_t fq_len = 0;
+    cudaEvent_t ev_copied = nullptr;  // last H2D chunk has landed
+    bool copy_pending = false;
+    bool ingested = false;
+    std::vector<ReadGroup> groups;
+    pedk_ingest_info info{};
+    // canonical count table
+    int k = 0;
+    uint64_t D = 0;
+    pedk::DBuf<uint64_t> ukey;
+    pedk::DBuf<uint32_t> ustart;
+    uint64_t n_corr = 0;
+    pedk::DBuf<uint64_t> ckey;
+    pedk::DBuf<uint32_t> cstart;
+    pedk_count_info cinfo{};
+    // host caches for the text emitters
+    bool have_table = false;
+    std::vector<uint64_t> h_kmer;
+    std::vector<uint32_t> h_cnt;
+    uint64_t tag_start[65] = {0};
+    bool have_reads = false;
+    std::vector<std::string> h_reads[64];  // sorted strand-closed reads per bucket
+};
+
+namespace pedk {
+// strand table of one sample (or the merged table of two) in HBM
+struct RowTable {
+    DBuf<uint64_t> key;
+    DBuf<uint32_t> val;
+    uint64_t n = 0;
+};
+// expand + sort; target may be null (single-sample table, sample bit 0)
+void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTable* out);
+void ensure_host_table(pedk_sample* s);
+std::string kmer_string(uint64_t v, int k);
+}  // namespace pedk

@@ -1,0 +1,106 @@
+"""Deterministic inputs shared by scripts/make_golden.py (which feeds them to the
+unmodified reference) and the tests (which feed them to the oracle and to the
+CUDA path).  Synthetic reads follow SURVEY.md section 8d."""
+from __future__ import annotations
+
+import numpy as np
+
+from ped_b200 import api
+
+# name -> recipe.  seeds follow SURVEY 8d: genome 1000+c, variants 2000+c, control reads 3000+c, target 4000+c
+CASES = {
+    # 3 kb genome, 800 reads per sample (survey probe P1 shape)
+    "tiny": dict(kind="synth", cfg=1, genome=3000, reads=800, L=150, snp_ppm=1000, indel_ppm=300, err_ppm=2000,
+                 n_ppm=1000, dup_ppm=0),
+    # config 1 at 40x: edges present
+    "c1_40x": dict(kind="synth", cfg=2, genome=30000, reads=8000, L=150, snp_ppm=1000, indel_ppm=100, err_ppm=2000,
+                   n_ppm=1000, dup_ppm=0),
+    # config 1 (BASELINE.json configs[0]): ~1000x, every count > 100 -> no edges
+    "c1_1000x": dict(kind="synth", cfg=3, genome=30000, reads=200000, L=150, snp_ppm=1000, indel_ppm=100,
+                     err_ppm=2000, n_ppm=1000, dup_ppm=0),
+    # many exact duplicate reads (same placement, error-free copies)
+    "dup": dict(kind="synth", cfg=4, genome=5000, reads=3000, L=150, snp_ppm=2000, indel_ppm=200, err_ppm=300,
+                n_ppm=5000, dup_ppm=400000),
+    # explicit clipping: one 100-base chunk per read / three 50-base chunks per read
+    "clip100": dict(kind="synth", cfg=5, genome=5000, reads=2000, L=150, snp_ppm=2000, indel_ppm=200, err_ppm=2000,
+                    n_ppm=1000, dup_ppm=0, clipping=100),
+    "clip50": dict(kind="synth", cfg=6, genome=4000, reads=1500, L=150, snp_ppm=2000, indel_ppm=200, err_ppm=2000,
+                   n_ppm=1000, dup_ppm=0, clipping=50),
+    # mixed read lengths, no clipping=: ped.pl's automatic clipping incl. the reads already written unclipped
+    "mixed": dict(kind="mixed", cfg=7, genome=5000, reads=2500, L=150, snp_ppm=2000, indel_ppm=200, err_ppm=2000,
+                  n_ppm=1000, dup_ppm=0),
+    # palindromic reads, palindromic 20-mers, reverse-complement duplicates, no final newline
+    "adversarial": dict(kind="adversarial", cfg=8, genome=4000, reads=1200, L=150, snp_ppm=2000, indel_ppm=200,
+                        err_ppm=1000, n_ppm=2000, dup_ppm=100000),
+}
+
+_COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def revcomp(s: bytes) -> bytes:
+    return s.translate(_COMP)[::-1]
+
+
+def genomes(case):
+    c = case["cfg"]
+    g = api.synth_genome(1000 + c, case["genome"])
+    if case["kind"] == "adversarial":
+        # plant two palindromic 20-mers (each equals its own reverse complement)
+        for pos, half in ((500, b"ACGTTGCAAT"), (2100, b"GGATCCATGA")):
+            pal = half + revcomp(half)
+            g[pos:pos + 20] = np.frombuffer(pal, dtype=np.uint8)
+    t = api.synth_mutate(g, 2000 + c, case["snp_ppm"], case["indel_ppm"])
+    return g, t
+
+
+def _records(fq: bytes):
+    lines = fq.split(b"\n")
+    assert lines[-1] == b""
+    lines = lines[:-1]
+    return [lines[i:i + 4] for i in range(0, len(lines), 4)]
+
+
+def _join(recs) -> bytes:
+    return b"".join(b"\n".join(r) + b"\n" for r in recs)
+
+
+def make_inputs(case):
+    """-> (control_fastq, target_fastq) as bytes."""
+    c = case["cfg"]
+    g, t = genomes(case)
+    kw = dict(read_len=case["L"], err_ppm=case["err_ppm"], n_ppm=case["n_ppm"], dup_ppm=case["dup_ppm"])
+    fc = api.synth_fastq(g, 3000 + c, case["reads"], **kw)
+    ft = api.synth_fastq(t, 4000 + c, case["reads"], **kw)
+    if case["kind"] == "synth":
+        return fc, ft
+    out = []
+    for si, fq in enumerate((fc, ft)):
+        recs = _records(fq)
+        if case["kind"] == "mixed":
+            for i, r in enumerate(recs):
+                if i < 300:
+                    continue  # a uniform prefix: these are written unclipped before the first length change
+                cut = 120 if i % 7 == 3 else 90 if i % 11 == 5 else 0
+                if cut:
+                    r[1] = r[1][:cut]
+                    r[3] = r[3][:cut]
+            out.append(_join(recs))
+        else:  # adversarial
+            gg = g if si == 0 else t
+            gb = gg.tobytes()
+            extra = []
+            # palindromic reads: x + revcomp(x); two copies of the first one
+            for j, pos in enumerate((100, 100, 900, 1700)):
+                x = gb[pos:pos + 75]
+                extra.append([b"@pal%d" % j, x + revcomp(x), b"+", b"I" * 150])
+            # the reverse complement of an existing read, and an exact copy of another
+            extra.append([b"@rc", revcomp(recs[10][1]) if b"N" not in recs[10][1] else revcomp(recs[11][1]), b"+",
+                          b"I" * 150])
+            extra.append([b"@copy", recs[20][1], b"+", b"I" * 150])
+            # reads covering the planted palindromic 20-mers on both samples
+            for j, pos in enumerate((430, 440, 450, 2050, 2060)):
+                extra.append([b"@cov%d" % j, gb[pos:pos + 150], b"+", b"I" * 150])
+            allr = recs[:600] + extra + recs[600:]
+            b = _join(allr)
+            out.append(b[:-1])  # no newline after the last quality line
+    return out[0], out[1]

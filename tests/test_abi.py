@@ -1,0 +1,73 @@
+"""The C-ABI library loads and exports every symbol include/pedk.h declares
+(no compute calls: this runs without a GPU)."""
+import os
+import re
+
+import pytest
+
+from ped_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "pedk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(pedk_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_symbols_exported(built):
+    lib = api.load_library()
+    names = declared_functions()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"libpedk.so does not export {n}"
+
+
+def test_python_mirror_covers_header(built):
+    assert sorted(api.SIGNATURES) == declared_functions()
+
+
+def test_struct_layouts_match_header(built):
+    import ctypes as C
+
+    assert C.sizeof(api.Edge) == 48 and api.EDGE_DTYPE.itemsize == 48
+    assert C.sizeof(api.IngestInfo) == 64
+    assert C.sizeof(api.CountInfo) == 32
+    assert C.sizeof(api.SynthParams) == 32
+
+
+def test_no_cpu_fallback(built):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.PedkError) as e:
+        api.Context(0)
+    assert e.value.code == -9  # PEDK_E_NODEVICE
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for d in ("ped_b200", "perl", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, d)):
+            if "build" in dp.split(os.sep):
+                continue
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c", ".pm", ".xs", ".pl")):
+                    s = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"ped_oracle|from oracle|import oracle|oracle/", s):
+                        bad.append(os.path.join(dp, f))
+    assert bad == [ROOT + "/ped_b200/build.py"] or bad == []  # build.py only compiles the checker
+
+
+def test_synth_slices_are_independent(built):
+    g = api.synth_genome(11, 2000)
+    whole = api.synth_fastq(g, 5, 230, read_len=100, dup_ppm=200000)
+    a = api.synth_fastq(g, 5, 100, read_len=100, dup_ppm=200000)
+    b = api.synth_fastq(g, 5, 130, read_len=100, dup_ppm=200000, first=100)
+    assert a + b == whole
+    assert len(whole) == api.synth_fastq_bytes(0, 230, 100)
+    t = api.synth_mutate(g, 3, 5000, 1000)
+    assert len(t) != 0 and bytes(t) != bytes(g)

@@ -1,0 +1,204 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the
+reference's own outputs (tests/golden/).  Bit-exact: everything here is byte,
+integer or index work.  B200 only."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from ped_b200 import api
+from tests.cases import CASES, make_inputs, revcomp
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu_run(ctx, fc: bytes, ft: bytes, k=20, clipping=0):
+    c, t = api.Sample(ctx), api.Sample(ctx)
+    c.add_fastq(fc)
+    t.add_fastq(ft)
+    ci = c.ingest(clipping)
+    ti = t.ingest(clipping)
+    c.count(k)
+    t.count(k)
+    r = ctx.join(c, t)
+    return c, t, ci, ti, r
+
+
+def check_sample(gs: api.Sample, info, os_: oracle.OracleSample, texts=True):
+    assert info.unique_reads == os_.num_reads
+    assert info.clipping_used == os_.clipping_used
+    assert bool(info.auto_clipped) == os_.auto_clipped
+    km, ct = gs.table()
+    okm, oct_ = os_.table()
+    assert km.shape == okm.shape and (km == okm).all()
+    assert (ct == oct_).all()
+    if texts:
+        for tag in range(64):
+            assert gs.sort_uniq_text(tag) == os_.sort_uniq_text(tag), ("sort_uniq", tag)
+            assert gs.count_text(tag) == os_.count_text(tag), ("count", tag)
+            assert gs.lbc_text(tag) == os_.lbc_text(tag), ("lbc", tag)
+
+
+def _sha_tags(fn):
+    h = hashlib.sha256()
+    for t in range(64):
+        h.update(fn(t))
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name", ["tiny", "adversarial", "mixed", "clip100", "clip50", "dup", "c1_40x", "c1_1000x"])
+def test_case_against_oracle_and_reference(ctx, name):
+    case = CASES[name]
+    fc, ft = make_inputs(case)
+    clip = case.get("clipping", 0)
+    oc, ot, osnp = oracle.run(fc, ft, 20, clip)
+    c, t, ci, ti, r = gpu_run(ctx, fc, ft, 20, clip)
+    try:
+        big = name == "c1_1000x"
+        check_sample(c, ci, oc, texts=not big)
+        check_sample(t, ti, ot, texts=not big)
+        assert r.text() == osnp
+        e = r.edges()
+        assert len(e) == osnp.count(b"\n") and (np.diff(e["prefix"].astype(np.int64)) >= 0).all()
+        gpath = os.path.join(GOLDEN, name + ".json")
+        if os.path.exists(gpath):
+            g = json.load(open(gpath))
+            assert r.text().decode() == g["kmer_snp"]
+            for key, s in (("control", c), ("target", t)):
+                assert _sha_tags(s.count_text) == g[key]["count_sha256"]
+                assert _sha_tags(s.lbc_text) == g[key]["lbc_sha256"]
+                assert _sha_tags(s.sort_uniq_text) == g[key]["sort_uniq_sha256"]
+    finally:
+        r.destroy(); c.destroy(); t.destroy()
+
+
+@pytest.mark.parametrize("k", [4, 5, 16, 19, 21, 31, 32])
+def test_other_k(ctx, k):
+    case = dict(CASES["adversarial"])
+    fc, ft = make_inputs(case)
+    oc, ot, osnp = oracle.run(fc, ft, k)
+    c, t, ci, ti, r = gpu_run(ctx, fc, ft, k)
+    try:
+        check_sample(c, ci, oc, texts=False)
+        check_sample(t, ti, ot, texts=False)
+        assert r.text() == osnp
+    finally:
+        r.destroy(); c.destroy(); t.destroy()
+
+
+def _fq(seqs):
+    return "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs)).encode()
+
+
+def test_corner_inputs(ctx):
+    import random
+
+    rnd = random.Random(7)
+    g = "".join(rnd.choice("ACGT") for _ in range(600))
+    reads = [g[i:i + 64] for i in range(0, 530, 2)]
+    half = g[100:132]
+    pal = half + revcomp(half.encode()).decode()
+    reads += [pal, pal, revcomp(reads[5].encode()).decode(), reads[7], "ACGTN" * 12 + "ACGT"]
+    tgt = list(reads)
+    tgt[30] = tgt[30][:20] + ("A" if tgt[30][20] != "A" else "C") + tgt[30][21:]
+    fc, ft = _fq(reads), _fq(tgt)
+    variants = [(fc, ft), (fc[:-1], ft[:-70]), (b"", ft), (fc, b""), (_fq(["NNNN" * 16]), ft), (b"@only\n", ft),
+                (_fq(["ACGTACGTACGTACGT"]), _fq(["ACGTACGTACGTACGT"]))]  # reads shorter than k
+    for a, b in variants:
+        oc, ot, osnp = oracle.run(a, b, 20)
+        c, t, ci, ti, r = gpu_run(ctx, a, b, 20)
+        try:
+            check_sample(c, ci, oc)
+            check_sample(t, ti, ot)
+            assert r.text() == osnp
+        finally:
+            r.destroy(); c.destroy(); t.destroy()
+
+
+def test_alphabet_error_is_loud(ctx):
+    s = api.Sample(ctx)
+    s.add_fastq(_fq(["ACGTRYACGTACGTACGTACGTACGT"]))
+    with pytest.raises(api.PedkError) as e:
+        s.ingest()
+    assert e.value.code == -5
+    s.destroy()
+
+
+def test_chunked_host_feed_and_fused_call(ctx):
+    import torch
+
+    case = CASES["c1_40x"]
+    fc, ft = make_inputs(case)
+    _, _, osnp = oracle.run(fc, ft, 20)
+    # (a) FASTQ fed in arbitrary pieces
+    c, t = api.Sample(ctx), api.Sample(ctx)
+    for s, fq in ((c, fc), (t, ft)):
+        for i in range(0, len(fq), 300_001):
+            s.add_fastq(fq[i:i + 300_001])
+        s.ingest()
+        s.count(20)
+    r = ctx.join(c, t)
+    assert r.text() == osnp
+    r.destroy(); c.destroy(); t.destroy()
+    # (b) the one-call path with host buffers (pinned) and with device buffers
+    hc = torch.frombuffer(bytearray(fc), dtype=torch.uint8).pin_memory()
+    ht = torch.frombuffer(bytearray(ft), dtype=torch.uint8).pin_memory()
+    r = ctx.kmer_edges(hc, len(fc), ht, len(ft), device_buffers=False)
+    assert r.text() == osnp
+    r.destroy()
+    dc, dt = hc.cuda(), ht.cuda()
+    torch.cuda.synchronize()
+    r = ctx.kmer_edges(dc, len(fc), dt, len(ft), device_buffers=True)
+    assert r.text() == osnp
+    r.destroy()
+
+
+def test_medium_scale_against_oracle(ctx):
+    """5 Mb genome, 30x (the survey's config-2 cut-down): table and edges vs the oracle."""
+    case = dict(kind="synth", cfg=12, genome=5_000_000, reads=1_000_000, L=150, snp_ppm=1000, indel_ppm=100,
+                err_ppm=2000, n_ppm=1000, dup_ppm=0)
+    fc, ft = make_inputs(case)
+    oc, ot, osnp = oracle.run(fc, ft, 20)
+    c, t, ci, ti, r = gpu_run(ctx, fc, ft, 20)
+    try:
+        check_sample(c, ci, oc, texts=False)
+        check_sample(t, ti, ot, texts=False)
+        assert r.text() == osnp
+        assert r.num_edges > 1000
+    finally:
+        r.destroy(); c.destroy(); t.destroy()
+
+
+def test_full_size_properties(ctx):
+    """Size-independent properties at a size the oracle is not asked to follow:
+    sortedness, strand symmetry, and conservation of instances."""
+    import torch
+
+    G, N, L, k = 20_000_000, 4_000_000, 150, 20
+    g = api.synth_genome(501, G)
+    gd = torch.from_numpy(g).cuda()
+    nb = api.synth_fastq_bytes(0, N, L)
+    buf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.synth_fastq_device(api.SynthParams(502, G, L, 2000, 1000, 0), gd, 0, N, buf)
+    s = api.Sample(ctx)
+    s.add_fastq_device(buf, nb)
+    info = s.ingest()
+    ci = s.count(k)
+    assert ci.instances * 2 - ci.correction_rows == info.unique_reads * (L - k + 1)
+    km, ct = s.table()
+    assert (km[1:] > km[:-1]).all()
+    assert int(ct.astype(np.uint64).sum()) == info.unique_reads * (L - k + 1)
+    # count(K) == count(revcomp K): reverse-complement every key and look it up
+    rc = np.zeros_like(km)
+    v = km.copy()
+    for _ in range(k):
+        rc = (rc << np.uint64(2)) | (np.uint64(3) - (v & np.uint64(3)))
+        v >>= np.uint64(2)
+    idx = np.searchsorted(km, rc)
+    assert (km[idx] == rc).all() and (ct[idx] == ct).all()
+    s.destroy()

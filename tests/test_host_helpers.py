@@ -1,0 +1,86 @@
+"""CPU checks of the bit-level helpers shared by host and device code."""
+import ctypes as C
+import os
+import random
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests.cases import revcomp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+@pytest.fixture(scope="module")
+def hd():
+    d = tempfile.mkdtemp(prefix="pedk_hd_")
+    so = os.path.join(d, "hd_shim.so")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", os.path.join(ROOT, "tests", "hd_shim.cpp"),
+                           "-o", so])
+    L = C.CDLL(so)
+    L.hd_kmer_revcomp.restype = C.c_uint64
+    L.hd_kmer_revcomp.argtypes = [C.c_uint64, C.c_int]
+    L.hd_kmer_at.restype = C.c_uint64
+    L.hd_kmer_at.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.hd_read_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.hd_words_cmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.hd_base_code.restype = C.c_uint32
+    L.hd_base_code.argtypes = [C.c_uint32]
+    return L
+
+
+def enc(s: str) -> int:
+    v = 0
+    for c in s:
+        v = (v << 2) | CODE[c]
+    return v
+
+
+def pack(s: str) -> np.ndarray:
+    W = (len(s) + 31) // 32
+    w = np.zeros(W, dtype=np.uint64)
+    for i, c in enumerate(s):
+        w[i >> 5] |= np.uint64(CODE[c] << (62 - 2 * (i & 31)))
+    return w
+
+
+def test_base_code(hd):
+    for c in "ACGT":
+        assert hd.hd_base_code(ord(c)) == CODE[c]
+
+
+@pytest.mark.parametrize("k", [4, 19, 20, 21, 31, 32])
+def test_kmer_revcomp(hd, k):
+    rnd = random.Random(k)
+    for _ in range(200):
+        s = "".join(rnd.choice("ACGT") for _ in range(k))
+        assert hd.hd_kmer_revcomp(enc(s), k) == enc(revcomp(s.encode()).decode())
+    pal = "ACGTTGCAAT"[: k // 2]
+    if k % 2 == 0 and len(pal) == k // 2:
+        p = pal + revcomp(pal.encode()).decode()
+        assert hd.hd_kmer_revcomp(enc(p), k) == enc(p)
+
+
+@pytest.mark.parametrize("L", [3, 31, 32, 33, 64, 75, 100, 150, 151, 256, 300, 512])
+def test_read_pack_revcomp_and_windows(hd, L):
+    rnd = random.Random(L)
+    for _ in range(20):
+        s = "".join(rnd.choice("ACGT") for _ in range(L))
+        w = pack(s)
+        W = len(w)
+        out = np.zeros(W, dtype=np.uint64)
+        hd.hd_read_revcomp(w.ctypes.data, W, L, out.ctypes.data)
+        r = revcomp(s.encode()).decode()
+        assert (out == pack(r)).all()
+        # numeric order of the word tuples == byte order of the strings
+        want = (s > r) - (s < r)
+        assert hd.hd_words_cmp(w.ctypes.data, out.ctypes.data, W) == want
+        for k in (4, 20, 31, 32):
+            if k > L:
+                continue
+            for i in {0, 1, 31, 32, 33, L - k, (L - k) // 2}:
+                if 0 <= i <= L - k:
+                    assert hd.hd_kmer_at(w.ctypes.data, W, i, k) == enc(s[i:i + k])

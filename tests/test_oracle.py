@@ -1,0 +1,118 @@
+"""The C oracle against (a) a naive Python restatement of ped.pl and (b) the
+outputs of the unmodified reference itself (tests/golden/, made by
+scripts/make_golden.py).  CPU only."""
+import hashlib
+import json
+import os
+
+import pytest
+
+from oracle import oracle
+from tests import pyref
+from tests.cases import CASES, make_inputs, revcomp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TAGS = oracle.TAGS
+
+
+def _sha_tags(fn):
+    h = hashlib.sha256()
+    rows = 0
+    for t in range(64):
+        b = fn(t)
+        h.update(b)
+        rows += b.count(b"\n")
+    return h.hexdigest(), rows
+
+
+def _check_against_pyref(fc: bytes, ft: bytes, k=20, clipping=0):
+    ref = pyref.run(fc.decode(), ft.decode(), k, clipping)
+    c, t, snp = oracle.run(fc, ft, k, clipping)
+    for name, o in (("control", c), ("target", t)):
+        r = ref[name]
+        assert o.clipping_used == r["clipping"]
+        for i, tag in enumerate(TAGS):
+            assert o.sort_uniq_text(i).decode() == "".join(x + "\n" for x in r["sort_uniq"][tag]), (name, tag)
+            assert o.count_text(i).decode() == "".join(f"{s}\t{n}\n" for s, n in r["count"][tag]), (name, tag)
+            assert o.lbc_text(i).decode() == r["lbc"][tag], (name, tag)
+    assert snp.decode() == ref["kmer_snp"]
+    return ref
+
+
+@pytest.mark.parametrize("name", ["tiny", "adversarial", "mixed", "clip50"])
+def test_oracle_matches_python_restatement(name, built):
+    case = dict(CASES[name])
+    if name != "tiny":
+        case["reads"] = min(case["reads"], 900)
+    fc, ft = make_inputs(case)
+    ref = _check_against_pyref(fc, ft, 20, case.get("clipping", 0))
+    if name == "tiny":
+        assert ref["kmer_snp"].count("\n") > 0
+
+
+def _fq(seqs):
+    return "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs)).encode()
+
+
+def test_oracle_hand_made_corner_cases(built):
+    import random
+
+    rnd = random.Random(7)
+    g = "".join(rnd.choice("ACGT") for _ in range(400))
+    reads = [g[i:i + 60] for i in range(0, 340, 3)]
+    half = g[100:130]
+    pal = half + revcomp(half.encode()).decode()  # a read equal to its own reverse complement
+    reads += [pal, pal, revcomp(reads[5].encode()).decode(), reads[7], "ACGTN" * 12, "AC"]
+    tgt = list(reads)
+    tgt[30] = tgt[30][:20] + ("A" if tgt[30][20] != "A" else "C") + tgt[30][21:]
+    fc, ft = _fq(reads), _fq(tgt)
+    _check_against_pyref(fc, ft)
+    # file that ends inside a record / without the last newline
+    _check_against_pyref(fc[:-1], ft[:-70])
+    # other k (the reference hard-codes 20: ped.pl:912-913 with the literal edited)
+    for k in (5, 19, 31, 32):
+        _check_against_pyref(fc, ft, k)
+    # empty and N-only inputs
+    _check_against_pyref(b"", ft)
+    _check_against_pyref(_fq(["NNNN" * 10]), ft)
+
+
+def test_oracle_strand_symmetry(built):
+    fc, ft = make_inputs(CASES["tiny"])
+    c, _, _ = oracle.run(fc, ft)
+    km, ct = c.table()
+    table = dict(zip(km.tolist(), ct.tolist()))
+    comp = {0: 3, 1: 2, 2: 1, 3: 0}
+    for kmer, n in table.items():
+        rc = 0
+        v = kmer
+        for _ in range(20):
+            rc = (rc << 2) | comp[v & 3]
+            v >>= 2
+        assert table[rc] == n  # the read set is closed under reverse complement
+
+
+def _goldens():
+    if not os.path.isdir(GOLDEN):
+        return []
+    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json"))
+
+
+@pytest.mark.parametrize("name", _goldens())
+def test_oracle_matches_reference_golden(name, built):
+    """Bit-exact against ped.pl's own sort_uniq/, count/, lbc/ and <t>.kmer.snp."""
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    case = CASES[name]
+    fc, ft = make_inputs(case)
+    c, t, snp = oracle.run(fc, ft, g["k"], case.get("clipping", 0))
+    for key, o in (("control", c), ("target", t)):
+        sha, rows = _sha_tags(o.sort_uniq_text)
+        assert (rows, sha) == (g[key]["sort_uniq_rows"], g[key]["sort_uniq_sha256"]), (key, "sort_uniq")
+        sha, rows = _sha_tags(o.count_text)
+        assert (rows, sha) == (g[key]["count_rows"], g[key]["count_sha256"]), (key, "count")
+        sha, rows = _sha_tags(o.lbc_text)
+        assert (rows, sha) == (g[key]["lbc_rows"], g[key]["lbc_sha256"]), (key, "lbc")
+    assert snp.decode() == g["kmer_snp"]
+    # "clipping : N" lines of <t>.log: one per mkSortUniq call, target first (ped.pl:291-297)
+    assert g["clipping_lines"] == [f"clipping : {t.clipping_used}", f"clipping : {c.clipping_used}"]
