@@ -150,8 +150,12 @@ int pedk_kmer_edges(pedk_ctx *ctx, const void *control_fastq, uint64_t control_b
 
 /* mkSortUniq (ped.pl:1365-1410): reads <wd>/<subject>/read/ (gz, bz2, xz and
  * *q files, grouped and ordered like ped.pl), writes
- * <wd>/<subject>/sort_uniq/<subject>.sort_uniq.TAG.gz. */
-int pedk_mk_sort_uniq(pedk_ctx *ctx, const char *wd, const char *subject, int clipping, int *clipping_used);
+ * <wd>/<subject>/sort_uniq/<subject>.sort_uniq.TAG.gz.  *clipping_used is the
+ * value of the "clipping :" log line; *auto_clipped is 1 when ped.pl would have
+ * assigned it to its global $clipping (ped.pl:1483), which makes it the
+ * explicit clipping of every later mkSortUniq call of the same run. */
+int pedk_mk_sort_uniq(pedk_ctx *ctx, const char *wd, const char *subject, int clipping, int *clipping_used,
+                      int *auto_clipped);
 /* countKmer (ped.pl:784-815): writes <wd>/<subject>/count/<subject>.count.TAG.gz */
 int pedk_count_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
 /* lbcKmer (ped.pl:817-831): writes <wd>/<subject>/lbc/<subject>.lbc.TAG.gz */

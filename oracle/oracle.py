@@ -165,8 +165,12 @@ def join_text(control: OracleSample, target: OracleSample) -> bytes:
 
 
 def run(control_fastq: bytes, target_fastq: bytes, k: int = 20, clipping: int = 0):
-    c = OracleSample(control_fastq, clipping)
+    """ped.pl main (291-297): the target is ingested first; `$clipping` is a global, so a
+    value chosen automatically for the target is an explicit clipping= for the control."""
     t = OracleSample(target_fastq, clipping)
+    if t.auto_clipped:
+        clipping = t.clipping_used
+    c = OracleSample(control_fastq, clipping)
     c.count(k)
     t.count(k)
     return c, t, join_text(c, t)

@@ -108,7 +108,7 @@ SIGNATURES = {
     "pedk_free": (None, [_P]),
     "pedk_result_destroy": (C.c_int, [_P]),
     "pedk_kmer_edges": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _PP]),
-    "pedk_mk_sort_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
+    "pedk_mk_sort_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pedk_count_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_lbc_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_join_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),

@@ -225,12 +225,14 @@ extern "C" int pedk_open(pedk_ctx** out, const int* devices, int ndev) {
 
 namespace pedk {
 void comm_destroy(pedk_ctx* ctx);
+void file_cache_destroy(pedk_ctx* ctx);
 }
 
 extern "C" int pedk_close(pedk_ctx* ctx) {
     if (!ctx) return PEDK_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    file_cache_destroy(ctx);
     comm_destroy(ctx);
     for (auto& p : ctx->pending) {
         cudaEventDestroy(p.a);

@@ -38,6 +38,7 @@ struct pedk_ctx {
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    void* file_cache = nullptr;  // files.cu: samples kept resident between the file-level calls
 };
 
 #define PEDK_API_BEGIN try {

@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(NL_THREADS) k_newline_count(const uint4* __res
 __global__ void __launch_bounds__(NL_THREADS) k_line_index(const uint8_t* __restrict__ fq, size_t n, size_t n_tiles,
                                                           const uint64_t* __restrict__ tile_prefix,
                                                           uint64_t* __restrict__ seq_start,
-                                                          uint64_t* __restrict__ seq_end, uint64_t n_records) {
+                                                          uint64_t* __restrict__ seq_end, uint64_t n_records,
+                                                          int plain_lines) {
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // blocked: thread t owns bytes [64t, 64t+64) of the tile
         size_t off = tile * INGEST_TILE_BYTES + (size_t)threadIdx.x * NL_BYTES_PER_THREAD;
@@ -69,7 +70,10 @@ __global__ void __launch_bounds__(NL_THREADS) k_line_index(const uint8_t* __rest
                     for (int b = 0; b < 4; ++b) {
                         if (((x >> (8 * b)) & 0xffu) == 0x0Au) {
                             size_t pos = off + 4 * j + b;
-                            if (pos < n) {
+                            if (pos < n && plain_lines) {
+                                if (line < n_records) seq_end[line] = pos;
+                                if (line + 1 < n_records) seq_start[line + 1] = pos + 1;
+                            } else if (pos < n) {
                                 uint64_t rec = line >> 2;
                                 unsigned phase = (unsigned)(line & 3);
                                 if (rec < n_records) {
@@ -220,11 +224,11 @@ void launch_newline_count(const uint8_t* fq, size_t n, uint32_t* tile_counts, cu
 }
 
 void launch_line_index(const uint8_t* fq, size_t n, const uint64_t* tile_prefix, uint64_t* seq_start,
-                       uint64_t* seq_end, uint64_t n_records, cudaStream_t st) {
+                       uint64_t* seq_end, uint64_t n_records, int plain_lines, cudaStream_t st) {
     size_t n_tiles = (n + INGEST_TILE_BYTES - 1) / INGEST_TILE_BYTES;
     if (!n_tiles) return;
     unsigned grid = (unsigned)(n_tiles < (size_t)kNumSMs * 8 ? n_tiles : (size_t)kNumSMs * 8);
-    k_line_index<<<grid, NL_THREADS, 0, st>>>(fq, n, n_tiles, tile_prefix, seq_start, seq_end, n_records);
+    k_line_index<<<grid, NL_THREADS, 0, st>>>(fq, n, n_tiles, tile_prefix, seq_start, seq_end, n_records, plain_lines);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

@@ -209,6 +209,9 @@ char* dup_text(const std::string& s, uint64_t* len) {
     return p;
 }
 
+}  // namespace
+
+namespace pedk {
 void ensure_host_reads(pedk_sample* s) {
     if (s->have_reads) return;
     pedk_ctx* ctx = s->ctx;
@@ -243,7 +246,7 @@ void ensure_host_reads(pedk_sample* s) {
     s->have_reads = true;
 }
 
-}  // namespace
+}  // namespace pedk
 
 extern "C" int pedk_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_result** out) {
     if (!ctx || !control || !target || !out) return PEDK_E_INVAL;
@@ -364,17 +367,21 @@ extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_
     if (rc == PEDK_OK) rc = pedk_sample_reserve(c, control_bytes);
     if (rc == PEDK_OK) rc = pedk_sample_reserve(t, target_bytes);
     if (rc == PEDK_OK)
-        rc = where ? pedk_sample_add_fastq_device(c, control_fastq, control_bytes)
-                   : pedk_sample_add_fastq(c, control_fastq, control_bytes);
-    if (rc == PEDK_OK)
         rc = where ? pedk_sample_add_fastq_device(t, target_fastq, target_bytes)
                    : pedk_sample_add_fastq(t, target_fastq, target_bytes);
+    if (rc == PEDK_OK)
+        rc = where ? pedk_sample_add_fastq_device(c, control_fastq, control_bytes)
+                   : pedk_sample_add_fastq(c, control_fastq, control_bytes);
+    // ped.pl:291-297 ingests the target first, and `$clipping` is a global: a value chosen
+    // automatically for the target is an explicit clipping= for the control
+    pedk_ingest_info ti;
+    if (rc == PEDK_OK) rc = pedk_sample_ingest(t, clipping, &ti);
+    if (rc == PEDK_OK && ti.auto_clipped) clipping = ti.clipping_used;
+    if (rc == PEDK_OK) rc = pedk_sample_count(t, k, nullptr);
+    if (rc == PEDK_OK) rc = pedk_sample_release_reads(t);
     if (rc == PEDK_OK) rc = pedk_sample_ingest(c, clipping, nullptr);
     if (rc == PEDK_OK) rc = pedk_sample_count(c, k, nullptr);
     if (rc == PEDK_OK) rc = pedk_sample_release_reads(c);
-    if (rc == PEDK_OK) rc = pedk_sample_ingest(t, clipping, nullptr);
-    if (rc == PEDK_OK) rc = pedk_sample_count(t, k, nullptr);
-    if (rc == PEDK_OK) rc = pedk_sample_release_reads(t);
     if (rc == PEDK_OK) rc = pedk_join(ctx, c, t, out);
     pedk_sample_destroy(c);
     pedk_sample_destroy(t);

@@ -15,8 +15,9 @@ constexpr int LEN_HIST_BINS = 1024;  // lengths >= LEN_HIST_BINS-1 land in the l
 // readable (and newline-free) up to the next multiple of INGEST_TILE_BYTES.
 void launch_newline_count(const uint8_t* fq, size_t n, uint32_t* tile_counts, cudaStream_t st);
 // seq_start[r] / seq_end[r]: byte span of line 4r+1 (ped.pl:1435-1436 state machine)
+// plain_lines != 0: every line is a read (sort_uniq text); seq_start[0] must be preset to 0
 void launch_line_index(const uint8_t* fq, size_t n, const uint64_t* tile_prefix, uint64_t* seq_start,
-                       uint64_t* seq_end, uint64_t n_records, cudaStream_t st);
+                       uint64_t* seq_end, uint64_t n_records, int plain_lines, cudaStream_t st);
 // rlen[r], rflag[r] (bit0: contains 'N' -> dropped, ped.pl:1436; bit1: byte outside ACGTN);
 // len_hist over reads without N; counters[0] += reads without N, counters[1] += kept reads with bad bytes
 void launch_read_scan(const uint8_t* fq, const uint64_t* seq_start, const uint64_t* seq_end, uint64_t n_records,

@@ -107,6 +107,7 @@ void do_ingest(pedk_sample* s, int clipping) {
     cudaStream_t st = ctx->stream;
     PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
     s->groups.clear();
+    s->reads_released = false;
     s->info = pedk_ingest_info{};
     s->info.fastq_bytes = s->fq_len;
     s->have_table = s->have_reads = false;
@@ -140,6 +141,7 @@ void do_ingest(pedk_sample* s, int clipping) {
     uint64_t NL = read_scalar(ctx, ctx->scalars);
     uint64_t TL = NL + (last_byte != '\n' ? 1 : 0);
     uint64_t R = TL >= 2 ? (TL - 2) / 4 + 1 : 0;  // records that have a sequence line (line 4r+1)
+    if (s->line_format) R = TL;
     s->info.records = R;
     if (R == 0) {
         s->fq.reset();
@@ -153,8 +155,9 @@ void do_ingest(pedk_sample* s, int clipping) {
     DBuf<unsigned long long> hist(ctx, LEN_HIST_BINS + 4);
     {
         StageScope sc(ctx, PEDK_ST_INGEST, 2);
-        launch_line_index(s->fq.p, n, tile_prefix.p, seq_start.p, seq_end.p, R, st);
-        if (last_byte != '\n' && ((TL - 1) & 3) == 1) {
+        if (s->line_format) PEDK_CUDA_TRY(cudaMemsetAsync(seq_start.p, 0, sizeof(uint64_t), st));
+        launch_line_index(s->fq.p, n, tile_prefix.p, seq_start.p, seq_end.p, R, s->line_format ? 1 : 0, st);
+        if (last_byte != '\n' && (s->line_format || ((TL - 1) & 3) == 1)) {
             // the file ends inside a sequence line: it has no terminating newline
             uint64_t end = n;
             PEDK_CUDA_TRY(cudaMemcpyAsync(seq_end.p + (R - 1), &end, sizeof end, cudaMemcpyHostToDevice, st));
@@ -187,7 +190,12 @@ void do_ingest(pedk_sample* s, int clipping) {
 
     // ---- the length mode ped.pl would end up in (ped.pl:1437-1464, 1478-1527) ----
     std::vector<GroupPlan> plans;
-    if (clipping > 0) {
+    if (s->line_format) {
+        // already strand-closed unique reads: one group per length, nothing is clipped
+        for (uint32_t l = 0; l < LEN_HIST_BINS - 1; ++l)
+            if (h_hist[l]) plans.push_back({l, 1, R});
+        s->info.clipping_used = (int32_t)only_len;
+    } else if (clipping > 0) {
         plans.push_back({(uint32_t)clipping, 0, R});
         // ped.pl:1526 logs the length of the last kept read even then
         std::vector<uint32_t> hl(R);
@@ -368,7 +376,8 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     cudaStream_t st = ctx->stream;
     const int k = control->k;
     const int n_pass = (2 * k + 7) / 8;
-    uint64_t cap = 2 * control->D + (target ? 2 * target->D : 0);
+    auto rows_of = [](pedk_sample* s) -> uint64_t { return !s ? 0 : s->host_only_table ? s->h_kmer.size() : 2 * s->D; };
+    uint64_t cap = rows_of(control) + rows_of(target);
     out->n = 0;
     if (cap == 0) return;
     DBuf<uint64_t> ka(ctx, cap), kb(ctx, cap);
@@ -377,6 +386,20 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     pedk_sample* ss[2] = {control, target};
     for (int i = 0; i < 2; ++i) {
         pedk_sample* s = ss[i];
+        if (s && s->host_only_table) {
+            // strand table read back from count files: upload it as rows
+            uint64_t m = s->h_kmer.size();
+            if (!m) continue;
+            std::vector<uint32_t> v(s->h_cnt);
+            if (i) for (auto& x : v) x |= 0x80000000u;
+            StageScope sc(ctx, PEDK_ST_COPY, 0);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(ka.p + rows, s->h_kmer.data(), m * 8, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaMemcpyAsync(va.p + rows, v.data(), m * 4, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->stats.h2d_bytes += m * 12;
+            rows += m;
+            continue;
+        }
         if (!s || !s->D) continue;
         unsigned long long preset = s->D;
         {
@@ -561,6 +584,7 @@ extern "C" int pedk_sample_release_reads(pedk_sample* s) {
         g.words.reset();
         g.pal.reset();
     }
+    s->reads_released = true;
     return PEDK_OK;
     PEDK_API_END(s->ctx)
 }

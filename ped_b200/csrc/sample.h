@@ -20,6 +20,9 @@ struct pedk_sample {
     cudaEvent_t ev_copied = nullptr;  // last H2D chunk has landed
     bool copy_pending = false;
     bool ingested = false;
+    bool line_format = false;      // text is one read per line (sort_uniq files), not FASTQ
+    bool reads_released = false;
+    bool host_only_table = false;  // strand table was loaded from count files; nothing in HBM
     std::vector<ReadGroup> groups;
     pedk_ingest_info info{};
     // canonical count table
@@ -50,5 +53,6 @@ struct RowTable {
 // expand + sort; target may be null (single-sample table, sample bit 0)
 void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTable* out);
 void ensure_host_table(pedk_sample* s);
+void ensure_host_reads(pedk_sample* s);
 std::string kmer_string(uint64_t v, int k);
 }  // namespace pedk

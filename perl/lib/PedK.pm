@@ -1,0 +1,15 @@
+package PedK;
+# Perl binding of libpedk.so, the B200-native k-mer hot path of PED.
+# The subs mirror the ped.pl subs they replace (see INTEGRATION.md):
+#   PedK::mk_sort_uniq($wd, $subject, $clipping)   -> ped.pl mkSortUniq  (1365-1410); returns (clipping value, automatic?)
+#   PedK::count_kmer($wd, $subject, $k)            -> ped.pl countKmer   (784-815)
+#   PedK::lbc_kmer($wd, $subject, $k)              -> ped.pl lbcKmer     (817-831)
+#   PedK::join_kmer($wd, $t, $c, $k, $tmpdir, $ref)-> ped.pl joinKmer    (687-701) + 374-378
+# Every sub dies with the library's message on failure; there is no CPU fallback.
+use strict;
+use warnings;
+our $VERSION = '0.01';
+require XSLoader;
+XSLoader::load('PedK', $VERSION);
+our @STAGES = qw(ingest dedup extract sort count expand rowsort edges copy exchange);
+1;

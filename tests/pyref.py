@@ -84,7 +84,7 @@ def sort_uniq(fastq: str, clipping: int = 0):
             elif count == 4:
                 count = 0
             count += 1
-    return {t: sorted(set(v)) for t, v in files.items()}, used
+    return {t: sorted(set(v)) for t, v in files.items()}, used, flag
 
 
 def count_table(su, k: int = 20):
@@ -204,8 +204,10 @@ def join_text(lbc_c: str, lbc_t: str) -> str:
 
 def run(control_fastq: str, target_fastq: str, k: int = 20, clipping: int = 0):
     res = {}
-    for name, fq in (("control", control_fastq), ("target", target_fastq)):
-        su, used = sort_uniq(fq, clipping)
+    for name, fq in (("target", target_fastq), ("control", control_fastq)):  # ped.pl:291-297 order
+        su, used, auto = sort_uniq(fq, clipping)
+        if auto:
+            clipping = used  # `$clipping` is a global in ped.pl
         ct = count_table(su, k)
         res[name] = dict(sort_uniq=su, clipping=used, count=ct, lbc={t: lbc_text(ct[t], k) for t in TAGS})
     # join needs the inputs sorted; the rows already are.  Unpaired keys are dropped.

@@ -1,0 +1,109 @@
+"""The file-level entry points ped.pl binds (pedk_mk_sort_uniq / count_kmer /
+lbc_kmer / join_kmer): same directories, names and `zcat` content as the
+reference's file contract.  B200 only."""
+import ctypes as C
+import gzip
+import json
+import os
+
+import pytest
+
+from oracle import oracle
+from ped_b200 import api
+from tests.cases import CASES, make_inputs
+
+pytestmark = pytest.mark.gpu
+TAGS = oracle.TAGS
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _zcat(p):
+    with gzip.open(p, "rb") as f:
+        return f.read()
+
+
+def _layout(tmp_path, fc, ft, gz=False):
+    wd = str(tmp_path)
+    for s, fq in (("C", fc), ("T", ft)):
+        os.makedirs(os.path.join(wd, s, "read"))
+        half = fq.find(b"\n@r", len(fq) // 2) + 1  # two files, split at a record boundary
+        parts = [fq[:half], fq[half:]]
+        for i, part in enumerate(parts):
+            if gz:
+                with gzip.open(os.path.join(wd, s, "read", f"{s}_{i + 1}.fastq.gz"), "wb") as f:
+                    f.write(part)
+            else:
+                with open(os.path.join(wd, s, "read", f"{s}_{i + 1}.fastq"), "wb") as f:
+                    f.write(part)
+    return wd
+
+
+def _check_files(wd, oc, ot, osnp):
+    for s, o in (("C", oc), ("T", ot)):
+        for i, tag in enumerate(TAGS):
+            assert _zcat(f"{wd}/{s}/sort_uniq/{s}.sort_uniq.{tag}.gz") == o.sort_uniq_text(i)
+            assert _zcat(f"{wd}/{s}/count/{s}.count.{tag}.gz") == o.count_text(i)
+            assert _zcat(f"{wd}/{s}/lbc/{s}.lbc.{tag}.gz") == o.lbc_text(i)
+    assert open(f"{wd}/T/T.kmer.snp", "rb").read() == osnp
+    assert not [f for d, _, fs in os.walk(wd) for f in fs if f.endswith(".tmp")]
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_drop_in_file_contract(built, tmp_path, gz):
+    case = CASES["c1_40x"]
+    fc, ft = make_inputs(case)
+    oc, ot, osnp = oracle.run(fc, ft, 20)
+    wd = _layout(tmp_path, fc, ft, gz)
+    ctx = api.Context(0)
+    lib = ctx.lib
+    used = C.c_int()
+    for s in ("T", "C"):
+        ctx.check(lib.pedk_mk_sort_uniq(ctx.h, wd.encode(), s.encode(), 0, C.byref(used), None))
+        assert used.value == 150
+    for s in ("T", "C"):
+        ctx.check(lib.pedk_count_kmer(ctx.h, wd.encode(), s.encode(), 20))
+    for s in ("T", "C"):
+        ctx.check(lib.pedk_lbc_kmer(ctx.h, wd.encode(), s.encode(), 20))
+    ctx.check(lib.pedk_join_kmer(ctx.h, wd.encode(), b"T", b"C", 20, None, 0))
+    ctx.close()
+    _check_files(wd, oc, ot, osnp)
+    g = json.load(open(os.path.join(GOLDEN, "c1_40x.json"))) if os.path.exists(os.path.join(GOLDEN, "c1_40x.json")) else None
+    if g:
+        assert open(f"{wd}/T/T.kmer.snp").read() == g["kmer_snp"]
+
+
+def test_resume_from_files_in_fresh_processes(built, tmp_path):
+    """Every stage in its own context: nothing but the files carries over
+    (ped.pl's gates, ped.pl:291-297, 369-372), incl. the ref-mode per-tag files."""
+    case = CASES["tiny"]
+    fc, ft = make_inputs(case)
+    oc, ot, osnp = oracle.run(fc, ft, 20)
+    wd = _layout(tmp_path, fc, ft)
+
+    def call(fn, *a):
+        ctx = api.Context(0)
+        try:
+            ctx.check(getattr(ctx.lib, fn)(ctx.h, *a))
+        finally:
+            ctx.close()
+
+    for s in (b"T", b"C"):
+        call("pedk_mk_sort_uniq", wd.encode(), s, 0, None, None)
+    for s in (b"T", b"C"):
+        call("pedk_count_kmer", wd.encode(), s, 20)
+    for s in (b"T", b"C"):
+        call("pedk_lbc_kmer", wd.encode(), s, 20)
+    call("pedk_join_kmer", wd.encode(), b"T", b"C", 20, None, 0)
+    _check_files(wd, oc, ot, osnp)
+    tmpdir = os.path.join(wd, "T", "tmp")
+    call("pedk_join_kmer", wd.encode(), b"T", b"C", 20, tmpdir.encode(), 1)
+    cat = b"".join(open(os.path.join(tmpdir, f"T.snp.{t}"), "rb").read() for t in TAGS)
+    assert cat == osnp
+
+
+def test_missing_input_is_an_error_not_a_gate_file(built, tmp_path):
+    ctx = api.Context(0)
+    rc = ctx.lib.pedk_mk_sort_uniq(ctx.h, str(tmp_path).encode(), b"nosuch", 0, None, None)
+    assert rc == -4 and b"nosuch" in ctx.lib.pedk_last_error(ctx.h)
+    assert not os.path.exists(os.path.join(str(tmp_path), "nosuch", "sort_uniq"))
+    ctx.close()

@@ -20,8 +20,8 @@ def gpu_run(ctx, fc: bytes, ft: bytes, k=20, clipping=0):
     c, t = api.Sample(ctx), api.Sample(ctx)
     c.add_fastq(fc)
     t.add_fastq(ft)
-    ci = c.ingest(clipping)
-    ti = t.ingest(clipping)
+    ti = t.ingest(clipping)  # ped.pl:291-297: target first; an automatic clipping sticks for the control
+    ci = c.ingest(ti.clipping_used if ti.auto_clipped else clipping)
     c.count(k)
     t.count(k)
     r = ctx.join(c, t)

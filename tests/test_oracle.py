@@ -115,4 +115,5 @@ def test_oracle_matches_reference_golden(name, built):
         assert (rows, sha) == (g[key]["lbc_rows"], g[key]["lbc_sha256"]), (key, "lbc")
     assert snp.decode() == g["kmer_snp"]
     # "clipping : N" lines of <t>.log: one per mkSortUniq call, target first (ped.pl:291-297)
-    assert g["clipping_lines"] == [f"clipping : {t.clipping_used}", f"clipping : {c.clipping_used}"]
+    want = [f"clipping : {case['clipping']}"] if case.get("clipping") else []  # the argument echo (ped.pl:105)
+    assert g["clipping_lines"] == want + [f"clipping : {t.clipping_used}", f"clipping : {c.clipping_used}"]
