@@ -3,6 +3,7 @@
 #include "ctx.h"
 
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -17,25 +18,77 @@ int ctx_fail(pedk_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
-void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
-    void* p = nullptr;
-    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, ctx->pool, ctx->stream);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        char b[256];
-        snprintf(b, sizeof b, "device allocation of %zu bytes failed (%zu in use): %s", bytes, ctx->cur_bytes,
-                 cudaGetErrorString(e));
-        throw PedkError(PEDK_E_NOMEM, b);
+// Device memory: a caching allocator private to the context.  Every stage of a step asks
+// for the same sizes as the step before, so after the first step no allocation reaches
+// the driver (cudaMalloc of tens of GB costs tens of ms and synchronises the device).
+// Blocks are handed out again in host order; all kernels of a context run on one stream
+// (the copy stream is fenced with events), so stream order makes the reuse safe.
+static size_t block_size_for(size_t bytes) {
+    const size_t g = bytes < (size_t(1) << 20) ? 512 : (size_t(2) << 20);
+    return (bytes + g - 1) / g * g;
+}
+
+static void release_cached(pedk_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->free_blocks) {
+        cudaFree(b.p);
+        ctx->reserved_bytes -= b.size;
     }
-    ctx->cur_bytes += bytes;
+    ctx->free_blocks.clear();
+}
+
+void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
+    const size_t want = block_size_for(bytes ? bytes : 1);
+    // best fit among cached blocks, but never waste more than 1/8 (+2 MiB) of a block
+    size_t best = (size_t)-1, best_size = (size_t)-1;
+    for (size_t i = 0; i < ctx->free_blocks.size(); ++i) {
+        size_t sz = ctx->free_blocks[i].size;
+        if (sz >= want && sz <= want + want / 8 + (size_t(2) << 20) && sz < best_size) {
+            best = i;
+            best_size = sz;
+        }
+    }
+    void* p = nullptr;
+    size_t got = want;
+    if (best != (size_t)-1) {
+        p = ctx->free_blocks[best].p;
+        got = best_size;
+        ctx->free_blocks.erase(ctx->free_blocks.begin() + (long)best);
+    } else {
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            release_cached(ctx);  // give the cached blocks back and try once more
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            char b[256];
+            snprintf(b, sizeof b, "device allocation of %zu bytes failed (%zu in use, %zu reserved): %s", want,
+                     ctx->cur_bytes, ctx->reserved_bytes, cudaGetErrorString(e));
+            throw PedkError(PEDK_E_NOMEM, b);
+        }
+        ctx->reserved_bytes += want;
+    }
+    ctx->live_blocks[p] = got;
+    ctx->cur_bytes += got;
     if (ctx->cur_bytes > ctx->stats.peak_device_bytes) ctx->stats.peak_device_bytes = ctx->cur_bytes;
     return p;
 }
 
-void dev_free(pedk_ctx* ctx, void* p, size_t bytes) {
+void dev_free(pedk_ctx* ctx, void* p, size_t /*bytes*/) {
     if (!p) return;
-    cudaFreeAsync(p, ctx->stream);
-    ctx->cur_bytes -= bytes;
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) return;
+    ctx->cur_bytes -= it->second;
+    ctx->free_blocks.push_back({p, it->second});
+    ctx->live_blocks.erase(it);
+}
+
+void dev_release_all(pedk_ctx* ctx) {
+    release_cached(ctx);
+    for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
+    ctx->live_blocks.clear();
 }
 
 static cudaEvent_t get_event(pedk_ctx* ctx) {
@@ -89,9 +142,6 @@ static void resolve_pending(pedk_ctx* ctx) {
 RadixWorkspace radix_workspace(pedk_ctx* ctx, size_t n_keys) {
     size_t tiles = radix_tiles(n_keys);
     size_t words = tiles * 256;
-    // the RLE look-back (one u64 per 4096-key tile) shares the buffer
-    size_t rle_words = rle_tiles(n_keys) * 2;
-    if (rle_words > words) words = rle_words;
     if (words > ctx->lookback_words) {
         if (ctx->lookback) dev_free(ctx, ctx->lookback, ctx->lookback_words * sizeof(uint32_t));
         ctx->lookback = nullptr;
@@ -127,6 +177,16 @@ int radix_sort(pedk_ctx* ctx, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* 
         cur ^= 1;
     }
     return cur;
+}
+
+void trace(pedk_ctx* ctx, const char* label) {
+    if (!ctx->trace) return;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (ctx->trace_t0 == 0) ctx->trace_t0 = ctx->trace_last = now;
+    fprintf(stderr, "[pedk %9.2f ms +%8.2f] %s\n", now - ctx->trace_t0, now - ctx->trace_last, label);
+    ctx->trace_last = now;
 }
 
 void check_err_flag(pedk_ctx* ctx, const char* what) {
@@ -193,22 +253,12 @@ extern "C" int pedk_open(pedk_ctx** out, const int* devices, int ndev) {
     }
     pedk_ctx* ctx = new pedk_ctx();
     ctx->device = dev;
+    ctx->trace = getenv("PEDK_TRACE") ? atoi(getenv("PEDK_TRACE")) : 0;
     try {
         PEDK_CUDA_TRY(cudaSetDevice(dev));
         PEDK_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         PEDK_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         PEDK_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
-        // a private stream-ordered pool: freed blocks stay cached for the next stage and
-        // nothing is taken from (or left in) the pool other libraries in the process use
-        cudaMemPoolProps props;
-        memset(&props, 0, sizeof props);
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = dev;
-        PEDK_CUDA_TRY(cudaMemPoolCreate(&ctx->pool, &props));
-        uint64_t thr = UINT64_MAX;
-        PEDK_CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr));
         PEDK_CUDA_TRY(cudaMalloc(&ctx->tile_ctr, sizeof(unsigned)));
         PEDK_CUDA_TRY(cudaMalloc(&ctx->err_flag, sizeof(int)));
         PEDK_CUDA_TRY(cudaMemset(ctx->err_flag, 0, sizeof(int)));
@@ -239,9 +289,8 @@ extern "C" int pedk_close(pedk_ctx* ctx) {
         cudaEventDestroy(p.b);
     }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    if (ctx->lookback) cudaFreeAsync(ctx->lookback, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    dev_release_all(ctx);
     cudaFree(ctx->tile_ctr);
     cudaFree(ctx->err_flag);
     cudaFree(ctx->scalars);
@@ -313,30 +362,20 @@ extern "C" int pedk_test_sort_pairs(pedk_ctx* ctx, uint64_t* keys_dev, uint32_t*
     PEDK_API_END(ctx)
 }
 
-namespace pedk {
-__global__ void k_start_to_count(const uint32_t* __restrict__ ustart, uint64_t D, uint32_t* __restrict__ cnt) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < D) cnt[r] = ustart[r + 1] - ustart[r];
-}
-}  // namespace pedk
-
 extern "C" int pedk_test_rle(pedk_ctx* ctx, const uint64_t* sorted_dev, uint64_t n, uint64_t* ukey_dev,
                              uint32_t* count_dev, uint64_t* n_runs) {
     if (!ctx || !n_runs) return PEDK_E_INVAL;
     PEDK_API_BEGIN
-    DBuf<uint32_t> ustart(ctx, n + 1);
-    RadixWorkspace ws = radix_workspace(ctx, n);
-    launch_rle(sorted_dev, n, ukey_dev, ustart.p, ws.lookback, ws.tile_ctr, ws.err, ctx->scalars, ctx->stream);
-    PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    check_err_flag(ctx, "run-length count");
-    uint64_t D = ctx->h_scalars[0];
-    *n_runs = D;
-    if (D) {
-        k_start_to_count<<<(unsigned)((D + 255) / 256), 256, 0, ctx->stream>>>(ustart.p, D, count_dev);
-        PEDK_CUDA_TRY(cudaGetLastError());
+    PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+        StageScope sc(ctx, PEDK_ST_COUNT, 1);
+        launch_count_rows(sorted_dev, n, 20, 0, 0, nullptr, nullptr, 0, ukey_dev, count_dev, n, ctx->scalars + 8,
+                          ctx->stream);
     }
+    PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
     PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *n_runs = ctx->h_scalars[8];
     return PEDK_OK;
     PEDK_API_END(ctx)
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -13,7 +14,13 @@
 struct pedk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaMemPool_t pool = nullptr;
+    struct Block {
+        void* p;
+        size_t size;
+    };
+    std::vector<Block> free_blocks;             // cached device blocks (see dev_alloc)
+    std::unordered_map<void*, size_t> live_blocks;
+    size_t reserved_bytes = 0;
     cudaStream_t copy_stream = nullptr;  // H2D of FASTQ text runs here, under the kernels of the other sample
     cudaEvent_t ev_alloc = nullptr;
     std::string err;
@@ -38,6 +45,8 @@ struct pedk_ctx {
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    int trace = 0;             // PEDK_TRACE=1: host wall-clock between sync points on stderr
+    double trace_t0 = 0, trace_last = 0;
     void* file_cache = nullptr;  // files.cu: samples kept resident between the file-level calls
 };
 
@@ -56,8 +65,9 @@ int ctx_fail(pedk_ctx* ctx, int code, const std::string& msg);
 
 void* dev_alloc(pedk_ctx* ctx, size_t bytes);
 void dev_free(pedk_ctx* ctx, void* p, size_t bytes);
+void dev_release_all(pedk_ctx* ctx);
 
-// RAII device array on the context's stream-ordered pool
+// RAII device array on the context's caching allocator
 template <typename T>
 struct DBuf {
     pedk_ctx* ctx = nullptr;
@@ -100,5 +110,6 @@ RadixWorkspace radix_workspace(pedk_ctx* ctx, size_t n_keys);
 int radix_sort(pedk_ctx* ctx, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* vb, size_t n, int n_pass,
                unsigned long long* digit_hist, int stage);
 void check_err_flag(pedk_ctx* ctx, const char* what);
+void trace(pedk_ctx* ctx, const char* label);
 
 }  // namespace pedk

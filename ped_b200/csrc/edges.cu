@@ -1,5 +1,4 @@
-// S5/S6: strand expansion of the canonical count tables, last-base-count
-// groups and the target/control last-base-difference test.
+// S5/S6: last-base-count groups and the target/control last-base-difference test.
 //
 // lbcKmerSub (ped.pl:833-860) groups the sorted 20-mer table by its 19-mer
 // prefix; joinKmerSub (ped.pl:703-782) inner-joins the control and target lbc
@@ -24,64 +23,40 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* a, uint64_t 
     return lo;
 }
 
-// Canonical row r -> strand rows.  count[K] for the reference's table
-// (SURVEY.md Appendix A.3): with I = canonical instances, C = windows of
-// palindromic reads among them (corr table), H = 2I - C half-units,
-//   count = H      if K == revcomp(K)   (both strands of a read hit the same row)
-//   count = H / 2  otherwise            (and revcomp(K) gets the same count)
-__global__ void __launch_bounds__(256) k_expand(const uint64_t* __restrict__ ukey, const uint32_t* __restrict__ ustart,
-                                               uint64_t D, int k, uint32_t sample_bit,
-                                               const uint64_t* __restrict__ corr_key,
-                                               const uint32_t* __restrict__ corr_start, uint64_t n_corr,
-                                               uint64_t* __restrict__ row_key, uint32_t* __restrict__ row_val,
-                                               unsigned long long* __restrict__ cursor) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = r < D;
-    uint64_t K = 0, rc = 0;
-    uint32_t v = 0;
-    bool emit_rc = false;
-    if (active) {
-        K = ukey[r];
-        uint64_t inst = (uint32_t)(ustart[r + 1] - ustart[r]);
-        uint64_t corr = 0;
-        if (n_corr) {
-            uint64_t q = lower_bound_u64(corr_key, n_corr, K);
-            if (q < n_corr && corr_key[q] == K) corr = (uint32_t)(corr_start[q + 1] - corr_start[q]);
-        }
-        rc = kmer_revcomp(K, k);
-        uint64_t H = 2 * inst - corr;
-        uint64_t cnt = (rc == K) ? H : (H >> 1);
-        if (cnt > 0x7fffffffull) cnt = 0x7fffffffull;
-        v = (uint32_t)cnt | sample_bit;
-        row_key[r] = K;
-        row_val[r] = v;
-        emit_rc = rc != K;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, emit_rc);
-    if (m) {
-        unsigned long long base = 0;
-        unsigned lane = lane_id();
-        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (emit_rc) {
-            unsigned long long o = base + __popc(m & lanemask_lt());
-            row_key[o] = rc;
-            row_val[o] = v;
-        }
+__global__ void __launch_bounds__(256) k_copy_rows(const uint64_t* __restrict__ src_key,
+                                                  const uint32_t* __restrict__ src_val, uint64_t n,
+                                                  uint64_t* __restrict__ dst_key, uint32_t* __restrict__ dst_val,
+                                                  uint32_t or_bits) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        dst_key[i] = src_key[i];
+        dst_val[i] = src_val[i] | or_bits;
     }
 }
 
+// One block per (sample, 3-nt bucket): the first row of that sample inside the bucket of
+// the merged, sorted table.  Rows of both samples interleave, so the hit is normally in
+// the first window of 256 rows; a bucket held by one sample only costs one sweep over it.
 __global__ void __launch_bounds__(256) k_first_of_bucket(const uint64_t* __restrict__ row_key,
                                                         const uint32_t* __restrict__ row_val, uint64_t n, int k,
                                                         unsigned long long* __restrict__ first) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t K = row_key[i];
-    unsigned s = row_val[i] >> 31;
-    unsigned tag = (unsigned)(K >> (2 * k - 6));
-    unsigned long long* f = first + s * 64 + tag;
-    // rows are sorted: only the first few rows of a bucket ever pass this filter
-    if (K < *(volatile unsigned long long*)f) atomicMin(f, (unsigned long long)K);
+    __shared__ unsigned long long s_lo, s_hi, s_min;
+    const unsigned s = blockIdx.x >> 6, tag = blockIdx.x & 63u;
+    if (threadIdx.x == 0) {
+        const int sh = 2 * k - 6;
+        s_lo = lower_bound_u64(row_key, n, (uint64_t)tag << sh);
+        s_hi = tag == 63u ? n : lower_bound_u64(row_key, n, (uint64_t)(tag + 1) << sh);
+        s_min = ~0ull;
+    }
+    __syncthreads();
+    const uint64_t lo = s_lo, hi = s_hi;
+    for (uint64_t base = lo; base < hi; base += 256) {
+        uint64_t i = base + threadIdx.x;
+        bool hit = i < hi && (row_val[i] >> 31) == s;
+        if (hit) atomicMin(&s_min, (unsigned long long)i);
+        if (__syncthreads_or(hit)) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) first[blockIdx.x] = s_min == ~0ull ? ~0ull : row_key[s_min];
 }
 
 __device__ __forceinline__ bool edge_test(const uint32_t* c, const uint32_t* t, uint8_t* cont, uint8_t* alt) {
@@ -176,19 +151,19 @@ __global__ void k_lookup_groups(const uint64_t* __restrict__ row_key, const uint
 
 }  // namespace
 
-void launch_expand(const uint64_t* ukey, const uint32_t* ustart, uint64_t D, int k, int sample,
-                   const uint64_t* corr_key, const uint32_t* corr_start, uint64_t n_corr, uint64_t* row_key,
-                   uint32_t* row_val, unsigned long long* cursor, cudaStream_t st) {
-    if (!D) return;
-    k_expand<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(ukey, ustart, D, k, sample ? 0x80000000u : 0u, corr_key,
-                                                           corr_start, n_corr, row_key, row_val, cursor);
+void launch_copy_rows(const uint64_t* src_key, const uint32_t* src_val, uint64_t n, uint64_t* dst_key,
+                      uint32_t* dst_val, uint32_t or_bits, cudaStream_t st) {
+    if (!n) return;
+    uint64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 16 ? blocks : (uint64_t)kNumSMs * 16);
+    k_copy_rows<<<grid, 256, 0, st>>>(src_key, src_val, n, dst_key, dst_val, or_bits);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
 void launch_first_of_bucket(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
                             unsigned long long* first, cudaStream_t st) {
     if (!n) return;
-    k_first_of_bucket<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_key, row_val, n, k, first);
+    k_first_of_bucket<<<128, 256, 0, st>>>(row_key, row_val, n, k, first);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

@@ -415,7 +415,7 @@ pedk_sample* sample_from_count_files(pedk_ctx* ctx, const std::string& wd, const
 
 pedk_sample* counted_sample(pedk_ctx* ctx, const std::string& wd, const std::string& subject, int k) {
     pedk_sample* s = cached(ctx, wd + "/" + subject);
-    if (s && s->k == k && (s->have_table || s->ukey.p)) return s;
+    if (s && s->k == k && (s->have_table || s->counted)) return s;
     return sample_from_count_files(ctx, wd, subject, k);
 }
 

@@ -26,8 +26,12 @@ namespace {
 
 void append_u(std::string& s, uint64_t v) {
     char b[24];
-    int n = snprintf(b, sizeof b, "%llu", (unsigned long long)v);
-    s.append(b, (size_t)n);
+    int n = 0;
+    do {
+        b[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) s.push_back(b[--n]);
 }
 
 std::string mask_string(unsigned m) {
@@ -97,7 +101,9 @@ bool quirk_row(const GroupRec& g, bool first_c, bool first_t, int k, pedk_edge* 
 void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_result* res) {
     cudaStream_t st = ctx->stream;
     PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
-    if (!control->k || control->k != target->k) throw PedkError(PEDK_E_INVAL, "pedk_join: samples not counted with the same k");
+    if (!control->k || control->k != target->k || !(control->counted || control->host_only_table) ||
+        !(target->counted || target->host_only_table))
+        throw PedkError(PEDK_E_INVAL, "pedk_join: samples not counted with the same k");
     const int k = control->k;
     res->k = k;
     RowTable rows;
@@ -134,6 +140,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     }
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
     ctx->stats.d2h_bytes += E * sizeof(EdgeRec) + 1024;
+    trace(ctx, "edges kernel + D2H");
 
     // ---- first-of-bucket rows: look the groups up and evaluate their text on the host ----
     std::vector<uint64_t> plist;
@@ -181,7 +188,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     std::sort(quirks.begin(), quirks.end());
     // ---- <target>.kmer.snp ----
     std::string& t = res->text;
-    t.reserve(res->edges.size() * 48);
+    t.reserve(res->edges.size() * 64);
     size_t qi = 0;
     for (const pedk_edge& e : res->edges) {
         if (e.quirk) {
@@ -189,15 +196,18 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
             t += quirks[qi].second;
             continue;
         }
-        t += kmer_string(e.prefix, k - 1);
+        for (int j = 0; j < k - 1; ++j) t.push_back("ACGT"[(e.prefix >> (2 * (k - 2 - j))) & 3]);
         t += '\t';
-        t += mask_string(e.cont_mask);
+        for (int x = 0; x < 4; ++x)
+            if (e.cont_mask & (1u << x)) t.push_back("ACGT"[x]);
         t += '\t';
-        t += mask_string(e.alt_mask);
+        for (int x = 0; x < 4; ++x)
+            if (e.alt_mask & (1u << x)) t.push_back("ACGT"[x]);
         for (int x = 0; x < 4; ++x) { t += '\t'; append_u(t, e.control[x]); }
         for (int x = 0; x < 4; ++x) { t += '\t'; append_u(t, e.target[x]); }
         t += '\n';
     }
+    trace(ctx, "host: sort edges + text");
 }
 
 char* dup_text(const std::string& s, uint64_t* len) {
@@ -385,5 +395,6 @@ extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_
     if (rc == PEDK_OK) rc = pedk_join(ctx, c, t, out);
     pedk_sample_destroy(c);
     pedk_sample_destroy(t);
+    pedk::trace(ctx, "samples destroyed (step end)");
     return rc;
 }

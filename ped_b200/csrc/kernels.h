@@ -71,20 +71,20 @@ void launch_digit_hist(const uint64_t* keys, size_t n, unsigned long long* digit
                        cudaStream_t st);
 void launch_hist_to_base(unsigned long long* digit_hist, int n_pass, cudaStream_t st);
 
-// ---------------- S4: run-length count (kmer.cu) ----------------
-size_t rle_tiles(size_t n);
-// ukey[r], ustart[r] (low 32 bits of the index where run r starts), ustart[D] = n; *n_runs = D.
-// Keys equal to ~0 (range-filtered placeholders) end the table.
-void launch_rle(const uint64_t* keys, size_t n, uint64_t* ukey, uint32_t* ustart, uint64_t* lookback,
-                unsigned int* tile_ctr, int* err, unsigned long long* n_runs, cudaStream_t st);
+// ---------------- S4: run-length count -> table rows (kmer.cu) ----------------
+// keys: sorted canonical instances.  strand == 0: rows (K, run length).  strand != 0: rows
+// (K, c | sample<<31) and (revcomp K, c | sample<<31) with c the reference's count; corr =
+// sorted (key, windows of palindromic reads) table, may be empty.  Rows are appended in no
+// particular order.  counters[0] = rows appended (keeps counting past cap), counters[1] +=
+// distinct canonical k-mers; both must be preset by the caller.
+void launch_count_rows(const uint64_t* keys, size_t n, int k, int strand, int sample, const uint64_t* corr_key,
+                       const uint32_t* corr_cnt, uint64_t n_corr, uint64_t* row_key, uint32_t* row_val, uint64_t cap,
+                       unsigned long long* counters, cudaStream_t st);
 
-// ---------------- S5/S6: strand expansion, lbc groups, edges (edges.cu) ----------------
-// rows (K, cnt | sample<<31) for K and revcomp(K) of every canonical row; corr = sorted
-// palindromic-read corrections (may be empty).  Forward rows go to rows [0, D), reverse
-// rows are appended through *cursor (preset to D).
-void launch_expand(const uint64_t* ukey, const uint32_t* ustart, uint64_t D, int k, int sample,
-                   const uint64_t* corr_key, const uint32_t* corr_start, uint64_t n_corr, uint64_t* row_key,
-                   uint32_t* row_val, unsigned long long* cursor, cudaStream_t st);
+// ---------------- S5/S6: lbc groups and edges (edges.cu) ----------------
+// dst rows = src rows with or_bits set in the value (bit 31 marks the target sample)
+void launch_copy_rows(const uint64_t* src_key, const uint32_t* src_val, uint64_t n, uint64_t* dst_key,
+                      uint32_t* dst_val, uint32_t or_bits, cudaStream_t st);
 // first[(sample*64 + tag)] = smallest key of that sample in 3-nt bucket `tag` (preset ~0)
 void launch_first_of_bucket(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
                             unsigned long long* first, cudaStream_t st);

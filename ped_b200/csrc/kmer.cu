@@ -10,8 +10,8 @@
 // table is rebuilt).
 //
 // S4 replaces `uniq -c | awk` and the 64-round `join` merge of countKmerMerge
-// (ped.pl:928, 862-889): one pass over the sorted stream, chained scan over the
-// number of run heads per tile.
+// (ped.pl:928, 862-889): one pass over the sorted stream that turns every run head
+// straight into the rows of the strand table (no scan, no intermediate table).
 #include "kernels.h"
 #include "util.cuh"
 
@@ -90,77 +90,150 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_pal(const uint64_t* __re
     }
 }
 
-constexpr int RL_THREADS = 256;
-constexpr int RL_ITEMS = 16;
-constexpr int RL_TILE = RL_THREADS * RL_ITEMS;
-constexpr int RL_WARPS = RL_THREADS / 32;
+constexpr int CR_THREADS = 256;
+constexpr int CR_ITEMS = 8;
+constexpr int CR_WARPS = CR_THREADS / 32;
+constexpr int CR_SEG = 32 * CR_ITEMS;        // keys per warp
+constexpr int CR_TILE = CR_SEG * CR_WARPS;   // keys per block
 
-__global__ void __launch_bounds__(RL_THREADS) k_rle(const uint64_t* __restrict__ keys, size_t n,
-                                                   uint64_t* __restrict__ ukey, uint32_t* __restrict__ ustart,
-                                                   uint64_t* __restrict__ lookback,
-                                                   unsigned int* __restrict__ tile_ctr, unsigned n_tiles,
-                                                   int* __restrict__ err, unsigned long long* __restrict__ n_runs) {
-    __shared__ unsigned s_tile;
-    __shared__ unsigned warp_heads[RL_WARPS];
-    __shared__ unsigned warp_excl[RL_WARPS];
-    __shared__ uint64_t s_tile_excl;
+__device__ __forceinline__ uint64_t lower_bound_dev(const uint64_t* a, uint64_t n, uint64_t key) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// first index >= from whose key differs from K (or n): a short linear probe, then a
+// gallop + bisection, so one k-mer with millions of instances costs ~60 loads, not millions
+__device__ __forceinline__ size_t run_end_from(const uint64_t* __restrict__ keys, size_t n, size_t from, uint64_t K) {
+    size_t j = from;
+    for (int s = 0; s < 8 && j < n && keys[j] == K; ++s) ++j;
+    if (j >= n || keys[j] != K) return j;
+    size_t lo = j, step = 32, hi;
+    for (;;) {
+        hi = lo + step;
+        if (hi >= n) { hi = n; break; }
+        if (keys[hi] != K) break;
+        lo = hi;
+        step <<= 1;
+    }
+    while (hi - lo > 1) {  // keys[lo] == K, (hi == n or keys[hi] != K)
+        size_t mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] == K) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+// One pass over the sorted canonical instances: every run head turns into table rows.
+//   STRAND == false: rows (K, run length)                      -- raw run-length count
+//   STRAND == true : rows (K, c | sample) and (revcomp K, c | sample), c = the reference's
+//                    count: with I instances and C windows of
+//                    palindromic reads among them (corr table), H = 2I - C half-units,
+//                    c = H if K == revcomp(K) else H / 2.
+// Rows are appended through a block-aggregated cursor, in no particular order: the row
+// table is sorted afterwards anyway, so no scan (and no chained look-back) is needed.
+// counters[0] = rows appended (continues past cap so the caller can retry), counters[1] += heads.
+template <bool STRAND>
+__global__ void __launch_bounds__(CR_THREADS) k_count_rows(const uint64_t* __restrict__ keys, size_t n, int k,
+                                                          uint32_t sample_bit,
+                                                          const uint64_t* __restrict__ corr_key,
+                                                          const uint32_t* __restrict__ corr_cnt, uint64_t n_corr,
+                                                          uint64_t* __restrict__ row_key,
+                                                          uint32_t* __restrict__ row_val, uint64_t cap,
+                                                          unsigned long long* __restrict__ counters) {
+    __shared__ unsigned w_rows[CR_WARPS], w_heads[CR_WARPS];
+    __shared__ unsigned long long s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_ctr, 1u);
-    __syncthreads();
-    const unsigned tile = s_tile;
-    const size_t seg = (size_t)tile * RL_TILE + (size_t)warp * (32 * RL_ITEMS);
+    const size_t seg = (size_t)blockIdx.x * CR_TILE + (size_t)warp * CR_SEG;
+    const size_t seg_end = seg + CR_SEG < n ? seg + CR_SEG : n;
 
-    uint64_t key[RL_ITEMS];
+    uint64_t key[CR_ITEMS];
 #pragma unroll
-    for (int j = 0; j < RL_ITEMS; ++j) {
+    for (int j = 0; j < CR_ITEMS; ++j) {
         size_t i = seg + 32 * j + lane;
         key[j] = i < n ? keys[i] : 0ull;
     }
-    unsigned heads[RL_ITEMS];  // ballot of head flags per item (warp-uniform)
-    unsigned wcount = 0;
-    uint64_t carry = (seg > 0 && seg <= n) ? keys[seg - 1] : 0ull;  // key just before the segment
+    unsigned H[CR_ITEMS], R[CR_ITEMS];  // ballots: run heads / heads that also emit a reverse row
+    unsigned nh = 0, nr = 0;
+    uint64_t carry = (seg > 0 && seg < n) ? keys[seg - 1] : 0ull;
 #pragma unroll
-    for (int j = 0; j < RL_ITEMS; ++j) {
+    for (int j = 0; j < CR_ITEMS; ++j) {
         size_t i = seg + 32 * j + lane;
         uint64_t prev = __shfl_up_sync(0xffffffffu, key[j], 1);
         if (lane == 0) prev = carry;
         bool head = i < n && (i == 0 || key[j] != prev);
-        heads[j] = __ballot_sync(0xffffffffu, head);
-        wcount += __popc(heads[j]);
+        bool rev = false;
+        if (STRAND) rev = head && kmer_revcomp(key[j], k) != key[j];
+        H[j] = __ballot_sync(0xffffffffu, head);
+        R[j] = __ballot_sync(0xffffffffu, rev);
+        nh += __popc(H[j]);
+        nr += __popc(R[j]);
         carry = __shfl_sync(0xffffffffu, key[j], 31);
     }
-    if (lane == 0) warp_heads[warp] = wcount;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned total = 0;
-#pragma unroll
-        for (int w = 0; w < RL_WARPS; ++w) {
-            warp_excl[w] = total;
-            total += warp_heads[w];
-        }
-        lb_store(lookback + tile, (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | (uint64_t)total);
-        uint64_t excl = 0;
-        if (tile > 0) {
-            excl = lb_exclusive_prefix(lookback, (long long)tile, 1, err);
-            lb_store(lookback + tile, LB_FLAG_INC | (excl + total));
-        }
-        s_tile_excl = excl;
-        if (tile == n_tiles - 1) {
-            ustart[excl + total] = (uint32_t)n;
-            *n_runs = excl + total;
-        }
+    if (lane == 0) {
+        w_rows[warp] = nh + nr;
+        w_heads[warp] = nh;
     }
     __syncthreads();
-    uint64_t r = s_tile_excl + warp_excl[warp];
+    if (tid == 0) {
+        unsigned rows = 0, heads = 0;
 #pragma unroll
-    for (int j = 0; j < RL_ITEMS; ++j) {
-        unsigned b = heads[j];
-        if (b & (1u << lane)) {
-            uint64_t o = r + __popc(b & lanemask_lt());
-            ukey[o] = key[j];
-            ustart[o] = (uint32_t)(seg + 32 * j + lane);
+        for (int w = 0; w < CR_WARPS; ++w) {
+            unsigned c = w_rows[w];
+            w_rows[w] = rows;
+            rows += c;
+            heads += w_heads[w];
         }
-        r += __popc(b);
+        s_base = rows ? atomicAdd(&counters[0], (unsigned long long)rows) : 0ull;
+        if (heads) atomicAdd(&counters[1], (unsigned long long)heads);
+    }
+    __syncthreads();
+    unsigned long long o = s_base + w_rows[warp];
+#pragma unroll
+    for (int j = 0; j < CR_ITEMS; ++j) {
+        const unsigned h = H[j], r = R[j];
+        if ((h >> lane) & 1u) {
+            const uint64_t K = key[j];
+            const size_t i = seg + 32 * j + lane;
+            // the next head inside this warp's segment ends the run
+            long next = -1;
+            unsigned m = h & ~((2u << lane) - 1u);
+            if (m) next = 32 * j + (__ffs(m) - 1);
+#pragma unroll
+            for (int j2 = 0; j2 < CR_ITEMS; ++j2)
+                if (j2 > j && next < 0 && H[j2]) next = 32 * j2 + (__ffs(H[j2]) - 1);
+            const size_t end = next >= 0 ? seg + (size_t)next : run_end_from(keys, n, seg_end, K);
+            uint64_t inst = end - i;
+            uint32_t v;
+            if (STRAND) {
+                uint64_t corr = 0;
+                if (n_corr) {
+                    uint64_t q = lower_bound_dev(corr_key, n_corr, K);
+                    if (q < n_corr && corr_key[q] == K) corr = corr_cnt[q];
+                }
+                uint64_t Hh = 2 * inst - corr;
+                uint64_t c = ((r >> lane) & 1u) ? (Hh >> 1) : Hh;
+                if (c > 0x7fffffffull) c = 0x7fffffffull;
+                v = (uint32_t)c | sample_bit;
+            } else {
+                v = inst > 0xffffffffull ? 0xffffffffu : (uint32_t)inst;
+            }
+            unsigned long long pf = o + __popc(h & lanemask_lt());
+            if (pf < cap) {
+                row_key[pf] = K;
+                row_val[pf] = v;
+            }
+            if (STRAND && ((r >> lane) & 1u)) {
+                unsigned long long pr = o + __popc(h) + __popc(r & lanemask_lt());
+                if (pr < cap) {
+                    row_key[pr] = kmer_revcomp(K, k);
+                    row_val[pr] = v;
+                }
+            }
+        }
+        o += __popc(h) + __popc(r);
     }
 }
 
@@ -184,20 +257,17 @@ void launch_extract_pal(const uint64_t* words, const uint8_t* pal, int W, int L,
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-size_t rle_tiles(size_t n) { return (n + RL_TILE - 1) / RL_TILE; }
-
-void launch_rle(const uint64_t* keys, size_t n, uint64_t* ukey, uint32_t* ustart, uint64_t* lookback,
-                unsigned int* tile_ctr, int* err, unsigned long long* n_runs, cudaStream_t st) {
-    if (!n) {
-        PEDK_CUDA_TRY(cudaMemsetAsync(n_runs, 0, sizeof(unsigned long long), st));
-        PEDK_CUDA_TRY(cudaMemsetAsync(ustart, 0, sizeof(uint32_t), st));
-        return;
-    }
-    size_t tiles = rle_tiles(n);
-    PEDK_CUDA_TRY(cudaMemsetAsync(lookback, 0, tiles * sizeof(uint64_t), st));
-    PEDK_CUDA_TRY(cudaMemsetAsync(tile_ctr, 0, sizeof(unsigned), st));
-    k_rle<<<(unsigned)tiles, RL_THREADS, 0, st>>>(keys, n, ukey, ustart, lookback, tile_ctr, (unsigned)tiles, err,
-                                                  n_runs);
+void launch_count_rows(const uint64_t* keys, size_t n, int k, int strand, int sample, const uint64_t* corr_key,
+                       const uint32_t* corr_cnt, uint64_t n_corr, uint64_t* row_key, uint32_t* row_val, uint64_t cap,
+                       unsigned long long* counters, cudaStream_t st) {
+    if (!n) return;
+    unsigned grid = (unsigned)((n + CR_TILE - 1) / CR_TILE);
+    if (strand)
+        k_count_rows<true><<<grid, CR_THREADS, 0, st>>>(keys, n, k, sample ? 0x80000000u : 0u, corr_key, corr_cnt,
+                                                        n_corr, row_key, row_val, cap, counters);
+    else
+        k_count_rows<false><<<grid, CR_THREADS, 0, st>>>(keys, n, k, 0u, nullptr, nullptr, 0, row_key, row_val, cap,
+                                                         counters);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

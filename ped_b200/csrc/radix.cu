@@ -15,6 +15,8 @@
 // Look-back words are 32 bit (2 flag + 30 value bits); inputs longer than
 // PORTION keys are sorted in portions, the last tile of a portion folding its
 // inclusive digit counts into bin_base for the next portion.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "util.cuh"
 
@@ -22,9 +24,9 @@ namespace pedk {
 
 namespace {
 
-constexpr int RS_THREADS = 384;
+constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 6144 keys
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr size_t RS_PORTION = ((size_t(1) << 30) / RS_TILE - 1) * RS_TILE;
 
@@ -41,11 +43,13 @@ __device__ __forceinline__ uint32_t lb32_load(const uint32_t* p) {
     return v;
 }
 
+enum { RANK_MATCH = 0, RANK_BALLOT = 1, RANK_OR = 2 };
+
 template <bool PAIRS>
 struct RadixSmem {
     uint64_t keys[RS_TILE];
     uint32_t warp_hist[RS_WARPS][256];
-    uint32_t bin_start[256];
+    uint32_t warp_mask[RS_WARPS][256];
     uint64_t gbase[256];
     unsigned tile;
 };
@@ -54,13 +58,13 @@ struct RadixSmem<true> {
     uint64_t keys[RS_TILE];
     uint32_t vals[RS_TILE];
     uint32_t warp_hist[RS_WARPS][256];
-    uint32_t bin_start[256];
+    uint32_t warp_mask[RS_WARPS][256];
     uint64_t gbase[256];
     unsigned tile;
 };
 
-template <bool PAIRS>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+template <bool PAIRS, int RANK>
+__global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
                                                           const uint32_t* __restrict__ vin,
                                                           uint32_t* __restrict__ vout, size_t n, int shift,
                                                           unsigned long long* __restrict__ bin_base,
@@ -73,7 +77,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_pass(const uint64_t* __res
 
     if (tid == 0) sm.tile = atomicAdd(tile_ctr, 1u);
 #pragma unroll
-    for (int i = 0; i < 256 / 32; ++i) sm.warp_hist[warp][i * 32 + lane] = 0;
+    for (int i = 0; i < 256 / 32; ++i) {
+        sm.warp_hist[warp][i * 32 + lane] = 0;
+        if constexpr (RANK == RANK_OR) sm.warp_mask[warp][i * 32 + lane] = 0;
+    }
     // read the global base before anything is published (see portion hand-over below)
     unsigned long long my_base = tid < 256 ? bin_base[tid] : 0ull;
     __syncthreads();
@@ -100,65 +107,105 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_pass(const uint64_t* __res
         }
     }
 
-    // ---- rank inside the warp ----
-    uint16_t rank[RS_ITEMS];
+    // ---- phase 1: per-warp digit counts (order does not matter yet) ----
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        unsigned d = (unsigned)(key[j] >> shift) & 255u;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        unsigned leader = __ffs(peers) - 1;
-        unsigned before = 0;
-        if (lane == leader) before = atomicAdd(&sm.warp_hist[warp][d], __popc(peers));
-        before = __shfl_sync(0xffffffffu, before, leader);
-        rank[j] = (uint16_t)(before + __popc(peers & lanemask_lt()));
-    }
+    for (int j = 0; j < RS_ITEMS; ++j) atomicAdd(&sm.warp_hist[warp][(unsigned)(key[j] >> shift) & 255u], 1u);
     __syncthreads();
 
-    // ---- per-digit: warp offsets, tile histogram, look-back ----
+    // ---- per digit: tile count -> publish the aggregate early, then turn the per-warp
+    //      counts into absolute positions in the staging buffer ----
     unsigned dcount = 0;
     if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            unsigned c = sm.warp_hist[w][tid];
-            sm.warp_hist[w][tid] = dcount;
-            dcount += c;
-        }
+        for (int w = 0; w < RS_WARPS; ++w) dcount += sm.warp_hist[w][tid];
         lb32_store(lookback + (size_t)tile * 256 + tid, (tile == 0 ? LB32_INC : LB32_AGG) | dcount);
     }
-    uint64_t ex = block_exclusive_scan<RS_THREADS>(dcount, nullptr);
+    const uint32_t ex = (uint32_t)block_exclusive_scan<RS_THREADS>(dcount, nullptr);
     if (tid < 256) {
-        sm.bin_start[tid] = (uint32_t)ex;
+        unsigned running = ex;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            unsigned c = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = running;
+            running += c;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: stable rank inside the warp, straight into the staging buffer.
+    // peers = lanes whose item j has the same digit:
+    //   RANK_MATCH  the match.any instruction (data dependent, slow on sm_100: profiles/)
+    //   RANK_BALLOT eight vote.ballot rounds, one per digit bit
+    //   RANK_OR     shared-memory atomicOr of the lane bit into a per-warp mask table
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        unsigned d = (unsigned)(key[j] >> shift) & 255u;
+        unsigned peers;
+        if constexpr (RANK == RANK_MATCH) {
+            peers = __match_any_sync(0xffffffffu, d);
+        } else if constexpr (RANK == RANK_BALLOT) {
+            peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                unsigned bit = (d >> b) & 1u;
+                unsigned m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
+        } else {
+            unsigned* mask = &sm.warp_mask[warp][d];
+            atomicOr(mask, 1u << lane);
+            __syncwarp();
+            peers = *mask;
+            __syncwarp();
+            *mask = 0;  // every peer stores the same 0
+            __syncwarp();
+        }
+        unsigned leader = __ffs(peers) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&sm.warp_hist[warp][d], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        unsigned pos = base + __popc(peers & lanemask_lt());
+        sm.keys[pos] = key[j];
+        if constexpr (PAIRS) sm.vals[pos] = val[j];
+    }
+
+    // ---- look-back: predecessors had the whole of phase 2 to publish ----
+    if (tid < 256) {
         uint32_t excl = 0;
         if (tile > 0) {
-            for (long long t = (long long)tile - 1; t >= 0; --t) {
-                uint32_t v;
-                unsigned spins = 0;
-                while (((v = lb32_load(lookback + (size_t)t * 256 + tid)) >> 30) == 0) {
-                    __nanosleep(32);
-                    if (++spins > (1u << 22)) {
-                        atomicExch(err, 1);
-                        v = LB32_INC;  // give up: the result is flagged invalid
+            long long t = (long long)tile - 1;
+            unsigned spins = 0;
+            while (t >= 0) {
+                // up to four predecessors in flight at once
+                uint32_t v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    v[q] = (t - q >= 0) ? lb32_load(lookback + (size_t)(t - q) * 256 + tid) : LB32_INC;
+                bool done = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (done) break;
+                    if ((v[q] >> 30) == 0) {  // not published yet: poll again from here
+                        done = true;
+                        if (++spins > (1u << 22)) {
+                            atomicExch(err, 1);
+                            t = -1;
+                        }
                         break;
                     }
+                    excl += v[q] & LB32_MASK;
+                    --t;
+                    if (v[q] & LB32_INC) {
+                        t = -1;
+                        done = true;
+                    }
                 }
-                excl += v & LB32_MASK;
-                if (v & LB32_INC) break;
             }
             lb32_store(lookback + (size_t)tile * 256 + tid, LB32_INC | (excl + dcount));
         }
         sm.gbase[tid] = my_base + excl - ex;
         // last tile of the portion: hand the running digit totals to the next portion
         if (tile == n_tiles - 1) bin_base[tid] = my_base + excl + dcount;
-    }
-    __syncthreads();
-
-    // ---- stage in shared memory in digit order ----
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        unsigned d = (unsigned)(key[j] >> shift) & 255u;
-        unsigned pos = sm.bin_start[d] + sm.warp_hist[warp][d] + rank[j];
-        sm.keys[pos] = key[j];
-        if constexpr (PAIRS) sm.vals[pos] = val[j];
     }
     __syncthreads();
 
@@ -210,33 +257,53 @@ size_t radix_tiles(size_t n) {
     return (p + RS_TILE - 1) / RS_TILE;
 }
 
+template <bool PAIRS, int RANK>
+static void launch_pass_variant(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t pn,
+                                int shift, unsigned long long* bin_base, RadixWorkspace ws, unsigned tiles,
+                                cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<PAIRS, RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(RadixSmem<PAIRS>)));
+        attr_set = true;
+    }
+    k_radix_pass<PAIRS, RANK><<<tiles, RS_THREADS, sizeof(RadixSmem<PAIRS>), st>>>(
+        in, out, vin, vout, pn, shift, bin_base, reinterpret_cast<uint32_t*>(ws.lookback), ws.tile_ctr, tiles, ws.err);
+}
+
+int radix_rank_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("PEDK_RANK_MODE");
+        mode = e ? atoi(e) : RANK_BALLOT;
+        if (mode < 0 || mode > 2) mode = RANK_BALLOT;
+    }
+    return mode;
+}
+
 void launch_radix_pass(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t n, int pass,
                        const unsigned long long* digit_hist, RadixWorkspace ws, cudaStream_t st) {
     if (!n) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(RadixSmem<false>)));
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(RadixSmem<true>)));
-        attr_set = true;
-    }
     unsigned long long* bin_base = const_cast<unsigned long long*>(digit_hist) + (size_t)pass * 256;
+    const int mode = radix_rank_mode();
     for (size_t off = 0; off < n; off += RS_PORTION) {
         size_t pn = (n - off) < RS_PORTION ? (n - off) : RS_PORTION;
         unsigned tiles = (unsigned)((pn + RS_TILE - 1) / RS_TILE);
         if (tiles > ws.tiles_cap) throw PedkError(-8, "radix workspace too small");
         PEDK_CUDA_TRY(cudaMemsetAsync(ws.lookback, 0, (size_t)tiles * 256 * sizeof(uint32_t), st));
         PEDK_CUDA_TRY(cudaMemsetAsync(ws.tile_ctr, 0, sizeof(unsigned), st));
+        const uint32_t* vi = vin ? vin + off : nullptr;
+#define PEDK_PASS(P, R) launch_pass_variant<P, R>(in + off, out, vi, vout, pn, 8 * pass, bin_base, ws, tiles, st)
         if (vin) {
-            k_radix_pass<true><<<tiles, RS_THREADS, sizeof(RadixSmem<true>), st>>>(
-                in + off, out, vin + off, vout, pn, 8 * pass, bin_base, reinterpret_cast<uint32_t*>(ws.lookback),
-                ws.tile_ctr, tiles, ws.err);
+            if (mode == RANK_MATCH) PEDK_PASS(true, RANK_MATCH);
+            else if (mode == RANK_OR) PEDK_PASS(true, RANK_OR);
+            else PEDK_PASS(true, RANK_BALLOT);
         } else {
-            k_radix_pass<false><<<tiles, RS_THREADS, sizeof(RadixSmem<false>), st>>>(
-                in + off, out, nullptr, nullptr, pn, 8 * pass, bin_base, reinterpret_cast<uint32_t*>(ws.lookback),
-                ws.tile_ctr, tiles, ws.err);
+            if (mode == RANK_MATCH) PEDK_PASS(false, RANK_MATCH);
+            else if (mode == RANK_OR) PEDK_PASS(false, RANK_OR);
+            else PEDK_PASS(false, RANK_BALLOT);
         }
+#undef PEDK_PASS
         PEDK_CUDA_TRY(cudaGetLastError());
     }
 }

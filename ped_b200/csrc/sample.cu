@@ -28,11 +28,13 @@ void fq_reserve(pedk_sample* s, size_t want) {
     s->fq = std::move(nb);
 }
 
-uint64_t read_scalar(pedk_ctx* ctx, const unsigned long long* dev) {
+uint64_t read_scalar(pedk_ctx* ctx, const unsigned long long* dev, const char* label) {
+    trace(ctx, "  (host enqueued)");
     PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += 8;
+    trace(ctx, label);
     return ctx->h_scalars[0];
 }
 
@@ -58,7 +60,7 @@ void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_star
         launch_chunk_count(rlen, rflag, R, plan.r_limit, plan.clip, plan.whole, chunks.p, st);
         exclusive_scan_u32(chunks.p, base.p, R, ctx->scalars, ws.p, st);
     }
-    n_c = read_scalar(ctx, ctx->scalars);
+    n_c = read_scalar(ctx, ctx->scalars, "chunk scan");
     *strand_reads += 2 * n_c;
     if (n_c == 0) return;
     if (n_c >= 0xFFFFFFF0ull) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^32 reads in one sample on one GPU");
@@ -84,7 +86,7 @@ void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_star
         launch_dedup(words.p, W, (uint32_t)n_c, table.p, cap, uniq.p, st);
         exclusive_scan_u8(uniq.p, pos.p, n_c, ctx->scalars, ws2.p, st);
     }
-    uint64_t U = read_scalar(ctx, ctx->scalars);
+    uint64_t U = read_scalar(ctx, ctx->scalars, "dedup");
     table.reset();
     ReadGroup g;
     g.L = L;
@@ -98,7 +100,7 @@ void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_star
         PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 1, 0, sizeof(unsigned long long), st));
         launch_count_flags(g.pal.p, U, ctx->scalars + 1, st);
     }
-    g.n_pal = read_scalar(ctx, ctx->scalars + 1);
+    g.n_pal = read_scalar(ctx, ctx->scalars + 1, "compact reads");
     s->groups.push_back(std::move(g));
 }
 
@@ -138,7 +140,7 @@ void do_ingest(pedk_sample* s, int clipping) {
     }
     uint8_t last_byte = 0;
     PEDK_CUDA_TRY(cudaMemcpyAsync(&last_byte, s->fq.p + n - 1, 1, cudaMemcpyDeviceToHost, st));
-    uint64_t NL = read_scalar(ctx, ctx->scalars);
+    uint64_t NL = read_scalar(ctx, ctx->scalars, "newline scan");
     uint64_t TL = NL + (last_byte != '\n' ? 1 : 0);
     uint64_t R = TL >= 2 ? (TL - 2) / 4 + 1 : 0;  // records that have a sequence line (line 4r+1)
     if (s->line_format) R = TL;
@@ -172,6 +174,7 @@ void do_ingest(pedk_sample* s, int clipping) {
     std::vector<unsigned long long> h_hist(LEN_HIST_BINS + 4);
     PEDK_CUDA_TRY(cudaMemcpyAsync(h_hist.data(), hist.p, hist.bytes(), cudaMemcpyDeviceToHost, st));
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    trace(ctx, "line index + read scan");
     ctx->stats.d2h_bytes += hist.bytes();
     const uint64_t kept = h_hist[LEN_HIST_BINS];
     const uint64_t bad = h_hist[LEN_HIST_BINS + 1];
@@ -271,25 +274,48 @@ void do_ingest(pedk_sample* s, int clipping) {
     s->ingested = true;
 }
 
-void rle_into(pedk_ctx* ctx, const uint64_t* sorted, size_t n, uint64_t* ukey_big, DBuf<uint64_t>* ukey,
-              DBuf<uint32_t>* ustart, uint64_t* D_out) {
+// Sorted instances -> table rows.  The rows first land in the idle half of the sort's
+// ping-pong buffer (room for 2/3 of n rows: enough unless more than a third of the
+// instances are distinct), then move to exact-size arrays.
+void count_rows_into(pedk_ctx* ctx, const uint64_t* sorted, size_t n, uint64_t* spare, int k, int strand,
+                     const uint64_t* corr_key, const uint32_t* corr_cnt, uint64_t n_corr, DBuf<uint64_t>* rkey,
+                     DBuf<uint32_t>* rval, uint64_t* n_rows, uint64_t* n_heads, int stage) {
     cudaStream_t st = ctx->stream;
-    DBuf<uint32_t> ustart_big(ctx, n + 1);
-    RadixWorkspace ws = radix_workspace(ctx, n);
-    {
-        StageScope sc(ctx, PEDK_ST_COUNT, 1);
-        launch_rle(sorted, n, ukey_big, ustart_big.p, ws.lookback, ws.tile_ctr, ws.err, ctx->scalars, st);
+    uint64_t cap = (2 * n) / 3;
+    uint64_t* tmp_key = spare;
+    uint32_t* tmp_val = reinterpret_cast<uint32_t*>(spare + cap);
+    DBuf<uint64_t> big_key;
+    DBuf<uint32_t> big_val;
+    for (int attempt = 0;; ++attempt) {
+        {
+            StageScope sc(ctx, stage, 1);
+            PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), st));
+            launch_count_rows(sorted, n, k, strand, 0, corr_key, corr_cnt, n_corr, tmp_key, tmp_val, cap,
+                              ctx->scalars + 8, st);
+        }
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 2 * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += 16;
+        trace(ctx, "count rows");
+        *n_rows = ctx->h_scalars[8];
+        *n_heads = ctx->h_scalars[9];
+        if (*n_rows <= cap) break;
+        if (attempt) throw PedkError(PEDK_E_INTERNAL, "row count changed between two passes");
+        // mostly distinct k-mers (very low coverage): run again into arrays of the exact size
+        cap = *n_rows;
+        big_key = DBuf<uint64_t>(ctx, cap);
+        big_val = DBuf<uint32_t>(ctx, cap);
+        tmp_key = big_key.p;
+        tmp_val = big_val.p;
     }
-    uint64_t D = read_scalar(ctx, ctx->scalars);
-    check_err_flag(ctx, "run-length count");
-    *ukey = DBuf<uint64_t>(ctx, D);
-    *ustart = DBuf<uint32_t>(ctx, D + 1);
-    {
-        StageScope sc(ctx, PEDK_ST_COUNT, 0);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(ukey->p, ukey_big, D * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-        PEDK_CUDA_TRY(cudaMemcpyAsync(ustart->p, ustart_big.p, (D + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    *rkey = DBuf<uint64_t>(ctx, *n_rows);
+    *rval = DBuf<uint32_t>(ctx, *n_rows);
+    if (*n_rows) {
+        StageScope sc(ctx, stage, 0);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(rkey->p, tmp_key, *n_rows * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(rval->p, tmp_val, *n_rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
-    *D_out = D;
 }
 
 void do_count(pedk_sample* s, int k) {
@@ -300,11 +326,13 @@ void do_count(pedk_sample* s, int k) {
     if (k < 4 || k > 32) throw PedkError(PEDK_E_INVAL, "k must be in [4, 32]");
     s->k = k;
     s->D = 0;
+    s->n_rows = 0;
     s->n_corr = 0;
-    s->ukey.reset();
-    s->ustart.reset();
+    s->rkey.reset();
+    s->rval.reset();
     s->ckey.reset();
-    s->cstart.reset();
+    s->ccnt.reset();
+    s->counted = false;
     s->have_table = false;
     s->cinfo = pedk_count_info{};
     s->cinfo.k = k;
@@ -318,32 +346,13 @@ void do_count(pedk_sample* s, int k) {
         }
     s->cinfo.instances = M;
     s->cinfo.correction_rows = Mpal;
-    s->ukey = DBuf<uint64_t>(ctx, 0);
-    s->ustart = DBuf<uint32_t>(ctx, 1);
-    PEDK_CUDA_TRY(cudaMemsetAsync(s->ustart.p, 0, sizeof(uint32_t), st));
+    s->counted = true;
     if (M == 0) return;
 
     DBuf<unsigned long long> hist(ctx, 8 * 256);
-    {
-        DBuf<uint64_t> a(ctx, M), b(ctx, M);
-        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-        uint64_t off = 0;
-        for (const ReadGroup& g : s->groups) {
-            if (g.L < k || !g.n) continue;
-            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
-            launch_extract(g.words.p, g.W, g.L, k, g.n, a.p + off, hist.p, n_pass, st);
-            off += g.n * (uint64_t)(g.L - k + 1);
-        }
-        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, M, n_pass, hist.p, PEDK_ST_SORT);
-        check_err_flag(ctx, "radix sort");
-        uint64_t* sorted = cur ? b.p : a.p;
-        uint64_t* spare = cur ? a.p : b.p;
-        rle_into(ctx, sorted, M, spare, &s->ukey, &s->ustart, &s->D);
-    }
-    s->cinfo.canonical_kmers = s->D;
-
     if (Mpal) {
-        // windows of palindromic reads: each was emitted once but stands for one strand only
+        // windows of palindromic reads: each is emitted once below but stands for one strand
+        // only; their sorted (k-mer, windows) table corrects the counts (Appendix A.3)
         DBuf<uint64_t> a(ctx, Mpal), b(ctx, Mpal);
         PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 2, 0, sizeof(unsigned long long), st));
         for (const ReadGroup& g : s->groups) {
@@ -358,8 +367,45 @@ void do_count(pedk_sample* s, int k) {
         }
         int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, Mpal, n_pass, hist.p, PEDK_ST_EXTRACT);
         check_err_flag(ctx, "radix sort (corrections)");
-        rle_into(ctx, cur ? b.p : a.p, Mpal, cur ? a.p : b.p, &s->ckey, &s->cstart, &s->n_corr);
+        DBuf<uint64_t> ck;
+        DBuf<uint32_t> cc;
+        uint64_t heads;
+        count_rows_into(ctx, cur ? b.p : a.p, Mpal, cur ? a.p : b.p, k, 0, nullptr, nullptr, 0, &ck, &cc, &s->n_corr,
+                        &heads, PEDK_ST_EXTRACT);
+        // the rows come out unordered: sort them so the count kernel can bisect
+        DBuf<uint64_t> ck2(ctx, s->n_corr);
+        DBuf<uint32_t> cc2(ctx, s->n_corr);
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        {
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            launch_digit_hist(ck.p, s->n_corr, hist.p, n_pass, st);
+        }
+        int c2 = radix_sort(ctx, ck.p, ck2.p, cc.p, cc2.p, s->n_corr, n_pass, hist.p, PEDK_ST_EXTRACT);
+        check_err_flag(ctx, "radix sort (correction table)");
+        s->ckey = std::move(c2 ? ck2 : ck);
+        s->ccnt = std::move(c2 ? cc2 : cc);
     }
+    {
+        DBuf<uint64_t> a(ctx, M), b(ctx, M);
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        uint64_t off = 0;
+        for (const ReadGroup& g : s->groups) {
+            if (g.L < k || !g.n) continue;
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            launch_extract(g.words.p, g.W, g.L, k, g.n, a.p + off, hist.p, n_pass, st);
+            off += g.n * (uint64_t)(g.L - k + 1);
+        }
+        trace(ctx, "  (extract enqueued)");
+        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, M, n_pass, hist.p, PEDK_ST_SORT);
+        trace(ctx, "  (sort enqueued)");
+        check_err_flag(ctx, "radix sort");
+        trace(ctx, "extract + radix sort");
+        uint64_t* sorted = cur ? b.p : a.p;
+        uint64_t* spare = cur ? a.p : b.p;
+        count_rows_into(ctx, sorted, M, spare, k, 1, s->ckey.p, s->ccnt.p, s->n_corr, &s->rkey, &s->rval, &s->n_rows,
+                        &s->D, PEDK_ST_COUNT);
+    }
+    s->cinfo.canonical_kmers = s->D;
 }
 
 }  // namespace
@@ -376,7 +422,7 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     cudaStream_t st = ctx->stream;
     const int k = control->k;
     const int n_pass = (2 * k + 7) / 8;
-    auto rows_of = [](pedk_sample* s) -> uint64_t { return !s ? 0 : s->host_only_table ? s->h_kmer.size() : 2 * s->D; };
+    auto rows_of = [](pedk_sample* s) -> uint64_t { return !s ? 0 : s->host_only_table ? s->h_kmer.size() : s->n_rows; };
     uint64_t cap = rows_of(control) + rows_of(target);
     out->n = 0;
     if (cap == 0) return;
@@ -400,15 +446,12 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
             rows += m;
             continue;
         }
-        if (!s || !s->D) continue;
-        unsigned long long preset = s->D;
+        if (!s || !s->n_rows) continue;
         {
             StageScope sc(ctx, PEDK_ST_EXPAND, 1);
-            PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 3, &preset, sizeof preset, cudaMemcpyHostToDevice, st));
-            launch_expand(s->ukey.p, s->ustart.p, s->D, k, i, s->ckey.p, s->cstart.p, s->n_corr, ka.p + rows,
-                          va.p + rows, ctx->scalars + 3, st);
+            launch_copy_rows(s->rkey.p, s->rval.p, s->n_rows, ka.p + rows, va.p + rows, i ? 0x80000000u : 0u, st);
         }
-        rows += read_scalar(ctx, ctx->scalars + 3);
+        rows += s->n_rows;
     }
     DBuf<unsigned long long> hist(ctx, 8 * 256);
     PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
@@ -418,6 +461,7 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     }
     int cur = radix_sort(ctx, ka.p, kb.p, va.p, vb.p, rows, n_pass, hist.p, PEDK_ST_ROWSORT);
     check_err_flag(ctx, "radix sort (rows)");
+    trace(ctx, "row sort");
     out->key = std::move(cur ? kb : ka);
     out->val = std::move(cur ? vb : va);
     out->n = rows;

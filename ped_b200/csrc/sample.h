@@ -27,12 +27,14 @@ struct pedk_sample {
     pedk_ingest_info info{};
     // canonical count table
     int k = 0;
-    uint64_t D = 0;
-    pedk::DBuf<uint64_t> ukey;
-    pedk::DBuf<uint32_t> ustart;
-    uint64_t n_corr = 0;
+    bool counted = false;
+    uint64_t D = 0;        // distinct canonical k-mers
+    uint64_t n_rows = 0;   // rows of the strand table (K and revcomp K), unordered, in HBM
+    pedk::DBuf<uint64_t> rkey;
+    pedk::DBuf<uint32_t> rval;
+    uint64_t n_corr = 0;   // sorted (k-mer, windows of palindromic reads) corrections
     pedk::DBuf<uint64_t> ckey;
-    pedk::DBuf<uint32_t> cstart;
+    pedk::DBuf<uint32_t> ccnt;
     pedk_count_info cinfo{};
     // host caches for the text emitters
     bool have_table = false;
