@@ -146,7 +146,7 @@ def run_reference(args, rank: int, world: int):
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["name"], "genome": wl["genome"], "reads_per_sample": wl["reads"],
                        "read_len": L, "k": K, "step": f"bounded sample: first {n} reads of each sample on the host CPU"},
             "cpu_baseline": base,
@@ -189,22 +189,32 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = api.Context(local_rank)
+    if world > 1:
+        # the library's own NCCL communicator: rank 0 makes the id, torch.distributed carries it
+        idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
     wl = workload(args.scale)
     cfg = wl["cfg"]
-    # weak scaling over independent sample pairs: rank r works on its own pair (seeds offset by rank)
-    N = wl["reads"]
+    # strong scaling: the SAME workload on N GPUs.  Rank r ingests reads [r*N/R, (r+1)*N/R) of
+    # both samples; reads, k-mers and table rows then change hands inside the library.
+    N_all = wl["reads"]
     G = wl["genome"]
-    g = api.synth_genome(1000 + cfg + 100 * rank, G)
-    t = api.synth_mutate(g, 2000 + cfg + 100 * rank, 1000, 100)
+    first = N_all * rank // world
+    N = N_all * (rank + 1) // world - first
+    g = api.synth_genome(1000 + cfg, G)
+    t = api.synth_mutate(g, 2000 + cfg, 1000, 100)
     gd, td = torch.from_numpy(g).cuda(), torch.from_numpy(t).cuda()
-    nb = api.synth_fastq_bytes(0, N, L)
+    nb = api.synth_fastq_bytes(first, N, L)
     dev_c = torch.empty(nb, dtype=torch.uint8, device="cuda")
     dev_t = torch.empty(nb, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
-    ctx.synth_fastq_device(api.SynthParams(3000 + cfg + 100 * rank, len(g), L, 2000, 1000, 0), gd, 0, N, dev_c)
-    ctx.synth_fastq_device(api.SynthParams(4000 + cfg + 100 * rank, len(t), L, 2000, 1000, 0), td, 0, N, dev_t)
+    ctx.synth_fastq_device(api.SynthParams(3000 + cfg, len(g), L, 2000, 1000, 0), gd, first, N, dev_c)
+    ctx.synth_fastq_device(api.SynthParams(4000 + cfg, len(t), L, 2000, 1000, 0), td, first, N, dev_t)
     del gd, td
-    bases_per_step = 2 * N * L
+    bases_per_step = 2 * N_all * L  # whole job
     stream = torch.cuda.ExternalStream(ctx.stream)
 
     def barrier():
@@ -237,14 +247,16 @@ def main():
         clocks = sampler.stop()
         st = ctx.stats()
         ms = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        ne = torch.tensor([edges or 0], dtype=torch.int64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms[0].item() / steps, ms[1].item() / steps, st, clocks, edges
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)  # every rank holds the edges of its bucket range
+        return ms[0].item() / steps, ms[1].item() / steps, st, clocks, int(ne.item())
 
     # ---- resident leg: FASTQ text already in HBM ----
     dev_ms, wall_ms, st, clocks, edges = timed(
         lambda: ctx.kmer_edges(dev_c, nb, dev_t, nb, device_buffers=True, k=K), args.steps, args.warmup)
-    value = world * bases_per_step / (dev_ms / 1000.0)
+    value = bases_per_step / (dev_ms / 1000.0)
     launches = st["kernel_launches"]
 
     peak, peak_src = peaks()
@@ -277,7 +289,7 @@ def main():
 
         e_dev_ms, e_wall_ms, e_st, _, _ = timed(step_e2e, max(1, args.steps), min(args.warmup, 3))
         steps_e = max(1, args.steps)
-        e2e = {"value": world * bases_per_step / (e_wall_ms / 1000.0), "unit": UNIT,
+        e2e = {"value": bases_per_step / (e_wall_ms / 1000.0), "unit": UNIT,
                "h2d_bytes_per_step": e_st["h2d_bytes"] / steps_e, "d2h_bytes_per_step": e_st["d2h_bytes"] / steps_e,
                "ms_per_step": e_wall_ms, "timing": "wall clock around the C-ABI call, synchronised on both sides"}
 
@@ -285,16 +297,17 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from ped_b200 import build
         build.build_oracle()
-        cpu, _ = cpu_arm(wl, max(10_000, min(args.cpu_sample_reads, N)), 0)
+        cpu, _ = cpu_arm(wl, max(10_000, min(args.cpu_sample_reads, N_all)), 0)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": wl["name"], "genome": G, "reads_per_sample": N, "read_len": L, "k": K,
-                           "bases_per_step_per_gpu": bases_per_step, "edges": edges,
+                "config": {"workload": wl["name"], "genome": G, "reads_per_sample": N_all, "read_len": L, "k": K,
+                           "bases_per_step": bases_per_step, "edges": edges,
                            "l2": "inputs larger than L2 (FASTQ text and k-mer stream are GBs)",
-                           "parallelism": f"{world} independent target/control pairs, one per GPU" if world > 1 else "1 GPU"},
+                           "parallelism": (f"{world} ranks: reads and canonical k-mers to their hash owner, table rows to "
+                                           f"their 3-nt bucket owner (NCCL all-to-all-v)") if world > 1 else "1 GPU"},
                 "wall_ms_per_step": wall_ms, "stage_ms_per_step": stage_ms, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
                 "peak_device_bytes": st["peak_device_bytes"]}

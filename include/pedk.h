@@ -200,6 +200,13 @@ int pedk_reset_stats(pedk_ctx *ctx);
  * the other ranks, every rank calls pedk_comm_init. */
 int pedk_comm_unique_id(pedk_ctx *ctx, void *id_bytes);
 int pedk_comm_init(pedk_ctx *ctx, const void *id_bytes, int rank, int nranks);
+/* Owner functions every rank evaluates identically (host copies of what the kernels use):
+ * canonical packed reads and canonical k-mers go to a rank by hash; table rows go to the
+ * rank that holds the 3-nt bucket of the k-mer, buckets being split into contiguous ranges
+ * balanced on a 64-bin histogram. */
+int pedk_owner_of_read(const uint64_t *words, int words_per_read, int nranks);
+int pedk_owner_of_kmer(uint64_t canonical_kmer, int nranks);
+int pedk_plan_bucket_owners(const uint64_t *hist64, int nranks, uint8_t *owner64);
 
 /* ---- synthetic reads (tests and bench.py) ---------------- */
 

@@ -116,6 +116,9 @@ SIGNATURES = {
     "pedk_reset_stats": (C.c_int, [_P]),
     "pedk_comm_unique_id": (C.c_int, [_P, _P]),
     "pedk_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "pedk_owner_of_read": (C.c_int, [_P, C.c_int, C.c_int]),
+    "pedk_owner_of_kmer": (C.c_int, [C.c_uint64, C.c_int]),
+    "pedk_plan_bucket_owners": (C.c_int, [_P, C.c_int, _P]),
     "pedk_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
     "pedk_synth_mutate": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _U64P]),
     "pedk_synth_fastq_bytes": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint32]),
@@ -202,6 +205,16 @@ class Context:
 
     def reset_stats(self) -> None:
         self.check(self.lib.pedk_reset_stats(self.h))
+
+    # ---- multi-GPU: one rank per process ----
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        self.check(self.lib.pedk_comm_unique_id(self.h, buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int) -> None:
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self.check(self.lib.pedk_comm_init(self.h, buf, rank, nranks))
 
     # ---- whole path ----
     def kmer_edges(self, control_fastq, control_bytes: int, target_fastq, target_bytes: int, *, device_buffers: bool,
@@ -347,6 +360,27 @@ class Result:
         out = np.zeros(n.value, dtype=EDGE_DTYPE)
         self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+
+# ---- sharding plan (host side; no GPU needed) ----
+
+def owner_of_read(words: np.ndarray, nranks: int) -> int:
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    return int(load_library().pedk_owner_of_read(_ptr(w), len(w), nranks))
+
+
+def owner_of_kmer(canonical_kmer: int, nranks: int) -> int:
+    return int(load_library().pedk_owner_of_kmer(int(canonical_kmer), nranks))
+
+
+def plan_bucket_owners(hist64, nranks: int) -> np.ndarray:
+    h = np.ascontiguousarray(hist64, dtype=np.uint64)
+    assert h.shape == (64,)
+    out = np.zeros(64, dtype=np.uint8)
+    rc = load_library().pedk_plan_bucket_owners(_ptr(h), nranks, _ptr(out))
+    if rc:
+        raise PedkError(rc, "pedk_plan_bucket_owners")
+    return out
 
 
 # ---- synthetic inputs (host side; no GPU needed) ----

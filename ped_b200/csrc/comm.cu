@@ -1,13 +1,339 @@
-// Multi-GPU plumbing (NCCL), one rank per process.  Filled in by the sharded path.
-#include "ctx.h"
+// Multi-GPU plumbing: one rank per process, NCCL over NVLink 5 / NVSwitch.
+//
+// ped.pl's own "collective" is a 64x64 matrix of files between countKmerSub and
+// countKmerMerge (ped.pl:894-918, 867-886).  Here three record
+// streams are exchanged, each by an owner function that every rank evaluates
+// identically:
+//   reads      (W words)  -> owner = hash of the canonical packed read: exact dedup stays local
+//   k-mers     (1 word)   -> owner = hash of the canonical k-mer: all instances of a k-mer meet
+//   table rows (2 words)  -> owner = rank that holds the 3-nt bucket of K (contiguous bucket
+//                            ranges balanced on the summed histogram of both samples), so no
+//                            (k-1)-mer group and no first-of-bucket row straddles two ranks
+// An exchange is: count per destination -> all-gather of the count matrix -> scatter into
+// per-destination runs -> grouped ncclSend/ncclRecv (all-to-all-v).  NCCL is bound with
+// dlopen so a single-GPU host needs no libnccl.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <vector>
+
+#include "comm.h"
 
 namespace pedk {
-void comm_destroy(pedk_ctx*) {}
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+#define PEDK_SYM(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym))
+            PEDK_SYM(GetUniqueId, "ncclGetUniqueId");
+            PEDK_SYM(CommInitRank, "ncclCommInitRank");
+            PEDK_SYM(CommDestroy, "ncclCommDestroy");
+            PEDK_SYM(AllReduce, "ncclAllReduce");
+            PEDK_SYM(AllGather, "ncclAllGather");
+            PEDK_SYM(Send, "ncclSend");
+            PEDK_SYM(Recv, "ncclRecv");
+            PEDK_SYM(GroupStart, "ncclGroupStart");
+            PEDK_SYM(GroupEnd, "ncclGroupEnd");
+            PEDK_SYM(GetErrorString, "ncclGetErrorString");
+#undef PEDK_SYM
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.AllGather ||
+        !api.AllReduce || !api.GroupStart || !api.GroupEnd)
+        throw PedkError(PEDK_E_NCCL, "libnccl.so.2 not found (needed only for multi-GPU runs)");
+    return &api;
+}
+
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) {
+        NcclApi* a = nccl();
+        throw PedkError(PEDK_E_NCCL, std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(r) : "NCCL error"));
+    }
+}
+
+ncclComm_t comm_of(pedk_ctx* ctx) { return static_cast<ncclComm_t>(ctx->nccl_comm); }
+
+__device__ __forceinline__ int dest_of(const uint64_t* rec, const DestSpec& s) {
+    if (s.mode == DEST_ROW) return s.owner[rec[0] >> s.bucket_shift];
+    uint64_t h = s.mode == DEST_READ ? words_hash(rec, s.stride) : mix64(rec[0]);
+    return (int)(((h >> 32) * (uint64_t)s.nranks) >> 32);
+}
+
+__global__ void __launch_bounds__(256) k_dest_count(const uint64_t* __restrict__ rec, uint64_t n, DestSpec s,
+                                                   unsigned long long* __restrict__ counts) {
+    const unsigned lane = lane_id();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) & ~31ull;  // whole warps iterate together
+    unsigned long long mine = 0;                 // lane r accumulates the count for destination r
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const int d = i < n ? dest_of(rec + i * s.stride, s) : -1;
+        for (int r = 0; r < s.nranks; ++r) {
+            unsigned m = __ballot_sync(0xffffffffu, d == r);
+            if (lane == (unsigned)r) mine += __popc(m);
+        }
+    }
+    if ((int)lane < s.nranks && mine) atomicAdd(&counts[lane], mine);
+}
+
+__global__ void __launch_bounds__(256) k_dest_scatter(const uint64_t* __restrict__ rec, uint64_t n, DestSpec s,
+                                                     unsigned long long* __restrict__ cursors,
+                                                     uint64_t* __restrict__ out) {
+    const unsigned lane = lane_id();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // whole warps iterate together so the ballots below always see 32 lanes
+    const uint64_t n_round = (n + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        const int d = valid ? dest_of(rec + i * s.stride, s) : -1;
+        unsigned long long pos = 0;
+        for (int r = 0; r < s.nranks; ++r) {
+            unsigned m = __ballot_sync(0xffffffffu, d == r);
+            if (!m) continue;
+            unsigned long long base = 0;
+            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&cursors[r], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (d == r) pos = base + __popc(m & lanemask_lt());
+        }
+        if (valid) {
+            const uint64_t* src = rec + i * s.stride;
+            uint64_t* dst = out + pos * s.stride;
+            for (int w = 0; w < s.stride; ++w) dst[w] = src[w];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pal_flags(const uint64_t* __restrict__ words, int W, int L, uint64_t n,
+                                                  uint8_t* __restrict__ pal) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t fw[PEDK_MAX_WORDS], rc[PEDK_MAX_WORDS];
+    for (int w = 0; w < W; ++w) fw[w] = words[i * W + w];
+    read_revcomp(fw, W, L, rc);
+    pal[i] = words_cmp(fw, rc, W) == 0 ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_rows_pack(const uint64_t* __restrict__ key, const uint32_t* __restrict__ val,
+                                                  uint64_t n, uint64_t* __restrict__ rec) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        rec[2 * i] = key[i];
+        rec[2 * i + 1] = val[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rows_unpack(const uint64_t* __restrict__ rec, uint64_t n,
+                                                    uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        key[i] = rec[2 * i];
+        val[i] = (uint32_t)rec[2 * i + 1];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bucket_hist(const uint64_t* __restrict__ key, uint64_t n, int shift,
+                                                    unsigned long long* __restrict__ hist) {
+    __shared__ unsigned h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned b = (unsigned)(key[i] >> shift);
+        unsigned m = __match_any_sync(__activemask(), b);
+        if ((m & lanemask_lt()) == 0) atomicAdd(&h[b], __popc(m));
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+unsigned grid_for(uint64_t n) {
+    uint64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks < 1) blocks = 1;
+    return (unsigned)(blocks < (uint64_t)kNumSMs * 16 ? blocks : (uint64_t)kNumSMs * 16);
+}
+
+}  // namespace
+
+void comm_destroy(pedk_ctx* ctx) {
+    if (ctx->nccl_comm) {
+        try {
+            nccl()->CommDestroy(comm_of(ctx));
+        } catch (...) {
+        }
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->rank = 0;
+    ctx->nranks = 1;
+}
+
+void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n) {
+    if (ctx->nranks <= 1 || !n) return;
+    StageScope sc(ctx, PEDK_ST_EXCHANGE, 0);
+    nccl_check(nccl()->AllReduce(dev, dev, n, ncclUint64, ncclSum, comm_of(ctx), ctx->stream), "ncclAllReduce");
+}
+
+uint64_t comm_allreduce_sum_host(pedk_ctx* ctx, uint64_t v) {
+    if (ctx->nranks <= 1) return v;
+    unsigned long long x = v;
+    PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 12, &x, sizeof x, cudaMemcpyHostToDevice, ctx->stream));
+    comm_allreduce_sum(ctx, ctx->scalars + 12, 1);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(&x, ctx->scalars + 12, sizeof x, cudaMemcpyDeviceToHost, ctx->stream));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return x;
+}
+
+// Contiguous ranges of the 64 buckets, one per rank, as even as the histogram allows.
+void plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64) {
+    uint64_t total = 0;
+    for (int b = 0; b < 64; ++b) total += hist64[b];
+    uint64_t acc = 0;
+    int r = 0;
+    for (int b = 0; b < 64; ++b) {
+        // move on once this rank holds its share, but keep a bucket for every remaining rank
+        if (r < nranks - 1 && total > 0 && acc * (uint64_t)nranks >= total * (uint64_t)(r + 1)) ++r;
+        if (64 - b <= nranks - 1 - r) r = nranks - 1 - (63 - b);
+        owner64[b] = (uint8_t)r;
+        acc += hist64[b];
+    }
+}
+
+void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec spec, DBuf<uint64_t>* recv,
+                      uint64_t* n_recv) {
+    cudaStream_t st = ctx->stream;
+    const int R = ctx->nranks, me = ctx->rank;
+    spec.nranks = R;
+    NcclApi* a = nccl();
+    StageScope sc(ctx, PEDK_ST_EXCHANGE, 2);
+    // counts per destination, then the whole R x R matrix on every rank
+    DBuf<unsigned long long> counts(ctx, (size_t)PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 2));
+    unsigned long long* my_counts = counts.p;
+    unsigned long long* all_counts = counts.p + PEDK_MAX_RANKS;
+    unsigned long long* cursors = counts.p + PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 1);
+    PEDK_CUDA_TRY(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));
+    if (n) k_dest_count<<<grid_for(n), 256, 0, st>>>(rec, n, spec, my_counts);
+    PEDK_CUDA_TRY(cudaGetLastError());
+    nccl_check(a->AllGather(my_counts, all_counts, PEDK_MAX_RANKS, ncclUint64, comm_of(ctx), st), "ncclAllGather");
+    std::vector<unsigned long long> h((size_t)PEDK_MAX_RANKS * R);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(h.data(), all_counts, h.size() * 8, cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    // h[src * MAX + dst]
+    std::vector<unsigned long long> send_off(R + 1, 0), recv_off(R + 1, 0);
+    for (int d = 0; d < R; ++d) send_off[d + 1] = send_off[d] + h[(size_t)me * PEDK_MAX_RANKS + d];
+    for (int s = 0; s < R; ++s) recv_off[s + 1] = recv_off[s] + h[(size_t)s * PEDK_MAX_RANKS + me];
+    if (send_off[R] != n) throw PedkError(PEDK_E_INTERNAL, "exchange: destination counts do not add up");
+    *n_recv = recv_off[R];
+    DBuf<uint64_t> sendbuf(ctx, n * spec.stride);
+    *recv = DBuf<uint64_t>(ctx, *n_recv * spec.stride);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(cursors, send_off.data(), R * 8, cudaMemcpyHostToDevice, st));
+    if (n) k_dest_scatter<<<grid_for(n), 256, 0, st>>>(rec, n, spec, cursors, sendbuf.p);
+    PEDK_CUDA_TRY(cudaGetLastError());
+    nccl_check(a->GroupStart(), "ncclGroupStart");
+    for (int p = 0; p < R; ++p) {
+        if (p == me) continue;
+        size_t ns = (size_t)(send_off[p + 1] - send_off[p]) * spec.stride;
+        size_t nr = (size_t)(recv_off[p + 1] - recv_off[p]) * spec.stride;
+        if (ns) nccl_check(a->Send(sendbuf.p + send_off[p] * spec.stride, ns, ncclUint64, p, comm_of(ctx), st), "ncclSend");
+        if (nr) nccl_check(a->Recv(recv->p + recv_off[p] * spec.stride, nr, ncclUint64, p, comm_of(ctx), st), "ncclRecv");
+    }
+    nccl_check(a->GroupEnd(), "ncclGroupEnd");
+    size_t self = (size_t)(send_off[me + 1] - send_off[me]) * spec.stride;
+    if (self)
+        PEDK_CUDA_TRY(cudaMemcpyAsync(recv->p + recv_off[me] * spec.stride, sendbuf.p + send_off[me] * spec.stride,
+                                      self * 8, cudaMemcpyDeviceToDevice, st));
+    // the send buffer goes back to the allocator in stream order
+    ctx->stats.kernel_launches += 2;
+}
+
+void launch_pal_flags(const uint64_t* words, int W, int L, uint64_t n, uint8_t* pal, cudaStream_t st) {
+    if (!n) return;
+    k_pal_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(words, W, L, n, pal);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_rows_pack(const uint64_t* key, const uint32_t* val, uint64_t n, uint64_t* rec, cudaStream_t st) {
+    if (!n) return;
+    k_rows_pack<<<grid_for(n), 256, 0, st>>>(key, val, n, rec);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_rows_unpack(const uint64_t* rec, uint64_t n, uint64_t* key, uint32_t* val, cudaStream_t st) {
+    if (!n) return;
+    k_rows_unpack<<<grid_for(n), 256, 0, st>>>(rec, n, key, val);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_bucket_hist(const uint64_t* key, uint64_t n, int k, unsigned long long* hist, cudaStream_t st) {
+    if (!n) return;
+    k_bucket_hist<<<grid_for(n), 256, 0, st>>>(key, n, 2 * k - 6, hist);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
 }  // namespace pedk
 
-extern "C" int pedk_comm_unique_id(pedk_ctx* ctx, void*) {
-    return pedk::ctx_fail(ctx, PEDK_E_UNSUPPORTED, "pedk_comm_unique_id: not built yet");
+using namespace pedk;
+
+extern "C" int pedk_comm_unique_id(pedk_ctx* ctx, void* id_bytes) {
+    if (!ctx || !id_bytes) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    static_assert(sizeof(ncclUniqueId) <= PEDK_COMM_ID_BYTES, "id size");
+    ncclUniqueId id;
+    nccl_check(nccl()->GetUniqueId(&id), "ncclGetUniqueId");
+    memset(id_bytes, 0, PEDK_COMM_ID_BYTES);
+    memcpy(id_bytes, &id, sizeof id);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
 }
-extern "C" int pedk_comm_init(pedk_ctx* ctx, const void*, int, int) {
-    return pedk::ctx_fail(ctx, PEDK_E_UNSUPPORTED, "pedk_comm_init: not built yet");
+
+extern "C" int pedk_comm_init(pedk_ctx* ctx, const void* id_bytes, int rank, int nranks) {
+    if (!ctx || !id_bytes || nranks < 1 || nranks > PEDK_MAX_RANKS || rank < 0 || rank >= nranks) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    comm_destroy(ctx);
+    if (nranks == 1) return PEDK_OK;
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclComm_t comm;
+    nccl_check(nccl()->CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank");
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+// host-side owner functions, identical to what the kernels evaluate (tests, planning)
+extern "C" int pedk_owner_of_read(const uint64_t* words, int words_per_read, int nranks) {
+    uint64_t h = words_hash(words, words_per_read);
+    return (int)(((h >> 32) * (uint64_t)nranks) >> 32);
+}
+
+extern "C" int pedk_owner_of_kmer(uint64_t canonical_kmer, int nranks) {
+    uint64_t h = mix64(canonical_kmer);
+    return (int)(((h >> 32) * (uint64_t)nranks) >> 32);
+}
+
+extern "C" int pedk_plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64) {
+    if (!hist64 || !owner64 || nranks < 1 || nranks > PEDK_MAX_RANKS) return PEDK_E_INVAL;
+    plan_bucket_owners(hist64, nranks, owner64);
+    return PEDK_OK;
 }

@@ -1,0 +1,32 @@
+// Multi-GPU exchange primitives (internal; comm.cu).
+#pragma once
+#include "ctx.h"
+
+#define PEDK_MAX_RANKS 8
+
+namespace pedk {
+
+enum { DEST_READ = 0, DEST_KMER = 1, DEST_ROW = 2 };
+
+struct DestSpec {
+    int mode = DEST_KMER;
+    int stride = 1;        // u64 words per record (reads: W, k-mers: 1, rows: 2)
+    int nranks = 1;
+    int bucket_shift = 0;  // rows: 2k-6, the key's first three bases
+    uint8_t owner[64] = {0};
+};
+
+void comm_destroy(pedk_ctx* ctx);
+// in-place sum over ranks of n u64 words in device memory (no-op on one rank)
+void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n);
+uint64_t comm_allreduce_sum_host(pedk_ctx* ctx, uint64_t v);
+void plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64);
+// all-to-all-v of n records; *recv holds the *n_recv records this rank owns, grouped by source rank
+void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec spec, DBuf<uint64_t>* recv,
+                      uint64_t* n_recv);
+void launch_pal_flags(const uint64_t* words, int W, int L, uint64_t n, uint8_t* pal, cudaStream_t st);
+void launch_rows_pack(const uint64_t* key, const uint32_t* val, uint64_t n, uint64_t* rec, cudaStream_t st);
+void launch_rows_unpack(const uint64_t* rec, uint64_t n, uint64_t* key, uint32_t* val, cudaStream_t st);
+void launch_bucket_hist(const uint64_t* key, uint64_t n, int k, unsigned long long* hist, cudaStream_t st);
+
+}  // namespace pedk

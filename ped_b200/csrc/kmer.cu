@@ -20,23 +20,24 @@ namespace pedk {
 namespace {
 
 constexpr int EX_THREADS = 256;
-constexpr int EX_MAX_PASS = 8;
 
+template <int NPASS>
 __global__ void __launch_bounds__(EX_THREADS) k_extract(const uint64_t* __restrict__ words, int W, int L, int k,
                                                        uint64_t n_reads, uint64_t* __restrict__ out,
-                                                       unsigned long long* __restrict__ digit_hist, int n_pass) {
-    __shared__ unsigned h[EX_MAX_PASS][256];
-    for (int i = threadIdx.x; i < EX_MAX_PASS * 256; i += EX_THREADS) (&h[0][0])[i] = 0;
+                                                       unsigned long long* __restrict__ digit_hist) {
+    __shared__ unsigned h[NPASS ? NPASS : 1][256];
+    for (int i = threadIdx.x; i < NPASS * 256; i += EX_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     const unsigned lane = lane_id();
     const uint64_t warp = ((uint64_t)blockIdx.x * EX_THREADS + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * EX_THREADS) >> 5;
     const int nwin = L - k + 1;
     const int kshift = 64 - 2 * k;
+    const int nt = (nwin + 31) >> 5;
     for (uint64_t r = warp; r < n_reads; r += n_warps) {
         uint64_t mine = (int)lane < W ? words[r * (uint64_t)W + lane] : 0ull;
         uint64_t* dst = out + r * (uint64_t)nwin;
-        for (int t = 0; 32 * t < nwin; ++t) {
+        for (int t = 0; t < nt; ++t) {
             uint64_t hi = __shfl_sync(0xffffffffu, mine, t);
             uint64_t lo = __shfl_sync(0xffffffffu, mine, t + 1);
             int i = 32 * t + (int)lane;
@@ -46,12 +47,15 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(const uint64_t* __restri
             uint64_t canon = km < rc ? km : rc;
             if (i < nwin) {
                 dst[i] = canon;
-                for (int p = 0; p < n_pass; ++p) atomicAdd(&h[p][(canon >> (8 * p)) & 255u], 1u);
+                const uint32_t clo = (uint32_t)canon, chi = (uint32_t)(canon >> 32);
+#pragma unroll
+                for (int p = 0; p < NPASS; ++p)
+                    atomicAdd(&h[p][((p < 4 ? clo : chi) >> (8 * (p & 3))) & 255u], 1u);
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_pass * 256; i += EX_THREADS) {
+    for (int i = threadIdx.x; i < NPASS * 256; i += EX_THREADS) {
         unsigned c = (&h[0][0])[i];
         if (c) atomicAdd(&digit_hist[i], (unsigned long long)c);
     }
@@ -143,34 +147,52 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const uint64_t* __res
                                                           uint64_t* __restrict__ row_key,
                                                           uint32_t* __restrict__ row_val, uint64_t cap,
                                                           unsigned long long* __restrict__ counters) {
+    // the run heads of a warp's 256 keys, compacted: (offset inside the segment, key)
+    __shared__ uint64_t s_key[CR_WARPS][CR_SEG];
+    __shared__ uint16_t s_pos[CR_WARPS][CR_SEG];
     __shared__ unsigned w_rows[CR_WARPS], w_heads[CR_WARPS];
     __shared__ unsigned long long s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const size_t seg = (size_t)blockIdx.x * CR_TILE + (size_t)warp * CR_SEG;
     const size_t seg_end = seg + CR_SEG < n ? seg + CR_SEG : n;
+    const unsigned lt = lanemask_lt();
 
-    uint64_t key[CR_ITEMS];
+    // ---- A: head flags for the whole segment; heads drop (offset, key) into the compact list ----
+    unsigned nh = 0;
+    {
+        uint64_t carry = (seg > 0 && seg < n) ? keys[seg - 1] : 0ull;  // key just before the segment
+        uint64_t key[CR_ITEMS];
 #pragma unroll
-    for (int j = 0; j < CR_ITEMS; ++j) {
-        size_t i = seg + 32 * j + lane;
-        key[j] = i < n ? keys[i] : 0ull;
+        for (int j = 0; j < CR_ITEMS; ++j) {
+            size_t i = seg + 32 * j + lane;
+            key[j] = i < n ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < CR_ITEMS; ++j) {
+            size_t i = seg + 32 * j + lane;
+            uint64_t prev = __shfl_up_sync(0xffffffffu, key[j], 1);
+            if (lane == 0) prev = carry;
+            const bool head = i < n && (i == 0 || key[j] != prev);
+            const unsigned h = __ballot_sync(0xffffffffu, head);
+            if (head) {
+                unsigned r = nh + __popc(h & lt);
+                s_key[warp][r] = key[j];
+                s_pos[warp][r] = (uint16_t)(32 * j + lane);
+            }
+            nh += __popc(h);
+            carry = __shfl_sync(0xffffffffu, key[j], 31);
+        }
     }
-    unsigned H[CR_ITEMS], R[CR_ITEMS];  // ballots: run heads / heads that also emit a reverse row
-    unsigned nh = 0, nr = 0;
-    uint64_t carry = (seg > 0 && seg < n) ? keys[seg - 1] : 0ull;
-#pragma unroll
-    for (int j = 0; j < CR_ITEMS; ++j) {
-        size_t i = seg + 32 * j + lane;
-        uint64_t prev = __shfl_up_sync(0xffffffffu, key[j], 1);
-        if (lane == 0) prev = carry;
-        bool head = i < n && (i == 0 || key[j] != prev);
-        bool rev = false;
-        if (STRAND) rev = head && kmer_revcomp(key[j], k) != key[j];
-        H[j] = __ballot_sync(0xffffffffu, head);
-        R[j] = __ballot_sync(0xffffffffu, rev);
-        nh += __popc(H[j]);
-        nr += __popc(R[j]);
-        carry = __shfl_sync(0xffffffffu, key[j], 31);
+    __syncwarp();
+
+    // ---- B1: how many reverse rows (heads that are not their own reverse complement) ----
+    unsigned nr = 0;
+    if (STRAND) {
+        for (unsigned r0 = 0; r0 < nh; r0 += 32) {
+            const unsigned r = r0 + lane;
+            const bool rev = r < nh && kmer_revcomp(s_key[warp][r], k) != s_key[warp][r];
+            nr += __popc(__ballot_sync(0xffffffffu, rev));
+        }
     }
     if (lane == 0) {
         w_rows[warp] = nh + nr;
@@ -190,50 +212,52 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const uint64_t* __res
         if (heads) atomicAdd(&counters[1], (unsigned long long)heads);
     }
     __syncthreads();
-    unsigned long long o = s_base + w_rows[warp];
-#pragma unroll
-    for (int j = 0; j < CR_ITEMS; ++j) {
-        const unsigned h = H[j], r = R[j];
-        if ((h >> lane) & 1u) {
-            const uint64_t K = key[j];
-            const size_t i = seg + 32 * j + lane;
-            // the next head inside this warp's segment ends the run
-            long next = -1;
-            unsigned m = h & ~((2u << lane) - 1u);
-            if (m) next = 32 * j + (__ffs(m) - 1);
-#pragma unroll
-            for (int j2 = 0; j2 < CR_ITEMS; ++j2)
-                if (j2 > j && next < 0 && H[j2]) next = 32 * j2 + (__ffs(H[j2]) - 1);
-            const size_t end = next >= 0 ? seg + (size_t)next : run_end_from(keys, n, seg_end, K);
-            uint64_t inst = end - i;
-            uint32_t v;
+
+    // ---- B2: one lane per head: run length -> count -> rows (forward rows, then reverse rows) ----
+    const unsigned long long of = s_base + w_rows[warp];
+    unsigned long long orv = of + nh;
+    for (unsigned r0 = 0; r0 < nh; r0 += 32) {
+        const unsigned r = r0 + lane;
+        const bool act = r < nh;
+        uint64_t K = 0;
+        uint32_t v = 0;
+        bool rev = false;
+        if (act) {
+            K = s_key[warp][r];
+            const size_t i = seg + s_pos[warp][r];
+            const size_t end = r + 1 < nh ? seg + s_pos[warp][r + 1] : run_end_from(keys, n, seg_end, K);
+            const uint64_t inst = end - i;
             if (STRAND) {
+                rev = kmer_revcomp(K, k) != K;
                 uint64_t corr = 0;
                 if (n_corr) {
                     uint64_t q = lower_bound_dev(corr_key, n_corr, K);
                     if (q < n_corr && corr_key[q] == K) corr = corr_cnt[q];
                 }
                 uint64_t Hh = 2 * inst - corr;
-                uint64_t c = ((r >> lane) & 1u) ? (Hh >> 1) : Hh;
+                uint64_t c = rev ? (Hh >> 1) : Hh;
                 if (c > 0x7fffffffull) c = 0x7fffffffull;
                 v = (uint32_t)c | sample_bit;
             } else {
                 v = inst > 0xffffffffull ? 0xffffffffu : (uint32_t)inst;
             }
-            unsigned long long pf = o + __popc(h & lanemask_lt());
+            const unsigned long long pf = of + r;
             if (pf < cap) {
                 row_key[pf] = K;
                 row_val[pf] = v;
             }
-            if (STRAND && ((r >> lane) & 1u)) {
-                unsigned long long pr = o + __popc(h) + __popc(r & lanemask_lt());
+        }
+        if (STRAND) {
+            const unsigned m = __ballot_sync(0xffffffffu, rev);
+            if (rev) {
+                const unsigned long long pr = orv + __popc(m & lt);
                 if (pr < cap) {
                     row_key[pr] = kmer_revcomp(K, k);
                     row_val[pr] = v;
                 }
             }
+            orv += __popc(m);
         }
-        o += __popc(h) + __popc(r);
     }
 }
 
@@ -244,7 +268,17 @@ void launch_extract(const uint64_t* words, int W, int L, int k, uint64_t n_reads
     if (!n_reads || L < k) return;
     uint64_t blocks = (n_reads + 7) / 8;
     unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
-    k_extract<<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist, n_pass);
+    switch (n_pass) {
+    case 0: k_extract<0><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 1: k_extract<1><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 2: k_extract<2><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 3: k_extract<3><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 4: k_extract<4><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 5: k_extract<5><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 6: k_extract<6><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    case 7: k_extract<7><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    default: k_extract<8><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, out, digit_hist); break;
+    }
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

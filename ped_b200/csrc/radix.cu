@@ -2,16 +2,24 @@
 // 32-bit payload), 8-bit digits, one "onesweep" pass per digit.
 //
 // Replaces `sort -S 1M` (ped.pl:928, 1416).  Per pass every key is read once
-// and written once (16 B/key of HBM traffic, 20 B/row with a payload):
+// and written once (16 B/key of HBM traffic, 24 B/row with a payload):
 //   * the global digit histograms are produced upstream (by the k-mer
 //     extraction kernel, or launch_digit_hist for row tables), so a pass is a
 //     single kernel;
-//   * a tile (THREADS x ITEMS keys) ranks its keys with warp match_any +
-//     per-warp shared-memory counters, finds its global offsets with a
-//     decoupled look-back over 256 per-digit counters, stages the keys in
-//     shared memory in digit order and writes each digit run contiguously;
+//   * a tile is 256 threads x 16 keys, four tiles resident per SM.  Phase 1
+//     counts digits per warp with shared-memory atomics; the tile aggregate is
+//     published for the decoupled look-back right away.  Phase 2 ranks the keys
+//     stably inside each warp (eight vote.ballot rounds find the lanes holding
+//     the same digit; match.any is data dependent and 2x slower on sm_100, and
+//     an atomicOr mask table measured the same as the ballots -- profiles/) and
+//     stores them straight into a shared-memory staging buffer in digit order.
+//     The look-back over the 256 digit counters comes after phase 2, so the
+//     predecessors have had that long to publish.  Phase 3 writes each digit
+//     run contiguously;
 //   * tiles take their index from an atomic ticket, so a tile only ever waits
-//     on tiles that are already running; the wait is bounded (err flag).
+//     on tiles that are already running; the wait is bounded (err flag);
+//   * the digit position is a template parameter: digit and ballot predicates
+//     are single instructions on one 32-bit half of the key.
 // Look-back words are 32 bit (2 flag + 30 value bits); inputs longer than
 // PORTION keys are sorted in portions, the last tile of a portion folding its
 // inclusive digit counts into bin_base for the next portion.
@@ -43,13 +51,10 @@ __device__ __forceinline__ uint32_t lb32_load(const uint32_t* p) {
     return v;
 }
 
-enum { RANK_MATCH = 0, RANK_BALLOT = 1, RANK_OR = 2 };
-
 template <bool PAIRS>
 struct RadixSmem {
     uint64_t keys[RS_TILE];
     uint32_t warp_hist[RS_WARPS][256];
-    uint32_t warp_mask[RS_WARPS][256];
     uint64_t gbase[256];
     unsigned tile;
 };
@@ -58,31 +63,38 @@ struct RadixSmem<true> {
     uint64_t keys[RS_TILE];
     uint32_t vals[RS_TILE];
     uint32_t warp_hist[RS_WARPS][256];
-    uint32_t warp_mask[RS_WARPS][256];
     uint64_t gbase[256];
     unsigned tile;
 };
 
-template <bool PAIRS, int RANK>
+// the 32-bit half of the key that holds the digit, and the digit itself
+template <int SHIFT>
+__device__ __forceinline__ uint32_t digit_word(uint64_t key) {
+    return SHIFT < 32 ? (uint32_t)key : (uint32_t)(key >> 32);
+}
+template <int SHIFT>
+__device__ __forceinline__ unsigned digit_of(uint64_t key) {
+    return (digit_word<SHIFT>(key) >> (SHIFT & 31)) & 255u;
+}
+
+template <bool PAIRS, int SHIFT>
 __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
-                                                          const uint32_t* __restrict__ vin,
-                                                          uint32_t* __restrict__ vout, size_t n, int shift,
-                                                          unsigned long long* __restrict__ bin_base,
-                                                          uint32_t* __restrict__ lookback,
-                                                          unsigned int* __restrict__ tile_ctr, unsigned n_tiles,
-                                                          int* __restrict__ err) {
+                                                             const uint32_t* __restrict__ vin,
+                                                             uint32_t* __restrict__ vout, size_t n,
+                                                             unsigned long long* __restrict__ bin_base,
+                                                             uint32_t* __restrict__ lookback,
+                                                             unsigned int* __restrict__ tile_ctr, unsigned n_tiles,
+                                                             int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RadixSmem<PAIRS>& sm = *reinterpret_cast<RadixSmem<PAIRS>*>(smem_raw);
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr int S = SHIFT & 31;
 
     if (tid == 0) sm.tile = atomicAdd(tile_ctr, 1u);
 #pragma unroll
-    for (int i = 0; i < 256 / 32; ++i) {
-        sm.warp_hist[warp][i * 32 + lane] = 0;
-        if constexpr (RANK == RANK_OR) sm.warp_mask[warp][i * 32 + lane] = 0;
-    }
+    for (int i = 0; i < 256 / 32; ++i) sm.warp_hist[warp][i * 32 + lane] = 0;
     // read the global base before anything is published (see portion hand-over below)
-    unsigned long long my_base = tid < 256 ? bin_base[tid] : 0ull;
+    const unsigned long long my_base = bin_base[tid];
     __syncthreads();
     const unsigned tile = sm.tile;
     const size_t tile_off = (size_t)tile * RS_TILE;
@@ -109,19 +121,17 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __
 
     // ---- phase 1: per-warp digit counts (order does not matter yet) ----
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) atomicAdd(&sm.warp_hist[warp][(unsigned)(key[j] >> shift) & 255u], 1u);
+    for (int j = 0; j < RS_ITEMS; ++j) atomicAdd(&sm.warp_hist[warp][digit_of<SHIFT>(key[j])], 1u);
     __syncthreads();
 
     // ---- per digit: tile count -> publish the aggregate early, then turn the per-warp
     //      counts into absolute positions in the staging buffer ----
     unsigned dcount = 0;
-    if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) dcount += sm.warp_hist[w][tid];
-        lb32_store(lookback + (size_t)tile * 256 + tid, (tile == 0 ? LB32_INC : LB32_AGG) | dcount);
-    }
+    for (int w = 0; w < RS_WARPS; ++w) dcount += sm.warp_hist[w][tid];
+    lb32_store(lookback + (size_t)tile * 256 + tid, (tile == 0 ? LB32_INC : LB32_AGG) | dcount);
     const uint32_t ex = (uint32_t)block_exclusive_scan<RS_THREADS>(dcount, nullptr);
-    if (tid < 256) {
+    {
         unsigned running = ex;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
@@ -132,45 +142,34 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __
     }
     __syncthreads();
 
-    // ---- phase 2: stable rank inside the warp, straight into the staging buffer.
-    // peers = lanes whose item j has the same digit:
-    //   RANK_MATCH  the match.any instruction (data dependent, slow on sm_100: profiles/)
-    //   RANK_BALLOT eight vote.ballot rounds, one per digit bit
-    //   RANK_OR     shared-memory atomicOr of the lane bit into a per-warp mask table
+    // ---- phase 2: stable rank inside the warp, straight into the staging buffer ----
+    const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
-        unsigned d = (unsigned)(key[j] >> shift) & 255u;
-        unsigned peers;
-        if constexpr (RANK == RANK_MATCH) {
-            peers = __match_any_sync(0xffffffffu, d);
-        } else if constexpr (RANK == RANK_BALLOT) {
-            peers = 0xffffffffu;
+        const uint32_t w = digit_word<SHIFT>(key[j]);
+        // peers = lanes whose item j has the same digit: one ballot per digit bit;
+        // acc collects the lanes that differ from this lane in some bit
+        unsigned acc = 0;
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                unsigned bit = (d >> b) & 1u;
-                unsigned m = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? m : ~m;
-            }
-        } else {
-            unsigned* mask = &sm.warp_mask[warp][d];
-            atomicOr(mask, 1u << lane);
-            __syncwarp();
-            peers = *mask;
-            __syncwarp();
-            *mask = 0;  // every peer stores the same 0
-            __syncwarp();
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (w >> (S + b)) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            acc |= m ^ (bit ? 0xffffffffu : 0u);
         }
-        unsigned leader = __ffs(peers) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&sm.warp_hist[warp][d], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        unsigned pos = base + __popc(peers & lanemask_lt());
+        const unsigned peers = ~acc;
+        const unsigned below = peers & lt;
+        unsigned* ctr = &sm.warp_hist[warp][(w >> S) & 255u];
+        const unsigned base = *ctr;  // every peer reads the same word
+        __syncwarp();
+        if (below == 0) *ctr = base + __popc(peers);  // the lowest peer moves the counter on
+        __syncwarp();
+        const unsigned pos = base + __popc(below);
         sm.keys[pos] = key[j];
         if constexpr (PAIRS) sm.vals[pos] = val[j];
     }
 
     // ---- look-back: predecessors had the whole of phase 2 to publish ----
-    if (tid < 256) {
+    {
         uint32_t excl = 0;
         if (tile > 0) {
             long long t = (long long)tile - 1;
@@ -209,14 +208,13 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __
     }
     __syncthreads();
 
-    // ---- write each digit run contiguously ----
+    // ---- phase 3: write each digit run contiguously ----
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; ++j) {
         unsigned i = j * RS_THREADS + tid;
         if (i < tile_n) {
             uint64_t k = sm.keys[i];
-            unsigned d = (unsigned)(k >> shift) & 255u;
-            size_t g = (size_t)(sm.gbase[d] + i);
+            size_t g = (size_t)(sm.gbase[digit_of<SHIFT>(k)] + i);
             out[g] = k;
             if constexpr (PAIRS) vout[g] = sm.vals[i];
         }
@@ -226,18 +224,20 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __
 constexpr int DH_THREADS = 256;
 constexpr int DH_MAX_PASS = 8;
 
+template <int NPASS>
 __global__ void __launch_bounds__(DH_THREADS) k_digit_hist(const uint64_t* __restrict__ keys, size_t n,
-                                                          unsigned long long* __restrict__ digit_hist, int n_pass) {
-    __shared__ unsigned h[DH_MAX_PASS][256];
-    for (int i = threadIdx.x; i < DH_MAX_PASS * 256; i += DH_THREADS) (&h[0][0])[i] = 0;
+                                                          unsigned long long* __restrict__ digit_hist) {
+    __shared__ unsigned h[NPASS][256];
+    for (int i = threadIdx.x; i < NPASS * 256; i += DH_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     size_t stride = (size_t)gridDim.x * DH_THREADS;
     for (size_t i = (size_t)blockIdx.x * DH_THREADS + threadIdx.x; i < n; i += stride) {
         uint64_t k = keys[i];
-        for (int p = 0; p < n_pass; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_pass * 256; i += DH_THREADS) {
+    for (int i = threadIdx.x; i < NPASS * 256; i += DH_THREADS) {
         unsigned c = (&h[0][0])[i];
         if (c) atomicAdd(&digit_hist[i], (unsigned long long)c);
     }
@@ -250,6 +250,35 @@ __global__ void __launch_bounds__(256) k_hist_to_base(unsigned long long* __rest
     h[threadIdx.x] = ex;
 }
 
+template <bool PAIRS, int SHIFT>
+void launch_pass_variant(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t pn,
+                         unsigned long long* bin_base, RadixWorkspace ws, unsigned tiles, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<PAIRS, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(RadixSmem<PAIRS>)));
+        attr_set = true;
+    }
+    k_radix_pass<PAIRS, SHIFT><<<tiles, RS_THREADS, sizeof(RadixSmem<PAIRS>), st>>>(
+        in, out, vin, vout, pn, bin_base, reinterpret_cast<uint32_t*>(ws.lookback), ws.tile_ctr, tiles, ws.err);
+}
+
+template <bool PAIRS>
+void launch_pass_shift(int pass, const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t pn,
+                       unsigned long long* bin_base, RadixWorkspace ws, unsigned tiles, cudaStream_t st) {
+    switch (pass) {
+    case 0: launch_pass_variant<PAIRS, 0>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 1: launch_pass_variant<PAIRS, 8>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 2: launch_pass_variant<PAIRS, 16>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 3: launch_pass_variant<PAIRS, 24>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 4: launch_pass_variant<PAIRS, 32>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 5: launch_pass_variant<PAIRS, 40>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 6: launch_pass_variant<PAIRS, 48>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    case 7: launch_pass_variant<PAIRS, 56>(in, out, vin, vout, pn, bin_base, ws, tiles, st); break;
+    default: throw PedkError(-8, "radix pass out of range");
+    }
+}
+
 }  // namespace
 
 size_t radix_tiles(size_t n) {
@@ -257,53 +286,20 @@ size_t radix_tiles(size_t n) {
     return (p + RS_TILE - 1) / RS_TILE;
 }
 
-template <bool PAIRS, int RANK>
-static void launch_pass_variant(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t pn,
-                                int shift, unsigned long long* bin_base, RadixWorkspace ws, unsigned tiles,
-                                cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<PAIRS, RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(RadixSmem<PAIRS>)));
-        attr_set = true;
-    }
-    k_radix_pass<PAIRS, RANK><<<tiles, RS_THREADS, sizeof(RadixSmem<PAIRS>), st>>>(
-        in, out, vin, vout, pn, shift, bin_base, reinterpret_cast<uint32_t*>(ws.lookback), ws.tile_ctr, tiles, ws.err);
-}
-
-int radix_rank_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("PEDK_RANK_MODE");
-        mode = e ? atoi(e) : RANK_BALLOT;
-        if (mode < 0 || mode > 2) mode = RANK_BALLOT;
-    }
-    return mode;
-}
-
 void launch_radix_pass(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t n, int pass,
                        const unsigned long long* digit_hist, RadixWorkspace ws, cudaStream_t st) {
     if (!n) return;
     unsigned long long* bin_base = const_cast<unsigned long long*>(digit_hist) + (size_t)pass * 256;
-    const int mode = radix_rank_mode();
     for (size_t off = 0; off < n; off += RS_PORTION) {
         size_t pn = (n - off) < RS_PORTION ? (n - off) : RS_PORTION;
         unsigned tiles = (unsigned)((pn + RS_TILE - 1) / RS_TILE);
         if (tiles > ws.tiles_cap) throw PedkError(-8, "radix workspace too small");
         PEDK_CUDA_TRY(cudaMemsetAsync(ws.lookback, 0, (size_t)tiles * 256 * sizeof(uint32_t), st));
         PEDK_CUDA_TRY(cudaMemsetAsync(ws.tile_ctr, 0, sizeof(unsigned), st));
-        const uint32_t* vi = vin ? vin + off : nullptr;
-#define PEDK_PASS(P, R) launch_pass_variant<P, R>(in + off, out, vi, vout, pn, 8 * pass, bin_base, ws, tiles, st)
-        if (vin) {
-            if (mode == RANK_MATCH) PEDK_PASS(true, RANK_MATCH);
-            else if (mode == RANK_OR) PEDK_PASS(true, RANK_OR);
-            else PEDK_PASS(true, RANK_BALLOT);
-        } else {
-            if (mode == RANK_MATCH) PEDK_PASS(false, RANK_MATCH);
-            else if (mode == RANK_OR) PEDK_PASS(false, RANK_OR);
-            else PEDK_PASS(false, RANK_BALLOT);
-        }
-#undef PEDK_PASS
+        if (vin)
+            launch_pass_shift<true>(pass, in + off, out, vin + off, vout, pn, bin_base, ws, tiles, st);
+        else
+            launch_pass_shift<false>(pass, in + off, out, nullptr, nullptr, pn, bin_base, ws, tiles, st);
         PEDK_CUDA_TRY(cudaGetLastError());
     }
 }
@@ -313,7 +309,16 @@ void launch_digit_hist(const uint64_t* keys, size_t n, unsigned long long* digit
     if (!n) return;
     size_t blocks = (n + DH_THREADS * 16 - 1) / (DH_THREADS * 16);
     unsigned grid = (unsigned)(blocks < (size_t)kNumSMs * 8 ? blocks : (size_t)kNumSMs * 8);
-    k_digit_hist<<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist, n_pass);
+    switch (n_pass) {
+    case 1: k_digit_hist<1><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    case 2: k_digit_hist<2><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    case 3: k_digit_hist<3><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    case 4: k_digit_hist<4><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    case 5: k_digit_hist<5><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    case 6: k_digit_hist<6><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    case 7: k_digit_hist<7><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    default: k_digit_hist<DH_MAX_PASS><<<grid, DH_THREADS, 0, st>>>(keys, n, digit_hist); break;
+    }
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

@@ -3,6 +3,8 @@
 // the few decisions ped.pl makes from whole-file statistics (read-length mode).
 #include "sample.h"
 
+#include "comm.h"
+
 #include <string.h>
 
 #include <algorithm>
@@ -44,36 +46,11 @@ struct GroupPlan {
     uint64_t r_limit;
 };
 
-// Build one read-length group: chunk -> pack -> dedup -> compact.
-void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_start, const uint32_t* rlen,
-                 const uint8_t* rflag, uint64_t R, uint64_t* strand_reads) {
+// Exact dedup of n packed canonical reads -> a ReadGroup of the sample.
+void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8_t>& pal, uint64_t n_c) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    const int L = (int)plan.clip;
-    const int W = (L + 31) / 32;
-    DBuf<uint32_t> chunks(ctx, R);
-    DBuf<uint64_t> base(ctx, R);
-    DBuf<uint64_t> ws(ctx, scan_workspace_words(R));
-    uint64_t n_c;
-    {
-        StageScope sc(ctx, PEDK_ST_INGEST, 4);
-        launch_chunk_count(rlen, rflag, R, plan.r_limit, plan.clip, plan.whole, chunks.p, st);
-        exclusive_scan_u32(chunks.p, base.p, R, ctx->scalars, ws.p, st);
-    }
-    n_c = read_scalar(ctx, ctx->scalars, "chunk scan");
-    *strand_reads += 2 * n_c;
-    if (n_c == 0) return;
     if (n_c >= 0xFFFFFFF0ull) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^32 reads in one sample on one GPU");
-    DBuf<uint64_t> words(ctx, n_c * W);
-    DBuf<uint8_t> pal(ctx, n_c);
-    {
-        StageScope sc(ctx, PEDK_ST_INGEST, 1);
-        launch_pack(s->fq.p, seq_start, chunks.p, base.p, R, plan.clip, W, words.p, pal.p, st);
-    }
-    chunks.reset();
-    base.reset();
-    ws.reset();
-    // exact dedup
     uint32_t cap = 1024;
     while ((uint64_t)cap < 2 * n_c) cap <<= 1;
     DBuf<uint32_t> table(ctx, cap);
@@ -104,6 +81,52 @@ void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_star
     s->groups.push_back(std::move(g));
 }
 
+// Build one read-length group: chunk -> pack -> (multi-GPU: route every read to the rank
+// that owns its hash) -> dedup -> compact.  R may be 0 on a rank of a multi-GPU job.
+void build_group(pedk_sample* s, const GroupPlan& plan, const uint64_t* seq_start, const uint32_t* rlen,
+                 const uint8_t* rflag, uint64_t R, uint64_t* strand_reads) {
+    pedk_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int L = (int)plan.clip;
+    const int W = (L + 31) / 32;
+    uint64_t n_c = 0;
+    DBuf<uint64_t> words;
+    DBuf<uint8_t> pal;
+    if (R) {
+        DBuf<uint32_t> chunks(ctx, R);
+        DBuf<uint64_t> base(ctx, R);
+        DBuf<uint64_t> ws(ctx, scan_workspace_words(R));
+        {
+            StageScope sc(ctx, PEDK_ST_INGEST, 4);
+            launch_chunk_count(rlen, rflag, R, plan.r_limit, plan.clip, plan.whole, chunks.p, st);
+            exclusive_scan_u32(chunks.p, base.p, R, ctx->scalars, ws.p, st);
+        }
+        n_c = read_scalar(ctx, ctx->scalars, "chunk scan");
+        words = DBuf<uint64_t>(ctx, n_c * W);
+        pal = DBuf<uint8_t>(ctx, n_c);
+        if (n_c) {
+            StageScope sc(ctx, PEDK_ST_INGEST, 1);
+            launch_pack(s->fq.p, seq_start, chunks.p, base.p, R, plan.clip, W, words.p, pal.p, st);
+        }
+    }
+    *strand_reads += 2 * n_c;
+    if (ctx->nranks > 1) {
+        DestSpec spec;
+        spec.mode = DEST_READ;
+        spec.stride = W;
+        DBuf<uint64_t> mine;
+        uint64_t n_mine = 0;
+        exchange_records(ctx, words.p, n_c, spec, &mine, &n_mine);
+        words = std::move(mine);
+        n_c = n_mine;
+        pal = DBuf<uint8_t>(ctx, n_c);
+        StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+        launch_pal_flags(words.p, W, L, n_c, pal.p, st);
+    }
+    if (n_c == 0) return;
+    dedup_group(s, L, W, words, pal, n_c);
+}
+
 void do_ingest(pedk_sample* s, int clipping) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -115,7 +138,8 @@ void do_ingest(pedk_sample* s, int clipping) {
     s->have_table = s->have_reads = false;
     const size_t n = s->fq_len;
     if (clipping < 0) throw PedkError(PEDK_E_INVAL, "clipping must be >= 0");
-    if (n == 0) {
+    const bool multi = ctx->nranks > 1;  // collective: a rank without input still takes part
+    if (n == 0 && !multi) {
         s->ingested = true;
         return;
     }
@@ -124,28 +148,32 @@ void do_ingest(pedk_sample* s, int clipping) {
         PEDK_CUDA_TRY(cudaStreamWaitEvent(st, s->ev_copied, 0));
         s->copy_pending = false;
     }
-    fq_reserve(s, n);
-    const size_t padded = round_up(n, FQ_ALIGN);
-    PEDK_CUDA_TRY(cudaMemsetAsync(s->fq.p + n, 0, padded - n, st));
-    const size_t tiles = padded / FQ_ALIGN;
-
-    // ---- record structure: newline count, scan, line index ----
-    DBuf<uint32_t> tile_counts(ctx, tiles);
-    DBuf<uint64_t> tile_prefix(ctx, tiles);
-    DBuf<uint64_t> ws(ctx, scan_workspace_words(tiles));
-    {
-        StageScope sc(ctx, PEDK_ST_INGEST, 4);
-        launch_newline_count(s->fq.p, n, tile_counts.p, st);
-        exclusive_scan_u32(tile_counts.p, tile_prefix.p, tiles, ctx->scalars, ws.p, st);
+    uint64_t R = 0, TL = 0;
+    uint8_t last_byte = '\n';
+    DBuf<uint32_t> tile_counts;
+    DBuf<uint64_t> tile_prefix, ws;
+    if (n) {
+        fq_reserve(s, n);
+        const size_t padded = round_up(n, FQ_ALIGN);
+        PEDK_CUDA_TRY(cudaMemsetAsync(s->fq.p + n, 0, padded - n, st));
+        const size_t tiles = padded / FQ_ALIGN;
+        // ---- record structure: newline count, scan, line index ----
+        tile_counts = DBuf<uint32_t>(ctx, tiles);
+        tile_prefix = DBuf<uint64_t>(ctx, tiles);
+        ws = DBuf<uint64_t>(ctx, scan_workspace_words(tiles));
+        {
+            StageScope sc(ctx, PEDK_ST_INGEST, 4);
+            launch_newline_count(s->fq.p, n, tile_counts.p, st);
+            exclusive_scan_u32(tile_counts.p, tile_prefix.p, tiles, ctx->scalars, ws.p, st);
+        }
+        PEDK_CUDA_TRY(cudaMemcpyAsync(&last_byte, s->fq.p + n - 1, 1, cudaMemcpyDeviceToHost, st));
+        uint64_t NL = read_scalar(ctx, ctx->scalars, "newline scan");
+        TL = NL + (last_byte != '\n' ? 1 : 0);
+        R = TL >= 2 ? (TL - 2) / 4 + 1 : 0;  // records that have a sequence line (line 4r+1)
+        if (s->line_format) R = TL;
     }
-    uint8_t last_byte = 0;
-    PEDK_CUDA_TRY(cudaMemcpyAsync(&last_byte, s->fq.p + n - 1, 1, cudaMemcpyDeviceToHost, st));
-    uint64_t NL = read_scalar(ctx, ctx->scalars, "newline scan");
-    uint64_t TL = NL + (last_byte != '\n' ? 1 : 0);
-    uint64_t R = TL >= 2 ? (TL - 2) / 4 + 1 : 0;  // records that have a sequence line (line 4r+1)
-    if (s->line_format) R = TL;
     s->info.records = R;
-    if (R == 0) {
+    if (R == 0 && !multi) {
         s->fq.reset();
         s->fq_len = 0;
         s->ingested = true;
@@ -157,17 +185,21 @@ void do_ingest(pedk_sample* s, int clipping) {
     DBuf<unsigned long long> hist(ctx, LEN_HIST_BINS + 4);
     {
         StageScope sc(ctx, PEDK_ST_INGEST, 2);
-        if (s->line_format) PEDK_CUDA_TRY(cudaMemsetAsync(seq_start.p, 0, sizeof(uint64_t), st));
-        launch_line_index(s->fq.p, n, tile_prefix.p, seq_start.p, seq_end.p, R, s->line_format ? 1 : 0, st);
-        if (last_byte != '\n' && (s->line_format || ((TL - 1) & 3) == 1)) {
-            // the file ends inside a sequence line: it has no terminating newline
-            uint64_t end = n;
-            PEDK_CUDA_TRY(cudaMemcpyAsync(seq_end.p + (R - 1), &end, sizeof end, cudaMemcpyHostToDevice, st));
-            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        }
         PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-        launch_read_scan(s->fq.p, seq_start.p, seq_end.p, R, rlen.p, rflag.p, hist.p, hist.p + LEN_HIST_BINS, st);
+        if (R) {
+            if (s->line_format) PEDK_CUDA_TRY(cudaMemsetAsync(seq_start.p, 0, sizeof(uint64_t), st));
+            launch_line_index(s->fq.p, n, tile_prefix.p, seq_start.p, seq_end.p, R, s->line_format ? 1 : 0, st);
+            if (last_byte != '\n' && (s->line_format || ((TL - 1) & 3) == 1)) {
+                // the file ends inside a sequence line: it has no terminating newline
+                uint64_t end = n;
+                PEDK_CUDA_TRY(cudaMemcpyAsync(seq_end.p + (R - 1), &end, sizeof end, cudaMemcpyHostToDevice, st));
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            }
+            launch_read_scan(s->fq.p, seq_start.p, seq_end.p, R, rlen.p, rflag.p, hist.p, hist.p + LEN_HIST_BINS, st);
+        }
     }
+    // every rank decides the length mode from the statistics of the whole sample
+    if (multi) comm_allreduce_sum(ctx, hist.p, LEN_HIST_BINS + 4);
     tile_counts.reset();
     tile_prefix.reset();
     ws.reset();
@@ -198,6 +230,9 @@ void do_ingest(pedk_sample* s, int clipping) {
         for (uint32_t l = 0; l < LEN_HIST_BINS - 1; ++l)
             if (h_hist[l]) plans.push_back({l, 1, R});
         s->info.clipping_used = (int32_t)only_len;
+    } else if (clipping > 0 && multi) {
+        plans.push_back({(uint32_t)clipping, 0, R});
+        s->info.clipping_used = n_lengths == 1 ? (int32_t)only_len : clipping;
     } else if (clipping > 0) {
         plans.push_back({(uint32_t)clipping, 0, R});
         // ped.pl:1526 logs the length of the last kept read even then
@@ -217,6 +252,10 @@ void do_ingest(pedk_sample* s, int clipping) {
     } else if (n_lengths <= 1) {
         s->info.clipping_used = (int32_t)only_len;
         if (kept) plans.push_back({only_len, 1, R});
+    } else if (multi) {
+        throw PedkError(PEDK_E_UNSUPPORTED,
+                        "mixed read lengths without clipping= need the file order of the whole sample: "
+                        "run on one GPU or pass clipping=");
     } else {
         // mixed lengths, no clipping=: reads before the first length change were already
         // written unclipped (ped.pl:1440-1464), then everything is re-read and clipped
@@ -347,30 +386,63 @@ void do_count(pedk_sample* s, int k) {
     s->cinfo.instances = M;
     s->cinfo.correction_rows = Mpal;
     s->counted = true;
-    if (M == 0) return;
+    const bool multi = ctx->nranks > 1;
+    // multi-GPU: the decisions below are collective, so they use the totals over all ranks
+    const uint64_t M_all = multi ? comm_allreduce_sum_host(ctx, M) : M;
+    const uint64_t Mpal_all = multi ? comm_allreduce_sum_host(ctx, Mpal) : Mpal;
+    if (M_all == 0) return;
 
     DBuf<unsigned long long> hist(ctx, 8 * 256);
-    if (Mpal) {
+    // extract (all windows, or only those of palindromic reads) -> [route every k-mer to the
+    // rank that owns its hash] -> sort.  Returns which of a/b holds the sorted instances.
+    auto extract_sort = [&](bool pal_only, uint64_t m_local, DBuf<uint64_t>& a, DBuf<uint64_t>& b, uint64_t& m_final,
+                            int stage) -> int {
+        a = DBuf<uint64_t>(ctx, m_local);
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        if (pal_only) PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 2, 0, sizeof(unsigned long long), st));
+        uint64_t off = 0;
+        for (const ReadGroup& g : s->groups) {
+            if (g.L < k || !g.n) continue;
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            if (pal_only) {
+                if (g.n_pal) launch_extract_pal(g.words.p, g.pal.p, g.W, g.L, k, g.n, a.p, ctx->scalars + 2, st);
+            } else {
+                // the histograms come for free here unless the keys are about to change hands
+                launch_extract(g.words.p, g.W, g.L, k, g.n, a.p + off, hist.p, multi ? 0 : n_pass, st);
+                off += g.n * (uint64_t)(g.L - k + 1);
+            }
+        }
+        m_final = m_local;
+        if (multi) {
+            DestSpec spec;
+            spec.mode = DEST_KMER;
+            spec.stride = 1;
+            DBuf<uint64_t> mine;
+            exchange_records(ctx, a.p, m_local, spec, &mine, &m_final);
+            a = std::move(mine);
+        }
+        if (multi || pal_only) {
+            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+            launch_digit_hist(a.p, m_final, hist.p, n_pass, st);
+        }
+        b = DBuf<uint64_t>(ctx, m_final);
+        trace(ctx, "  (extract enqueued)");
+        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, m_final, n_pass, hist.p, stage);
+        check_err_flag(ctx, "radix sort");
+        trace(ctx, "extract + radix sort");
+        return cur;
+    };
+
+    if (Mpal_all) {
         // windows of palindromic reads: each is emitted once below but stands for one strand
         // only; their sorted (k-mer, windows) table corrects the counts (Appendix A.3)
-        DBuf<uint64_t> a(ctx, Mpal), b(ctx, Mpal);
-        PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 2, 0, sizeof(unsigned long long), st));
-        for (const ReadGroup& g : s->groups) {
-            if (g.L < k || !g.n_pal) continue;
-            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
-            launch_extract_pal(g.words.p, g.pal.p, g.W, g.L, k, g.n, a.p, ctx->scalars + 2, st);
-        }
-        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-        {
-            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
-            launch_digit_hist(a.p, Mpal, hist.p, n_pass, st);
-        }
-        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, Mpal, n_pass, hist.p, PEDK_ST_EXTRACT);
-        check_err_flag(ctx, "radix sort (corrections)");
+        DBuf<uint64_t> a, b;
+        uint64_t m = 0;
+        int cur = extract_sort(true, Mpal, a, b, m, PEDK_ST_EXTRACT);
         DBuf<uint64_t> ck;
         DBuf<uint32_t> cc;
         uint64_t heads;
-        count_rows_into(ctx, cur ? b.p : a.p, Mpal, cur ? a.p : b.p, k, 0, nullptr, nullptr, 0, &ck, &cc, &s->n_corr,
+        count_rows_into(ctx, cur ? b.p : a.p, m, cur ? a.p : b.p, k, 0, nullptr, nullptr, 0, &ck, &cc, &s->n_corr,
                         &heads, PEDK_ST_EXTRACT);
         // the rows come out unordered: sort them so the count kernel can bisect
         DBuf<uint64_t> ck2(ctx, s->n_corr);
@@ -386,23 +458,13 @@ void do_count(pedk_sample* s, int k) {
         s->ccnt = std::move(c2 ? cc2 : cc);
     }
     {
-        DBuf<uint64_t> a(ctx, M), b(ctx, M);
-        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-        uint64_t off = 0;
-        for (const ReadGroup& g : s->groups) {
-            if (g.L < k || !g.n) continue;
-            StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
-            launch_extract(g.words.p, g.W, g.L, k, g.n, a.p + off, hist.p, n_pass, st);
-            off += g.n * (uint64_t)(g.L - k + 1);
-        }
-        trace(ctx, "  (extract enqueued)");
-        int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, M, n_pass, hist.p, PEDK_ST_SORT);
-        trace(ctx, "  (sort enqueued)");
-        check_err_flag(ctx, "radix sort");
-        trace(ctx, "extract + radix sort");
+        DBuf<uint64_t> a, b;
+        uint64_t m = 0;
+        int cur = extract_sort(false, M, a, b, m, PEDK_ST_SORT);
+        s->cinfo.instances = m;
         uint64_t* sorted = cur ? b.p : a.p;
         uint64_t* spare = cur ? a.p : b.p;
-        count_rows_into(ctx, sorted, M, spare, k, 1, s->ckey.p, s->ccnt.p, s->n_corr, &s->rkey, &s->rval, &s->n_rows,
+        count_rows_into(ctx, sorted, m, spare, k, 1, s->ckey.p, s->ccnt.p, s->n_corr, &s->rkey, &s->rval, &s->n_rows,
                         &s->D, PEDK_ST_COUNT);
     }
     s->cinfo.canonical_kmers = s->D;
@@ -424,10 +486,11 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     const int n_pass = (2 * k + 7) / 8;
     auto rows_of = [](pedk_sample* s) -> uint64_t { return !s ? 0 : s->host_only_table ? s->h_kmer.size() : s->n_rows; };
     uint64_t cap = rows_of(control) + rows_of(target);
+    const bool multi = ctx->nranks > 1;
     out->n = 0;
-    if (cap == 0) return;
-    DBuf<uint64_t> ka(ctx, cap), kb(ctx, cap);
-    DBuf<uint32_t> va(ctx, cap), vb(ctx, cap);
+    if (cap == 0 && !multi) return;
+    DBuf<uint64_t> ka(ctx, cap), kb;
+    DBuf<uint32_t> va(ctx, cap), vb;
     uint64_t rows = 0;
     pedk_sample* ss[2] = {control, target};
     for (int i = 0; i < 2; ++i) {
@@ -454,6 +517,43 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
         rows += s->n_rows;
     }
     DBuf<unsigned long long> hist(ctx, 8 * 256);
+    if (multi) {
+        // rows move to the rank that holds their 3-nt bucket: contiguous bucket ranges, balanced
+        // on the histogram of both samples over all ranks, so every (k-1)-mer group and every
+        // first-of-bucket row is local to one rank and rank order is key order
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, 64 * sizeof(unsigned long long), st));
+        {
+            StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+            launch_bucket_hist(ka.p, rows, k, hist.p, st);
+        }
+        comm_allreduce_sum(ctx, hist.p, 64);
+        uint64_t h64[64];
+        PEDK_CUDA_TRY(cudaMemcpyAsync(h64, hist.p, sizeof h64, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        DestSpec spec;
+        spec.mode = DEST_ROW;
+        spec.stride = 2;
+        spec.bucket_shift = 2 * k - 6;
+        plan_bucket_owners(h64, ctx->nranks, spec.owner);
+        DBuf<uint64_t> rec(ctx, 2 * rows), mine;
+        uint64_t n_mine = 0;
+        {
+            StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+            launch_rows_pack(ka.p, va.p, rows, rec.p, st);
+        }
+        exchange_records(ctx, rec.p, rows, spec, &mine, &n_mine);
+        rec.reset();
+        rows = n_mine;
+        ka = DBuf<uint64_t>(ctx, rows);
+        va = DBuf<uint32_t>(ctx, rows);
+        {
+            StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+            launch_rows_unpack(mine.p, rows, ka.p, va.p, st);
+        }
+    }
+    if (rows == 0) return;
+    kb = DBuf<uint64_t>(ctx, rows);
+    vb = DBuf<uint32_t>(ctx, rows);
     PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
     {
         StageScope sc(ctx, PEDK_ST_ROWSORT, 1);

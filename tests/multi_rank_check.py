@@ -1,0 +1,93 @@
+"""Launched by torchrun (one rank per GPU): the sharded path must reproduce the oracle.
+
+Rank r ingests a contiguous slice of the records of both samples; reads, canonical k-mers
+and table rows change hands inside libpedk (NCCL).  Rank order is key order, so the
+concatenation over ranks of the tables / edge texts must equal the single-process oracle.
+usage: torchrun --nproc-per-node N tests/multi_rank_check.py case [case ...]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle  # noqa: E402
+from ped_b200 import api  # noqa: E402
+from tests.cases import CASES, make_inputs  # noqa: E402
+
+
+def slice_records(fq: bytes, rank: int, world: int) -> bytes:
+    lines = fq.split(b"\n")
+    tail = lines[-1]
+    lines = lines[:-1]
+    n_rec = (len(lines) + 3) // 4
+    a, b = n_rec * rank // world, n_rec * (rank + 1) // world
+    part = lines[4 * a:4 * b]
+    out = b"".join(l + b"\n" for l in part)
+    if rank == world - 1 and tail:
+        out += tail
+    return out
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = api.Context(local)
+    idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.comm_init(idt.cpu().numpy().tobytes(), rank, world)
+    ok = True
+    for name in sys.argv[1:]:
+        case = CASES[name]
+        fc, ft = make_inputs(case)
+        clip = case.get("clipping", 0)
+        c, t = api.Sample(ctx), api.Sample(ctx)
+        c.add_fastq(slice_records(fc, rank, world))
+        t.add_fastq(slice_records(ft, rank, world))
+        ti = t.ingest(clip)
+        ci = c.ingest(clip)
+        c.count(20)
+        t.count(20)
+        r = ctx.join(c, t)
+        ck, cc = c.table()
+        tk, tc = t.table()
+        parts = [None] * world
+        dist.all_gather_object(parts, dict(text=r.text(), ck=ck, cc=cc, tk=tk, tc=tc,
+                                           cu=int(ci.unique_reads), tu=int(ti.unique_reads)))
+        if rank == 0:
+            oc, ot, osnp = oracle.run(fc, ft, 20, clip)
+            text = b"".join(p["text"] for p in parts)
+            for key, cnt, o in (("ck", "cc", oc), ("tk", "tc", ot)):
+                km = np.concatenate([p[key] for p in parts])
+                ct = np.concatenate([p[cnt] for p in parts])
+                okm, oct_ = o.table()
+                good = km.shape == okm.shape and (km == okm).all() and (ct == oct_).all()
+                print(f"[{name}] {key[0]} table rows {len(km)} vs oracle {len(okm)}: {'ok' if good else 'MISMATCH'}")
+                ok &= bool(good)
+            uc = sum(p["cu"] for p in parts), sum(p["tu"] for p in parts)
+            good = uc == (oc.num_reads, ot.num_reads)
+            print(f"[{name}] unique reads {uc} vs oracle {(oc.num_reads, ot.num_reads)}: {'ok' if good else 'MISMATCH'}")
+            ok &= good
+            good = text == osnp
+            print(f"[{name}] edges {text.count(b'%c' % 10)} vs oracle {osnp.count(b'%c' % 10)}: {'ok' if good else 'MISMATCH'}")
+            ok &= good
+        r.destroy(); c.destroy(); t.destroy()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    ctx.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_RANK_CHECK", "PASS" if ok else "FAIL")
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
