@@ -79,8 +79,8 @@ ncclComm_t comm_of(pedk_ctx* ctx) { return static_cast<ncclComm_t>(ctx->nccl_com
 
 __device__ __forceinline__ int dest_of(const uint64_t* rec, const DestSpec& s) {
     if (s.mode == DEST_ROW) return s.owner[rec[0] >> s.bucket_shift];
-    uint64_t h = s.mode == DEST_READ ? words_hash(rec, s.stride) : mix64(rec[0]);
-    return (int)(((h >> 32) * (uint64_t)s.nranks) >> 32);
+    if (s.mode == DEST_READ) return read_owner_rank(rec, s.stride, s.nranks);
+    return kmer_owner_rank(rec[0], s.nranks);
 }
 
 __global__ void __launch_bounds__(256) k_dest_count(const uint64_t* __restrict__ rec, uint64_t n, DestSpec s,
@@ -99,30 +99,64 @@ __global__ void __launch_bounds__(256) k_dest_count(const uint64_t* __restrict__
     if ((int)lane < s.nranks && mine) atomicAdd(&counts[lane], mine);
 }
 
+constexpr int XS_ITEMS = 8;
+constexpr int XS_TILE = 256 * XS_ITEMS;
+
+// Scatter into per-destination runs.  One global atomic per destination per 2048-record
+// tile (a per-warp atomic on R shared addresses would serialise in L2: 150 ms for 1.2 G
+// records, measured in round 1); inside the tile positions come from ballots.
 __global__ void __launch_bounds__(256) k_dest_scatter(const uint64_t* __restrict__ rec, uint64_t n, DestSpec s,
                                                      unsigned long long* __restrict__ cursors,
                                                      uint64_t* __restrict__ out) {
-    const unsigned lane = lane_id();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    // whole warps iterate together so the ballots below always see 32 lanes
-    const uint64_t n_round = (n + 31) & ~31ull;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < n;
-        const int d = valid ? dest_of(rec + i * s.stride, s) : -1;
-        unsigned long long pos = 0;
-        for (int r = 0; r < s.nranks; ++r) {
-            unsigned m = __ballot_sync(0xffffffffu, d == r);
-            if (!m) continue;
-            unsigned long long base = 0;
-            if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(&cursors[r], (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (d == r) pos = base + __popc(m & lanemask_lt());
+    __shared__ unsigned w_cnt[8][PEDK_MAX_RANKS];
+    __shared__ unsigned long long b_base[PEDK_MAX_RANKS];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned lt = lanemask_lt();
+    const uint64_t n_tiles = (n + XS_TILE - 1) / XS_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t warp_base = tile * XS_TILE + (uint64_t)warp * (32 * XS_ITEMS);
+        int d[XS_ITEMS];
+        unsigned mine = 0;  // lane r counts the records of this warp that go to rank r
+#pragma unroll
+        for (int j = 0; j < XS_ITEMS; ++j) {
+            const uint64_t i = warp_base + 32 * j + lane;
+            d[j] = i < n ? dest_of(rec + i * s.stride, s) : -1;
+            for (int r = 0; r < s.nranks; ++r) {
+                unsigned m = __ballot_sync(0xffffffffu, d[j] == r);
+                if (lane == (unsigned)r) mine += __popc(m);
+            }
         }
-        if (valid) {
-            const uint64_t* src = rec + i * s.stride;
-            uint64_t* dst = out + pos * s.stride;
-            for (int w = 0; w < s.stride; ++w) dst[w] = src[w];
+        if ((int)lane < s.nranks) w_cnt[warp][lane] = mine;
+        __syncthreads();
+        if ((int)tid < s.nranks) {
+            unsigned tot = 0;
+            for (int w = 0; w < 8; ++w) {
+                unsigned c = w_cnt[w][tid];
+                w_cnt[w][tid] = tot;
+                tot += c;
+            }
+            b_base[tid] = tot ? atomicAdd(&cursors[tid], (unsigned long long)tot) : 0ull;
         }
+        __syncthreads();
+        unsigned long long running = (int)lane < s.nranks ? b_base[lane] + w_cnt[warp][lane] : 0ull;
+#pragma unroll
+        for (int j = 0; j < XS_ITEMS; ++j) {
+            unsigned mym = 0, add = 0;
+            for (int r = 0; r < s.nranks; ++r) {
+                unsigned m = __ballot_sync(0xffffffffu, d[j] == r);
+                if (d[j] == r) mym = m;
+                if (lane == (unsigned)r) add = __popc(m);
+            }
+            const unsigned long long base = __shfl_sync(0xffffffffu, running, d[j] < 0 ? 0 : d[j]);
+            running += add;
+            if (d[j] >= 0) {
+                const uint64_t i = warp_base + 32 * j + lane;
+                const uint64_t* src = rec + i * s.stride;
+                uint64_t* dst = out + (base + __popc(mym & lt)) * s.stride;
+                for (int w = 0; w < s.stride; ++w) dst[w] = src[w];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -175,6 +209,7 @@ unsigned grid_for(uint64_t n) {
 }  // namespace
 
 void comm_destroy(pedk_ctx* ctx) {
+    comm_ipc_destroy(ctx);
     if (ctx->nccl_comm) {
         try {
             nccl()->CommDestroy(comm_of(ctx));
@@ -236,6 +271,7 @@ void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec s
     std::vector<unsigned long long> h((size_t)PEDK_MAX_RANKS * R);
     PEDK_CUDA_TRY(cudaMemcpyAsync(h.data(), all_counts, h.size() * 8, cudaMemcpyDeviceToHost, st));
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    trace(ctx, "  exchange: counts");
     // h[src * MAX + dst]
     std::vector<unsigned long long> send_off(R + 1, 0), recv_off(R + 1, 0);
     for (int d = 0; d < R; ++d) send_off[d + 1] = send_off[d] + h[(size_t)me * PEDK_MAX_RANKS + d];
@@ -247,6 +283,10 @@ void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec s
     PEDK_CUDA_TRY(cudaMemcpyAsync(cursors, send_off.data(), R * 8, cudaMemcpyHostToDevice, st));
     if (n) k_dest_scatter<<<grid_for(n), 256, 0, st>>>(rec, n, spec, cursors, sendbuf.p);
     PEDK_CUDA_TRY(cudaGetLastError());
+    if (ctx->trace) {
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        trace(ctx, "  exchange: scatter");
+    }
     nccl_check(a->GroupStart(), "ncclGroupStart");
     for (int p = 0; p < R; ++p) {
         if (p == me) continue;
@@ -260,8 +300,93 @@ void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec s
     if (self)
         PEDK_CUDA_TRY(cudaMemcpyAsync(recv->p + recv_off[me] * spec.stride, sendbuf.p + send_off[me] * spec.stride,
                                       self * 8, cudaMemcpyDeviceToDevice, st));
+    if (ctx->trace) {
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        char b[96];
+        snprintf(b, sizeof b, "  exchange: send/recv (%llu records x %d words out)", (unsigned long long)n, spec.stride);
+        trace(ctx, b);
+    }
     // the send buffer goes back to the allocator in stream order
     ctx->stats.kernel_launches += 2;
+}
+
+// ---- NVLink peer memory through CUDA IPC --------------------------------------------------
+// Every rank publishes the IPC handle of one of its device blocks; the others map it once
+// (the caching allocator hands the same block to the same stage on every step, so the
+// mapping is reused) and can then store into it from their own kernels.
+struct IpcCache {
+    struct Entry {
+        cudaIpcMemHandle_t h;
+        void* p;
+    };
+    std::vector<Entry> entries[PEDK_MAX_RANKS];
+};
+
+static IpcCache* ipc_cache(pedk_ctx* ctx) {
+    if (!ctx->ipc_cache) ctx->ipc_cache = new IpcCache();
+    return static_cast<IpcCache*>(ctx->ipc_cache);
+}
+
+void comm_ipc_destroy(pedk_ctx* ctx) {
+    if (!ctx->ipc_cache) return;
+    IpcCache* c = static_cast<IpcCache*>(ctx->ipc_cache);
+    for (auto& v : c->entries)
+        for (auto& e : v) cudaIpcCloseMemHandle(e.p);
+    delete c;
+    ctx->ipc_cache = nullptr;
+}
+
+// my_block must be the base of a block of the context's allocator (a whole cudaMalloc)
+void comm_peer_pointers(pedk_ctx* ctx, void* my_block, void** peers) {
+    const int R = ctx->nranks, me = ctx->rank;
+    cudaStream_t st = ctx->stream;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DBuf<unsigned long long> buf(ctx, (size_t)8 * (PEDK_MAX_RANKS + 1));
+    cudaIpcMemHandle_t mine;
+    PEDK_CUDA_TRY(cudaIpcGetMemHandle(&mine, my_block));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(buf.p, &mine, 64, cudaMemcpyHostToDevice, st));
+    nccl_check(nccl()->AllGather(buf.p, buf.p + 8, 8, ncclUint64, comm_of(ctx), st), "ncclAllGather (ipc handles)");
+    std::vector<cudaIpcMemHandle_t> all((size_t)R);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), buf.p + 8, (size_t)R * 64, cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    IpcCache* c = ipc_cache(ctx);
+    for (int r = 0; r < R; ++r) {
+        if (r == me) {
+            peers[r] = my_block;
+            continue;
+        }
+        void* p = nullptr;
+        for (auto& e : c->entries[r])
+            if (memcmp(&e.h, &all[(size_t)r], 64) == 0) p = e.p;
+        if (!p) {
+            cudaError_t err = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+            if (err != cudaSuccess) {
+                cudaGetLastError();
+                throw PedkError(PEDK_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(err) +
+                                                 " (peer access between the ranks' GPUs is required)");
+            }
+            c->entries[r].push_back({all[(size_t)r], p});
+        }
+        peers[r] = p;
+    }
+}
+
+// all ranks' earlier work on their streams (incl. stores into peer memory) is complete
+void comm_barrier(pedk_ctx* ctx) {
+    if (ctx->nranks <= 1) return;
+    PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 13, 0, sizeof(unsigned long long), ctx->stream));
+    comm_allreduce_sum(ctx, ctx->scalars + 13, 1);
+}
+
+// R x R matrix of per-destination counts: counts_dev[PEDK_MAX_RANKS] of this rank in,
+// h[src * PEDK_MAX_RANKS + dst] out (host), all ranks
+void comm_count_matrix(pedk_ctx* ctx, unsigned long long* counts_dev, unsigned long long* all_dev,
+                       std::vector<unsigned long long>* h) {
+    cudaStream_t st = ctx->stream;
+    nccl_check(nccl()->AllGather(counts_dev, all_dev, PEDK_MAX_RANKS, ncclUint64, comm_of(ctx), st), "ncclAllGather");
+    h->resize((size_t)PEDK_MAX_RANKS * ctx->nranks);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(h->data(), all_dev, h->size() * 8, cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
 }
 
 void launch_pal_flags(const uint64_t* words, int W, int L, uint64_t n, uint8_t* pal, cudaStream_t st) {
@@ -323,13 +448,11 @@ extern "C" int pedk_comm_init(pedk_ctx* ctx, const void* id_bytes, int rank, int
 
 // host-side owner functions, identical to what the kernels evaluate (tests, planning)
 extern "C" int pedk_owner_of_read(const uint64_t* words, int words_per_read, int nranks) {
-    uint64_t h = words_hash(words, words_per_read);
-    return (int)(((h >> 32) * (uint64_t)nranks) >> 32);
+    return read_owner_rank(words, words_per_read, nranks);
 }
 
 extern "C" int pedk_owner_of_kmer(uint64_t canonical_kmer, int nranks) {
-    uint64_t h = mix64(canonical_kmer);
-    return (int)(((h >> 32) * (uint64_t)nranks) >> 32);
+    return kmer_owner_rank(canonical_kmer, nranks);
 }
 
 extern "C" int pedk_plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64) {

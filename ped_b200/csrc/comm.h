@@ -1,5 +1,7 @@
 // Multi-GPU exchange primitives (internal; comm.cu).
 #pragma once
+#include <vector>
+
 #include "ctx.h"
 
 #define PEDK_MAX_RANKS 8
@@ -17,6 +19,7 @@ struct DestSpec {
 };
 
 void comm_destroy(pedk_ctx* ctx);
+void comm_ipc_destroy(pedk_ctx* ctx);
 // in-place sum over ranks of n u64 words in device memory (no-op on one rank)
 void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n);
 uint64_t comm_allreduce_sum_host(pedk_ctx* ctx, uint64_t v);
@@ -24,6 +27,11 @@ void plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64);
 // all-to-all-v of n records; *recv holds the *n_recv records this rank owns, grouped by source rank
 void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec spec, DBuf<uint64_t>* recv,
                       uint64_t* n_recv);
+// NVLink peer memory: peers[r] = rank r's block mapped into this process (peers[me] = my_block)
+void comm_peer_pointers(pedk_ctx* ctx, void* my_block, void** peers);
+void comm_barrier(pedk_ctx* ctx);
+void comm_count_matrix(pedk_ctx* ctx, unsigned long long* counts_dev, unsigned long long* all_dev,
+                       std::vector<unsigned long long>* h);
 void launch_pal_flags(const uint64_t* words, int W, int L, uint64_t n, uint8_t* pal, cudaStream_t st);
 void launch_rows_pack(const uint64_t* key, const uint32_t* val, uint64_t n, uint64_t* rec, cudaStream_t st);
 void launch_rows_unpack(const uint64_t* rec, uint64_t n, uint64_t* key, uint32_t* val, cudaStream_t st);

@@ -108,4 +108,20 @@ PEDK_HD uint64_t words_hash(const uint64_t* a, int W) {
     return h;
 }
 
+// Owner rank of a canonical k-mer in a multi-GPU job: a cheap 32-bit mix of both halves (the
+// fused extract+exchange kernel evaluates it once per k-mer), identical on host and device.
+PEDK_HD int kmer_owner_rank(uint64_t canon, int nranks) {
+    uint32_t h = (uint32_t)canon * 0x9E3779B1u;
+    h ^= (uint32_t)(canon >> 32) * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return (int)(((uint64_t)h * (uint64_t)nranks) >> 32);
+}
+
+// Owner rank of a packed canonical read.
+PEDK_HD int read_owner_rank(const uint64_t* words, int W, int nranks) {
+    return (int)(((words_hash(words, W) >> 32) * (uint64_t)nranks) >> 32);
+}
+
 }  // namespace pedk

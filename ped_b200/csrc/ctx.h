@@ -44,6 +44,7 @@ struct pedk_ctx {
     unsigned long long* h_scalars = nullptr;  // pinned mirror
     // multi-GPU
     void* nccl_comm = nullptr;
+    void* ipc_cache = nullptr;  // comm.cu: peer blocks mapped through CUDA IPC
     int rank = 0, nranks = 1;
     int trace = 0;             // PEDK_TRACE=1: host wall-clock between sync points on stderr
     double trace_t0 = 0, trace_last = 0;

@@ -15,9 +15,13 @@ namespace {
 
 __global__ void __launch_bounds__(256) k_dedup(const uint64_t* __restrict__ words, int W, uint32_t n,
                                               uint32_t* __restrict__ table, uint32_t mask,
-                                              uint8_t* __restrict__ uniq) {
+                                              const uint8_t* __restrict__ valid, uint8_t* __restrict__ uniq) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (valid && !valid[i]) {
+        uniq[i] = 0;
+        return;
+    }
     const uint64_t* me = words + (uint64_t)i * W;
     uint64_t key[PEDK_MAX_WORDS];
 #pragma unroll
@@ -87,10 +91,10 @@ void launch_count_flags(const uint8_t* flags, uint64_t n, unsigned long long* ou
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, uint8_t* uniq,
-                  cudaStream_t st) {
+void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, const uint8_t* valid,
+                  uint8_t* uniq, cudaStream_t st) {
     if (!n) return;
-    k_dedup<<<(n + 255) / 256, 256, 0, st>>>(words, W, n, table, capacity - 1, uniq);
+    k_dedup<<<(n + 255) / 256, 256, 0, st>>>(words, W, n, table, capacity - 1, valid, uniq);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

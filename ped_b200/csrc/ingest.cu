@@ -213,6 +213,110 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ fq, co
     }
 }
 
+// min / max of the sequence-line lengths of all records (no byte of the text is read)
+__global__ void __launch_bounds__(256) k_len_stats(const uint64_t* __restrict__ seq_start,
+                                                  const uint64_t* __restrict__ seq_end, uint64_t n_records,
+                                                  unsigned* __restrict__ minmax) {
+    unsigned lo = 0xffffffffu, hi = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_records;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned len = (unsigned)(seq_end[r] - seq_start[r]);
+        lo = len < lo ? len : lo;
+        hi = len > hi ? len : hi;
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane_id() == 0) {
+        atomicMin(&minmax[0], lo);
+        atomicMax(&minmax[1], hi);
+    }
+}
+
+// 0xff in every byte of x that is one of A, C, G, T
+__device__ __forceinline__ uint32_t acgt_bytes(uint32_t x) {
+    return __vcmpeq4(x, 0x41414141u) | __vcmpeq4(x, 0x43434343u) | __vcmpeq4(x, 0x47474747u) |
+           __vcmpeq4(x, 0x54545454u);
+}
+
+// Fixed-length fast path (all records carry L bases, no clipping=): the N test, the alphabet
+// test, the 2-bit pack and the canonical choice in one pass.  GS lanes share a read, lane g
+// builds word g from 32 bytes (nine aligned 32-bit loads + funnel shifts; four bases become
+// eight bits with one multiply).  Slot = record index; dropped reads get valid = 0.
+template <int GS>
+__global__ void __launch_bounds__(256) k_pack_fixed(const uint8_t* __restrict__ fq,
+                                                   const uint64_t* __restrict__ seq_start, uint64_t n_records,
+                                                   int L, int W, uint64_t* __restrict__ words,
+                                                   uint8_t* __restrict__ pal, uint8_t* __restrict__ valid,
+                                                   unsigned long long* __restrict__ counters) {
+    constexpr int RPW = 32 / GS;  // reads per warp
+    const unsigned lane = lane_id();
+    const unsigned g = lane % GS, grp = lane / GS, gbase = grp * GS;
+    const unsigned gmask = (GS == 32 ? 0xffffffffu : ((1u << GS) - 1u));
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long kept = 0, bad_reads = 0;
+    for (uint64_t r0 = warp * RPW; r0 < n_records; r0 += n_warps * RPW) {
+        const uint64_t r = r0 + grp;
+        const bool live = r < n_records;
+        uint64_t mine = 0;
+        bool has_n = false, bad = false;
+        if (live && (int)g < W) {
+            const uint64_t addr = seq_start[r] + 32ull * g;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(fq + (addr & ~3ull));
+            const unsigned sh = (unsigned)(addr & 3) * 8;
+            uint32_t u[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) u[i] = __ldg(p + i);
+            const int nvalid = L - 32 * (int)g;  // bases of this word that belong to the read
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t x = __funnelshift_r(u[i], u[i + 1], sh);
+                const int nb = nvalid - 4 * i;  // valid bytes of this group of four
+                const uint32_t m = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (0xffffffffu >> (32 - 8 * nb));
+                x = (x & m) | (0x41414141u & ~m);  // beyond the read: 'A' (code 0)
+                has_n |= __vcmpeq4(x, 0x4E4E4E4Eu) != 0;
+                bad |= (acgt_bytes(x) | __vcmpeq4(x, 0x4E4E4E4Eu)) != 0xffffffffu;
+                const uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                mine |= (uint64_t)((c * 0x40100401u) >> 24) << (56 - 8 * i);
+            }
+        }
+        // flags of the whole read
+        const unsigned any_n = (__ballot_sync(0xffffffffu, has_n) >> gbase) & gmask;
+        const unsigned any_bad = (__ballot_sync(0xffffffffu, bad) >> gbase) & gmask;
+        // reverse complement: lane g needs 32 bases starting at L-32g-32
+        const int sbase = L - 32 * (int)g - 32;
+        const int wi = sbase >> 5, o = sbase & 31;
+        uint64_t hi = __shfl_sync(0xffffffffu, mine, gbase + ((unsigned)wi & (GS - 1)));
+        uint64_t lo = __shfl_sync(0xffffffffu, mine, gbase + ((unsigned)(wi + 1) & (GS - 1)));
+        if (wi < 0 || wi >= W) hi = 0;
+        if (wi + 1 < 0 || wi + 1 >= W) lo = 0;
+        const uint64_t win = o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+        const uint64_t rc = (int)g < W ? (revcomp_groups64(win) & tail_mask(L, (int)g)) : 0ull;
+        const unsigned diff = (__ballot_sync(0xffffffffu, mine != rc) >> gbase) & gmask;
+        // groups of one warp differ in `diff`: the shuffle must not sit under a divergent branch
+        const int f = diff ? __ffs(diff) - 1 : 0;
+        const bool use_rc = (__shfl_sync(0xffffffffu, rc < mine ? 1 : 0, gbase + f) != 0) && diff != 0;
+        if (live) {
+            const bool keep = !any_n && !any_bad;
+            if ((int)g < W) words[r * (uint64_t)W + g] = use_rc ? rc : mine;
+            if (g == 0) {
+                pal[r] = diff == 0 ? 1 : 0;
+                valid[r] = keep ? 1 : 0;
+                if (!any_n) {
+                    ++kept;
+                    if (any_bad) ++bad_reads;
+                }
+            }
+        }
+    }
+    kept = __reduce_add_sync(0xffffffffu, (unsigned)kept);
+    bad_reads = __reduce_add_sync(0xffffffffu, (unsigned)bad_reads);
+    if (lane == 0) {
+        if (kept) atomicAdd(&counters[0], kept);
+        if (bad_reads) atomicAdd(&counters[1], bad_reads);
+    }
+}
+
 }  // namespace
 
 void launch_newline_count(const uint8_t* fq, size_t n, uint32_t* tile_counts, cudaStream_t st) {
@@ -257,6 +361,34 @@ void launch_pack(const uint8_t* fq, const uint64_t* seq_start, const uint32_t* c
     uint64_t blocks = (n_records + 7) / 8;
     unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
     k_pack<<<grid, 256, 0, st>>>(fq, seq_start, chunks, chunk_base, n_records, clip, W, words, pal);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+}  // namespace pedk
+
+namespace pedk {
+
+void launch_len_stats(const uint64_t* seq_start, const uint64_t* seq_end, uint64_t n_records, unsigned* minmax,
+                      cudaStream_t st) {
+    if (!n_records) return;
+    uint64_t blocks = (n_records + 256 * 16 - 1) / (256 * 16);
+    unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_len_stats<<<grid, 256, 0, st>>>(seq_start, seq_end, n_records, minmax);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_pack_fixed(const uint8_t* fq, const uint64_t* seq_start, uint64_t n_records, int L, int W,
+                       uint64_t* words, uint8_t* pal, uint8_t* valid, unsigned long long* counters,
+                       cudaStream_t st) {
+    if (!n_records) return;
+    const int gs = W <= 8 ? 8 : 16;
+    uint64_t warps = (n_records + (32 / gs) * 16 - 1) / ((32 / gs) * 16);  // ~16 rounds per warp
+    uint64_t blocks = (warps + 7) / 8;
+    unsigned grid = (unsigned)(blocks < 1 ? 1 : blocks < (uint64_t)kNumSMs * 16 ? blocks : (uint64_t)kNumSMs * 16);
+    if (gs == 8)
+        k_pack_fixed<8><<<grid, 256, 0, st>>>(fq, seq_start, n_records, L, W, words, pal, valid, counters);
+    else
+        k_pack_fixed<16><<<grid, 256, 0, st>>>(fq, seq_start, n_records, L, W, words, pal, valid, counters);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

@@ -16,10 +16,11 @@
 using namespace pedk;
 
 struct pedk_result {
-    std::vector<pedk_edge> edges;
-    std::vector<std::string> quirk_text;  // parallel to edges where quirk == 1 (else empty)
+    std::vector<pedk_edge> edges;                           // unordered until finalised
+    std::vector<std::pair<uint64_t, std::string>> quirks;   // literal lines of the F7 rows
     std::string text;
     int k = 0;
+    bool finalised = false;
 };
 
 namespace {
@@ -168,7 +169,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         e.cont_mask = h_edges[i].cont;
         e.alt_mask = h_edges[i].alt;
     }
-    std::vector<std::pair<uint64_t, std::string>> quirks;
+    auto& quirks = res->quirks;
     for (const GroupRec& g : groups) {
         bool pc = g.hasc[0] | g.hasc[1] | g.hasc[2] | g.hasc[3];
         bool pt = g.hast[0] | g.hast[1] | g.hast[2] | g.hast[3];
@@ -183,6 +184,15 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
             quirks.emplace_back(g.p, line);
         }
     }
+    trace(ctx, "host: edges collected");
+}
+
+// Sort the edges by their (k-1)-mer and lay out <target>.kmer.snp: done on first access, so a
+// caller that only wants the count does not pay for the text.
+void finalise(pedk_result* res) {
+    if (res->finalised) return;
+    const int k = res->k;
+    auto& quirks = res->quirks;
     std::sort(res->edges.begin(), res->edges.end(),
               [](const pedk_edge& x, const pedk_edge& y) { return x.prefix < y.prefix; });
     std::sort(quirks.begin(), quirks.end());
@@ -207,7 +217,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         for (int x = 0; x < 4; ++x) { t += '\t'; append_u(t, e.target[x]); }
         t += '\n';
     }
-    trace(ctx, "host: sort edges + text");
+    res->finalised = true;
 }
 
 char* dup_text(const std::string& s, uint64_t* len) {
@@ -278,6 +288,7 @@ extern "C" uint64_t pedk_result_num_edges(const pedk_result* r) { return r ? r->
 
 extern "C" int pedk_result_text(const pedk_result* r, const char** text, uint64_t* len) {
     if (!r || !text || !len) return PEDK_E_INVAL;
+    finalise(const_cast<pedk_result*>(r));
     *text = r->text.c_str();
     *len = r->text.size();
     return PEDK_OK;
@@ -285,6 +296,7 @@ extern "C" int pedk_result_text(const pedk_result* r, const char** text, uint64_
 
 extern "C" int pedk_result_edges(const pedk_result* r, pedk_edge* out, uint64_t cap, uint64_t* n) {
     if (!r || !n) return PEDK_E_INVAL;
+    finalise(const_cast<pedk_result*>(r));
     *n = r->edges.size();
     if (out) {
         if (cap < *n) return PEDK_E_INVAL;

@@ -32,11 +32,22 @@ void launch_chunk_count(const uint32_t* rlen, const uint8_t* rflag, uint64_t n_r
 void launch_pack(const uint8_t* fq, const uint64_t* seq_start, const uint32_t* chunks, const uint64_t* chunk_base,
                  uint64_t n_records, uint32_t clip, int W, uint64_t* words, uint8_t* pal, cudaStream_t st);
 
+// minmax[0] = min, minmax[1] = max sequence-line length over all records (preset 0xffffffff, 0)
+void launch_len_stats(const uint64_t* seq_start, const uint64_t* seq_end, uint64_t n_records, unsigned* minmax,
+                      cudaStream_t st);
+// fixed-length fast path: every record has L bases; slot = record index; valid[r] = 0 for reads
+// with an N (dropped, ped.pl:1436); counters[0] += reads without N, counters[1] += of those
+// the reads with a byte outside ACGT
+void launch_pack_fixed(const uint8_t* fq, const uint64_t* seq_start, uint64_t n_records, int L, int W,
+                       uint64_t* words, uint8_t* pal, uint8_t* valid, unsigned long long* counters,
+                       cudaStream_t st);
+
 // ---------------- S1: exact read dedup (dedup.cu) ----------------
 // table: capacity slots (power of two) preset to 0xFFFFFFFF; uniq[i] = 1 iff chunk i is
 // the representative of its value
-void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, uint8_t* uniq,
-                  cudaStream_t st);
+// valid (may be null): slots with valid[i] == 0 are skipped
+void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, const uint8_t* valid,
+                  uint8_t* uniq, cudaStream_t st);
 void launch_compact_reads(const uint64_t* words, const uint8_t* pal, const uint8_t* uniq, const uint64_t* pos,
                           int W, uint32_t n, uint64_t* out_words, uint8_t* out_pal, cudaStream_t st);
 
@@ -52,6 +63,17 @@ void launch_extract(const uint64_t* words, int W, int L, int k, uint64_t n_reads
 // canonical k-mers of every window of the palindromic reads only (count corrections)
 void launch_extract_pal(const uint64_t* words, const uint8_t* pal, int W, int L, int k, uint64_t n_reads,
                         uint64_t* out, unsigned long long* cursor, cudaStream_t st);
+
+// multi-GPU: extraction fused with owner binning and the exchange (kmer.cu).  Rank r's
+// receive buffer is dst.p[r] (peer memory over NVLink for r != me).
+constexpr int PEDK_MAX_PEERS = 8;
+struct PeerPtrs {
+    uint64_t* p[PEDK_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+void launch_extract_owner_count(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
+                                unsigned long long* counts, cudaStream_t st);
+void launch_extract_owner_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
+                                  unsigned long long* cursors, const PeerPtrs& dst, cudaStream_t st);
 
 // ---------------- S3: LSD radix sort (radix.cu) ----------------
 struct RadixWorkspace {

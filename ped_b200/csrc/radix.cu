@@ -77,6 +77,32 @@ __device__ __forceinline__ unsigned digit_of(uint64_t key) {
     return (digit_word<SHIFT>(key) >> (SHIFT & 31)) & 255u;
 }
 
+// Lanes whose digit differs from this lane's in bit POS: ballot of the bit, flipped for the
+// lanes that have it set.  Written in PTX so that each bit costs a predicate-setting LOP3,
+// the VOTE, a SELP and one fused LOP3 (the C++ form compiled to seven instructions per bit).
+template <int POS>
+__device__ __forceinline__ unsigned bit_differs(uint32_t w) {
+    unsigned r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, m;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.b32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "selp.b32 t, -1, 0, p;\n\t"
+        "xor.b32 %0, m, t;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"(w), "n"(1u << POS));
+    return r;
+}
+template <int S>
+__device__ __forceinline__ unsigned differing_lanes(uint32_t w) {
+    return bit_differs<S>(w) | bit_differs<S + 1>(w) | bit_differs<S + 2>(w) | bit_differs<S + 3>(w) |
+           bit_differs<S + 4>(w) | bit_differs<S + 5>(w) | bit_differs<S + 6>(w) | bit_differs<S + 7>(w);
+}
+
 template <bool PAIRS, int SHIFT>
 __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
                                                              const uint32_t* __restrict__ vin,
@@ -149,13 +175,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_radix_pass(const uint64_t* __
         const uint32_t w = digit_word<SHIFT>(key[j]);
         // peers = lanes whose item j has the same digit: one ballot per digit bit;
         // acc collects the lanes that differ from this lane in some bit
-        unsigned acc = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (w >> (S + b)) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            acc |= m ^ (bit ? 0xffffffffu : 0u);
-        }
+        const unsigned acc = differing_lanes<S>(w);
         const unsigned peers = ~acc;
         const unsigned below = peers & lt;
         unsigned* ctr = &sm.warp_hist[warp][(w >> S) & 255u];

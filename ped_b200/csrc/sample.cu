@@ -47,7 +47,8 @@ struct GroupPlan {
 };
 
 // Exact dedup of n packed canonical reads -> a ReadGroup of the sample.
-void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8_t>& pal, uint64_t n_c) {
+void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8_t>& pal, uint64_t n_c,
+                 const uint8_t* valid = nullptr) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     if (n_c >= 0xFFFFFFF0ull) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^32 reads in one sample on one GPU");
@@ -60,7 +61,7 @@ void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8
     {
         StageScope sc(ctx, PEDK_ST_DEDUP, 4);
         PEDK_CUDA_TRY(cudaMemsetAsync(table.p, 0xFF, table.bytes(), st));
-        launch_dedup(words.p, W, (uint32_t)n_c, table.p, cap, uniq.p, st);
+        launch_dedup(words.p, W, (uint32_t)n_c, table.p, cap, valid, uniq.p, st);
         exclusive_scan_u8(uniq.p, pos.p, n_c, ctx->scalars, ws2.p, st);
     }
     uint64_t U = read_scalar(ctx, ctx->scalars, "dedup");
@@ -183,9 +184,12 @@ void do_ingest(pedk_sample* s, int clipping) {
     DBuf<uint32_t> rlen(ctx, R);
     DBuf<uint8_t> rflag(ctx, R);
     DBuf<unsigned long long> hist(ctx, LEN_HIST_BINS + 4);
+    unsigned* minmax = reinterpret_cast<unsigned*>(ctx->scalars + 6);
     {
         StageScope sc(ctx, PEDK_ST_INGEST, 2);
         PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        const unsigned preset[2] = {0xffffffffu, 0u};
+        PEDK_CUDA_TRY(cudaMemcpyAsync(minmax, preset, sizeof preset, cudaMemcpyHostToDevice, st));
         if (R) {
             if (s->line_format) PEDK_CUDA_TRY(cudaMemsetAsync(seq_start.p, 0, sizeof(uint64_t), st));
             launch_line_index(s->fq.p, n, tile_prefix.p, seq_start.p, seq_end.p, R, s->line_format ? 1 : 0, st);
@@ -195,8 +199,95 @@ void do_ingest(pedk_sample* s, int clipping) {
                 PEDK_CUDA_TRY(cudaMemcpyAsync(seq_end.p + (R - 1), &end, sizeof end, cudaMemcpyHostToDevice, st));
                 PEDK_CUDA_TRY(cudaStreamSynchronize(st));
             }
-            launch_read_scan(s->fq.p, seq_start.p, seq_end.p, R, rlen.p, rflag.p, hist.p, hist.p + LEN_HIST_BINS, st);
+            launch_len_stats(seq_start.p, seq_end.p, R, minmax, st);
         }
+    }
+    // ---- fast path: every record of the sample has the same length and clipping= is not
+    //      given -> ped.pl's fixed-length mode; test, pack and canonicalise in one pass ----
+    if (clipping == 0) {
+        unsigned mm[2];
+        PEDK_CUDA_TRY(cudaMemcpyAsync(mm, minmax, sizeof mm, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        uint64_t has = R ? 1 : 0, uni = (R && mm[0] == mm[1]) ? 1 : 0, Lf = uni ? mm[0] : 0;
+        uint64_t sum_has = has, sum_uni = uni, sum_l = Lf, sum_ll = Lf * Lf;
+        if (multi) {
+            unsigned long long v[4] = {has, uni, Lf, Lf * Lf};
+            PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 12, v, sizeof v, cudaMemcpyHostToDevice, st));
+            comm_allreduce_sum(ctx, ctx->scalars + 12, 4);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(v, ctx->scalars + 12, sizeof v, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            sum_has = v[0]; sum_uni = v[1]; sum_l = v[2]; sum_ll = v[3];
+        }
+        // all ranks that hold records agree on one length  <=>  sum(L)^2 == n * sum(L^2)
+        const bool uniform = sum_has && sum_uni == sum_has && sum_l * sum_l == sum_ll * sum_has;
+        const uint64_t Lall = uniform ? sum_l / sum_has : 0;
+        if (uniform && Lall >= 3 && Lall <= 32 * PEDK_MAX_WORDS) {
+            const int L = (int)Lall, W = (L + 31) / 32;
+            tile_counts.reset();
+            tile_prefix.reset();
+            ws.reset();
+            DBuf<uint64_t> words(ctx, R * W);
+            DBuf<uint8_t> pal(ctx, R), valid(ctx, R);
+            {
+                StageScope sc(ctx, PEDK_ST_INGEST, 1);
+                launch_pack_fixed(s->fq.p, seq_start.p, R, L, W, words.p, pal.p, valid.p, hist.p + LEN_HIST_BINS, st);
+            }
+            if (multi) comm_allreduce_sum(ctx, hist.p + LEN_HIST_BINS, 2);
+            unsigned long long cnt[2];
+            PEDK_CUDA_TRY(cudaMemcpyAsync(cnt, hist.p + LEN_HIST_BINS, sizeof cnt, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            trace(ctx, "pack (fixed length)");
+            s->info.reads_kept = cnt[0];
+            if (cnt[1]) {
+                char b[200];
+                snprintf(b, sizeof b,
+                         "%llu reads hold a byte outside ACGTN (ped.pl would carry them as text; not supported)", cnt[1]);
+                throw PedkError(PEDK_E_ALPHABET, b);
+            }
+            s->info.clipping_used = cnt[0] ? L : 0;
+            s->fq.reset();
+            s->fq_len = 0;
+            uint64_t n_c = R;
+            if (multi) {
+                // only the kept reads travel: compact, route by hash, recompute the palindrome flags
+                DBuf<uint64_t> pos(ctx, R), ws2(ctx, scan_workspace_words(R));
+                {
+                    StageScope sc(ctx, PEDK_ST_INGEST, 3);
+                    exclusive_scan_u8(valid.p, pos.p, R, ctx->scalars, ws2.p, st);
+                }
+                uint64_t kept_local = read_scalar(ctx, ctx->scalars, "kept scan");
+                DBuf<uint64_t> cw(ctx, kept_local * W);
+                DBuf<uint8_t> cp(ctx, kept_local);
+                if (R) {
+                    StageScope sc(ctx, PEDK_ST_INGEST, 1);
+                    launch_compact_reads(words.p, pal.p, valid.p, pos.p, W, (uint32_t)R, cw.p, cp.p, st);
+                }
+                DestSpec spec;
+                spec.mode = DEST_READ;
+                spec.stride = W;
+                DBuf<uint64_t> mine;
+                exchange_records(ctx, cw.p, kept_local, spec, &mine, &n_c);
+                words = std::move(mine);
+                pal = DBuf<uint8_t>(ctx, n_c);
+                valid.reset();
+                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+                launch_pal_flags(words.p, W, L, n_c, pal.p, st);
+            }
+            if (n_c) dedup_group(s, L, W, words, pal, n_c, multi ? nullptr : valid.p);
+            // strand_reads: what ped.pl writes to the TAG.tmp files (kept reads and their complements)
+            s->info.strand_reads = 2 * (multi ? n_c : cnt[0]);
+            s->info.n_groups = (int32_t)s->groups.size();
+            for (const ReadGroup& g : s->groups) {
+                s->info.unique_reads += 2 * g.n - g.n_pal;
+                s->info.palindromes += g.n_pal;
+            }
+            s->ingested = true;
+            return;
+        }
+    }
+    if (R) {
+        StageScope sc(ctx, PEDK_ST_INGEST, 1);
+        launch_read_scan(s->fq.p, seq_start.p, seq_end.p, R, rlen.p, rflag.p, hist.p, hist.p + LEN_HIST_BINS, st);
     }
     // every rank decides the length mode from the statistics of the whole sample
     if (multi) comm_allreduce_sum(ctx, hist.p, LEN_HIST_BINS + 4);
@@ -397,8 +488,60 @@ void do_count(pedk_sample* s, int k) {
     // rank that owns its hash] -> sort.  Returns which of a/b holds the sorted instances.
     auto extract_sort = [&](bool pal_only, uint64_t m_local, DBuf<uint64_t>& a, DBuf<uint64_t>& b, uint64_t& m_final,
                             int stage) -> int {
-        a = DBuf<uint64_t>(ctx, m_local);
         PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        static const bool use_p2p = !(getenv("PEDK_P2P") && atoi(getenv("PEDK_P2P")) == 0);
+        if (multi && !pal_only && use_p2p) {
+            // ONE kernel extracts every k-mer, bins it by owner and stores it into the owner's
+            // receive buffer over NVLink (peer memory mapped with CUDA IPC): no staging copy,
+            // no separate all-to-all.  A counting pass over the reads (no stores) sizes the runs.
+            const int R = ctx->nranks, me = ctx->rank;
+            DBuf<unsigned long long> cbuf(ctx, (size_t)PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 2));
+            unsigned long long* my_counts = cbuf.p;
+            unsigned long long* all_counts = cbuf.p + PEDK_MAX_RANKS;
+            unsigned long long* cursors = cbuf.p + PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 1);
+            std::vector<unsigned long long> h;
+            {
+                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+                PEDK_CUDA_TRY(cudaMemsetAsync(cbuf.p, 0, cbuf.bytes(), st));
+                for (const ReadGroup& g : s->groups)
+                    if (g.L >= k && g.n) launch_extract_owner_count(g.words.p, g.W, g.L, k, g.n, R, my_counts, st);
+                comm_count_matrix(ctx, my_counts, all_counts, &h);
+            }
+            trace(ctx, "  fused exchange: counts");
+            std::vector<unsigned long long> off(R, 0);  // where my run starts inside rank d's buffer
+            m_final = 0;
+            for (int d = 0; d < R; ++d)
+                for (int src = 0; src < me; ++src) off[d] += h[(size_t)src * PEDK_MAX_RANKS + d];
+            for (int src = 0; src < R; ++src) m_final += h[(size_t)src * PEDK_MAX_RANKS + me];
+            a = DBuf<uint64_t>(ctx, m_final);
+            void* peers[PEDK_MAX_RANKS];
+            comm_peer_pointers(ctx, a.p, peers);
+            PeerPtrs dst;
+            for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
+            {
+                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(cursors, off.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+                // nobody may store into a buffer before its owner is done with the previous contents
+                comm_barrier(ctx);
+                for (const ReadGroup& g : s->groups)
+                    if (g.L >= k && g.n) launch_extract_owner_scatter(g.words.p, g.W, g.L, k, g.n, R, cursors, dst, st);
+                comm_barrier(ctx);  // every rank's stores have landed
+            }
+            if (ctx->trace) {
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                trace(ctx, "  fused exchange: extract + bin + NVLink stores");
+            }
+            {
+                StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
+                launch_digit_hist(a.p, m_final, hist.p, n_pass, st);
+            }
+            b = DBuf<uint64_t>(ctx, m_final);
+            int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, m_final, n_pass, hist.p, stage);
+            check_err_flag(ctx, "radix sort");
+            trace(ctx, "extract + radix sort");
+            return cur;
+        }
+        a = DBuf<uint64_t>(ctx, m_local);
         if (pal_only) PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 2, 0, sizeof(unsigned long long), st));
         uint64_t off = 0;
         for (const ReadGroup& g : s->groups) {
