@@ -189,7 +189,23 @@ typedef struct pedk_stats {
     double sort_pass_ms;                  /* their summed duration */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t peak_device_bytes;
+    /* per kernel class (PEDK_KC_*): launches, summed duration and the ALGORITHMIC bytes
+     * (what the kernel must read and write) of those launches */
+    double kc_ms[8];
+    uint64_t kc_bytes[8];
+    uint64_t kc_launches[8];
 } pedk_stats;
+enum {
+    PEDK_KC_RADIX_KEYS = 0,   /* k_radix_pass over 8-byte keys: 16 B/key */
+    PEDK_KC_RADIX_PAIRS = 1,  /* k_radix_pass over (key, count) rows: 24 B/row */
+    PEDK_KC_PART = 2,         /* k_part_scatter: packed reads in, hashed remainders out */
+    PEDK_KC_SUB_HIST = 3,     /* k_sub_hist: one read of the instance stream */
+    PEDK_KC_SUB_SCATTER = 4,  /* k_sub_scatter: one read + one write */
+    PEDK_KC_BUCKET_COUNT = 5, /* k_bucket_count: one read + 12 B per row */
+    PEDK_KC_PACK = 6,         /* k_pack_fixed: FASTQ text in, packed reads out */
+    PEDK_KC_PART_COUNT = 7,   /* k_part_count: packed reads in */
+    PEDK_N_KC = 8
+};
 int pedk_get_stats(pedk_ctx *ctx, pedk_stats *out);   /* synchronises the stream */
 int pedk_reset_stats(pedk_ctx *ctx);
 
@@ -201,11 +217,16 @@ int pedk_reset_stats(pedk_ctx *ctx);
 int pedk_comm_unique_id(pedk_ctx *ctx, void *id_bytes);
 int pedk_comm_init(pedk_ctx *ctx, const void *id_bytes, int rank, int nranks);
 /* Owner functions every rank evaluates identically (host copies of what the kernels use):
- * canonical packed reads and canonical k-mers go to a rank by hash; table rows go to the
+ * canonical packed reads go to a rank by hash, canonical k-mers by the top bits of
+ * pedk_kmer_hash (contiguous ranges of the level-A bins); table rows go to the
  * rank that holds the 3-nt bucket of the k-mer, buckets being split into contiguous ranges
  * balanced on a 64-bin histogram. */
 int pedk_owner_of_read(const uint64_t *words, int words_per_read, int nranks);
-int pedk_owner_of_kmer(uint64_t canonical_kmer, int nranks);
+int pedk_owner_of_kmer(uint64_t canonical_kmer, int k, int nranks);
+/* The bijection on 2k-bit integers whose top bits bin a canonical k-mer (level-A bin = the
+ * top min(8,k) bits, owner rank = bin * nranks >> bits) and its inverse. */
+uint64_t pedk_kmer_hash(uint64_t kmer, int k);
+uint64_t pedk_kmer_unhash(uint64_t hash, int k);
 int pedk_plan_bucket_owners(const uint64_t *hist64, int nranks, uint8_t *owner64);
 
 /* ---- synthetic reads (tests and bench.py) ---------------- */

@@ -21,6 +21,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpedk.so")
 
 PEDK_N_STAGES = 10
 STAGES = ["ingest", "dedup", "extract", "sort", "count", "expand", "rowsort", "edges", "copy", "exchange"]
+KERNEL_CLASSES = ["radix_keys", "radix_pairs", "part_scatter", "sub_hist", "sub_scatter", "bucket_count", "pack",
+                  "part_count"]
 COMM_ID_BYTES = 128
 
 
@@ -55,7 +57,8 @@ class Stats(C.Structure):
     _fields_ = [("stage_ms", C.c_double * PEDK_N_STAGES), ("stage_launches", C.c_uint64 * PEDK_N_STAGES),
                 ("kernel_launches", C.c_uint64), ("sort_pass_launches", C.c_uint64), ("sort_pass_keys", C.c_uint64),
                 ("sort_pass_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("peak_device_bytes", C.c_uint64)]
+                ("peak_device_bytes", C.c_uint64), ("kc_ms", C.c_double * 8), ("kc_bytes", C.c_uint64 * 8),
+                ("kc_launches", C.c_uint64 * 8)]
 
     def as_dict(self) -> dict:
         return {
@@ -68,6 +71,8 @@ class Stats(C.Structure):
             "h2d_bytes": int(self.h2d_bytes),
             "d2h_bytes": int(self.d2h_bytes),
             "peak_device_bytes": int(self.peak_device_bytes),
+            "kernels": {KERNEL_CLASSES[i]: {"ms": float(self.kc_ms[i]), "bytes": int(self.kc_bytes[i]),
+                                            "launches": int(self.kc_launches[i])} for i in range(8)},
         }
 
 
@@ -117,7 +122,9 @@ SIGNATURES = {
     "pedk_comm_unique_id": (C.c_int, [_P, _P]),
     "pedk_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "pedk_owner_of_read": (C.c_int, [_P, C.c_int, C.c_int]),
-    "pedk_owner_of_kmer": (C.c_int, [C.c_uint64, C.c_int]),
+    "pedk_owner_of_kmer": (C.c_int, [C.c_uint64, C.c_int, C.c_int]),
+    "pedk_kmer_hash": (C.c_uint64, [C.c_uint64, C.c_int]),
+    "pedk_kmer_unhash": (C.c_uint64, [C.c_uint64, C.c_int]),
     "pedk_plan_bucket_owners": (C.c_int, [_P, C.c_int, _P]),
     "pedk_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
     "pedk_synth_mutate": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _U64P]),
@@ -369,8 +376,17 @@ def owner_of_read(words: np.ndarray, nranks: int) -> int:
     return int(load_library().pedk_owner_of_read(_ptr(w), len(w), nranks))
 
 
-def owner_of_kmer(canonical_kmer: int, nranks: int) -> int:
-    return int(load_library().pedk_owner_of_kmer(int(canonical_kmer), nranks))
+def owner_of_kmer(canonical_kmer: int, k: int, nranks: int) -> int:
+    return int(load_library().pedk_owner_of_kmer(int(canonical_kmer), k, nranks))
+
+
+def kmer_hash(kmer: int, k: int) -> int:
+    """The bijection on 2k-bit integers whose top bits bin a canonical k-mer."""
+    return int(load_library().pedk_kmer_hash(int(kmer), k))
+
+
+def kmer_unhash(h: int, k: int) -> int:
+    return int(load_library().pedk_kmer_unhash(int(h), k))
 
 
 def plan_bucket_owners(hist64, nranks: int) -> np.ndarray:

@@ -80,7 +80,7 @@ ncclComm_t comm_of(pedk_ctx* ctx) { return static_cast<ncclComm_t>(ctx->nccl_com
 __device__ __forceinline__ int dest_of(const uint64_t* rec, const DestSpec& s) {
     if (s.mode == DEST_ROW) return s.owner[rec[0] >> s.bucket_shift];
     if (s.mode == DEST_READ) return read_owner_rank(rec, s.stride, s.nranks);
-    return kmer_owner_rank(rec[0], s.nranks);
+    return kmer_owner_rank(rec[0], s.k, s.nranks);
 }
 
 __global__ void __launch_bounds__(256) k_dest_count(const uint64_t* __restrict__ rec, uint64_t n, DestSpec s,
@@ -378,6 +378,12 @@ void comm_barrier(pedk_ctx* ctx) {
     comm_allreduce_sum(ctx, ctx->scalars + 13, 1);
 }
 
+void comm_allgather_u64(pedk_ctx* ctx, const unsigned long long* send, unsigned long long* recv, size_t n) {
+    if (ctx->nranks <= 1) return;
+    StageScope sc(ctx, PEDK_ST_EXCHANGE, 0);
+    nccl_check(nccl()->AllGather(send, recv, n, ncclUint64, comm_of(ctx), ctx->stream), "ncclAllGather");
+}
+
 // R x R matrix of per-destination counts: counts_dev[PEDK_MAX_RANKS] of this rank in,
 // h[src * PEDK_MAX_RANKS + dst] out (host), all ranks
 void comm_count_matrix(pedk_ctx* ctx, unsigned long long* counts_dev, unsigned long long* all_dev,
@@ -451,9 +457,13 @@ extern "C" int pedk_owner_of_read(const uint64_t* words, int words_per_read, int
     return read_owner_rank(words, words_per_read, nranks);
 }
 
-extern "C" int pedk_owner_of_kmer(uint64_t canonical_kmer, int nranks) {
-    return kmer_owner_rank(canonical_kmer, nranks);
+extern "C" int pedk_owner_of_kmer(uint64_t canonical_kmer, int k, int nranks) {
+    if (k < 4 || k > 32 || nranks < 1) return PEDK_E_INVAL;
+    return kmer_owner_rank(canonical_kmer, k, nranks);
 }
+
+extern "C" uint64_t pedk_kmer_hash(uint64_t kmer, int k) { return kmer_hash(kmer, 2 * k); }
+extern "C" uint64_t pedk_kmer_unhash(uint64_t hash, int k) { return kmer_unhash(hash, 2 * k); }
 
 extern "C" int pedk_plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64) {
     if (!hist64 || !owner64 || nranks < 1 || nranks > PEDK_MAX_RANKS) return PEDK_E_INVAL;

@@ -15,6 +15,7 @@ struct DestSpec {
     int stride = 1;        // u64 words per record (reads: W, k-mers: 1, rows: 2)
     int nranks = 1;
     int bucket_shift = 0;  // rows: 2k-6, the key's first three bases
+    int k = 20;            // k-mers: the owner is a function of kmer_hash(K, 2k)
     uint8_t owner[64] = {0};
 };
 
@@ -30,6 +31,8 @@ void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec s
 // NVLink peer memory: peers[r] = rank r's block mapped into this process (peers[me] = my_block)
 void comm_peer_pointers(pedk_ctx* ctx, void* my_block, void** peers);
 void comm_barrier(pedk_ctx* ctx);
+// all-gather of n u64 words per rank (device memory), rank r's words land at recv + r*n
+void comm_allgather_u64(pedk_ctx* ctx, const unsigned long long* send, unsigned long long* recv, size_t n);
 void comm_count_matrix(pedk_ctx* ctx, unsigned long long* counts_dev, unsigned long long* all_dev,
                        std::vector<unsigned long long>* h);
 void launch_pal_flags(const uint64_t* words, int W, int L, uint64_t n, uint8_t* pal, cudaStream_t st);

@@ -108,15 +108,36 @@ PEDK_HD uint64_t words_hash(const uint64_t* a, int W) {
     return h;
 }
 
-// Owner rank of a canonical k-mer in a multi-GPU job: a cheap 32-bit mix of both halves (the
-// fused extract+exchange kernel evaluates it once per k-mer), identical on host and device.
-PEDK_HD int kmer_owner_rank(uint64_t canon, int nranks) {
-    uint32_t h = (uint32_t)canon * 0x9E3779B1u;
-    h ^= (uint32_t)(canon >> 32) * 0x85EBCA77u;
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    h ^= h >> 13;
-    return (int)(((uint64_t)h * (uint64_t)nranks) >> 32);
+// Bijection on 2k-bit integers that spreads canonical k-mers evenly over their high bits
+// (canonical k-mers crowd the low prefixes, and genomes are not uniform): multiply by an odd
+// constant, fold the high half onto the low half, multiply again, all modulo 2^(2k).  The
+// counting path bins a k-mer by the TOP bits of kmer_hash -- level-A bin, level-B bin -- and
+// keeps only the remaining low bits (32 of them at k = 20); kmer_unhash gives the k-mer back.
+PEDK_HD uint64_t kmer_hash(uint64_t kmer, int nbits) {
+    const uint64_t mask = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1);
+    const int s = (nbits + 1) >> 1;
+    uint64_t h = (kmer * 0x9E3779B97F4A7C15ull) & mask;
+    h ^= h >> s;
+    return (h * 0xD6E8FEB86659FD93ull) & mask;
+}
+PEDK_HD uint64_t kmer_unhash(uint64_t h, int nbits) {
+    const uint64_t mask = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1);
+    const int s = (nbits + 1) >> 1;
+    h = (h * 0xCFEE444D8B59A89Bull) & mask;  // inverse of the second constant modulo 2^64
+    h ^= h >> s;                             // 2s >= nbits: the fold is its own inverse
+    return (h * 0xF1DE83E19937733Dull) & mask;
+}
+
+// Bits of the two binning levels for a given k: a + b <= 2k, at most 8 each.
+PEDK_HD int kmer_bits_a(int k) { return 2 * k / 2 < 8 ? 2 * k / 2 : 8; }
+PEDK_HD int kmer_bits_b(int k) { int r = 2 * k - kmer_bits_a(k); return r < 8 ? r : 8; }
+
+// Owner rank of a canonical k-mer in a multi-GPU job: the ranks own contiguous ranges of the
+// level-A bins (the top bits of kmer_hash), identical on host and device.
+PEDK_HD int kmer_owner_rank(uint64_t canon, int k, int nranks) {
+    const int a = kmer_bits_a(k);
+    const uint64_t bin = kmer_hash(canon, 2 * k) >> (2 * k - a);
+    return (int)((bin * (uint64_t)nranks) >> a);
 }
 
 // Owner rank of a packed canonical read.

@@ -102,7 +102,8 @@ static cudaEvent_t get_event(pedk_ctx* ctx) {
     return e;
 }
 
-StageScope::StageScope(pedk_ctx* c, int stage, uint64_t launches, uint64_t sort_keys, uint64_t sort_launches)
+StageScope::StageScope(pedk_ctx* c, int stage, uint64_t launches, uint64_t sort_keys, uint64_t sort_launches,
+                       int kclass, uint64_t kbytes)
     : ctx(c) {
     pedk_ctx::Pending p;
     p.a = get_event(c);
@@ -110,6 +111,8 @@ StageScope::StageScope(pedk_ctx* c, int stage, uint64_t launches, uint64_t sort_
     p.stage = stage;
     p.sort_keys = sort_keys;
     p.sort_launches = sort_launches;
+    p.kclass = kclass;
+    p.kbytes = kbytes;
     PEDK_CUDA_TRY(cudaEventRecord(p.a, c->stream));
     idx = c->pending.size();
     c->pending.push_back(p);
@@ -125,6 +128,11 @@ static void resolve_pending(pedk_ctx* ctx) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             ctx->stats.stage_ms[p.stage] += ms;
+            if (p.kclass >= 0 && p.kclass < PEDK_N_KC) {
+                ctx->stats.kc_ms[p.kclass] += ms;
+                ctx->stats.kc_bytes[p.kclass] += p.kbytes;
+                ctx->stats.kc_launches[p.kclass] += 1;
+            }
             if (p.sort_keys) {
                 ctx->stats.sort_pass_ms += ms;
                 ctx->stats.sort_pass_keys += p.sort_keys;
@@ -169,7 +177,8 @@ int radix_sort(pedk_ctx* ctx, uint64_t* a, uint64_t* b, uint32_t* va, uint32_t* 
     size_t portions = (n + ((size_t(1) << 30) - 1)) >> 30;  // upper bound, only for launch accounting
     if (portions == 0) portions = 1;
     for (int p = 0; p < n_pass; ++p) {
-        StageScope sc(ctx, stage, portions, stage == PEDK_ST_SORT ? n : 0, stage == PEDK_ST_SORT ? portions : 0);
+        StageScope sc(ctx, stage, portions, stage == PEDK_ST_SORT ? n : 0, stage == PEDK_ST_SORT ? portions : 0,
+                      va ? PEDK_KC_RADIX_PAIRS : PEDK_KC_RADIX_KEYS, (uint64_t)n * (va ? 24 : 16));
         if (cur == 0)
             launch_radix_pass(a, b, va, vb, n, p, digit_hist, ws, ctx->stream);
         else

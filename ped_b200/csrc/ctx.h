@@ -30,6 +30,8 @@ struct pedk_ctx {
         int stage;
         uint64_t sort_keys;  // != 0: an instance-stream radix pass
         uint64_t sort_launches;
+        int kclass;          // PEDK_KC_* or -1
+        uint64_t kbytes;     // algorithmic bytes of the launches in the scope
     };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
@@ -101,7 +103,8 @@ struct DBuf {
 struct StageScope {
     pedk_ctx* ctx;
     size_t idx;
-    StageScope(pedk_ctx* c, int stage, uint64_t launches, uint64_t sort_keys = 0, uint64_t sort_launches = 0);
+    StageScope(pedk_ctx* c, int stage, uint64_t launches, uint64_t sort_keys = 0, uint64_t sort_launches = 0,
+               int kclass = -1, uint64_t kbytes = 0);
     ~StageScope();
 };
 

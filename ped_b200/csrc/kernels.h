@@ -71,9 +71,36 @@ struct PeerPtrs {
     uint64_t* p[PEDK_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 void launch_extract_owner_count(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
-                                unsigned long long* counts, cudaStream_t st);
+                                unsigned long long* counts, cudaStream_t st);  // (legacy sort path)
 void launch_extract_owner_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
                                   unsigned long long* cursors, const PeerPtrs& dst, cudaStream_t st);
+
+// ---------------- S2-S4 bucketed: bin, bin again, count per bucket (bucket.cu) ----------------
+// a, b = bits of the two binning levels (common.cuh kmer_bits_a/_b); wide != 0: the stored
+// remainder (2k - a bits of kmer_hash) needs 64-bit words (k > 20), else 32-bit words.
+// histA[bin] += canonical k-mers of the reads whose hash falls into level-A bin `bin`
+void launch_part_count(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a,
+                       unsigned long long* histA, cudaStream_t st);
+// every canonical k-mer of the reads -> low 2k-a bits of its hash, appended to its bin's run:
+// cur[bin] = next free element of that bin inside the buffer of the rank that owns it
+// (dst.p[owner], owner = bin * nranks >> a; peer memory over NVLink for owner != me)
+void launch_part_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks, int wide,
+                         unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st);
+unsigned sub_tile_keys();
+// level-A bins (offA[n_bins + 1] element offsets, tile_prefix[n_bins + 1] = tiles of sub_tile_keys()
+// before each bin) -> histB[bin * 256 + sub]
+void launch_sub_hist(const void* keys, int wide, const unsigned long long* offA, const unsigned* tile_prefix,
+                     int n_bins, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st);
+// curB[bin * 256 + sub] = next free element of that bucket in `out`
+void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* offA,
+                        const unsigned* tile_prefix, int n_bins, unsigned n_tiles, int k, int a, int b,
+                        unsigned long long* curB, cudaStream_t st);
+// buckets (offB[n_buckets + 1]) -> table rows, as launch_count_rows below; ticket = 1 device
+// word, err = device flag raised when a bucket cannot be split any further
+void launch_bucket_count(const void* keys, int wide, const unsigned long long* offB, unsigned n_buckets, int k, int a,
+                         int b, int log_slots, int strand, const uint64_t* corr_key, const uint32_t* corr_cnt,
+                         uint64_t n_corr, uint64_t* row_key, uint32_t* row_val, uint64_t cap,
+                         unsigned long long* counters, unsigned* ticket, int* err, cudaStream_t st);
 
 // ---------------- S3: LSD radix sort (radix.cu) ----------------
 struct RadixWorkspace {

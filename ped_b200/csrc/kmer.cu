@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_pal(const uint64_t* __re
 // ---- multi-GPU: extraction fused with the owner binning and the exchange ----
 // owner of a canonical k-mer: common.cuh kmer_owner_rank (also comm.cu's DEST_KMER and
 // pedk_owner_of_kmer on the host)
-__device__ __forceinline__ int kmer_owner(uint64_t canon, int nranks) { return kmer_owner_rank(canon, nranks); }
+__device__ __forceinline__ int kmer_owner(uint64_t canon, int k, int nranks) { return kmer_owner_rank(canon, k, nranks); }
 
 constexpr int XO_MAX_ITEMS = 16;  // windows per lane per read: reads up to 512 bases
 
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_owner(const uint64_t* __
                 const uint64_t km = x >> kshift;
                 const uint64_t rc = revcomp_groups64(km) >> kshift;
                 key[t] = km < rc ? km : rc;
-                if (live && i < nwin) own[t] = kmer_owner(key[t], nranks);
+                if (live && i < nwin) own[t] = kmer_owner(key[t], k, nranks);
                 for (int q = 0; q < nranks; ++q) {
                     unsigned m = __ballot_sync(0xffffffffu, own[t] == q);
                     if (lane == (unsigned)q) cnt += __popc(m);

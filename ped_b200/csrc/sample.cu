@@ -14,6 +14,7 @@ using namespace pedk;
 namespace {
 
 constexpr size_t FQ_ALIGN = INGEST_TILE_BYTES;
+constexpr int NBINS_MAX = 256;  // bins per binning level (bucket.cu)
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -229,7 +230,7 @@ void do_ingest(pedk_sample* s, int clipping) {
             DBuf<uint64_t> words(ctx, R * W);
             DBuf<uint8_t> pal(ctx, R), valid(ctx, R);
             {
-                StageScope sc(ctx, PEDK_ST_INGEST, 1);
+                StageScope sc(ctx, PEDK_ST_INGEST, 1, 0, 0, PEDK_KC_PACK, R * (uint64_t)(L + 8 + 8 * W + 2));
                 launch_pack_fixed(s->fq.p, seq_start.p, R, L, W, words.p, pal.p, valid.p, hist.p + LEN_HIST_BINS, st);
             }
             if (multi) comm_allreduce_sum(ctx, hist.p + LEN_HIST_BINS, 2);
@@ -448,6 +449,182 @@ void count_rows_into(pedk_ctx* ctx, const uint64_t* sorted, size_t n, uint64_t* 
     }
 }
 
+// ---- bucketed counting (bucket.cu): reads -> level-A bins (-> their owner rank) -> buckets ->
+//      shared-memory hash tables -> strand rows.  Collective on several ranks. ----
+int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    int x = atoi(v);
+    return x < lo ? lo : x > hi ? hi : x;
+}
+
+void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
+    pedk_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const bool multi = ctx->nranks > 1;
+    const int R = ctx->nranks, me = ctx->rank;
+    const int nbits = 2 * k;
+    const int a = kmer_bits_a(k);
+    const int b = env_int("PEDK_BUCKET_B", kmer_bits_b(k), nbits - a < 1 ? 0 : 1, kmer_bits_b(k));
+    const int log_slots = env_int("PEDK_BUCKET_SLOTS_LOG2", 13, 8, 13);
+    const int nbA = 1 << a;
+    const int wide = (nbits - a) > 32 ? 1 : 0;
+    const size_t ksz = wide ? 8 : 4;
+    const int exch_stage = multi ? PEDK_ST_EXCHANGE : PEDK_ST_EXTRACT;
+
+    // (1) exact sizes of the level-A bins: one pass over the packed reads, no stores
+    DBuf<unsigned long long> histA(ctx, (size_t)NBINS_MAX * (PEDK_MAX_RANKS + 1));
+    uint64_t packed_bytes = 0, m_local = 0;
+    {
+        for (const ReadGroup& g : s->groups)
+            if (g.L >= k && g.n) {
+                packed_bytes += g.n * (uint64_t)g.W * 8;
+                m_local += g.n * (uint64_t)(g.L - k + 1);
+            }
+        StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART_COUNT, packed_bytes);
+        PEDK_CUDA_TRY(cudaMemsetAsync(histA.p, 0, histA.bytes(), st));
+        for (const ReadGroup& g : s->groups)
+            if (g.L >= k && g.n) launch_part_count(g.words.p, g.W, g.L, k, g.n, a, histA.p, st);
+    }
+    std::vector<unsigned long long> all((size_t)NBINS_MAX * R, 0);
+    if (multi) {
+        comm_allgather_u64(ctx, histA.p, histA.p + NBINS_MAX, NBINS_MAX);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p + NBINS_MAX, all.size() * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, (size_t)NBINS_MAX * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->stats.d2h_bytes += all.size() * 8;
+    trace(ctx, "  bins: counts");
+
+    // (2) the plan: where every (source rank, bin) run starts inside the owner's buffer
+    const unsigned TILE = sub_tile_keys();
+    std::vector<unsigned long long> offA((size_t)nbA + 1, 0), curA(NBINS_MAX, 0), owner_fill(R, 0);
+    std::vector<unsigned> tile_prefix((size_t)nbA + 1, 0);
+    uint64_t sent = 0;
+    for (int bin = 0; bin < nbA; ++bin) {
+        const int owner = (int)(((uint64_t)bin * (uint64_t)R) >> a);
+        unsigned long long tot = 0, before_me = 0;
+        for (int src = 0; src < R; ++src) {
+            const unsigned long long c = all[(size_t)src * NBINS_MAX + bin];
+            if (src < me) before_me += c;
+            tot += c;
+        }
+        curA[bin] = owner_fill[owner] + before_me;
+        owner_fill[owner] += tot;
+        const unsigned long long mine = owner == me ? tot : 0;
+        offA[bin + 1] = offA[bin] + mine;
+        const unsigned long long tiles = (mine + TILE - 1) / TILE;
+        if ((unsigned long long)tile_prefix[bin] + tiles > 0xfffffff0ull)
+            throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^45 k-mer instances on one GPU");
+        tile_prefix[bin + 1] = tile_prefix[bin] + (unsigned)tiles;
+        sent += all[(size_t)me * NBINS_MAX + bin];
+    }
+    if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
+    const uint64_t m = offA[nbA];
+    const unsigned n_tiles = tile_prefix[nbA];
+    *m_out = m;
+
+    DBuf<unsigned long long> plan(ctx, (size_t)NBINS_MAX + nbA + 1);
+    DBuf<unsigned> tprefix(ctx, (size_t)nbA + 1);
+    unsigned long long* d_curA = plan.p;
+    unsigned long long* d_offA = plan.p + NBINS_MAX;
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_curA, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_offA, offA.data(), ((size_t)nbA + 1) * 8, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)nbA + 1) * 4, cudaMemcpyHostToDevice, st));
+
+    // (3) extract + hash + bin, each bin's run stored straight into its owner's buffer
+    DBuf<uint8_t> keysA(ctx, m * ksz);
+    PeerPtrs dst;
+    if (multi) {
+        void* peers[PEDK_MAX_RANKS];
+        comm_peer_pointers(ctx, keysA.p, peers);
+        for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
+    } else {
+        dst.p[0] = reinterpret_cast<uint64_t*>(keysA.p);
+    }
+    {
+        StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART, packed_bytes + m_local * ksz);
+        // nobody may store into a buffer before its owner is done with the previous contents
+        if (multi) comm_barrier(ctx);
+        for (const ReadGroup& g : s->groups)
+            if (g.L >= k && g.n) launch_part_scatter(g.words.p, g.W, g.L, k, g.n, a, R, wide, d_curA, dst, st);
+        if (multi) comm_barrier(ctx);  // every rank's stores have landed
+    }
+    if (ctx->trace) {
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        trace(ctx, multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+    }
+    if (m == 0) return;
+
+    // (4) exact bucket sizes, (5) their offsets
+    const size_t n_buckets = (size_t)nbA * NBINS_MAX;
+    DBuf<unsigned> histB(ctx, n_buckets);
+    DBuf<unsigned long long> offB(ctx, n_buckets + 1), curB(ctx, n_buckets);
+    DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
+    {
+        StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_HIST, m * ksz);
+        PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
+        launch_sub_hist(keysA.p, wide, d_offA, tprefix.p, nbA, n_tiles, k, a, b, histB.p, st);
+    }
+    {
+        StageScope sc(ctx, PEDK_ST_SORT, 3);
+        exclusive_scan_u32(histB.p, reinterpret_cast<uint64_t*>(offB.p), n_buckets, ctx->scalars + 3, ws.p, st);
+        const unsigned long long total = m;
+        PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    // (6) second binning level
+    DBuf<uint8_t> keysB(ctx, m * ksz);
+    {
+        StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
+        launch_sub_scatter(keysA.p, keysB.p, wide, d_offA, tprefix.p, nbA, n_tiles, k, a, b, curB.p, st);
+    }
+    if (ctx->trace) {
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        trace(ctx, "  buckets: histogram + scan + scatter");
+    }
+    // (7) one CTA per bucket: count, rows.  The rows first land in the level-A buffer (free
+    // now: room for a row per three 4-byte instances), then move to exact-size arrays.
+    uint64_t cap = m * ksz / 12;
+    uint64_t* tmp_key = reinterpret_cast<uint64_t*>(keysA.p);
+    uint32_t* tmp_val = reinterpret_cast<uint32_t*>(tmp_key + cap);
+    DBuf<uint64_t> big_key;
+    DBuf<uint32_t> big_val;
+    for (int attempt = 0;; ++attempt) {
+        {
+            StageScope sc(ctx, PEDK_ST_COUNT, 1, 0, 0, PEDK_KC_BUCKET_COUNT, m * ksz);
+            PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), st));
+            launch_bucket_count(keysB.p, wide, offB.p, (unsigned)n_buckets, k, a, b, log_slots, 1, s->ckey.p, s->ccnt.p,
+                                s->n_corr, tmp_key, tmp_val, cap, ctx->scalars + 8, ctx->tile_ctr, ctx->err_flag, st);
+        }
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 2 * sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += 16;
+        trace(ctx, "  buckets: count -> rows");
+        s->n_rows = ctx->h_scalars[8];
+        s->D = ctx->h_scalars[9];
+        if (s->n_rows <= cap) break;
+        if (attempt) throw PedkError(PEDK_E_INTERNAL, "row count changed between two passes");
+        // mostly distinct k-mers (very low coverage): run again into arrays of the exact size
+        cap = s->n_rows;
+        big_key = DBuf<uint64_t>(ctx, cap);
+        big_val = DBuf<uint32_t>(ctx, cap);
+        tmp_key = big_key.p;
+        tmp_val = big_val.p;
+    }
+    check_err_flag(ctx, "bucket count");
+    ctx->stats.kc_bytes[PEDK_KC_BUCKET_COUNT] += s->n_rows * 12;
+    s->rkey = DBuf<uint64_t>(ctx, s->n_rows);
+    s->rval = DBuf<uint32_t>(ctx, s->n_rows);
+    if (s->n_rows) {
+        StageScope sc(ctx, PEDK_ST_COUNT, 0);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(s->rkey.p, tmp_key, s->n_rows * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(s->rval.p, tmp_val, s->n_rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+}
+
 void do_count(pedk_sample* s, int k) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -560,6 +737,7 @@ void do_count(pedk_sample* s, int k) {
             DestSpec spec;
             spec.mode = DEST_KMER;
             spec.stride = 1;
+            spec.k = k;
             DBuf<uint64_t> mine;
             exchange_records(ctx, a.p, m_local, spec, &mine, &m_final);
             a = std::move(mine);
@@ -600,7 +778,13 @@ void do_count(pedk_sample* s, int k) {
         s->ckey = std::move(c2 ? ck2 : ck);
         s->ccnt = std::move(c2 ? cc2 : cc);
     }
-    {
+    const bool sort_mode = getenv("PEDK_COUNT_MODE") && !strcmp(getenv("PEDK_COUNT_MODE"), "sort");
+    if (!sort_mode) {
+        uint64_t m = 0;
+        count_bucketed(s, k, &m);
+        s->cinfo.instances = m;
+        s->cinfo.sort_passes = 0;
+    } else {
         DBuf<uint64_t> a, b;
         uint64_t m = 0;
         int cur = extract_sort(false, M, a, b, m, PEDK_ST_SORT);

@@ -64,7 +64,7 @@ def main():
             for i in range(len(s) - K + 1):
                 km = s[i:i + K]
                 c = min(km, revcomp(km))
-                out[api.owner_of_kmer(enc(c), world)].append((c, w))
+                out[api.owner_of_kmer(enc(c), K, world)].append((c, w))
         half = Counter()
         for c, w in all_to_all(rank, world, out):
             half[c] += w

@@ -202,3 +202,54 @@ def test_full_size_properties(ctx):
     idx = np.searchsorted(km, rc)
     assert (km[idx] == rc).all() and (ct[idx] == ct).all()
     s.destroy()
+
+
+@pytest.mark.parametrize("env", [{"PEDK_BUCKET_SLOTS_LOG2": "8"}, {"PEDK_BUCKET_SLOTS_LOG2": "8", "PEDK_BUCKET_B": "1"},
+                                 {"PEDK_BUCKET_B": "2"}, {"PEDK_COUNT_MODE": "sort"}])
+@pytest.mark.parametrize("k", [20, 31])
+def test_bucket_table_overflow_and_legacy_path(ctx, env, k):
+    """The per-bucket hash table is forced to overflow (256 slots, buckets 128x larger) so that
+    buckets are split by further hash bits and re-read; PEDK_COUNT_MODE=sort is the extract +
+    LSD radix sort + run-length path the buckets replaced.  All must give the reference's table."""
+    case = dict(kind="synth", cfg=13, genome=300_000, reads=60_000, L=150, snp_ppm=1000, indel_ppm=100,
+                err_ppm=2000, n_ppm=1000, dup_ppm=0)
+    fc, ft = make_inputs(case)
+    oc, ot, osnp = oracle.run(fc, ft, k)
+    old = {n: os.environ.get(n) for n in env}
+    os.environ.update(env)
+    try:
+        c, t, ci, ti, r = gpu_run(ctx, fc, ft, k)
+    finally:
+        for n, v in old.items():
+            if v is None:
+                os.environ.pop(n, None)
+            else:
+                os.environ[n] = v
+    try:
+        check_sample(c, ci, oc, texts=False)
+        check_sample(t, ti, ot, texts=False)
+        assert r.text() == osnp
+    finally:
+        r.destroy(); c.destroy(); t.destroy()
+
+
+def test_one_kmer_with_many_instances(ctx):
+    """Low-complexity reads: a handful of k-mers carry almost all instances (one table slot each)."""
+    import random
+
+    rnd = random.Random(11)
+    reads = []
+    for i in range(3000):
+        u = "".join(rnd.choice("ACGT") for _ in range(10))
+        reads.append(u + "A" * 130 + "".join(rnd.choice("ACGT") for _ in range(10)))
+        reads.append(u + "AC" * 65 + "".join(rnd.choice("ACGT") for _ in range(10)))
+    fc = _fq(reads)
+    ft = _fq(reads[: len(reads) // 2] + ["ACGT" * 37 + "AC"] * 3)
+    oc, ot, osnp = oracle.run(fc, ft, 20)
+    c, t, ci, ti, r = gpu_run(ctx, fc, ft, 20)
+    try:
+        check_sample(c, ci, oc, texts=False)
+        check_sample(t, ti, ot, texts=False)
+        assert r.text() == osnp
+    finally:
+        r.destroy(); c.destroy(); t.destroy()

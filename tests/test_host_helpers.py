@@ -84,3 +84,51 @@ def test_read_pack_revcomp_and_windows(hd, L):
             for i in {0, 1, 31, 32, 33, L - k, (L - k) // 2}:
                 if 0 <= i <= L - k:
                     assert hd.hd_kmer_at(w.ctypes.data, W, i, k) == enc(s[i:i + k])
+
+
+@pytest.mark.parametrize("k", [4, 5, 7, 8, 16, 19, 20, 21, 31, 32])
+def test_kmer_hash_is_a_bijection_and_spreads(built, k):
+    """kmer_hash (common.cuh) bins canonical k-mers by its top bits and keeps only the low bits:
+    it must be invertible on 2k-bit integers, and its top bits must spread k-mers that share
+    long prefixes (consecutive windows of a read) evenly."""
+    from ped_b200 import api
+
+    rnd = random.Random(k)
+    n = 2 * k
+    top = (1 << n) - 1
+    xs = [0, 1, top, top - 1] + [rnd.getrandbits(n) for _ in range(2000)]
+    for x in xs:
+        h = api.kmer_hash(x, k)
+        assert 0 <= h <= top
+        assert api.kmer_unhash(h, k) == x
+    if k <= 8:  # exhaustive: a permutation of the whole space
+        hs = {api.kmer_hash(x, k) for x in range(1 << n)}
+        assert len(hs) == 1 << n
+    if k >= 16:
+        # windows sliding over one random sequence: adjacent keys share k-1 bases
+        seq = [rnd.randrange(4) for _ in range(20000 + k)]
+        v = 0
+        bins = np.zeros(256, dtype=np.int64)
+        for i, c in enumerate(seq):
+            v = ((v << 2) | c) & top
+            if i >= k - 1:
+                bins[api.kmer_hash(v, k) >> (n - 8)] += 1
+        assert bins.min() > 0.5 * bins.mean() and bins.max() < 1.6 * bins.mean()
+        # low-entropy input: keys that differ only in their low bits
+        bins[:] = 0
+        for x in range(20000):
+            bins[api.kmer_hash(x, k) >> (n - 8)] += 1
+        assert bins.min() > 0.5 * bins.mean() and bins.max() < 1.6 * bins.mean()
+
+
+def test_kmer_owner_is_a_contiguous_range_of_bins(built):
+    from ped_b200 import api
+
+    rnd = random.Random(5)
+    for k in (4, 20, 32):
+        a = min(8, k)
+        for world in (1, 2, 3, 4, 8):
+            for _ in range(300):
+                x = rnd.getrandbits(2 * k)
+                b = api.kmer_hash(x, k) >> (2 * k - a)
+                assert api.owner_of_kmer(x, k, world) == (b * world) >> a

@@ -27,7 +27,7 @@ def test_bucket_plan_is_contiguous_balanced_and_total(built):
 def test_owner_functions_are_deterministic_and_spread(built):
     ks = np.arange(1, 20001, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
     for world in (2, 8):
-        o = np.array([api.owner_of_kmer(int(k), world) for k in ks[:4000]])
+        o = np.array([api.owner_of_kmer(int(k), 20, world) for k in ks[:4000]])
         assert o.min() == 0 and o.max() == world - 1
         assert np.bincount(o, minlength=world).min() > 4000 / world * 0.8
         w = np.array([7, 8, 9, 10, 11], dtype=np.uint64)
