@@ -63,7 +63,7 @@ def build_libpedk(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(jobs) or 1)) as ex:
         list(ex.map(run, jobs))
-    if jobs or force or not os.path.exists(LIB):
+    if jobs or force or not _newer(LIB, objs):
         run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-ldl",
              "-lpthread"])
     return LIB

@@ -41,31 +41,74 @@ namespace {
 constexpr int NB = 256;  // bins per level (stride of the bucket index even when 2^b < 256)
 constexpr unsigned FULL = 0xffffffffu;
 
+
+// Canonical k-mers of one read for one lane.  `mine` = word `lane` of the packed read (0 beyond
+// the read).  Two layouts of the windows over the lanes:
+//   CONTIG  lane l takes windows l*NT .. l*NT+NT-1: ONE 32-base window is cut out of the words
+//           (two shuffles, one funnel shift) and reverse-complemented once; the NT k-mers and
+//           their reverse complements are shifts of those two words.  Needs NT - 1 + k <= 32.
+//   else    lane l takes windows l, l+32, ...: every k-mer is cut out and reversed on its own.
+// The alu pipe (shifts, logic) is what bounds these kernels, so CONTIG is ~2x faster.
+template <int NT, bool CONTIG>
+__device__ __forceinline__ void lane_kmers(uint64_t mine, unsigned lane, const int k, int nwin, bool live,
+                                           uint64_t (&canon)[NT], bool (&valid)[NT]) {
+    const int kshift = 64 - 2 * k;
+    if (CONTIG) {
+        const int p = (int)lane * NT;
+        const int w = p >> 5, o = p & 31;
+        const uint64_t hi = __shfl_sync(FULL, mine, w);
+        const uint64_t lo = __shfl_sync(FULL, mine, w + 1);
+        const uint64_t x = o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+        const uint64_t rcx = revcomp_groups64(x);
+        const uint64_t mask = kshift ? (~0ull >> kshift) : ~0ull;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const uint64_t km = (x >> (kshift - 2 * j)) & mask;
+            const uint64_t rc = (rcx >> (2 * j)) & mask;
+            canon[j] = km < rc ? km : rc;
+            valid[j] = live && p + j < nwin;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const uint64_t hi = __shfl_sync(FULL, mine, t);
+            const uint64_t lo = __shfl_sync(FULL, mine, t + 1);
+            const uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
+            const uint64_t km = x >> kshift;
+            const uint64_t rc = revcomp_groups64(km) >> kshift;
+            canon[t] = km < rc ? km : rc;
+            valid[t] = live && 32 * t + (int)lane < nwin;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ level A: count
 constexpr int PC_THREADS = 256;
 
-__global__ void __launch_bounds__(PC_THREADS) k_part_count(const uint64_t* __restrict__ words, int W, int L, int k,
-                                                          uint64_t n_reads, int shiftA,
+// KC = k when it is known at compile time (20, the reference's only k), else 0: with a constant k
+// the shifts and masks of the extraction and of kmer_hash fold into immediates.
+template <int NT, bool CONTIG, int KC>
+__global__ void __launch_bounds__(PC_THREADS) k_part_count(const uint64_t* __restrict__ words, int W, int L, int k_rt,
+                                                          uint64_t n_reads, int shiftA_rt,
                                                           unsigned long long* __restrict__ histA) {
+    const int k = KC ? KC : k_rt;
+    const int shiftA = KC ? 2 * KC - 8 : shiftA_rt;  // KC >= 8: eight level-A bits
     __shared__ unsigned h[NB];
     h[threadIdx.x] = 0;
     __syncthreads();
     const unsigned lane = lane_id();
     const uint64_t warp = ((uint64_t)blockIdx.x * PC_THREADS + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * PC_THREADS) >> 5;
-    const int nwin = L - k + 1, kshift = 64 - 2 * k, nbits = 2 * k;
-    const int nt = (nwin + 31) >> 5;
+    const int nwin = L - k + 1, nbits = 2 * k;
     for (uint64_t r = warp; r < n_reads; r += n_warps) {
         const uint64_t mine = (int)lane < W ? words[r * (uint64_t)W + lane] : 0ull;
-        for (int t = 0; t < nt; ++t) {
-            const uint64_t hi = __shfl_sync(FULL, mine, t);
-            const uint64_t lo = __shfl_sync(FULL, mine, t + 1);
-            const int i = 32 * t + (int)lane;
-            const uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-            const uint64_t km = x >> kshift;
-            const uint64_t rc = revcomp_groups64(km) >> kshift;
-            const uint64_t canon = km < rc ? km : rc;
-            if (i < nwin) atomicAdd(&h[kmer_hash(canon, nbits) >> shiftA], 1u);
+        uint64_t canon[NT];
+        bool valid[NT];
+        lane_kmers<NT, CONTIG>(mine, lane, k, nwin, true, canon, valid);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const unsigned bin = (unsigned)(kmer_hash(canon[t], nbits) >> shiftA);
+            if (valid[t]) atomicAdd(&h[bin], 1u);
         }
     }
     __syncthreads();
@@ -89,10 +132,12 @@ struct KeyBudget<uint64_t> {
 
 // NT = windows per lane per read (ceil((L-k+1)/32) rounded up to an instantiated value),
 // RPW = reads per warp per tile.
-template <typename KT, int NT, int RPW>
+template <typename KT, int NT, int RPW, bool CONTIG, int KC>
 __global__ void __launch_bounds__(PT_THREADS, 2)
-    k_part_scatter(const uint64_t* __restrict__ words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
+    k_part_scatter(const uint64_t* __restrict__ words, int W, int L, int k_rt, uint64_t n_reads, int a_rt, int nranks,
                    unsigned long long* __restrict__ cur, PeerPtrs dst) {
+    const int k = KC ? KC : k_rt;
+    const int a = KC ? 8 : a_rt;
     constexpr int ITEMS = NT * RPW;
     constexpr int TILE = PT_THREADS * ITEMS;
     static_assert(TILE <= 65536, "ranks are kept in 16 bits");
@@ -101,10 +146,10 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
     uint8_t* sbin = reinterpret_cast<uint8_t*>(stage + TILE);
     __shared__ unsigned hist[NB];
     __shared__ unsigned off[NB];
-    __shared__ unsigned long long gdelta[NB];
+    __shared__ KT* s_out[NB];  // per tile: where stage[0] would go if the whole tile were this bin's run
     __shared__ KT* s_ptr[NB];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const int nwin = L - k + 1, kshift = 64 - 2 * k, nbits = 2 * k;
+    const int nwin = L - k + 1, nbits = 2 * k;
     const int shiftA = nbits - a;
     const uint64_t maskS = (1ull << shiftA) - 1;  // shiftA <= 56
     if (tid < NB) {
@@ -124,25 +169,17 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
             const uint64_t r = tile * READS_PER_TILE + (uint64_t)warp * RPW + rr;
             const bool live = r < n_reads;
             const uint64_t mine = (live && (int)lane < W) ? words[r * (uint64_t)W + lane] : 0ull;
+            uint64_t canon[NT];
+            bool valid[NT];
+            lane_kmers<NT, CONTIG>(mine, lane, k, nwin, live, canon, valid);
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
                 const int idx = rr * NT + t;
-                const uint64_t hi = __shfl_sync(FULL, mine, t);
-                const uint64_t lo = __shfl_sync(FULL, mine, t + 1);
-                const int i = 32 * t + (int)lane;
-                const uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-                const uint64_t km = x >> kshift;
-                const uint64_t rc = revcomp_groups64(km) >> kshift;
-                const uint64_t canon = km < rc ? km : rc;
+                const uint64_t h = kmer_hash(canon[t], nbits);
+                const unsigned bin = (unsigned)(h >> shiftA);
+                keyv[idx] = (KT)(h & maskS);
                 meta[idx] = 0xffffffffu;
-                keyv[idx] = 0;
-                if (live && i < nwin) {
-                    const uint64_t h = kmer_hash(canon, nbits);
-                    const unsigned bin = (unsigned)(h >> shiftA);
-                    const unsigned rank = atomicAdd(&hist[bin], 1u);
-                    keyv[idx] = (KT)(h & maskS);
-                    meta[idx] = (bin << 16) | rank;
-                }
+                if (valid[t]) meta[idx] = (bin << 16) | atomicAdd(&hist[bin], 1u);
             }
         }
         __syncthreads();
@@ -153,7 +190,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
         if (tid < NB) {
             const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
             off[tid] = (unsigned)ex;
-            gdelta[tid] = g - ex;
+            s_out[tid] = s_ptr[tid] + (g - ex);
         }
         __syncthreads();
 #pragma unroll
@@ -168,10 +205,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
         __syncthreads();
         // ---- every bin's run goes out contiguously (to the owner's memory) ----
         const unsigned n_staged = (unsigned)total;
-        for (unsigned i = tid; i < n_staged; i += PT_THREADS) {
-            const unsigned bin = sbin[i];
-            s_ptr[bin][gdelta[bin] + i] = stage[i];
-        }
+        for (unsigned i = tid; i < n_staged; i += PT_THREADS) s_out[sbin[i]][i] = stage[i];
     }
 }
 
@@ -226,6 +260,61 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
     if (cur_bin >= 0 && h[tid]) atomicAdd(&histB[(size_t)cur_bin * NB + tid], h[tid]);
 }
 
+// One tile of a level-A bin -> its 2^b sub-bins.  WHOLE: the tile holds SUB_TILE keys (all but
+// the last tile of a bin), so no index is tested.  A thread keeps its 16 keys and their ranks
+// (two 16-bit ranks per register; the sub-bin is recomputed from the key) between the phases.
+template <typename KT, bool WHOLE>
+__device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, unsigned n, KT* __restrict__ out,
+                                                 unsigned long long* __restrict__ cur, int shiftB, unsigned maskB,
+                                                 KT* stage, uint8_t* ssub, unsigned* hist, unsigned* off,
+                                                 KT** s_out) {
+    const unsigned tid = threadIdx.x;
+    KT key[SS_ITEMS];
+    uint32_t rank2[SS_ITEMS / 2];
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; ++j) {
+        const unsigned i = j * SS_THREADS + tid;
+        key[j] = (WHOLE || i < n) ? src[i] : KT(0);
+    }
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; ++j) {
+        const unsigned i = j * SS_THREADS + tid;
+        unsigned r = 0xffffu;
+        if (WHOLE || i < n) r = atomicAdd(&hist[(unsigned)(key[j] >> shiftB) & maskB], 1u);
+        if (j & 1) rank2[j / 2] |= r << 16;
+        else rank2[j / 2] = r;
+    }
+    __syncthreads();
+    const unsigned c = tid < NB ? hist[tid] : 0u;
+    const uint64_t ex = block_exclusive_scan<SS_THREADS>(c, nullptr);
+    if (tid < NB) {
+        const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
+        off[tid] = (unsigned)ex;
+        s_out[tid] = out + (g - ex);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; ++j) {
+        const unsigned r = (j & 1) ? rank2[j / 2] >> 16 : rank2[j / 2] & 0xffffu;
+        if (WHOLE || r != 0xffffu) {
+            const unsigned sub = (unsigned)(key[j] >> shiftB) & maskB;
+            const unsigned pos = off[sub] + r;
+            stage[pos] = key[j];
+            ssub[pos] = (uint8_t)sub;
+        }
+    }
+    __syncthreads();
+    if (WHOLE) {
+#pragma unroll
+        for (int j = 0; j < SS_ITEMS; ++j) {
+            const unsigned i = j * SS_THREADS + tid;
+            s_out[ssub[i]][i] = stage[i];
+        }
+    } else {
+        for (unsigned i = tid; i < n; i += SS_THREADS) s_out[ssub[i]][i] = stage[i];
+    }
+}
+
 template <typename KT>
 __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restrict__ in, KT* __restrict__ out,
                                                               const unsigned long long* __restrict__ offA,
@@ -237,7 +326,7 @@ __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restr
     uint8_t* ssub = reinterpret_cast<uint8_t*>(stage + SUB_TILE);
     __shared__ unsigned hist[NB];
     __shared__ unsigned off[NB];
-    __shared__ unsigned long long gdelta[NB];
+    __shared__ KT* s_out[NB];
     const unsigned tid = threadIdx.x;
     const unsigned t = blockIdx.x;
     if (t >= n_tiles) return;
@@ -247,51 +336,18 @@ __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restr
     const unsigned n = (unsigned)(start + SUB_TILE < lim ? SUB_TILE : lim - start);
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
-    KT key[SS_ITEMS];
-    uint32_t meta[SS_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SS_ITEMS; ++j) {
-        const unsigned i = j * SS_THREADS + tid;
-        key[j] = i < n ? in[start + i] : KT(0);
-    }
-#pragma unroll
-    for (int j = 0; j < SS_ITEMS; ++j) {
-        const unsigned i = j * SS_THREADS + tid;
-        meta[j] = 0xffffffffu;
-        if (i < n) {
-            const unsigned sub = (unsigned)(key[j] >> shiftB) & maskB;
-            meta[j] = (sub << 16) | atomicAdd(&hist[sub], 1u);
-        }
-    }
-    __syncthreads();
-    const unsigned c = tid < NB ? hist[tid] : 0u;
-    const uint64_t ex = block_exclusive_scan<SS_THREADS>(c, nullptr);
-    if (tid < NB) {
-        const unsigned long long g = c ? atomicAdd(&curB[(size_t)bin * NB + tid], (unsigned long long)c) : 0ull;
-        off[tid] = (unsigned)ex;
-        gdelta[tid] = g - ex;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < SS_ITEMS; ++j) {
-        if (meta[j] != 0xffffffffu) {
-            const unsigned sub = meta[j] >> 16;
-            const unsigned pos = off[sub] + (meta[j] & 0xffffu);
-            stage[pos] = key[j];
-            ssub[pos] = (uint8_t)sub;
-        }
-    }
-    __syncthreads();
-    for (unsigned i = tid; i < n; i += SS_THREADS) {
-        const unsigned sub = ssub[i];
-        out[gdelta[sub] + i] = stage[i];
-    }
+    if (n == SUB_TILE)
+        sub_scatter_tile<KT, true>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, ssub, hist, off,
+                                   s_out);
+    else
+        sub_scatter_tile<KT, false>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, ssub, hist, off,
+                                    s_out);
 }
 
 // ------------------------------------------------------------------ buckets -> rows
-constexpr int BC_THREADS = 256;
+constexpr int BC_THREADS = 1024;
 constexpr int BC_WARPS = BC_THREADS / 32;
-constexpr int BC_UNROLL = 4;
+constexpr int BC_UNROLL = 4;  // (the slow path of k_bucket_count selects among exactly four keys)
 
 __device__ __forceinline__ uint32_t fold32(uint32_t x) { return x; }
 __device__ __forceinline__ uint32_t fold32(uint64_t x) { return (uint32_t)x ^ ((uint32_t)(x >> 32) * 0x9E3779B1u); }
@@ -299,6 +355,20 @@ __device__ __forceinline__ uint32_t fold32(uint64_t x) { return (uint32_t)x ^ ((
 __device__ __forceinline__ uint32_t cas_key(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
 __device__ __forceinline__ uint64_t cas_key(uint64_t* p, uint64_t cmp, uint64_t v) {
     return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)v);
+}
+
+// the GS keys of one 16-byte group of the table, read in one go and never from a register copy
+__device__ __forceinline__ void load_group(const uint32_t* p, uint32_t (&q)[4]) {
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3])
+                 : "r"((unsigned)__cvta_generic_to_shared(p))
+                 : "memory");
+}
+__device__ __forceinline__ void load_group(const uint64_t* p, uint64_t (&q)[2]) {
+    asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(q[0]), "=l"(q[1])
+                 : "r"((unsigned)__cvta_generic_to_shared(p))
+                 : "memory");
 }
 
 __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* a, uint64_t n, uint64_t key) {
@@ -310,28 +380,140 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* a, uint64_t 
     return lo;
 }
 
+// Insert the n keys at bkeys into the table (round rd of R, see k_bucket_count).
+//  (1) dense: every lane looks at the home group of each of its four keys: a k-mer that is
+//      already there (~25 of 26 instances at 30x) costs a vector load, four compares and one
+//      fire-and-forget add, without a divergent loop;
+//  (2) the rest (first instance of a k-mer, or a home group full of other k-mers) probes
+//      group by group, one pending key per lane and turn.
+// A slot only ever goes EMPTY -> key, so plain loads are safe for hits, and everybody agrees
+// on the first free slot of a group.  New k-mers are counted per thread and added up once
+// per iteration; beyond `limit` of them the round is abandoned (s_overflow).
+template <typename KT, bool MULTI>
+__device__ __forceinline__ void bucket_insert(const KT* __restrict__ bkeys, unsigned n, KT* tkey, uint32_t* tcnt,
+                                              int log_slots, KT maskR, unsigned R, unsigned rd, unsigned limit,
+                                              unsigned* s_distinct, unsigned* s_overflow) {
+    constexpr int GS = 16 / sizeof(KT);  // slots per 16-byte group
+    constexpr int GS_LOG = sizeof(KT) == 4 ? 2 : 1;
+    const KT EMPTY = ~KT(0);
+    const unsigned n_groups = (1u << log_slots) >> GS_LOG;
+    const unsigned gmask = n_groups - 1;
+    const int gshift = 32 - log_slots + GS_LOG;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    unsigned my_new = 0;
+    for (unsigned base = 0; base < n; base += BC_THREADS * BC_UNROLL) {
+        if (__any_sync(FULL, *(volatile unsigned*)s_overflow != 0)) break;
+        KT x[BC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BC_UNROLL; ++u) {
+            const unsigned i = base + u * BC_THREADS + tid;
+            x[u] = i < n ? (KT)(bkeys[i] & maskR) : EMPTY;  // keys are <= maskR < EMPTY
+        }
+        unsigned want = 0;
+#pragma unroll
+        for (int u = 0; u < BC_UNROLL; ++u) {
+            bool w = x[u] != EMPTY;
+            if (MULTI) w = w && (((fold32(x[u]) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
+            want |= (w ? 1u : 0u) << u;
+        }
+        // a warp full of ONE k-mer (repeats, low-complexity sequence): a single update
+        const KT s0 = __shfl_sync(FULL, x[0], 0);
+        unsigned add = 1;
+        if (__all_sync(FULL, want == 15u && x[0] == s0 && x[1] == s0 && x[2] == s0 && x[3] == s0)) {
+            want = lane == 0 ? 1u : 0u;
+            add = 32 * BC_UNROLL;
+        }
+        unsigned pend = 0;
+#pragma unroll
+        for (int u = 0; u < BC_UNROLL; ++u) {
+            const unsigned g = ((fold32(x[u]) * 0x9E3779B1u) >> gshift) & gmask;
+            KT q[GS];
+            load_group(tkey + g * GS, q);
+            int hit = -1;
+#pragma unroll
+            for (int j = GS - 1; j >= 0; --j)
+                if (q[j] == x[u]) hit = j;
+            if ((want >> u) & 1u) {
+                if (hit >= 0) atomicAdd(&tcnt[g * GS + hit], add);
+                else pend |= 1u << u;
+            }
+        }
+        while (__any_sync(FULL, pend != 0)) {
+            if (pend) {
+                const int u = __ffs(pend) - 1;
+                pend &= pend - 1;
+                const KT xs = u == 0 ? x[0] : u == 1 ? x[1] : u == 2 ? x[2] : x[3];
+                unsigned g = ((fold32(xs) * 0x9E3779B1u) >> gshift) & gmask;
+                unsigned probes = 0;
+                for (;;) {
+                    KT q[GS];
+                    load_group(tkey + g * GS, q);
+                    int hit = -1, free_slot = -1;
+#pragma unroll
+                    for (int j = GS - 1; j >= 0; --j) {
+                        if (q[j] == EMPTY) free_slot = j;
+                        if (q[j] == xs) hit = j;
+                    }
+                    if (hit < 0 && free_slot >= 0) {
+                        // not here yet and the group has room: claim its FIRST free slot
+                        const KT old = cas_key(&tkey[g * GS + free_slot], EMPTY, xs);
+                        if (old == EMPTY) {
+                            ++my_new;
+                            hit = free_slot;
+                        } else if (old == xs) {
+                            hit = free_slot;
+                        } else {
+                            continue;  // another k-mer took it: look at the group again
+                        }
+                    }
+                    if (hit >= 0) {
+                        atomicAdd(&tcnt[g * GS + hit], add);
+                        break;
+                    }
+                    g = (g + 1) & gmask;  // group full of other k-mers
+                    if (++probes > n_groups) {
+                        *s_overflow = 1;
+                        break;
+                    }
+                }
+            }
+        }
+        const unsigned wn = __reduce_add_sync(FULL, my_new);
+        my_new = 0;
+        if (wn && lane == 0 && atomicAdd(s_distinct, wn) + wn > limit) *s_overflow = 1;
+    }
+}
+
 // strand != 0: rows (K, c) and (revcomp K, c), c = the reference's count (SURVEY.md Appendix
 //              A.3): with I instances and C windows of palindromic reads among them (corr
 //              table), H = 2I - C half-units, c = H if K == revcomp(K) else H / 2.
 // strand == 0: rows (K, I).
 // counters[0] = rows appended (keeps counting past cap so the caller can retry with room),
 // counters[1] += distinct canonical k-mers.  err is raised if a bucket cannot be split further.
+//
+// Shared memory: tkey[slots], tcnt[slots], list[slots] (u16: the occupied slots, compacted).
+// A slot only ever goes EMPTY -> key, so the common case (the k-mer is already in the table:
+// ~25 of 26 instances at 30x) is a plain load, a compare and one fire-and-forget atomic add;
+// only the first instance of a k-mer pays for a compare-and-swap.
 template <typename KT>
-__global__ void __launch_bounds__(BC_THREADS) k_bucket_count(const KT* __restrict__ keys,
-                                                            const unsigned long long* __restrict__ offB,
-                                                            unsigned n_buckets, int k, int a, int b, int log_slots,
-                                                            int strand, const uint64_t* __restrict__ corr_key,
-                                                            const uint32_t* __restrict__ corr_cnt, uint64_t n_corr,
-                                                            uint64_t* __restrict__ row_key,
-                                                            uint32_t* __restrict__ row_val, uint64_t cap,
-                                                            unsigned long long* __restrict__ counters,
-                                                            unsigned* __restrict__ ticket, int* __restrict__ err) {
+__global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __restrict__ keys,
+                                                               const unsigned long long* __restrict__ offB,
+                                                               unsigned n_buckets, int k, int a, int b,
+                                                               int log_slots, int strand,
+                                                               const uint64_t* __restrict__ corr_key,
+                                                               const uint32_t* __restrict__ corr_cnt,
+                                                               uint64_t n_corr, uint64_t* __restrict__ row_key,
+                                                               uint32_t* __restrict__ row_val, uint64_t cap,
+                                                               unsigned long long* __restrict__ counters,
+                                                               unsigned* __restrict__ ticket,
+                                                               int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char bc_smem[];
     const unsigned slots = 1u << log_slots;
     KT* tkey = reinterpret_cast<KT*>(bc_smem);
     uint32_t* tcnt = reinterpret_cast<uint32_t*>(tkey + slots);
-    __shared__ unsigned s_bucket, s_distinct, s_overflow;
-    __shared__ unsigned w_nh[BC_WARPS], w_nr[BC_WARPS];
+    uint16_t* list = reinterpret_cast<uint16_t*>(tcnt + slots);
+    __shared__ unsigned s_bucket, s_distinct, s_overflow, s_nh, s_nr, s_rcur;
+    __shared__ unsigned w_cnt[BC_WARPS];
     __shared__ unsigned long long s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
@@ -339,7 +521,7 @@ __global__ void __launch_bounds__(BC_THREADS) k_bucket_count(const KT* __restric
     const KT EMPTY = ~KT(0);  // r < bits of KT, so no key is all ones
     const KT maskR = (KT)(((KT)1 << r) - 1);
     const unsigned limit = slots - (slots >> 2);
-    const unsigned per_warp = slots / BC_WARPS;  // >= 32: log_slots >= 8
+    const unsigned per_warp = slots / BC_WARPS;  // >= 32: log_slots >= 10
 
     for (;;) {
         if (tid == 0) s_bucket = atomicAdd(ticket, 1u);
@@ -364,49 +546,19 @@ __global__ void __launch_bounds__(BC_THREADS) k_bucket_count(const KT* __restric
             if (tid == 0) {
                 s_distinct = 0;
                 s_overflow = 0;
+                s_nr = 0;    // palindromic k-mers met in this round
+                s_rcur = 0;  // reverse rows placed so far (only used when there is a palindrome)
             }
             __syncthreads();
-            for (unsigned long long base = lo; base < hi; base += BC_THREADS * BC_UNROLL) {
-                if (__any_sync(FULL, *(volatile unsigned*)&s_overflow != 0)) break;
-                KT x[BC_UNROLL];
-                bool v[BC_UNROLL];
-#pragma unroll
-                for (int u = 0; u < BC_UNROLL; ++u) {
-                    const unsigned long long i = base + (unsigned long long)u * BC_THREADS + tid;
-                    v[u] = i < hi;
-                    x[u] = v[u] ? (KT)(keys[i] & maskR) : EMPTY;
-                }
-#pragma unroll
-                for (int u = 0; u < BC_UNROLL; ++u) {
-                    bool want = v[u];
-                    if (R > 1) want = want && (((fold32(x[u]) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
-                    // a warp full of one k-mer (repeats, low-complexity sequence): one update
-                    const KT x0 = __shfl_sync(FULL, x[u], 0);
-                    unsigned add = 1;
-                    if (__all_sync(FULL, want && x[u] == x0)) {
-                        want = lane == 0;
-                        add = 32;
-                    }
-                    if (want) {
-                        unsigned slot = ((fold32(x[u]) * 0x9E3779B1u) >> (32 - log_slots)) & (slots - 1);
-                        unsigned probes = 0;
-                        for (;;) {
-                            const KT old = cas_key(&tkey[slot], EMPTY, x[u]);
-                            if (old == EMPTY) {
-                                if (atomicAdd(&s_distinct, 1u) >= limit) s_overflow = 1;
-                            }
-                            if (old == EMPTY || old == x[u]) {
-                                atomicAdd(&tcnt[slot], add);
-                                break;
-                            }
-                            slot = (slot + 1) & (slots - 1);
-                            if (++probes > slots) {
-                                s_overflow = 1;
-                                break;
-                            }
-                        }
-                    }
-                }
+            // ---- insert (in pieces of < 2^30 keys so that the inner indices are 32 bit) ----
+            for (unsigned long long seg = lo; seg < hi; seg += 1ull << 30) {
+                const unsigned seg_n = hi - seg < (1ull << 30) ? (unsigned)(hi - seg) : 1u << 30;
+                if (R == 1)
+                    bucket_insert<KT, false>(keys + seg, seg_n, tkey, tcnt, log_slots, maskR, R, rd, limit, &s_distinct,
+                                             &s_overflow);
+                else
+                    bucket_insert<KT, true>(keys + seg, seg_n, tkey, tcnt, log_slots, maskR, R, rd, limit, &s_distinct,
+                                            &s_overflow);
             }
             __syncthreads();
             if (s_overflow) {
@@ -418,49 +570,72 @@ __global__ void __launch_bounds__(BC_THREADS) k_bucket_count(const KT* __restric
                 R <<= 1;  // rd stays: the first half of the round that overflowed
                 continue;
             }
-            // ---- rows of this round: count per warp, reserve once per block, write ----
+            // ---- compact the occupied slots: count per warp, offsets, write the slot list ----
             const unsigned s_lo = warp * per_warp, s_hi = s_lo + per_warp;
-            unsigned nh = 0, nr = 0;
-            for (unsigned s0 = s_lo; s0 < s_hi; s0 += 32) {
-                const KT x = tkey[s0 + lane];
-                const bool occ = x != EMPTY;
-                nh += __popc(__ballot_sync(FULL, occ));
-                if (strand) {
-                    const uint64_t K = kmer_unhash(hbase | (uint64_t)x, nbits);
-                    nr += __popc(__ballot_sync(FULL, occ && kmer_revcomp(K, k) != K));
+            unsigned nh_w = 0;
+            for (unsigned s0 = s_lo; s0 < s_hi; s0 += 32) nh_w += __popc(__ballot_sync(FULL, tkey[s0 + lane] != EMPTY));
+            if (lane == 0) w_cnt[warp] = nh_w;
+            __syncthreads();
+            if (warp == 0) {
+                const unsigned c = w_cnt[lane];
+                unsigned inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned o = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= (unsigned)d) inc += o;
                 }
-            }
-            if (lane == 0) {
-                w_nh[warp] = nh;
-                w_nr[warp] = nr;
+                w_cnt[lane] = inc - c;
+                if (lane == 31) s_nh = inc;
             }
             __syncthreads();
+            {
+                unsigned run = w_cnt[warp];
+                for (unsigned s0 = s_lo; s0 < s_hi; s0 += 32) {
+                    const bool occ = tkey[s0 + lane] != EMPTY;
+                    const unsigned m = __ballot_sync(FULL, occ);
+                    if (occ) list[run + __popc(m & lt)] = (uint16_t)(s0 + lane);
+                    run += __popc(m);
+                }
+            }
+            __syncthreads();
+            const unsigned nh = s_nh;
+            // ---- reverse rows: every head that is not its own reverse complement (odd k: all) ----
+            unsigned nr = 0;
+            if (strand) {
+                nr = nh;
+                if ((k & 1) == 0) {
+                    unsigned pal = 0;
+                    for (unsigned e0 = 0; e0 < nh; e0 += BC_THREADS) {
+                        const unsigned e = e0 + tid;
+                        bool p = false;
+                        if (e < nh) {
+                            const uint64_t K = kmer_unhash(hbase | (uint64_t)tkey[list[e]], nbits);
+                            p = kmer_revcomp(K, k) == K;
+                        }
+                        pal += __popc(__ballot_sync(FULL, p));
+                    }
+                    if (lane == 0 && pal) atomicAdd(&s_nr, pal);
+                    __syncthreads();
+                    nr = nh - s_nr;
+                }
+            }
             if (tid == 0) {
-                unsigned rows = 0, heads = 0;
-                for (int w = 0; w < BC_WARPS; ++w) {
-                    const unsigned cw = w_nh[w] + w_nr[w];
-                    heads += w_nh[w];
-                    w_nr[w] = rows;  // becomes the warp's offset inside the block's reservation
-                    rows += cw;
-                }
+                const unsigned rows = nh + nr;
                 s_base = rows ? atomicAdd(&counters[0], (unsigned long long)rows) : 0ull;
-                if (heads) atomicAdd(&counters[1], (unsigned long long)heads);
+                if (nh) atomicAdd(&counters[1], (unsigned long long)nh);
             }
             __syncthreads();
-            unsigned long long of = s_base + w_nr[warp];
-            unsigned long long orv = of + nh;
-            for (unsigned s0 = s_lo; s0 < s_hi; s0 += 32) {
-                const KT x = tkey[s0 + lane];
-                const bool occ = x != EMPTY;
-                uint64_t K = 0, rcK = 0;
-                uint32_t val = 0;
-                bool rev = false;
-                if (occ) {
-                    K = kmer_unhash(hbase | (uint64_t)x, nbits);
-                    const uint64_t inst = tcnt[s0 + lane];
+            const unsigned long long base_f = s_base, base_r = s_base + nh;
+            for (unsigned e0 = 0; e0 < nh; e0 += BC_THREADS) {
+                const unsigned e = e0 + tid;
+                if (e < nh) {
+                    const unsigned slot = list[e];
+                    const uint64_t K = kmer_unhash(hbase | (uint64_t)tkey[slot], nbits);
+                    const uint64_t inst = tcnt[slot];
+                    uint32_t val;
                     if (strand) {
-                        rcK = kmer_revcomp(K, k);
-                        rev = rcK != K;
+                        const uint64_t rcK = kmer_revcomp(K, k);
+                        const bool rev = rcK != K;
                         uint64_t corr = 0;
                         if (n_corr) {
                             const uint64_t q = lower_bound_u64(corr_key, n_corr, K);
@@ -470,29 +645,23 @@ __global__ void __launch_bounds__(BC_THREADS) k_bucket_count(const KT* __restric
                         uint64_t c = rev ? (Hh >> 1) : Hh;
                         if (c > 0x7fffffffull) c = 0x7fffffffull;
                         val = (uint32_t)c;
+                        if (rev) {
+                            // no palindrome in this round (almost always): the reverse row of head e
+                            // sits at e; otherwise the reverse rows take the next free position
+                            const unsigned long long pr = base_r + (nr == nh ? e : atomicAdd(&s_rcur, 1u));
+                            if (pr < cap) {
+                                row_key[pr] = rcK;
+                                row_val[pr] = val;
+                            }
+                        }
                     } else {
-                        val = (uint32_t)inst;
+                        val = inst > 0xffffffffull ? 0xffffffffu : (uint32_t)inst;
                     }
-                }
-                const unsigned hm = __ballot_sync(FULL, occ);
-                if (occ) {
-                    const unsigned long long pf = of + __popc(hm & lt);
+                    const unsigned long long pf = base_f + e;
                     if (pf < cap) {
                         row_key[pf] = K;
                         row_val[pf] = val;
                     }
-                }
-                of += __popc(hm);
-                if (strand) {
-                    const unsigned rm = __ballot_sync(FULL, rev);
-                    if (rev) {
-                        const unsigned long long pr = orv + __popc(rm & lt);
-                        if (pr < cap) {
-                            row_key[pr] = rcK;
-                            row_val[pr] = val;
-                        }
-                    }
-                    orv += __popc(rm);
                 }
             }
             __syncthreads();  // the table is cleared next
@@ -507,7 +676,7 @@ __global__ void __launch_bounds__(BC_THREADS) k_bucket_count(const KT* __restric
     }
 }
 
-template <typename KT, int NT>
+template <typename KT, int NT, bool CONTIG, int KC>
 void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                             unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st) {
     constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
@@ -515,29 +684,50 @@ void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t
     constexpr size_t SMEM = (size_t)TILE * (sizeof(KT) + 1);
     static bool attr_set = false;
     if (!attr_set) {
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_part_scatter<KT, NT, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)SMEM));
+        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_part_scatter<KT, NT, RPW, CONTIG, KC>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
     const uint64_t tiles = (n_reads + (uint64_t)PT_WARPS * RPW - 1) / ((uint64_t)PT_WARPS * RPW);
     const unsigned grid = (unsigned)(tiles < (uint64_t)kNumSMs * 2 ? tiles : (uint64_t)kNumSMs * 2);
-    k_part_scatter<KT, NT, RPW><<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, dst);
+    k_part_scatter<KT, NT, RPW, CONTIG, KC>
+        <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, dst);
 }
+
+// windows per lane, rounded up to an instantiated value
+int nt_of(int L, int k) {
+    const int nt = (L - k + 1 + 31) / 32;
+    return nt <= 6 ? nt : nt <= 8 ? 8 : nt <= 12 ? 12 : 16;
+}
+// lane l can take nt consecutive windows out of one 32-base word
+bool contiguous_ok(int nt, int k) { return nt - 1 + k <= 32; }
 
 template <typename KT>
 void launch_part_scatter_t(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                            unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st) {
-    const int nt = (L - k + 1 + 31) / 32;
-#define PEDK_PS(N) launch_part_scatter_nt<KT, N>(words, W, L, k, n_reads, a, nranks, cur, dst, st)
-    if (nt <= 1) PEDK_PS(1);
-    else if (nt <= 2) PEDK_PS(2);
-    else if (nt <= 3) PEDK_PS(3);
-    else if (nt <= 4) PEDK_PS(4);
-    else if (nt <= 5) PEDK_PS(5);
-    else if (nt <= 6) PEDK_PS(6);
-    else if (nt <= 8) PEDK_PS(8);
-    else if (nt <= 12) PEDK_PS(12);
-    else PEDK_PS(16);
+    const int nt = nt_of(L, k);
+    const bool contig = contiguous_ok(nt, k);
+    if (k == 20 && sizeof(KT) == 4 && contig && nt >= 2 && nt <= 6) {
+        // the reference's k, short reads: k folded into the kernel
+        switch (nt) {
+        case 2: launch_part_scatter_nt<KT, 2, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
+        case 3: launch_part_scatter_nt<KT, 3, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
+        case 4: launch_part_scatter_nt<KT, 4, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
+        case 5: launch_part_scatter_nt<KT, 5, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
+        default: launch_part_scatter_nt<KT, 6, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
+        }
+        return;
+    }
+#define PEDK_PS(N)                                                                                        \
+    case N:                                                                                               \
+        if (contig) launch_part_scatter_nt<KT, N, true, 0>(words, W, L, k, n_reads, a, nranks, cur, dst, st); \
+        else launch_part_scatter_nt<KT, N, false, 0>(words, W, L, k, n_reads, a, nranks, cur, dst, st);   \
+        break;
+    switch (nt) {
+        PEDK_PS(1) PEDK_PS(2) PEDK_PS(3) PEDK_PS(4) PEDK_PS(5) PEDK_PS(6) PEDK_PS(8) PEDK_PS(12)
+    default:
+        launch_part_scatter_nt<KT, 16, false, 0>(words, W, L, k, n_reads, a, nranks, cur, dst, st);
+    }
 #undef PEDK_PS
 }
 
@@ -548,7 +738,30 @@ void launch_part_count(const uint64_t* words, int W, int L, int k, uint64_t n_re
     if (!n_reads || L < k) return;
     const uint64_t blocks = (n_reads + 7) / 8;
     const unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
-    k_part_count<<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA);
+    const int nt = nt_of(L, k);
+    const bool contig = contiguous_ok(nt, k);
+    if (k == 20 && contig && nt >= 2 && nt <= 6) {
+        switch (nt) {
+        case 2: k_part_count<2, true, 20><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA); break;
+        case 3: k_part_count<3, true, 20><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA); break;
+        case 4: k_part_count<4, true, 20><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA); break;
+        case 5: k_part_count<5, true, 20><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA); break;
+        default: k_part_count<6, true, 20><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA); break;
+        }
+        PEDK_CUDA_TRY(cudaGetLastError());
+        return;
+    }
+#define PEDK_PC(N)                                                                                             \
+    case N:                                                                                                    \
+        if (contig) k_part_count<N, true, 0><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA); \
+        else k_part_count<N, false, 0><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA);  \
+        break;
+    switch (nt) {
+        PEDK_PC(1) PEDK_PC(2) PEDK_PC(3) PEDK_PC(4) PEDK_PC(5) PEDK_PC(6) PEDK_PC(8) PEDK_PC(12)
+    default:
+        k_part_count<16, false, 0><<<grid, PC_THREADS, 0, st>>>(words, W, L, k, n_reads, 2 * k - a, histA);
+    }
+#undef PEDK_PC
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
@@ -610,19 +823,19 @@ void launch_bucket_count(const void* keys, int wide, const unsigned long long* o
                          uint64_t n_corr, uint64_t* row_key, uint32_t* row_val, uint64_t cap,
                          unsigned long long* counters, unsigned* ticket, int* err, cudaStream_t st) {
     if (!n_buckets) return;
-    if (log_slots < 8) log_slots = 8;
+    if (log_slots < 10) log_slots = 10;
     if (log_slots > 13) log_slots = 13;
-    const size_t smem = ((size_t)1 << log_slots) * ((wide ? sizeof(uint64_t) : sizeof(uint32_t)) + sizeof(uint32_t));
+    const size_t per_slot = (wide ? sizeof(uint64_t) : sizeof(uint32_t)) + sizeof(uint32_t) + sizeof(uint16_t);
+    const size_t smem = ((size_t)1 << log_slots) * per_slot;
     PEDK_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-    // enough resident CTAs to fill the machine; buckets are handed out by ticket
-    const unsigned per_sm = (unsigned)(200 * 1024 / (smem + 1024));
-    unsigned grid = kNumSMs * (per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm);
+    // two resident CTAs of 1024 threads per SM; buckets are handed out by ticket
+    unsigned grid = kNumSMs * (smem > 100 * 1024 ? 1 : 2);
     if (grid > n_buckets) grid = n_buckets;
     if (wide) {
         static bool attr_set = false;
         if (!attr_set) {
             PEDK_CUDA_TRY(cudaFuncSetAttribute(k_bucket_count<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(((size_t)1 << 13) * 12)));
+                                               (int)(((size_t)1 << 13) * 14)));
             attr_set = true;
         }
         k_bucket_count<uint64_t><<<grid, BC_THREADS, smem, st>>>(static_cast<const uint64_t*>(keys), offB, n_buckets,
@@ -632,7 +845,7 @@ void launch_bucket_count(const void* keys, int wide, const unsigned long long* o
         static bool attr_set = false;
         if (!attr_set) {
             PEDK_CUDA_TRY(cudaFuncSetAttribute(k_bucket_count<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(((size_t)1 << 13) * 8)));
+                                               (int)(((size_t)1 << 13) * 10)));
             attr_set = true;
         }
         k_bucket_count<uint32_t><<<grid, BC_THREADS, smem, st>>>(static_cast<const uint32_t*>(keys), offB, n_buckets,

@@ -91,6 +91,18 @@ void dev_release_all(pedk_ctx* ctx) {
     ctx->live_blocks.clear();
 }
 
+void* host_stage(pedk_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->h_stage_bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_bytes = 0;
+        size_t want = bytes + bytes / 4 + (1u << 20);
+        PEDK_CUDA_TRY(cudaMallocHost(&ctx->h_stage, want));
+        ctx->h_stage_bytes = want;
+    }
+    return ctx->h_stage;
+}
+
 static cudaEvent_t get_event(pedk_ctx* ctx) {
     if (!ctx->event_pool.empty()) {
         cudaEvent_t e = ctx->event_pool.back();
@@ -273,6 +285,12 @@ extern "C" int pedk_open(pedk_ctx** out, const int* devices, int ndev) {
         PEDK_CUDA_TRY(cudaMemset(ctx->err_flag, 0, sizeof(int)));
         PEDK_CUDA_TRY(cudaMalloc(&ctx->scalars, 16 * sizeof(unsigned long long)));
         PEDK_CUDA_TRY(cudaMallocHost(&ctx->h_scalars, 16 * sizeof(unsigned long long)));
+        {
+            std::vector<uint32_t> bits(2048);
+            build_edge_pass1_table(bits.data());
+            PEDK_CUDA_TRY(cudaMalloc(&ctx->edge_pass1, 2048 * sizeof(uint32_t)));
+            PEDK_CUDA_TRY(cudaMemcpy(ctx->edge_pass1, bits.data(), 2048 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
     } catch (const CudaError& err) {
         g_open_error = err.msg;
         delete ctx;
@@ -303,7 +321,9 @@ extern "C" int pedk_close(pedk_ctx* ctx) {
     cudaFree(ctx->tile_ctr);
     cudaFree(ctx->err_flag);
     cudaFree(ctx->scalars);
+    cudaFree(ctx->edge_pass1);
     cudaFreeHost(ctx->h_scalars);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaEventDestroy(ctx->ev_alloc);

@@ -44,6 +44,9 @@ struct pedk_ctx {
     int* err_flag = nullptr;
     unsigned long long* scalars = nullptr;  // 16 device words for counters
     unsigned long long* h_scalars = nullptr;  // pinned mirror
+    uint32_t* edge_pass1 = nullptr;           // device: truth table of joinKmerSub's pass 1 (edges.cu)
+    void* h_stage = nullptr;                  // pinned staging buffer for results (grown on demand)
+    size_t h_stage_bytes = 0;
     // multi-GPU
     void* nccl_comm = nullptr;
     void* ipc_cache = nullptr;  // comm.cu: peer blocks mapped through CUDA IPC
@@ -69,6 +72,8 @@ int ctx_fail(pedk_ctx* ctx, int code, const std::string& msg);
 void* dev_alloc(pedk_ctx* ctx, size_t bytes);
 void dev_free(pedk_ctx* ctx, void* p, size_t bytes);
 void dev_release_all(pedk_ctx* ctx);
+// pinned host buffer of at least `bytes`, owned by the context, valid until the next call
+void* host_stage(pedk_ctx* ctx, size_t bytes);
 
 // RAII device array on the context's caching allocator
 template <typename T>

@@ -90,33 +90,74 @@ __device__ __forceinline__ bool edge_test(const uint32_t* c, const uint32_t* t, 
     return true;
 }
 
-__global__ void __launch_bounds__(256) k_edges(const uint64_t* __restrict__ row_key,
-                                              const uint32_t* __restrict__ row_val, uint64_t n, int k,
-                                              const unsigned long long* __restrict__ first,
-                                              EdgeRec* __restrict__ edges, uint64_t cap,
-                                              unsigned long long* __restrict__ n_edges) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t K = row_key[i];
-    uint64_t P = K >> 2;
-    if (i > 0 && (row_key[i - 1] >> 2) == P) return;  // not the head of its group
-    uint32_t c[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
-    bool hasc = false, hast = false;
-    for (uint64_t j = i; j < n && j < i + 8; ++j) {
-        uint64_t Kj = row_key[j];
-        if ((Kj >> 2) != P) break;
-        uint32_t v = row_val[j];
-        unsigned x = (unsigned)(Kj & 3);
-        if (v >> 31) { t[x] = v & 0x7fffffffu; hast = true; }
-        else { c[x] = v; hasc = true; }
+constexpr int ED_THREADS = 256;
+constexpr int ED_HALO = 8;  // a group has at most 4 bases x 2 samples rows
+
+// Pass 1 of joinKmerSub (ped.pl:720-744) looks at every count only through four classes:
+//   0: <= 1 (or absent) -> "nohit",  1: == 2,  2: 3..100 -> allele,  3: > 100 -> repeat.
+// A (k-1)-mer group therefore boils down to 16 bits, two per (sample, last base) slot, and
+// whether it passes is a 65536-entry truth table (8 KiB, built once on the host from the same
+// rules, L1-resident).  Every row contributes its two bits; the head of a group ORs the <= 8
+// words of its group and looks the answer up.  Only the few groups that pass (and are present
+// in both samples) gather their counts for pass 2 (ped.pl:750-781).
+__host__ __device__ inline unsigned count_class(uint32_t c) { return c > 100 ? 3u : c >= 3 ? 2u : c <= 1 ? 0u : 1u; }
+
+__global__ void __launch_bounds__(ED_THREADS) k_edges(const uint64_t* __restrict__ row_key,
+                                                     const uint32_t* __restrict__ row_val, uint64_t n, int k,
+                                                     const unsigned long long* __restrict__ first,
+                                                     const uint32_t* __restrict__ pass1_bits,
+                                                     EdgeRec* __restrict__ edges, uint64_t cap,
+                                                     unsigned long long* __restrict__ n_edges) {
+    // per staged row: bits 0-15 class bits of its slot, bit 16/17 control/target present,
+    // bit 31 = same (k-1)-mer as the row before
+    __shared__ uint32_t s_w[ED_THREADS + ED_HALO];
+    const unsigned tid = threadIdx.x;
+    const uint64_t base = (uint64_t)blockIdx.x * ED_THREADS;
+    const uint64_t left = n - base;
+    const unsigned loaded = left < (uint64_t)(ED_THREADS + ED_HALO) ? (unsigned)left : (unsigned)(ED_THREADS + ED_HALO);
+    uint64_t myK = 0;
+    for (unsigned j = tid; j < loaded; j += ED_THREADS) {
+        const uint64_t K = row_key[base + j];
+        const uint32_t v = row_val[base + j];
+        const uint64_t prevK = base + j ? row_key[base + j - 1] : ~K;
+        const unsigned s = v >> 31, x = (unsigned)(K & 3);
+        uint32_t w = (count_class(v & 0x7fffffffu) << (2 * (4 * s + x))) | (1u << (16 + s));
+        if (base + j && (prevK >> 2) == (K >> 2)) w |= 0x80000000u;
+        s_w[j] = w;
+        if (j == tid) myK = K;
     }
-    if (!(hasc && hast)) return;  // `join` is an inner join (ped.pl:709)
-    unsigned tag = (unsigned)(K >> (2 * k - 6));
-    unsigned long long fc = first[tag], ft = first[64 + tag];
+    __syncthreads();
+    if (tid >= loaded) return;
+    uint32_t acc = s_w[tid];
+    if (acc >> 31) return;  // not the head of its group
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        if (tid + j >= loaded) break;
+        const uint32_t w = s_w[tid + j];
+        if (!(w >> 31)) break;
+        acc |= w;
+    }
+    if (((acc >> 16) & 3u) != 3u) return;  // `join` is an inner join (ped.pl:709)
+    const unsigned code = acc & 0xffffu;
+    if (!((__ldg(pass1_bits + (code >> 5)) >> (code & 31u)) & 1u)) return;
+    // ---- rare from here on: the full evaluation on the counts ----
+    const uint64_t P = myK >> 2;
+    const unsigned tag = (unsigned)(myK >> (2 * k - 6));
+    const unsigned long long fc = first[tag], ft = first[64 + tag];
     if ((fc != ~0ull && (fc >> 2) == P) || (ft != ~0ull && (ft >> 2) == P)) return;  // F7 rows: host
+    uint32_t c[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
+    const uint64_t i = base + tid;
+    for (uint64_t j = i; j < n && j < i + 8; ++j) {
+        const uint64_t Kj = row_key[j];
+        if ((Kj >> 2) != P) break;
+        const uint32_t v = row_val[j];
+        const unsigned x = (unsigned)(Kj & 3);
+        if (v >> 31) t[x] = v & 0x7fffffffu;
+        else c[x] = v;
+    }
     uint8_t cont, alt;
     if (!edge_test(c, t, &cont, &alt)) return;
-    unsigned long long o = atomicAdd(n_edges, 1ull);
+    const unsigned long long o = atomicAdd(n_edges, 1ull);
     if (o < cap) {
         EdgeRec e;
         e.p = P;
@@ -167,11 +208,32 @@ void launch_first_of_bucket(const uint64_t* row_key, const uint32_t* row_val, ui
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
+// truth table of pass 1 over the 16 class bits of a group (see k_edges)
+void build_edge_pass1_table(uint32_t* bits /* 2048 words */) {
+    for (unsigned w = 0; w < 2048; ++w) bits[w] = 0;
+    for (unsigned code = 0; code < 65536; ++code) {
+        int rep = 0, nohita = 0, nohitb = 0, pola = 0, polb = 0;
+        unsigned a = 0, b = 0;
+        for (int x = 0; x < 4; ++x) {
+            const unsigned cv = (code >> (2 * x)) & 3u, tv = (code >> (2 * (4 + x))) & 3u;
+            if (cv == 3) ++rep;
+            else if (cv == 2) { a |= 1u << x; if (tv == 0) ++pola; }
+            else if (cv == 0) ++nohita;
+            if (tv == 3) ++rep;
+            else if (tv == 2) { b |= 1u << x; if (cv == 0) ++polb; }
+            else if (tv == 0) ++nohitb;
+        }
+        if (a != b && a && b && rep == 0 && nohita >= 2 && nohitb >= 2 && (pola == 1 || polb == 1))
+            bits[code >> 5] |= 1u << (code & 31u);
+    }
+}
+
 void launch_edges(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
-                  const unsigned long long* first, EdgeRec* edges, uint64_t cap, unsigned long long* n_edges,
-                  cudaStream_t st) {
+                  const unsigned long long* first, const uint32_t* pass1_bits, EdgeRec* edges, uint64_t cap,
+                  unsigned long long* n_edges, cudaStream_t st) {
     if (!n) return;
-    k_edges<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(row_key, row_val, n, k, first, edges, cap, n_edges);
+    k_edges<<<(unsigned)((n + ED_THREADS - 1) / ED_THREADS), ED_THREADS, 0, st>>>(row_key, row_val, n, k, first,
+                                                                                 pass1_bits, edges, cap, n_edges);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

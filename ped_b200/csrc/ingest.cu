@@ -43,48 +43,76 @@ __global__ void __launch_bounds__(NL_THREADS) k_newline_count(const uint4* __res
     }
 }
 
+// newline flags of 16 bytes as a 16-bit mask (bit b = byte b)
+__device__ __forceinline__ unsigned nl_mask4(uint32_t x) {
+    // 0xff per matching byte -> one bit per byte, gathered into bits 24..27 by one multiply
+    return ((__vcmpeq4(x, 0x0A0A0A0Au) & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ unsigned nl_mask16(uint4 v) {
+    return nl_mask4(v.x) | (nl_mask4(v.y) << 4) | (nl_mask4(v.z) << 8) | (nl_mask4(v.w) << 12);
+}
+
+// Line numbers -> byte spans of the sequence lines.  A warp owns 2 KiB of the tile as four
+// 512-byte rows (lane l reads 16 bytes of each: coalesced); newline counts are ranked with
+// warp shuffles, so a lane knows the line number of each of its newlines and writes the
+// span ends straight away.  One read of the text, no per-byte branches.
 __global__ void __launch_bounds__(NL_THREADS) k_line_index(const uint8_t* __restrict__ fq, size_t n, size_t n_tiles,
                                                           const uint64_t* __restrict__ tile_prefix,
                                                           uint64_t* __restrict__ seq_start,
                                                           uint64_t* __restrict__ seq_end, uint64_t n_records,
                                                           int plain_lines) {
+    constexpr int WARPS = NL_THREADS / 32;
+    constexpr int ROWS = INGEST_TILE_BYTES / (WARPS * 512);  // 4
+    __shared__ unsigned warp_cnt[WARPS];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // blocked: thread t owns bytes [64t, 64t+64) of the tile
-        size_t off = tile * INGEST_TILE_BYTES + (size_t)threadIdx.x * NL_BYTES_PER_THREAD;
-        const uint4* p = reinterpret_cast<const uint4*>(fq + off);
-        uint4 v[4];
-        unsigned c = 0;
+        const size_t warp_off = tile * INGEST_TILE_BYTES + (size_t)warp * (ROWS * 512);
+        unsigned mask[ROWS], ex[ROWS];
+        unsigned row_base = 0;  // newlines of this warp before row j
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            v[j] = __ldg(p + j);
-            c += count_nl16(v[j]);
+        for (int j = 0; j < ROWS; ++j)
+            mask[j] = nl_mask16(__ldg(reinterpret_cast<const uint4*>(fq + warp_off + (size_t)j * 512) + lane));
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            const unsigned c = __popc(mask[j]);
+            unsigned inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (unsigned)d) inc += o;
+            }
+            ex[j] = row_base + inc - c;
+            row_base += __shfl_sync(0xffffffffu, inc, 31);
         }
-        uint64_t line = block_exclusive_scan<NL_THREADS>(c, nullptr) + tile_prefix[tile];
-        if (c) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(v);
+        __syncthreads();  // warp_cnt of the previous tile has been read
+        if (lane == 0) warp_cnt[warp] = row_base;
+        __syncthreads();
+        uint64_t line0 = tile_prefix[tile];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                uint32_t x = w[j];
-                if (__vcmpeq4(x, 0x0A0A0A0Au)) {
+        for (int w = 0; w < WARPS; ++w)
+            if (w < (int)warp) line0 += warp_cnt[w];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        if (((x >> (8 * b)) & 0xffu) == 0x0Au) {
-                            size_t pos = off + 4 * j + b;
-                            if (pos < n && plain_lines) {
-                                if (line < n_records) seq_end[line] = pos;
-                                if (line + 1 < n_records) seq_start[line + 1] = pos + 1;
-                            } else if (pos < n) {
-                                uint64_t rec = line >> 2;
-                                unsigned phase = (unsigned)(line & 3);
-                                if (rec < n_records) {
-                                    if (phase == 0) seq_start[rec] = pos + 1;  // end of the header line
-                                    if (phase == 1) seq_end[rec] = pos;        // end of the sequence line
-                                }
-                            }
-                            ++line;
+        for (int j = 0; j < ROWS; ++j) {
+            uint64_t line = line0 + ex[j];
+            unsigned m = mask[j];
+            const size_t off = warp_off + (size_t)j * 512 + (size_t)lane * 16;
+            while (m) {
+                const size_t pos = off + (__ffs(m) - 1);
+                m &= m - 1;
+                if (pos < n) {
+                    if (plain_lines) {
+                        if (line < n_records) seq_end[line] = pos;
+                        if (line + 1 < n_records) seq_start[line + 1] = pos + 1;
+                    } else {
+                        const uint64_t rec = line >> 2;
+                        const unsigned phase = (unsigned)(line & 3);
+                        if (rec < n_records) {
+                            if (phase == 0) seq_start[rec] = pos + 1;  // end of the header line
+                            if (phase == 1) seq_end[rec] = pos;        // end of the sequence line
                         }
                     }
                 }
+                ++line;
             }
         }
     }

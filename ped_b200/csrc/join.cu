@@ -123,7 +123,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
             PEDK_CUDA_TRY(cudaMemsetAsync(first.p, 0xFF, first.bytes(), st));
             PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 4, 0, sizeof(unsigned long long), st));
             launch_first_of_bucket(rows.key.p, rows.val.p, rows.n, k, first.p, st);
-            launch_edges(rows.key.p, rows.val.p, rows.n, k, first.p, edges.p, cap, ctx->scalars + 4, st);
+            launch_edges(rows.key.p, rows.val.p, rows.n, k, first.p, ctx->edge_pass1, edges.p, cap, ctx->scalars + 4, st);
         }
         PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->scalars + 4, 8, cudaMemcpyDeviceToHost, st));
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
@@ -132,12 +132,15 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         cap = E;  // rare: more edges than one row in sixteen
         edges = DBuf<EdgeRec>(ctx, cap);
     }
-    std::vector<EdgeRec> h_edges(E);
-    std::vector<unsigned long long> h_first(128);
+    // EdgeRec and pedk_edge share one layout (quirk = first pad byte = 0): the records go through
+    // a pinned staging buffer of the context straight into the result
+    static_assert(sizeof(EdgeRec) == sizeof(pedk_edge), "edge record layout");
+    unsigned char* stage = static_cast<unsigned char*>(host_stage(ctx, E * sizeof(EdgeRec) + 1024));
+    unsigned long long* h_first = reinterpret_cast<unsigned long long*>(stage + E * sizeof(EdgeRec));
     {
         StageScope sc(ctx, PEDK_ST_COPY, 0);
-        if (E) PEDK_CUDA_TRY(cudaMemcpyAsync(h_edges.data(), edges.p, E * sizeof(EdgeRec), cudaMemcpyDeviceToHost, st));
-        PEDK_CUDA_TRY(cudaMemcpyAsync(h_first.data(), first.p, 128 * 8, cudaMemcpyDeviceToHost, st));
+        if (E) PEDK_CUDA_TRY(cudaMemcpyAsync(stage, edges.p, E * sizeof(EdgeRec), cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(h_first, first.p, 128 * 8, cudaMemcpyDeviceToHost, st));
     }
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
     ctx->stats.d2h_bytes += E * sizeof(EdgeRec) + 1024;
@@ -146,7 +149,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     // ---- first-of-bucket rows: look the groups up and evaluate their text on the host ----
     std::vector<uint64_t> plist;
     for (int i = 0; i < 128; ++i)
-        if (h_first[(size_t)i] != ~0ull) plist.push_back(h_first[(size_t)i] >> 2);
+        if (h_first[i] != ~0ull) plist.push_back(h_first[i] >> 2);
     std::sort(plist.begin(), plist.end());
     plist.erase(std::unique(plist.begin(), plist.end()), plist.end());
     std::vector<GroupRec> groups(plist.size());
@@ -161,14 +164,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     }
 
     res->edges.resize(E);
-    for (uint64_t i = 0; i < E; ++i) {
-        pedk_edge& e = res->edges[i];
-        memset(&e, 0, sizeof e);
-        e.prefix = h_edges[i].p;
-        for (int x = 0; x < 4; ++x) { e.control[x] = h_edges[i].c[x]; e.target[x] = h_edges[i].t[x]; }
-        e.cont_mask = h_edges[i].cont;
-        e.alt_mask = h_edges[i].alt;
-    }
+    if (E) memcpy(static_cast<void*>(res->edges.data()), stage, E * sizeof(pedk_edge));
     auto& quirks = res->quirks;
     for (const GroupRec& g : groups) {
         bool pc = g.hasc[0] | g.hasc[1] | g.hasc[2] | g.hasc[3];

@@ -149,9 +149,11 @@ struct EdgeRec {
 // joinKmerSub (ped.pl:703-782) on every (k-1)-mer group of the merged table that is not the
 // first group of its bucket in either sample (those rows carry the F7 text quirk and are
 // evaluated on the host).  Edges are appended through *n_edges; at most cap are stored.
+// pass1_bits: device copy of the 2048-word table build_edge_pass1_table fills (host)
+void build_edge_pass1_table(uint32_t* bits);
 void launch_edges(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
-                  const unsigned long long* first, EdgeRec* edges, uint64_t cap, unsigned long long* n_edges,
-                  cudaStream_t st);
+                  const unsigned long long* first, const uint32_t* pass1_bits, EdgeRec* edges, uint64_t cap,
+                  unsigned long long* n_edges, cudaStream_t st);
 struct GroupRec {
     uint64_t p;
     uint32_t c[4], t[4];

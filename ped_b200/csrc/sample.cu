@@ -466,7 +466,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     const int nbits = 2 * k;
     const int a = kmer_bits_a(k);
     const int b = env_int("PEDK_BUCKET_B", kmer_bits_b(k), nbits - a < 1 ? 0 : 1, kmer_bits_b(k));
-    const int log_slots = env_int("PEDK_BUCKET_SLOTS_LOG2", 13, 8, 13);
+    const int log_slots = env_int("PEDK_BUCKET_SLOTS_LOG2", 13, 10, 13);
     const int nbA = 1 << a;
     const int wide = (nbits - a) > 32 ? 1 : 0;
     const size_t ksz = wide ? 8 : 4;
