@@ -96,6 +96,21 @@ int pedk_sample_add_fastq_device(pedk_sample *s, const void *device_bytes, uint6
  * given -> fixed length, or ped.pl's automatic choice for mixed lengths),
  * strand closure, exact de-duplication.  Frees the FASTQ text. */
 int pedk_sample_ingest(pedk_sample *s, int clipping, pedk_ingest_info *info);
+/* a10 = mkChrFromFile + mkControlReadChr + mkControlReadSub (ped.pl:1027-1060, 1089-1136):
+ * the control of a `ref=` run is the reference itself.  Feed the FASTA text with
+ * pedk_sample_add_fastq (any chunking), then: every sequence is cleaned (upper case,
+ * non-ACGT -> N, headers and newlines dropped; a sequence whose name repeats replaces the
+ * earlier one, like ped.pl's open ">"), tiled into `window`-base windows every `step` bases
+ * (0, 0 = ped.pl's 100 and 2), windows holding an N are dropped, the rest go through strand
+ * closure and exact de-duplication.  The sample is then in the state pedk_sample_ingest
+ * leaves it in (info->records = windows, reads_kept = windows without N). */
+int pedk_sample_ingest_reference(pedk_sample *s, int window, int step, pedk_ingest_info *info);
+/* The chromosome files mkChrFromFile writes: name is "chr" + the name ped.pl derives from the
+ * header line, seq the cleaned sequence (NULL: length only).  *overwritten = 1 for a sequence
+ * that a later one of the same name replaced. */
+int pedk_sample_num_chromosomes(pedk_sample *s, int *n);
+int pedk_sample_chromosome(pedk_sample *s, int i, char *name, uint64_t name_cap, uint64_t *length,
+                           int *overwritten, char *seq, uint64_t seq_cap);
 /* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer
  * of every unique read, sorted and counted.  4 <= k <= 32 (the reference
  * hard-codes 20, ped.pl:912-913).  Leaves the canonical table in HBM. */
@@ -156,6 +171,11 @@ int pedk_kmer_edges(pedk_ctx *ctx, const void *control_fastq, uint64_t control_b
  * explicit clipping of every later mkSortUniq call of the same run. */
 int pedk_mk_sort_uniq(pedk_ctx *ctx, const char *wd, const char *subject, int clipping, int *clipping_used,
                       int *auto_clipped);
+/* mkChrFromFile + mkControlRead (ped.pl:1027-1060, 1062-1136): reads <wd>/<ref>/<file> (FASTA;
+ * .gz and .bz2 like ped.pl), writes <wd>/<ref>/chrNAME and
+ * <wd>/<ref>/sort_uniq/<ref>.sort_uniq.TAG.gz.  The reference stays resident as a sample, so
+ * pedk_count_kmer(wd, ref) continues from HBM. */
+int pedk_mk_control_read(pedk_ctx *ctx, const char *wd, const char *ref, const char *file);
 /* countKmer (ped.pl:784-815): writes <wd>/<subject>/count/<subject>.count.TAG.gz */
 int pedk_count_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
 /* lbcKmer (ped.pl:817-831): writes <wd>/<subject>/lbc/<subject>.lbc.TAG.gz */

@@ -62,6 +62,16 @@ def lib() -> C.CDLL:
         L.oracle_join_text.restype = P
         L.oracle_join_text.argtypes = [P, P, C.POINTER(C.c_size_t)]
         L.oracle_free.argtypes = [P]
+        L.oracle_ingest_reference.argtypes = [P, C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        L.oracle_ref_parse.restype = P
+        L.oracle_ref_parse.argtypes = [C.c_char_p, C.c_size_t]
+        L.oracle_ref_num.restype = C.c_size_t
+        L.oracle_ref_num.argtypes = [P]
+        L.oracle_ref_name.restype = C.c_char_p
+        L.oracle_ref_name.argtypes = [P, C.c_size_t]
+        L.oracle_ref_seq.restype = C.c_size_t
+        L.oracle_ref_seq.argtypes = [P, C.c_size_t, C.POINTER(C.c_char_p)]
+        L.oracle_ref_free.argtypes = [P]
         _lib = L
     return _lib
 
@@ -89,6 +99,13 @@ class OracleSample:
 
     def ingest(self, fastq: bytes, clipping: int = 0) -> None:
         rc = self.L.oracle_ingest(self.h, fastq, len(fastq), clipping)
+        if rc:
+            raise RuntimeError(self.L.oracle_error(self.h).decode())
+        self.L.oracle_dedup(self.h)
+
+    def ingest_reference(self, fasta: bytes, window: int = 0, step: int = 0) -> None:
+        """mkChrFromFile + mkControlReadChr/Sub (ped.pl:1027-1060, 1089-1136)."""
+        rc = self.L.oracle_ingest_reference(self.h, fasta, len(fasta), window, step)
         if rc:
             raise RuntimeError(self.L.oracle_error(self.h).decode())
         self.L.oracle_dedup(self.h)
@@ -171,6 +188,31 @@ def run(control_fastq: bytes, target_fastq: bytes, k: int = 20, clipping: int = 
     if t.auto_clipped:
         clipping = t.clipping_used
     c = OracleSample(control_fastq, clipping)
+    c.count(k)
+    t.count(k)
+    return c, t, join_text(c, t)
+
+
+def ref_chromosomes(fasta: bytes):
+    """The chromosome files mkChrFromFile leaves: {file name: cleaned sequence}."""
+    L = lib()
+    r = L.oracle_ref_parse(fasta, len(fasta))
+    try:
+        out = {}
+        p = C.c_char_p()
+        for i in range(L.oracle_ref_num(r)):
+            n = L.oracle_ref_seq(r, i, C.byref(p))
+            out[L.oracle_ref_name(r, i).decode()] = C.string_at(p, n) if n else b""
+        return out
+    finally:
+        L.oracle_ref_free(r)
+
+
+def run_ref(ref_fasta: bytes, target_fastq: bytes, k: int = 20, clipping: int = 0):
+    """`ref=` run: the control is the reference tiled into reads (ped.pl:193, 1062-1136)."""
+    t = OracleSample(target_fastq, clipping)
+    c = OracleSample()
+    c.ingest_reference(ref_fasta)
     c.count(k)
     t.count(k)
     return c, t, join_text(c, t)

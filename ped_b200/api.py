@@ -113,6 +113,10 @@ SIGNATURES = {
     "pedk_free": (None, [_P]),
     "pedk_result_destroy": (C.c_int, [_P]),
     "pedk_kmer_edges": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _PP]),
+    "pedk_sample_ingest_reference": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(IngestInfo)]),
+    "pedk_sample_num_chromosomes": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "pedk_sample_chromosome": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _U64P, C.POINTER(C.c_int), _P, C.c_uint64]),
+    "pedk_mk_control_read": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_mk_sort_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pedk_count_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_lbc_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
@@ -285,6 +289,32 @@ class Sample:
         info = IngestInfo()
         self.ctx.check(self.ctx.lib.pedk_sample_ingest(self.h, clipping, C.byref(info)))
         return info
+
+    def ingest_reference(self, window: int = 0, step: int = 0) -> IngestInfo:
+        """mkChrFromFile + mkControlRead (ped.pl:1027-1060, 1089-1136): the text fed with add_fastq is
+        a reference FASTA; its 100-base windows every 2 bases become the reads of this sample."""
+        info = IngestInfo()
+        self.ctx.check(self.ctx.lib.pedk_sample_ingest_reference(self.h, window, step, C.byref(info)))
+        return info
+
+    def chromosomes(self, sequences: bool = True):
+        """[(file name ped.pl gives it, cleaned sequence or length, overwritten by a later one)]"""
+        n = C.c_int()
+        self.ctx.check(self.ctx.lib.pedk_sample_num_chromosomes(self.h, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            name = C.create_string_buffer(4096)
+            length = C.c_uint64()
+            ow = C.c_int()
+            self.ctx.check(self.ctx.lib.pedk_sample_chromosome(self.h, i, name, 4096, C.byref(length), C.byref(ow),
+                                                               None, 0))
+            seq = length.value
+            if sequences:
+                buf = C.create_string_buffer(max(1, length.value))
+                self.ctx.check(self.ctx.lib.pedk_sample_chromosome(self.h, i, None, 0, None, None, buf, length.value))
+                seq = buf.raw[:length.value]
+            out.append((name.value.decode(), seq, bool(ow.value)))
+        return out
 
     def count(self, k: int = 20) -> CountInfo:
         """countKmer (ped.pl:784-932)."""

@@ -325,6 +325,48 @@ void do_mk_sort_uniq(pedk_ctx* ctx, const std::string& wd, const std::string& su
     s->have_reads = false;
 }
 
+// mkChrFromFile + mkControlRead: the reference FASTA as the control sample
+void do_mk_control_read(pedk_ctx* ctx, const std::string& wd, const std::string& ref, const std::string& file) {
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    const std::string dir = wd + "/" + ref;
+    const std::string path = dir + "/" + file;
+    if (!exists(path)) throw PedkError(PEDK_E_IO, file + " is not found in " + dir);  // ped.pl:1031
+    pedk_sample* s = fresh_sample(ctx, wd + "/" + ref);
+    {
+        Feeder feed(s);
+        if (ends_with(file, "gz")) feed.feed_gz(path);                                   // ped.pl:1033-1038
+        else if (ends_with(file, "bz2")) feed.feed_pipe("bzcat " + shell_quote(path));
+        else feed.feed_plain(path);
+        feed.flush();
+    }
+    must(ctx, pedk_sample_ingest_reference(s, 0, 0, nullptr));
+    // the chromosome files (later stages of ped.pl read them; a repeated name overwrites)
+    for (size_t i = 0; i < s->chromosomes.size(); ++i) {
+        const pedk_sample::Chromosome& c = s->chromosomes[i];
+        if (!c.live) continue;
+        std::string seq((size_t)c.length, '\0');
+        must(ctx, pedk_sample_chromosome(s, (int)i, nullptr, 0, nullptr, nullptr, c.length ? &seq[0] : nullptr,
+                                         c.length));
+        write_plain_atomic(dir + "/" + c.name, seq.data(), seq.size());
+    }
+    const std::string od = dir + "/sort_uniq";
+    mkdir_p(od);
+    ensure_host_reads(s);
+    for_each_tag([&](int t) {
+        std::string text;
+        size_t bytes = 0;
+        for (const std::string& r : s->h_reads[t]) bytes += r.size() + 1;
+        text.reserve(bytes);
+        for (const std::string& r : s->h_reads[t]) {
+            text += r;
+            text += '\n';
+        }
+        write_gz_atomic(od + "/" + ref + ".sort_uniq." + tag_name(t) + ".gz", text.data(), text.size());
+    });
+    for (auto& v : s->h_reads) std::vector<std::string>().swap(v);
+    s->have_reads = false;
+}
+
 // a sample whose reads come from existing sort_uniq files (one read per line)
 pedk_sample* sample_from_sort_uniq(pedk_ctx* ctx, const std::string& wd, const std::string& subject) {
     pedk_sample* s = fresh_sample(ctx, wd + "/" + subject);
@@ -478,6 +520,14 @@ void file_cache_destroy(pedk_ctx* ctx) {
     ctx->file_cache = nullptr;
 }
 }  // namespace pedk
+
+extern "C" int pedk_mk_control_read(pedk_ctx* ctx, const char* wd, const char* ref, const char* file) {
+    if (!ctx || !wd || !ref || !file) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_mk_control_read(ctx, wd, ref, file);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
 
 extern "C" int pedk_mk_sort_uniq(pedk_ctx* ctx, const char* wd, const char* subject, int clipping,
                                  int* clipping_used, int* auto_clipped) {

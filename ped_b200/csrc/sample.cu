@@ -47,9 +47,12 @@ struct GroupPlan {
     uint64_t r_limit;
 };
 
+}  // namespace
+
+namespace pedk {
 // Exact dedup of n packed canonical reads -> a ReadGroup of the sample.
 void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8_t>& pal, uint64_t n_c,
-                 const uint8_t* valid = nullptr) {
+                 const uint8_t* valid) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     if (n_c >= 0xFFFFFFF0ull) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^32 reads in one sample on one GPU");
@@ -82,6 +85,10 @@ void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8
     g.n_pal = read_scalar(ctx, ctx->scalars + 1, "compact reads");
     s->groups.push_back(std::move(g));
 }
+
+}  // namespace pedk
+
+namespace {
 
 // Build one read-length group: chunk -> pack -> (multi-GPU: route every read to the rank
 // that owns its hash) -> dedup -> compact.  R may be 0 on a rank of a multi-GPU job.

@@ -43,6 +43,15 @@ struct pedk_sample {
     uint64_t tag_start[65] = {0};
     bool have_reads = false;
     std::vector<std::string> h_reads[64];  // sorted strand-closed reads per bucket
+    // reference as a sample (reference.cu): the cleaned chromosomes, back to back in HBM
+    struct Chromosome {
+        std::string name;   // "chr" + the name ped.pl derives from the header (ped.pl:1045-1050)
+        uint64_t start = 0, length = 0;
+        bool live = true;   // false: a later sequence of the same name overwrote this one
+    };
+    std::vector<Chromosome> chromosomes;
+    pedk::DBuf<uint8_t> ref_clean;
+    uint64_t ref_clean_len = 0;
 };
 
 namespace pedk {
@@ -55,6 +64,11 @@ struct RowTable {
 // expand + sort; target may be null (single-sample table, sample bit 0)
 void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTable* out);
 void ensure_host_table(pedk_sample* s);
+// exact de-duplication of n_c packed canonical reads (valid[i] == 0: skip) -> a ReadGroup of s
+void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8_t>& pal, uint64_t n_c,
+                 const uint8_t* valid = nullptr);
+// reads the sequence read_scalar-style helpers of sample.cu rely on
+
 void ensure_host_reads(pedk_sample* s);
 std::string kmer_string(uint64_t v, int k);
 }  // namespace pedk

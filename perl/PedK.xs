@@ -66,6 +66,15 @@ mk_sort_uniq(wd, subject, clipping)
     }
 
 void
+mk_control_read(wd, ref, file)
+    const char *wd
+    const char *ref
+    const char *file
+  CODE:
+    /* mkChrFromFile + mkControlRead (ped.pl:1027-1136) */
+    check(aTHX_ pedk_mk_control_read(ctx_or_croak(aTHX), wd, ref, file), "mk_control_read");
+
+void
 count_kmer(wd, subject, k)
     const char *wd
     const char *subject

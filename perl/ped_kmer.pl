@@ -7,8 +7,12 @@
 # positional form `T C` and the environment form.  Same files as ped.pl's
 # method=kmer without ref= (ped.pl:368-378): <wd>/<s>/sort_uniq/, count/, lbc/,
 # <wd>/<t>/<t>.kmer.snp, <t>.log with the `clipping :` lines, <t>.report; a stage
-# is skipped when its TTT file exists (ped.pl:291-297, 369-372).  The four heavy
+# is skipped when its TTT file exists (ped.pl:291-297, 369-372).  The heavy
 # subs are calls into libpedk.so through PedK.xs; nothing here forks.
+#
+# `ref=REF,file=REF.fa` (no target) builds the control reads of a reference like
+# ped.pl's mkRef does (ped.pl:1027-1136: <wd>/REF/chrNAME and REF/sort_uniq/); a
+# later `target=T,control=REF` then compares T with the tiled reference.
 #
 use strict;
 use warnings;
@@ -21,7 +25,7 @@ $ENV{LANG} = "C";
 my %opt = (k => 20);
 my $arg0 = defined $ARGV[0] ? $ARGV[0] : "";
 my $log = "script : ped_kmer.pl\nargument : $arg0\n";
-if ($arg0 =~ /target/) {
+if ($arg0 =~ /target/ || $arg0 =~ /ref=.*file=|file=.*ref=/) {
     foreach (sort split(',', $arg0)) {
         next if $_ eq "";
         my ($name, $val) = split('=', $_);
@@ -35,7 +39,16 @@ if ($arg0 =~ /target/) {
 } else {
     die "usage: perl ped_kmer.pl target=T,control=C[,wd=DIR][,clipping=L]\n";
 }
-die "ped_kmer.pl runs the k-mer method without ref=; use ped.pl (with the PedK patch of INTEGRATION.md) for ref mode\n"
+if (defined $opt{ref} && $opt{ref} ne "" && defined $opt{file} && $opt{file} ne "" && !defined $opt{target}) {
+    # mkRef for a local FASTA (ped.pl:1017-1025): chromosome files + control reads
+    my $wd = (defined $opt{wd} && $opt{wd} ne "") ? $opt{wd} : getcwd();
+    PedK::open_device();
+    PedK::mk_control_read($wd, $opt{ref}, $opt{file});
+    PedK::close_device();
+    print "control reads of $opt{ref} written to $wd/$opt{ref}/sort_uniq\n";
+    exit 0;
+}
+die "ped_kmer.pl runs the k-mer comparison itself; with ref= the mapping stages of ped.pl follow: use ped.pl with the PedK patch of INTEGRATION.md\n"
     if defined $opt{ref} && $opt{ref} ne "";
 die "method must be kmer\n" if defined $opt{method} && $opt{method} ne "kmer";
 my ($target, $control) = ($opt{target}, $opt{control});

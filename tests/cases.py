@@ -104,3 +104,39 @@ def make_inputs(case):
             b = _join(allr)
             out.append(b[:-1])  # no newline after the last quality line
     return out[0], out[1]
+
+
+# ---- the reference as the control (BASELINE config 5 shape) ----
+REF_CASES = {
+    # 30 kb reference in two sequences: 60-column lines, a soft-masked stretch, a run of N, an
+    # IUPAC code, a CRLF line, a sequence shorter than one window, a name that comes back
+    # (the later sequence replaces the earlier file), text before the first header
+    "ref30k": dict(cfg=2, genome=30000, reads=8000, L=150, snp_ppm=1000, indel_ppm=100, err_ppm=2000, n_ppm=1000,
+                   dup_ppm=0),
+}
+
+
+def make_ref_inputs(case):
+    """-> (reference FASTA bytes, target FASTQ bytes).  The target reads come from the mutated genome."""
+    c = case["cfg"]
+    g = api.synth_genome(1000 + c, case["genome"])
+    t = api.synth_mutate(g, 2000 + c, case["snp_ppm"], case["indel_ppm"])
+    ft = api.synth_fastq(t, 4000 + c, case["reads"], read_len=case["L"], err_ppm=case["err_ppm"],
+                         n_ppm=case["n_ppm"], dup_ppm=case["dup_ppm"])
+    gb = g.tobytes()
+    half = len(gb) * 3 // 5
+    c1, c2 = bytearray(gb[:half]), bytearray(gb[half:])
+    c1[5000:5040] = b"N" * 40
+    c1[9000:9100] = bytes(c1[9000:9100]).lower()
+    c2[3000] = ord("R")
+
+    def fa(name, seq, width=60, crlf_at=-1):
+        s = bytes(seq)
+        lines = [s[i:i + width] for i in range(0, len(s), width)]
+        if 0 <= crlf_at < len(lines):
+            lines[crlf_at] += b"\r"
+        return b">" + name + b"\n" + b"\n".join(lines) + b"\n"
+
+    text = (b"ACGTACGT stray line before any header\n" + fa(b"chr01 first sequence", c1, crlf_at=7) +
+            fa(b"scaffoldX", gb[100:160]) + fa(b"Chr2\tsecond", gb[200:900], width=70) + fa(b"2 again", c2, width=80))
+    return text[:-1], ft  # no newline after the last sequence line

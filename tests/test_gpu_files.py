@@ -10,7 +10,7 @@ import pytest
 
 from oracle import oracle
 from ped_b200 import api
-from tests.cases import CASES, make_inputs
+from tests.cases import CASES, REF_CASES, make_inputs, make_ref_inputs
 
 pytestmark = pytest.mark.gpu
 TAGS = oracle.TAGS
@@ -107,3 +107,40 @@ def test_missing_input_is_an_error_not_a_gate_file(built, tmp_path):
     assert rc == -4 and b"nosuch" in ctx.lib.pedk_last_error(ctx.h)
     assert not os.path.exists(os.path.join(str(tmp_path), "nosuch", "sort_uniq"))
     ctx.close()
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_reference_as_control_file_contract(built, tmp_path, gz):
+    """`perl ped.pl ref=REF,file=REF.fa` then `target=T,ref=REF,method=kmer`: pedk_mk_control_read
+    leaves REF/chrNAME and REF/sort_uniq/ (ped.pl:1027-1136), the usual calls do the rest with the
+    tiled reference as the control; the per-tag edge files go to tmpdir (have_ref, ped.pl:687-701)."""
+    fa, ft = make_ref_inputs(REF_CASES["ref30k"])
+    oc, ot, osnp = oracle.run_ref(fa, ft, 20)
+    wd = str(tmp_path)
+    os.makedirs(f"{wd}/REF")
+    os.makedirs(f"{wd}/T/read")
+    name = "REF.fa.gz" if gz else "REF.fa"
+    with (gzip.open if gz else open)(f"{wd}/REF/{name}", "wb") as f:
+        f.write(fa)
+    open(f"{wd}/T/read/T.fastq", "wb").write(ft)
+    ctx = api.Context(0)
+    lib = ctx.lib
+    ctx.check(lib.pedk_mk_control_read(ctx.h, wd.encode(), b"REF", name.encode()))
+    ctx.check(lib.pedk_mk_sort_uniq(ctx.h, wd.encode(), b"T", 0, None, None))
+    for s in (b"T", b"REF"):
+        ctx.check(lib.pedk_count_kmer(ctx.h, wd.encode(), s, 20))
+        ctx.check(lib.pedk_lbc_kmer(ctx.h, wd.encode(), s, 20))
+    tmpdir = f"{wd}/T/tmp"
+    ctx.check(lib.pedk_join_kmer(ctx.h, wd.encode(), b"T", b"REF", 20, tmpdir.encode(), 1))
+    assert lib.pedk_mk_control_read(ctx.h, wd.encode(), b"REF", b"nosuch.fa") == -4
+    ctx.close()
+    for fn, seq in oracle.ref_chromosomes(fa).items():
+        assert open(f"{wd}/REF/{fn}", "rb").read() == seq
+    for s, o in (("REF", oc), ("T", ot)):
+        for i, tag in enumerate(TAGS):
+            assert _zcat(f"{wd}/{s}/sort_uniq/{s}.sort_uniq.{tag}.gz") == o.sort_uniq_text(i)
+            assert _zcat(f"{wd}/{s}/count/{s}.count.{tag}.gz") == o.count_text(i)
+            assert _zcat(f"{wd}/{s}/lbc/{s}.lbc.{tag}.gz") == o.lbc_text(i)
+    assert b"".join(open(f"{tmpdir}/T.snp.{t}", "rb").read() for t in TAGS) == osnp
+    g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
+    assert osnp.decode() == g["kmer_snp"]

@@ -10,7 +10,7 @@ import pytest
 
 from oracle import oracle
 from ped_b200 import api
-from tests.cases import CASES, make_inputs, revcomp
+from tests.cases import CASES, REF_CASES, make_inputs, make_ref_inputs, revcomp
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -253,3 +253,88 @@ def test_one_kmer_with_many_instances(ctx):
         assert r.text() == osnp
     finally:
         r.destroy(); c.destroy(); t.destroy()
+
+
+def test_reference_as_control(ctx):
+    """a10 (BASELINE config 5 shape): the control is the reference FASTA tiled into 100-base
+    windows every 2 bases (ped.pl:1027-1136).  Chromosome files, tables, texts and the edge list
+    against the oracle and against ped.pl's own outputs (tests/golden/ref30k.json)."""
+    fa, ft = make_ref_inputs(REF_CASES["ref30k"])
+    oc, ot, osnp = oracle.run_ref(fa, ft, 20)
+    c, t = api.Sample(ctx), api.Sample(ctx)
+    for i in range(0, len(fa), 7001):  # arbitrary chunking
+        c.add_fastq(fa[i:i + 7001])
+    t.add_fastq(ft)
+    ti = t.ingest()
+    ci = c.ingest_reference()
+    c.count(20)
+    t.count(20)
+    r = ctx.join(c, t)
+    try:
+        want = oracle.ref_chromosomes(fa)
+        got = {name: seq for name, seq, overwritten in c.chromosomes() if not overwritten}
+        assert got == want
+        assert any(ow for _, _, ow in c.chromosomes())  # the sequence whose name came back
+        assert ci.reads_kept == oc.reads_kept and ci.clipping_used == 100
+        check_sample(c, ci, oc)
+        check_sample(t, ti, ot)
+        assert r.text() == osnp
+        g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
+        assert r.text().decode() == g["kmer_snp"]
+        assert {k: hashlib.sha256(v).hexdigest() for k, v in got.items()} == {
+            k: v["sha256"] for k, v in g["chromosomes"].items()}
+        for key, s in (("control", c), ("target", t)):
+            assert _sha_tags(s.count_text) == g[key]["count_sha256"]
+            assert _sha_tags(s.lbc_text) == g[key]["lbc_sha256"]
+            assert _sha_tags(s.sort_uniq_text) == g[key]["sort_uniq_sha256"]
+    finally:
+        r.destroy(); c.destroy(); t.destroy()
+
+
+def test_reference_corner_inputs(ctx):
+    for fa in (b"", b"no header at all\nACGT\n", b">only\n", b">a\n" + b"ACGT" * 24 + b"\n",
+               b">a\n" + b"ACGT" * 30 + b"\n>b\n" + b"ACGTN" * 40 + b"\n>a\n" + b"GATTACA" * 20,
+               b">x\n" + b"A" * 300 + b"\n"):
+        o = oracle.OracleSample()
+        o.ingest_reference(fa)
+        o.count(20)
+        s = api.Sample(ctx)
+        s.add_fastq(fa)
+        info = s.ingest_reference()
+        s.count(20)
+        try:
+            assert info.unique_reads == o.num_reads and info.reads_kept == o.reads_kept
+            km, ct = s.table()
+            okm, oct_ = o.table()
+            assert km.shape == okm.shape and (km == okm).all() and (ct == oct_).all()
+            for tag in range(64):
+                assert s.sort_uniq_text(tag) == o.sort_uniq_text(tag)
+        finally:
+            s.destroy()
+
+
+def test_reference_tiling_properties_at_scale(ctx):
+    """20 Mb reference (config 5 cut down), sizes the oracle is not asked to follow: window
+    arithmetic, conservation of k-mer instances and strand symmetry of the table."""
+    G, k = 20_000_000, 20
+    g = api.synth_genome(777, G).tobytes()
+    fa = b">chr1\n" + b"\n".join(g[i:i + 80] for i in range(0, G // 2, 80)) + b"\n>chr2 x\n" + g[G // 2:] + b"\n"
+    s = api.Sample(ctx)
+    s.add_fastq(fa)
+    info = s.ingest_reference()
+    n_win = 2 * ((G // 2 - 100) // 2 + 1)
+    assert info.records == n_win and info.reads_kept == n_win  # no N in a synthetic genome
+    assert info.unique_reads <= 2 * n_win and info.unique_reads > 1.99 * n_win  # a random genome has no repeats
+    ci = s.count(k)
+    assert ci.instances * 2 - ci.correction_rows == info.unique_reads * (100 - k + 1)
+    km, ct = s.table()
+    assert (km[1:] > km[:-1]).all()
+    assert int(ct.astype(np.uint64).sum()) == info.unique_reads * (100 - k + 1)
+    rc = np.zeros_like(km)
+    v = km.copy()
+    for _ in range(k):
+        rc = (rc << np.uint64(2)) | (np.uint64(3) - (v & np.uint64(3)))
+        v >>= np.uint64(2)
+    idx = np.searchsorted(km, rc)
+    assert (km[idx] == rc).all() and (ct[idx] == ct).all()
+    s.destroy()

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import oracle
 from tests import pyref
-from tests.cases import CASES, make_inputs, revcomp
+from tests.cases import CASES, REF_CASES, make_inputs, make_ref_inputs, revcomp
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TAGS = oracle.TAGS
@@ -95,7 +95,7 @@ def test_oracle_strand_symmetry(built):
 def _goldens():
     if not os.path.isdir(GOLDEN):
         return []
-    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json"))
+    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json") and f[:-5] in CASES)
 
 
 @pytest.mark.parametrize("name", _goldens())
@@ -117,3 +117,39 @@ def test_oracle_matches_reference_golden(name, built):
     # "clipping : N" lines of <t>.log: one per mkSortUniq call, target first (ped.pl:291-297)
     want = [f"clipping : {case['clipping']}"] if case.get("clipping") else []  # the argument echo (ped.pl:105)
     assert g["clipping_lines"] == want + [f"clipping : {t.clipping_used}", f"clipping : {c.clipping_used}"]
+
+
+@pytest.mark.parametrize("name", sorted(REF_CASES))
+def test_oracle_reference_as_control_matches_reference_golden(name, built):
+    """a10: mkChrFromFile + mkControlRead (ped.pl:1027-1136) -- the chromosome files, the tiled
+    reference's sort_uniq/, count/, lbc/ and the edge list against ped.pl's own outputs
+    (scripts/make_golden_ref.py)."""
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    fa, ft = make_ref_inputs(REF_CASES[name])
+    chrs = oracle.ref_chromosomes(fa)
+    assert {k: (len(v), hashlib.sha256(v).hexdigest()) for k, v in chrs.items()} == {
+        k: (v["length"], v["sha256"]) for k, v in g["chromosomes"].items()}
+    c, t, snp = oracle.run_ref(fa, ft, g["k"])
+    for key, o in (("control", c), ("target", t)):
+        sha, rows = _sha_tags(o.sort_uniq_text)
+        assert (rows, sha) == (g[key]["sort_uniq_rows"], g[key]["sort_uniq_sha256"]), (key, "sort_uniq")
+        sha, rows = _sha_tags(o.count_text)
+        assert (rows, sha) == (g[key]["count_rows"], g[key]["count_sha256"]), (key, "count")
+        sha, rows = _sha_tags(o.lbc_text)
+        assert (rows, sha) == (g[key]["lbc_rows"], g[key]["lbc_sha256"]), (key, "lbc")
+    assert snp.decode() == g["kmer_snp"]
+
+
+def test_oracle_reference_parsing_corner_cases(built):
+    """Header forms (ped.pl:1045-1050) and what the tiling does at the edges."""
+    fa = b">chr007 x\nACGT\n>Chr3\nAC\n>7\nGGGG\n>\nTT\n> spaced\nCC\n>scaf_1|a b\nacgtnRYK\n"
+    chrs = oracle.ref_chromosomes(fa)
+    # chr007 -> 7, then ">7" truncates it; ">" and "> spaced" both name the file "chr"
+    assert chrs == {"chr7": b"GGGG", "chr3": b"AC", "chr": b"CC", "chrscaf_1|a": b"ACGTNNNN"}
+    s = oracle.OracleSample()
+    s.ingest_reference(b">a\n" + b"ACGT" * 30 + b"\n", window=100, step=2)  # 120 bases: windows at 0..20
+    assert s.reads_kept == 11
+    s = oracle.OracleSample()
+    s.ingest_reference(b">a\n" + b"ACGT" * 24 + b"\n")  # 96 bases: no window
+    assert s.num_reads == 0
