@@ -135,7 +135,8 @@ struct KeyBudget<uint64_t> {
 template <typename KT, int NT, int RPW, bool CONTIG, int KC>
 __global__ void __launch_bounds__(PT_THREADS, 2)
     k_part_scatter(const uint64_t* __restrict__ words, int W, int L, int k_rt, uint64_t n_reads, int a_rt, int nranks,
-                   unsigned long long* __restrict__ cur, PeerPtrs dst) {
+                   unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
+                   int* __restrict__ overflow, PeerPtrs dst) {
     const int k = KC ? KC : k_rt;
     const int a = KC ? 8 : a_rt;
     constexpr int ITEMS = NT * RPW;
@@ -190,7 +191,11 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
         if (tid < NB) {
             const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
             off[tid] = (unsigned)ex;
-            s_out[tid] = s_ptr[tid] + (g - ex);
+            // optimistic sizing (lim != null): a run that does not fit its segment is dropped and
+            // the flag raised -- the caller then sizes the bins exactly and runs again
+            const bool fits = !lim || g + c <= lim[tid];
+            if (!fits) *overflow = 1;
+            s_out[tid] = fits ? s_ptr[tid] + (g - ex) : nullptr;
         }
         __syncthreads();
 #pragma unroll
@@ -205,7 +210,10 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
         __syncthreads();
         // ---- every bin's run goes out contiguously (to the owner's memory) ----
         const unsigned n_staged = (unsigned)total;
-        for (unsigned i = tid; i < n_staged; i += PT_THREADS) s_out[sbin[i]][i] = stage[i];
+        for (unsigned i = tid; i < n_staged; i += PT_THREADS) {
+            KT* p = s_out[sbin[i]];
+            if (p) p[i] = stage[i];
+        }
     }
 }
 
@@ -216,7 +224,9 @@ constexpr int SH_GROUP = 8;  // tiles per CTA of the histogram kernel
 constexpr int SS_THREADS = 512;
 constexpr int SS_ITEMS = SUB_TILE / SS_THREADS;
 
-// largest bin with tile_prefix[bin] <= t (bins without tiles are never returned)
+// A level-A bin arrives as one or more SEGMENTS (one per source rank, or one per bin when the
+// bins were sized exactly): seg[0][s] = first element, seg[1][s] = end, seg[2][s] = bin.
+// largest segment with tile_prefix[seg] <= t (segments without tiles are never returned)
 __device__ __forceinline__ int bin_of_tile(const unsigned* __restrict__ tile_prefix, int n_bins, unsigned t) {
     int lo = 0, hi = n_bins;
     while (hi - lo > 1) {
@@ -228,7 +238,7 @@ __device__ __forceinline__ int bin_of_tile(const unsigned* __restrict__ tile_pre
 
 template <typename KT>
 __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ keys,
-                                                        const unsigned long long* __restrict__ offA,
+                                                        const unsigned long long* __restrict__ seg,
                                                         const unsigned* __restrict__ tile_prefix, int n_bins,
                                                         unsigned n_tiles, int shiftB, unsigned maskB,
                                                         unsigned* __restrict__ histB) {
@@ -240,7 +250,8 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
     const unsigned t0 = blockIdx.x * SH_GROUP;
     const unsigned t1 = t0 + SH_GROUP < n_tiles ? t0 + SH_GROUP : n_tiles;
     for (unsigned t = t0; t < t1; ++t) {
-        const int bin = bin_of_tile(tile_prefix, n_bins, t);
+        const int sg = bin_of_tile(tile_prefix, n_bins, t);
+        const int bin = (int)seg[2 * (size_t)n_bins + sg];
         if (bin != cur_bin) {
             if (cur_bin >= 0) {
                 __syncthreads();
@@ -250,8 +261,8 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
             }
             cur_bin = bin;
         }
-        const unsigned long long start = offA[bin] + (unsigned long long)(t - tile_prefix[bin]) * SUB_TILE;
-        const unsigned long long lim = offA[bin + 1];
+        const unsigned long long start = seg[sg] + (unsigned long long)(t - tile_prefix[sg]) * SUB_TILE;
+        const unsigned long long lim = seg[(size_t)n_bins + sg];
         const unsigned long long end = start + SUB_TILE < lim ? start + SUB_TILE : lim;
         for (unsigned long long i = start + tid; i < end; i += SH_THREADS)
             atomicAdd(&h[(unsigned)(keys[i] >> shiftB) & maskB], 1u);
@@ -317,7 +328,7 @@ __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, uns
 
 template <typename KT>
 __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restrict__ in, KT* __restrict__ out,
-                                                              const unsigned long long* __restrict__ offA,
+                                                              const unsigned long long* __restrict__ seg,
                                                               const unsigned* __restrict__ tile_prefix, int n_bins,
                                                               unsigned n_tiles, int shiftB, unsigned maskB,
                                                               unsigned long long* __restrict__ curB) {
@@ -330,9 +341,10 @@ __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restr
     const unsigned tid = threadIdx.x;
     const unsigned t = blockIdx.x;
     if (t >= n_tiles) return;
-    const int bin = bin_of_tile(tile_prefix, n_bins, t);
-    const unsigned long long start = offA[bin] + (unsigned long long)(t - tile_prefix[bin]) * SUB_TILE;
-    const unsigned long long lim = offA[bin + 1];
+    const int sg = bin_of_tile(tile_prefix, n_bins, t);
+    const int bin = (int)seg[2 * (size_t)n_bins + sg];
+    const unsigned long long start = seg[sg] + (unsigned long long)(t - tile_prefix[sg]) * SUB_TILE;
+    const unsigned long long lim = seg[(size_t)n_bins + sg];
     const unsigned n = (unsigned)(start + SUB_TILE < lim ? SUB_TILE : lim - start);
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
@@ -678,7 +690,8 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
 
 template <typename KT, int NT, bool CONTIG, int KC>
 void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
-                            unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st) {
+                            unsigned long long* cur, const unsigned long long* lim, int* overflow,
+                            const PeerPtrs& dst, cudaStream_t st) {
     constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
     constexpr int TILE = PT_THREADS * NT * RPW;
     constexpr size_t SMEM = (size_t)TILE * (sizeof(KT) + 1);
@@ -691,7 +704,7 @@ void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t
     const uint64_t tiles = (n_reads + (uint64_t)PT_WARPS * RPW - 1) / ((uint64_t)PT_WARPS * RPW);
     const unsigned grid = (unsigned)(tiles < (uint64_t)kNumSMs * 2 ? tiles : (uint64_t)kNumSMs * 2);
     k_part_scatter<KT, NT, RPW, CONTIG, KC>
-        <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, dst);
+        <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst);
 }
 
 // windows per lane, rounded up to an instantiated value
@@ -704,29 +717,30 @@ bool contiguous_ok(int nt, int k) { return nt - 1 + k <= 32; }
 
 template <typename KT>
 void launch_part_scatter_t(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
-                           unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st) {
+                           unsigned long long* cur, const unsigned long long* lim, int* overflow, const PeerPtrs& dst,
+                           cudaStream_t st) {
     const int nt = nt_of(L, k);
     const bool contig = contiguous_ok(nt, k);
     if (k == 20 && sizeof(KT) == 4 && contig && nt >= 2 && nt <= 6) {
         // the reference's k, short reads: k folded into the kernel
         switch (nt) {
-        case 2: launch_part_scatter_nt<KT, 2, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
-        case 3: launch_part_scatter_nt<KT, 3, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
-        case 4: launch_part_scatter_nt<KT, 4, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
-        case 5: launch_part_scatter_nt<KT, 5, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
-        default: launch_part_scatter_nt<KT, 6, true, 20>(words, W, L, k, n_reads, a, nranks, cur, dst, st); break;
+        case 2: launch_part_scatter_nt<KT, 2, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
+        case 3: launch_part_scatter_nt<KT, 3, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
+        case 4: launch_part_scatter_nt<KT, 4, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
+        case 5: launch_part_scatter_nt<KT, 5, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
+        default: launch_part_scatter_nt<KT, 6, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
         }
         return;
     }
 #define PEDK_PS(N)                                                                                        \
     case N:                                                                                               \
-        if (contig) launch_part_scatter_nt<KT, N, true, 0>(words, W, L, k, n_reads, a, nranks, cur, dst, st); \
-        else launch_part_scatter_nt<KT, N, false, 0>(words, W, L, k, n_reads, a, nranks, cur, dst, st);   \
+        if (contig) launch_part_scatter_nt<KT, N, true, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); \
+        else launch_part_scatter_nt<KT, N, false, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);   \
         break;
     switch (nt) {
         PEDK_PS(1) PEDK_PS(2) PEDK_PS(3) PEDK_PS(4) PEDK_PS(5) PEDK_PS(6) PEDK_PS(8) PEDK_PS(12)
     default:
-        launch_part_scatter_nt<KT, 16, false, 0>(words, W, L, k, n_reads, a, nranks, cur, dst, st);
+        launch_part_scatter_nt<KT, 16, false, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);
     }
 #undef PEDK_PS
 }
@@ -766,19 +780,39 @@ void launch_part_count(const uint64_t* words, int W, int L, int k, uint64_t n_re
 }
 
 void launch_part_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks, int wide,
-                         unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st) {
+                         unsigned long long* cur, const unsigned long long* lim, int* overflow, const PeerPtrs& dst,
+                         cudaStream_t st) {
     if (!n_reads || L < k) return;
     if (wide)
-        launch_part_scatter_t<uint64_t>(words, W, L, k, n_reads, a, nranks, cur, dst, st);
+        launch_part_scatter_t<uint64_t>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);
     else
-        launch_part_scatter_t<uint32_t>(words, W, L, k, n_reads, a, nranks, cur, dst, st);
+        launch_part_scatter_t<uint32_t>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
 unsigned sub_tile_keys() { return SUB_TILE; }
 
-void launch_sub_hist(const void* keys, int wide, const unsigned long long* offA, const unsigned* tile_prefix,
-                     int n_bins, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st) {
+namespace {
+__global__ void k_cursor_counts(const unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
+                                unsigned long long cap, int n, unsigned long long* __restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long start = lim[i] - cap;
+    const unsigned long long c = cur[i] - start;
+    cnt[i] = c > cap ? cap : c;  // beyond cap only after an overflow (the flag is raised then)
+}
+}  // namespace
+
+void launch_cursor_counts(const unsigned long long* cur, const unsigned long long* lim, unsigned long long cap, int n,
+                          unsigned long long* cnt, cudaStream_t st) {
+    k_cursor_counts<<<(n + 255) / 256, 256, 0, st>>>(cur, lim, cap, n, cnt);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
+                     int n_seg, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st) {
+    const unsigned long long* offA = seg;
+    const int n_bins = n_seg;
     if (!n_tiles) return;
     const int shiftB = 2 * k - a - b;
     const unsigned maskB = (1u << b) - 1;
@@ -792,9 +826,11 @@ void launch_sub_hist(const void* keys, int wide, const unsigned long long* offA,
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* offA,
-                        const unsigned* tile_prefix, int n_bins, unsigned n_tiles, int k, int a, int b,
+void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* seg,
+                        const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int k, int a, int b,
                         unsigned long long* curB, cudaStream_t st) {
+    const unsigned long long* offA = seg;
+    const int n_bins = n_seg;
     if (!n_tiles) return;
     const int shiftB = 2 * k - a - b;
     const unsigned maskB = (1u << b) - 1;

@@ -23,13 +23,27 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* a, uint64_t 
     return lo;
 }
 
+template <int NPASS>
 __global__ void __launch_bounds__(256) k_copy_rows(const uint64_t* __restrict__ src_key,
                                                   const uint32_t* __restrict__ src_val, uint64_t n,
                                                   uint64_t* __restrict__ dst_key, uint32_t* __restrict__ dst_val,
-                                                  uint32_t or_bits) {
+                                                  uint32_t or_bits, unsigned long long* __restrict__ digit_hist) {
+    __shared__ unsigned h[NPASS ? NPASS : 1][256];
+    for (int i = threadIdx.x; i < NPASS * 256; i += 256) (&h[0][0])[i] = 0;
+    if (NPASS) __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        dst_key[i] = src_key[i];
+        const uint64_t k = src_key[i];
+        dst_key[i] = k;
         dst_val[i] = src_val[i] | or_bits;
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+    }
+    if (NPASS) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < NPASS * 256; i += 256) {
+            const unsigned c = (&h[0][0])[i];
+            if (c) atomicAdd(&digit_hist[i], (unsigned long long)c);
+        }
     }
 }
 
@@ -193,11 +207,18 @@ __global__ void k_lookup_groups(const uint64_t* __restrict__ row_key, const uint
 }  // namespace
 
 void launch_copy_rows(const uint64_t* src_key, const uint32_t* src_val, uint64_t n, uint64_t* dst_key,
-                      uint32_t* dst_val, uint32_t or_bits, cudaStream_t st) {
+                      uint32_t* dst_val, uint32_t or_bits, unsigned long long* digit_hist, int n_pass,
+                      cudaStream_t st) {
     if (!n) return;
     uint64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
     unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 16 ? blocks : (uint64_t)kNumSMs * 16);
-    k_copy_rows<<<grid, 256, 0, st>>>(src_key, src_val, n, dst_key, dst_val, or_bits);
+#define PEDK_CR(N) \
+    case N: k_copy_rows<N><<<grid, 256, 0, st>>>(src_key, src_val, n, dst_key, dst_val, or_bits, digit_hist); break;
+    switch (digit_hist ? n_pass : 0) {
+        PEDK_CR(0) PEDK_CR(1) PEDK_CR(2) PEDK_CR(3) PEDK_CR(4) PEDK_CR(5) PEDK_CR(6) PEDK_CR(7)
+    default: k_copy_rows<8><<<grid, 256, 0, st>>>(src_key, src_val, n, dst_key, dst_val, or_bits, digit_hist);
+    }
+#undef PEDK_CR
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

@@ -83,17 +83,24 @@ void launch_part_count(const uint64_t* words, int W, int L, int k, uint64_t n_re
                        unsigned long long* histA, cudaStream_t st);
 // every canonical k-mer of the reads -> low 2k-a bits of its hash, appended to its bin's run:
 // cur[bin] = next free element of that bin inside the buffer of the rank that owns it
-// (dst.p[owner], owner = bin * nranks >> a; peer memory over NVLink for owner != me)
+// (dst.p[owner], owner = bin * nranks >> a; peer memory over NVLink for owner != me).
+// lim != null (optimistic sizing): lim[bin] = end of the segment this rank may fill; a run that
+// does not fit is dropped and *overflow set.
 void launch_part_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks, int wide,
-                         unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st);
+                         unsigned long long* cur, const unsigned long long* lim, int* overflow, const PeerPtrs& dst,
+                         cudaStream_t st);
 unsigned sub_tile_keys();
-// level-A bins (offA[n_bins + 1] element offsets, tile_prefix[n_bins + 1] = tiles of sub_tile_keys()
-// before each bin) -> histB[bin * 256 + sub]
-void launch_sub_hist(const void* keys, int wide, const unsigned long long* offA, const unsigned* tile_prefix,
-                     int n_bins, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st);
+// optimistic sizing: cnt[i] = cur[i] - (lim[i] - cap), what really went into segment i
+void launch_cursor_counts(const unsigned long long* cur, const unsigned long long* lim, unsigned long long cap, int n,
+                          unsigned long long* cnt, cudaStream_t st);
+// A level-A bin is held as one or more segments: seg[s] = first element, seg[n_seg + s] = end,
+// seg[2 n_seg + s] = bin; tile_prefix[n_seg + 1] = tiles of sub_tile_keys() before each segment.
+// -> histB[bin * 256 + sub]
+void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
+                     int n_seg, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st);
 // curB[bin * 256 + sub] = next free element of that bucket in `out`
-void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* offA,
-                        const unsigned* tile_prefix, int n_bins, unsigned n_tiles, int k, int a, int b,
+void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* seg,
+                        const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int k, int a, int b,
                         unsigned long long* curB, cudaStream_t st);
 // buckets (offB[n_buckets + 1]) -> table rows, as launch_count_rows below; ticket = 1 device
 // word, err = device flag raised when a bucket cannot be split any further
@@ -132,8 +139,10 @@ void launch_count_rows(const uint64_t* keys, size_t n, int k, int strand, int sa
 
 // ---------------- S5/S6: lbc groups and edges (edges.cu) ----------------
 // dst rows = src rows with or_bits set in the value (bit 31 marks the target sample)
+// digit_hist != null: also accumulates the 8-bit digit histograms of the keys for n_pass passes
 void launch_copy_rows(const uint64_t* src_key, const uint32_t* src_val, uint64_t n, uint64_t* dst_key,
-                      uint32_t* dst_val, uint32_t or_bits, cudaStream_t st);
+                      uint32_t* dst_val, uint32_t or_bits, unsigned long long* digit_hist, int n_pass,
+                      cudaStream_t st);
 // first[(sample*64 + tag)] = smallest key of that sample in 3-nt bucket `tag` (preset ~0)
 void launch_first_of_bucket(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int k,
                             unsigned long long* first, cudaStream_t st);

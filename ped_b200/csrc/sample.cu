@@ -479,90 +479,171 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     const size_t ksz = wide ? 8 : 4;
     const int exch_stage = multi ? PEDK_ST_EXCHANGE : PEDK_ST_EXTRACT;
 
-    // (1) exact sizes of the level-A bins: one pass over the packed reads, no stores
-    DBuf<unsigned long long> histA(ctx, (size_t)NBINS_MAX * (PEDK_MAX_RANKS + 1));
     uint64_t packed_bytes = 0, m_local = 0;
-    {
-        for (const ReadGroup& g : s->groups)
-            if (g.L >= k && g.n) {
-                packed_bytes += g.n * (uint64_t)g.W * 8;
-                m_local += g.n * (uint64_t)(g.L - k + 1);
-            }
-        StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART_COUNT, packed_bytes);
-        PEDK_CUDA_TRY(cudaMemsetAsync(histA.p, 0, histA.bytes(), st));
-        for (const ReadGroup& g : s->groups)
-            if (g.L >= k && g.n) launch_part_count(g.words.p, g.W, g.L, k, g.n, a, histA.p, st);
-    }
-    std::vector<unsigned long long> all((size_t)NBINS_MAX * R, 0);
-    if (multi) {
-        comm_allgather_u64(ctx, histA.p, histA.p + NBINS_MAX, NBINS_MAX);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p + NBINS_MAX, all.size() * 8, cudaMemcpyDeviceToHost, st));
-    } else {
-        PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, (size_t)NBINS_MAX * 8, cudaMemcpyDeviceToHost, st));
-    }
-    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-    ctx->stats.d2h_bytes += all.size() * 8;
-    trace(ctx, "  bins: counts");
-
-    // (2) the plan: where every (source rank, bin) run starts inside the owner's buffer
-    const unsigned TILE = sub_tile_keys();
-    std::vector<unsigned long long> offA((size_t)nbA + 1, 0), curA(NBINS_MAX, 0), owner_fill(R, 0);
-    std::vector<unsigned> tile_prefix((size_t)nbA + 1, 0);
-    uint64_t sent = 0;
-    for (int bin = 0; bin < nbA; ++bin) {
-        const int owner = (int)(((uint64_t)bin * (uint64_t)R) >> a);
-        unsigned long long tot = 0, before_me = 0;
-        for (int src = 0; src < R; ++src) {
-            const unsigned long long c = all[(size_t)src * NBINS_MAX + bin];
-            if (src < me) before_me += c;
-            tot += c;
+    for (const ReadGroup& g : s->groups)
+        if (g.L >= k && g.n) {
+            packed_bytes += g.n * (uint64_t)g.W * 8;
+            m_local += g.n * (uint64_t)(g.L - k + 1);
         }
-        curA[bin] = owner_fill[owner] + before_me;
-        owner_fill[owner] += tot;
-        const unsigned long long mine = owner == me ? tot : 0;
-        offA[bin + 1] = offA[bin] + mine;
-        const unsigned long long tiles = (mine + TILE - 1) / TILE;
-        if ((unsigned long long)tile_prefix[bin] + tiles > 0xfffffff0ull)
-            throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^45 k-mer instances on one GPU");
-        tile_prefix[bin + 1] = tile_prefix[bin] + (unsigned)tiles;
-        sent += all[(size_t)me * NBINS_MAX + bin];
-    }
-    if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
-    const uint64_t m = offA[nbA];
-    const unsigned n_tiles = tile_prefix[nbA];
-    *m_out = m;
-
-    DBuf<unsigned long long> plan(ctx, (size_t)NBINS_MAX + nbA + 1);
-    DBuf<unsigned> tprefix(ctx, (size_t)nbA + 1);
-    unsigned long long* d_curA = plan.p;
-    unsigned long long* d_offA = plan.p + NBINS_MAX;
-    PEDK_CUDA_TRY(cudaMemcpyAsync(d_curA, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
-    PEDK_CUDA_TRY(cudaMemcpyAsync(d_offA, offA.data(), ((size_t)nbA + 1) * 8, cudaMemcpyHostToDevice, st));
-    PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)nbA + 1) * 4, cudaMemcpyHostToDevice, st));
-
-    // (3) extract + hash + bin, each bin's run stored straight into its owner's buffer
-    DBuf<uint8_t> keysA(ctx, m * ksz);
-    PeerPtrs dst;
-    if (multi) {
-        void* peers[PEDK_MAX_RANKS];
-        comm_peer_pointers(ctx, keysA.p, peers);
-        for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
-    } else {
-        dst.p[0] = reinterpret_cast<uint64_t*>(keysA.p);
-    }
-    {
+    const unsigned TILE = sub_tile_keys();
+    // what the level-A pass leaves for the level-B passes: the segments of this rank's bins
+    std::vector<unsigned long long> seg_start, seg_end, seg_bin;
+    DBuf<uint8_t> keysA;
+    DBuf<unsigned long long> histA(ctx, (size_t)(NBINS_MAX + 1) * (PEDK_MAX_RANKS + 1));
+    std::vector<unsigned long long> all((size_t)(NBINS_MAX + 1) * R, 0);
+    auto owner_of_bin = [&](int bin) { return (int)(((uint64_t)bin * (uint64_t)R) >> a); };
+    auto scatter_all = [&](unsigned long long* d_cur, const unsigned long long* d_lim, int* d_ovf) {
+        PeerPtrs dst;
+        if (multi) {
+            void* peers[PEDK_MAX_RANKS];
+            comm_peer_pointers(ctx, keysA.p, peers);
+            for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
+        } else {
+            dst.p[0] = reinterpret_cast<uint64_t*>(keysA.p);
+        }
         StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART, packed_bytes + m_local * ksz);
         // nobody may store into a buffer before its owner is done with the previous contents
         if (multi) comm_barrier(ctx);
         for (const ReadGroup& g : s->groups)
-            if (g.L >= k && g.n) launch_part_scatter(g.words.p, g.W, g.L, k, g.n, a, R, wide, d_curA, dst, st);
-        if (multi) comm_barrier(ctx);  // every rank's stores have landed
-    }
-    if (ctx->trace) {
+            if (g.L >= k && g.n)
+                launch_part_scatter(g.words.p, g.W, g.L, k, g.n, a, R, wide, d_cur, d_lim, d_ovf, dst, st);
+    };
+
+    // (1) OPTIMISTIC: the hash spreads the k-mers evenly over the bins, so every (source rank,
+    // bin) run gets a segment of the expected size plus 1/8 (+4096) and the reads are sliced
+    // ONCE.  If a run does not fit (a k-mer with millions of instances), fall through to (2).
+    bool done = false;
+    const bool force_exact = getenv("PEDK_BUCKET_EXACT") && atoi(getenv("PEDK_BUCKET_EXACT")) != 0;
+    if (!force_exact) {
+        uint64_t m_max = m_local;
+        if (multi) {
+            PEDK_CUDA_TRY(cudaMemcpyAsync(histA.p, &m_local, 8, cudaMemcpyHostToDevice, st));
+            comm_allgather_u64(ctx, histA.p, histA.p + 8, 1);
+            std::vector<unsigned long long> mm((size_t)R);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(mm.data(), histA.p + 8, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            for (int r = 0; r < R; ++r) m_max = std::max<uint64_t>(m_max, mm[(size_t)r]);
+        }
+        const uint64_t C = ((m_max / nbA) + (m_max / nbA) / 8 + 4096 + 31) / 32 * 32;
+        // segment of (bin, src) inside the owner's buffer: ((bin's index among the owner's bins) * R + src) * C
+        std::vector<unsigned long long> curA(NBINS_MAX, 0), limA(NBINS_MAX, 0);
+        std::vector<int> local_index(nbA, 0), owned(R, 0);
+        for (int bin = 0; bin < nbA; ++bin) {
+            const int o = owner_of_bin(bin);
+            local_index[bin] = owned[o]++;
+            curA[bin] = ((unsigned long long)local_index[bin] * R + me) * C;
+            limA[bin] = curA[bin] + C;
+        }
+        const uint64_t seg_slots = (uint64_t)owned[me] * R;
+        keysA = DBuf<uint8_t>(ctx, seg_slots * C * ksz);
+        DBuf<unsigned long long> plan(ctx, (size_t)3 * NBINS_MAX + 8);
+        unsigned long long* d_cur = plan.p;
+        unsigned long long* d_lim = plan.p + NBINS_MAX;
+        unsigned long long* d_cnt = plan.p + 2 * NBINS_MAX;  // [NBINS_MAX] counts, then the overflow flag
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_cur, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_lim, limA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, ((size_t)NBINS_MAX + 8) * 8, st));
+        int* d_ovf = reinterpret_cast<int*>(d_cnt + NBINS_MAX);
+        scatter_all(d_cur, d_lim, d_ovf);
+        // what every rank really stored: cursor - start per bin (+ the flag), to all ranks.  On
+        // several ranks this all-gather is also the fence "every rank's stores have landed".
+        launch_cursor_counts(d_cur, d_lim, C, NBINS_MAX, d_cnt, st);
+        if (multi) {
+            comm_allgather_u64(ctx, d_cnt, histA.p, NBINS_MAX + 1);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), d_cnt, ((size_t)NBINS_MAX + 1) * 8, cudaMemcpyDeviceToHost, st));
+        }
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        trace(ctx, multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+        ctx->stats.d2h_bytes += all.size() * 8;
+        bool overflow = false;
+        for (int r = 0; r < R; ++r) overflow |= all[(size_t)r * (NBINS_MAX + 1) + NBINS_MAX] != 0;
+        trace(ctx, overflow ? "  bins: extract + hash + bin (optimistic sizes overflowed)"
+                            : multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+        if (!overflow) {
+            for (int bin = 0; bin < nbA; ++bin) {
+                if (owner_of_bin(bin) != me) continue;
+                for (int src = 0; src < R; ++src) {
+                    const unsigned long long st0 = ((unsigned long long)local_index[bin] * R + src) * C;
+                    seg_start.push_back(st0);
+                    seg_end.push_back(st0 + all[(size_t)src * (NBINS_MAX + 1) + bin]);
+                    seg_bin.push_back((unsigned long long)bin);
+                }
+            }
+            uint64_t sent = 0;
+            for (int bin = 0; bin < nbA; ++bin) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
+            if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
+            done = true;
+        }
     }
+    if (!done) {
+        // (2) EXACT: size the bins with a pass over the packed reads (no stores), then slice again
+        {
+            StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART_COUNT, packed_bytes);
+            PEDK_CUDA_TRY(cudaMemsetAsync(histA.p, 0, histA.bytes(), st));
+            for (const ReadGroup& g : s->groups)
+                if (g.L >= k && g.n) launch_part_count(g.words.p, g.W, g.L, k, g.n, a, histA.p, st);
+        }
+        if (multi) {
+            comm_allgather_u64(ctx, histA.p, histA.p + NBINS_MAX + 1, NBINS_MAX + 1);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p + NBINS_MAX + 1, all.size() * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, ((size_t)NBINS_MAX + 1) * 8, cudaMemcpyDeviceToHost, st));
+        }
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += all.size() * 8;
+        trace(ctx, "  bins: counts");
+        std::vector<unsigned long long> curA(NBINS_MAX, 0), owner_fill(R, 0);
+        uint64_t sent = 0;
+        for (int bin = 0; bin < nbA; ++bin) {
+            const int owner = owner_of_bin(bin);
+            unsigned long long tot = 0, before_me = 0;
+            for (int src = 0; src < R; ++src) {
+                const unsigned long long c = all[(size_t)src * (NBINS_MAX + 1) + bin];
+                if (src < me) before_me += c;
+                tot += c;
+            }
+            curA[bin] = owner_fill[owner] + before_me;
+            if (owner == me) {
+                seg_start.push_back(owner_fill[owner]);
+                seg_end.push_back(owner_fill[owner] + tot);
+                seg_bin.push_back((unsigned long long)bin);
+            }
+            owner_fill[owner] += tot;
+            sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
+        }
+        if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
+        keysA = DBuf<uint8_t>(ctx, owner_fill[me] * ksz);
+        DBuf<unsigned long long> plan(ctx, NBINS_MAX);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(plan.p, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+        scatter_all(plan.p, nullptr, nullptr);
+        if (multi) comm_barrier(ctx);  // every rank's stores have landed
+        if (ctx->trace) {
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            trace(ctx, multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+        }
+    }
+    // the segments of this rank's bins, their tiles
+    const int n_seg = (int)seg_start.size();
+    std::vector<unsigned> tile_prefix((size_t)n_seg + 1, 0);
+    uint64_t m = 0;
+    for (int sg = 0; sg < n_seg; ++sg) {
+        const unsigned long long len = seg_end[(size_t)sg] - seg_start[(size_t)sg];
+        const unsigned long long tiles = (len + TILE - 1) / TILE;
+        if ((unsigned long long)tile_prefix[(size_t)sg] + tiles > 0xfffffff0ull)
+            throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^45 k-mer instances on one GPU");
+        tile_prefix[(size_t)sg + 1] = tile_prefix[(size_t)sg] + (unsigned)tiles;
+        m += len;
+    }
+    const unsigned n_tiles = tile_prefix[(size_t)n_seg];
+    *m_out = m;
     if (m == 0) return;
+    DBuf<unsigned long long> d_seg(ctx, (size_t)3 * n_seg);
+    DBuf<unsigned> tprefix(ctx, (size_t)n_seg + 1);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p, seg_start.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + n_seg, seg_end.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + 2 * n_seg, seg_bin.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
 
     // (4) exact bucket sizes, (5) their offsets
     const size_t n_buckets = (size_t)nbA * NBINS_MAX;
@@ -572,7 +653,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     {
         StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_HIST, m * ksz);
         PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
-        launch_sub_hist(keysA.p, wide, d_offA, tprefix.p, nbA, n_tiles, k, a, b, histB.p, st);
+        launch_sub_hist(keysA.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, histB.p, st);
     }
     {
         StageScope sc(ctx, PEDK_ST_SORT, 3);
@@ -585,7 +666,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     DBuf<uint8_t> keysB(ctx, m * ksz);
     {
         StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
-        launch_sub_scatter(keysA.p, keysB.p, wide, d_offA, tprefix.p, nbA, n_tiles, k, a, b, curB.p, st);
+        launch_sub_scatter(keysA.p, keysB.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, curB.p, st);
     }
     if (ctx->trace) {
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
@@ -593,7 +674,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     }
     // (7) one CTA per bucket: count, rows.  The rows first land in the level-A buffer (free
     // now: room for a row per three 4-byte instances), then move to exact-size arrays.
-    uint64_t cap = m * ksz / 12;
+    uint64_t cap = keysA.n / 12;
     uint64_t* tmp_key = reinterpret_cast<uint64_t*>(keysA.p);
     uint32_t* tmp_val = reinterpret_cast<uint32_t*>(tmp_key + cap);
     DBuf<uint64_t> big_key;
@@ -623,12 +704,14 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     }
     check_err_flag(ctx, "bucket count");
     ctx->stats.kc_bytes[PEDK_KC_BUCKET_COUNT] += s->n_rows * 12;
-    s->rkey = DBuf<uint64_t>(ctx, s->n_rows);
-    s->rval = DBuf<uint32_t>(ctx, s->n_rows);
-    if (s->n_rows) {
-        StageScope sc(ctx, PEDK_ST_COUNT, 0);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(s->rkey.p, tmp_key, s->n_rows * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-        PEDK_CUDA_TRY(cudaMemcpyAsync(s->rval.p, tmp_val, s->n_rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if (big_key.p) {
+        s->rkey = std::move(big_key);
+        s->rval = std::move(big_val);
+    } else {
+        // the rows stay in the level-A buffer: no copy to exact-size arrays
+        s->row_key_in_store = tmp_key;
+        s->row_val_in_store = tmp_val;
+        s->row_store = std::move(keysA);
     }
 }
 
@@ -644,6 +727,7 @@ void do_count(pedk_sample* s, int k) {
     s->n_corr = 0;
     s->rkey.reset();
     s->rval.reset();
+    s->row_store.reset();
     s->ckey.reset();
     s->ccnt.reset();
     s->counted = false;
@@ -825,6 +909,11 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     if (cap == 0 && !multi) return;
     DBuf<uint64_t> ka(ctx, cap), kb;
     DBuf<uint32_t> va(ctx, cap), vb;
+    DBuf<unsigned long long> hist(ctx, 8 * 256);
+    PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+    // one rank: the digit histograms of the row sort are taken while the rows are copied
+    const bool single_rank = !multi;
+    bool hist_done = single_rank;
     uint64_t rows = 0;
     pedk_sample* ss[2] = {control, target};
     for (int i = 0; i < 2; ++i) {
@@ -841,16 +930,17 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
             PEDK_CUDA_TRY(cudaStreamSynchronize(st));
             ctx->stats.h2d_bytes += m * 12;
             rows += m;
+            hist_done = false;
             continue;
         }
         if (!s || !s->n_rows) continue;
         {
             StageScope sc(ctx, PEDK_ST_EXPAND, 1);
-            launch_copy_rows(s->rkey.p, s->rval.p, s->n_rows, ka.p + rows, va.p + rows, i ? 0x80000000u : 0u, st);
+            launch_copy_rows(s->row_key_ptr(), s->row_val_ptr(), s->n_rows, ka.p + rows, va.p + rows, i ? 0x80000000u : 0u,
+                             single_rank ? hist.p : nullptr, n_pass, st);
         }
         rows += s->n_rows;
     }
-    DBuf<unsigned long long> hist(ctx, 8 * 256);
     if (multi) {
         // rows move to the rank that holds their 3-nt bucket: contiguous bucket ranges, balanced
         // on the histogram of both samples over all ranks, so every (k-1)-mer group and every
@@ -888,8 +978,8 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     if (rows == 0) return;
     kb = DBuf<uint64_t>(ctx, rows);
     vb = DBuf<uint32_t>(ctx, rows);
-    PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-    {
+    if (!hist_done) {
+        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
         StageScope sc(ctx, PEDK_ST_ROWSORT, 1);
         launch_digit_hist(ka.p, rows, hist.p, n_pass, st);
     }

@@ -32,6 +32,13 @@ struct pedk_sample {
     uint64_t n_rows = 0;   // rows of the strand table (K and revcomp K), unordered, in HBM
     pedk::DBuf<uint64_t> rkey;
     pedk::DBuf<uint32_t> rval;
+    // bucketed path: the rows stay where the count kernel wrote them (the level-A buffer,
+    // free by then) instead of being copied to exact-size arrays
+    pedk::DBuf<uint8_t> row_store;
+    const uint64_t* row_key_ptr() const { return row_store.p ? row_key_in_store : rkey.p; }
+    const uint32_t* row_val_ptr() const { return row_store.p ? row_val_in_store : rval.p; }
+    const uint64_t* row_key_in_store = nullptr;
+    const uint32_t* row_val_in_store = nullptr;
     uint64_t n_corr = 0;   // sorted (k-mer, windows of palindromic reads) corrections
     pedk::DBuf<uint64_t> ckey;
     pedk::DBuf<uint32_t> ccnt;

@@ -205,11 +205,12 @@ def test_full_size_properties(ctx):
 
 
 @pytest.mark.parametrize("env", [{"PEDK_BUCKET_SLOTS_LOG2": "10"}, {"PEDK_BUCKET_SLOTS_LOG2": "10", "PEDK_BUCKET_B": "1"},
-                                 {"PEDK_BUCKET_B": "2"}, {"PEDK_COUNT_MODE": "sort"}])
+                                 {"PEDK_BUCKET_B": "2"}, {"PEDK_BUCKET_EXACT": "1"}, {"PEDK_COUNT_MODE": "sort"}])
 @pytest.mark.parametrize("k", [20, 31])
 def test_bucket_table_overflow_and_legacy_path(ctx, env, k):
     """The per-bucket hash table is forced to overflow (1024 slots, buckets 128x larger) so that
-    buckets are split by further hash bits and re-read; PEDK_COUNT_MODE=sort is the extract +
+    buckets are split by further hash bits and re-read; PEDK_BUCKET_EXACT=1 sizes the level-A bins
+    with a counting pass instead of optimistically; PEDK_COUNT_MODE=sort is the extract +
     LSD radix sort + run-length path the buckets replaced.  All must give the reference's table."""
     case = dict(kind="synth", cfg=13, genome=300_000, reads=60_000, L=150, snp_ppm=1000, indel_ppm=100,
                 err_ppm=2000, n_ppm=1000, dup_ppm=0)
