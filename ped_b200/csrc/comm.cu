@@ -191,13 +191,86 @@ __global__ void __launch_bounds__(256) k_bucket_hist(const uint64_t* __restrict_
     __shared__ unsigned h[64];
     if (threadIdx.x < 64) h[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        unsigned b = (unsigned)(key[i] >> shift);
-        unsigned m = __match_any_sync(__activemask(), b);
-        if ((m & lanemask_lt()) == 0) atomicAdd(&h[b], __popc(m));
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[(unsigned)(key[i] >> shift) & 63u], 1u);
     __syncthreads();
     if (threadIdx.x < 64 && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+// Table rows -> the rank that holds their 3-nt bucket, in ONE kernel: a tile of rows is grouped
+// by destination in shared memory and every destination's run is stored straight into that
+// rank's (key, value) arrays (peer memory over NVLink for the other ranks), at the slots this
+// rank reserved with one atomic per (tile, destination).  Replaces copy + pack + count +
+// scatter + ncclSend/Recv + unpack.
+constexpr int RR_THREADS = 256;
+constexpr int RR_ITEMS = 8;
+constexpr int RR_TILE = RR_THREADS * RR_ITEMS;
+
+struct RowPeers {
+    uint64_t* key[PEDK_MAX_RANKS];
+    uint32_t* val[PEDK_MAX_RANKS];
+    uint8_t owner[64];
+};
+
+__global__ void __launch_bounds__(RR_THREADS) k_rows_route(const uint64_t* __restrict__ key,
+                                                          const uint32_t* __restrict__ val, uint64_t n,
+                                                          uint32_t or_bits, int shift, int nranks, RowPeers peers,
+                                                          unsigned long long* __restrict__ cursors) {
+    __shared__ uint64_t s_key[RR_TILE];
+    __shared__ uint32_t s_val[RR_TILE];
+    __shared__ uint8_t s_dst[RR_TILE];
+    __shared__ unsigned cnt[PEDK_MAX_RANKS], off[PEDK_MAX_RANKS + 1];
+    __shared__ unsigned long long base[PEDK_MAX_RANKS];
+    const unsigned tid = threadIdx.x;
+    const uint64_t n_tiles = (n + RR_TILE - 1) / RR_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid < PEDK_MAX_RANKS) cnt[tid] = 0;
+        __syncthreads();
+        uint64_t k[RR_ITEMS];
+        uint32_t v[RR_ITEMS];
+        unsigned meta[RR_ITEMS];  // dest << 16 | rank inside (tile, dest); ~0: no row
+#pragma unroll
+        for (int j = 0; j < RR_ITEMS; ++j) {
+            const uint64_t i = tile * RR_TILE + (uint64_t)j * RR_THREADS + tid;
+            meta[j] = 0xffffffffu;
+            if (i < n) {
+                k[j] = key[i];
+                v[j] = val[i] | or_bits;
+                const unsigned d = peers.owner[(unsigned)(k[j] >> shift) & 63u];
+                meta[j] = (d << 16) | atomicAdd(&cnt[d], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned acc = 0;
+            for (int d = 0; d < nranks; ++d) {
+                off[d] = acc;
+                acc += cnt[d];
+            }
+            off[nranks] = acc;
+        }
+        if ((int)tid < nranks) base[tid] = cnt[tid] ? atomicAdd(&cursors[tid], (unsigned long long)cnt[tid]) : 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RR_ITEMS; ++j) {
+            if (meta[j] != 0xffffffffu) {
+                const unsigned d = meta[j] >> 16;
+                const unsigned p = off[d] + (meta[j] & 0xffffu);
+                s_key[p] = k[j];
+                s_val[p] = v[j];
+                s_dst[p] = (uint8_t)d;
+            }
+        }
+        __syncthreads();
+        const unsigned total = off[nranks];
+        for (unsigned i = tid; i < total; i += RR_THREADS) {
+            const unsigned d = s_dst[i];
+            const unsigned long long o = base[d] + (i - off[d]);
+            peers.key[d][o] = s_key[i];
+            peers.val[d][o] = s_val[i];
+        }
+        __syncthreads();
+    }
 }
 
 unsigned grid_for(uint64_t n) {
@@ -308,6 +381,63 @@ void exchange_records(pedk_ctx* ctx, const uint64_t* rec, uint64_t n, DestSpec s
     }
     // the send buffer goes back to the allocator in stream order
     ctx->stats.kernel_launches += 2;
+}
+
+}  // namespace pedk (reopened below)
+
+namespace pedk {
+
+// Both samples' strand rows -> the ranks that own their 3-nt buckets (see k_rows_route).
+// src_key/src_val/src_n/or_bits: the row stores of the (up to two) samples.  local_hist64 /
+// global_hist64: this rank's and all ranks' rows per bucket (host).  Returns this rank's rows
+// in *ka / *va (unordered).
+void route_rows(pedk_ctx* ctx, const uint64_t* const* src_key, const uint32_t* const* src_val, const uint64_t* src_n,
+                const uint32_t* or_bits, int n_src, int k, const uint64_t* local_hist64,
+                const uint64_t* global_hist64, DBuf<uint64_t>* ka, DBuf<uint32_t>* va, uint64_t* n_rows) {
+    cudaStream_t st = ctx->stream;
+    const int R = ctx->nranks, me = ctx->rank;
+    RowPeers peers;
+    plan_bucket_owners(global_hist64, R, peers.owner);
+    // rows this rank sends to every rank, then the whole matrix on every rank
+    unsigned long long mine[PEDK_MAX_RANKS] = {0};
+    for (int b = 0; b < 64; ++b) mine[peers.owner[b]] += local_hist64[b];
+    DBuf<unsigned long long> cbuf(ctx, (size_t)PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 2));
+    std::vector<unsigned long long> h;
+    PEDK_CUDA_TRY(cudaMemcpyAsync(cbuf.p, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    comm_count_matrix(ctx, cbuf.p, cbuf.p + PEDK_MAX_RANKS, &h);
+    uint64_t recv = 0;
+    unsigned long long start[PEDK_MAX_RANKS] = {0};
+    for (int src = 0; src < R; ++src) recv += h[(size_t)src * PEDK_MAX_RANKS + me];
+    for (int d = 0; d < R; ++d)
+        for (int src = 0; src < me; ++src) start[d] += h[(size_t)src * PEDK_MAX_RANKS + d];
+    *n_rows = recv;
+    *ka = DBuf<uint64_t>(ctx, recv);
+    *va = DBuf<uint32_t>(ctx, recv);
+    void* pk[PEDK_MAX_RANKS];
+    void* pv[PEDK_MAX_RANKS];
+    comm_peer_pointers(ctx, ka->p, pk);
+    comm_peer_pointers(ctx, va->p, pv);
+    for (int d = 0; d < R; ++d) {
+        peers.key[d] = static_cast<uint64_t*>(pk[d]);
+        peers.val[d] = static_cast<uint32_t*>(pv[d]);
+    }
+    unsigned long long* cursors = cbuf.p + PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 1);
+    StageScope sc(ctx, PEDK_ST_EXCHANGE, 2);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(cursors, start, sizeof start, cudaMemcpyHostToDevice, st));
+    comm_barrier(ctx);  // every rank's receive arrays exist and are free
+    for (int i = 0; i < n_src; ++i) {
+        if (!src_n[i]) continue;
+        const uint64_t tiles = (src_n[i] + RR_TILE - 1) / RR_TILE;
+        const unsigned grid = (unsigned)(tiles < (uint64_t)kNumSMs * 8 ? tiles : (uint64_t)kNumSMs * 8);
+        k_rows_route<<<grid, RR_THREADS, 0, st>>>(src_key[i], src_val[i], src_n[i], or_bits[i], 2 * k - 6, R, peers,
+                                                  cursors);
+        PEDK_CUDA_TRY(cudaGetLastError());
+    }
+    comm_barrier(ctx);  // every rank's stores have landed
+    if (ctx->trace) {
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        trace(ctx, "  rows: route + NVLink stores");
+    }
 }
 
 // ---- NVLink peer memory through CUDA IPC --------------------------------------------------

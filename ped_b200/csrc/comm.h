@@ -35,6 +35,11 @@ void comm_barrier(pedk_ctx* ctx);
 void comm_allgather_u64(pedk_ctx* ctx, const unsigned long long* send, unsigned long long* recv, size_t n);
 void comm_count_matrix(pedk_ctx* ctx, unsigned long long* counts_dev, unsigned long long* all_dev,
                        std::vector<unsigned long long>* h);
+// both samples' strand rows -> the ranks owning their 3-nt buckets, one fused kernel per sample
+// storing into the owners' arrays over NVLink (comm.cu)
+void route_rows(pedk_ctx* ctx, const uint64_t* const* src_key, const uint32_t* const* src_val, const uint64_t* src_n,
+                const uint32_t* or_bits, int n_src, int k, const uint64_t* local_hist64,
+                const uint64_t* global_hist64, DBuf<uint64_t>* ka, DBuf<uint32_t>* va, uint64_t* n_rows);
 void launch_pal_flags(const uint64_t* words, int W, int L, uint64_t n, uint8_t* pal, cudaStream_t st);
 void launch_rows_pack(const uint64_t* key, const uint32_t* val, uint64_t n, uint64_t* rec, cudaStream_t st);
 void launch_rows_unpack(const uint64_t* rec, uint64_t n, uint64_t* key, uint32_t* val, cudaStream_t st);

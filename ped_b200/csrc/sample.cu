@@ -907,72 +907,104 @@ void build_rows(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, RowTab
     const bool multi = ctx->nranks > 1;
     out->n = 0;
     if (cap == 0 && !multi) return;
-    DBuf<uint64_t> ka(ctx, cap), kb;
-    DBuf<uint32_t> va(ctx, cap), vb;
+    DBuf<uint64_t> ka, kb;
+    DBuf<uint32_t> va, vb;
     DBuf<unsigned long long> hist(ctx, 8 * 256);
     PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-    // one rank: the digit histograms of the row sort are taken while the rows are copied
-    const bool single_rank = !multi;
-    bool hist_done = single_rank;
     uint64_t rows = 0;
     pedk_sample* ss[2] = {control, target};
-    for (int i = 0; i < 2; ++i) {
-        pedk_sample* s = ss[i];
-        if (s && s->host_only_table) {
-            // strand table read back from count files: upload it as rows
-            uint64_t m = s->h_kmer.size();
-            if (!m) continue;
-            std::vector<uint32_t> v(s->h_cnt);
-            if (i) for (auto& x : v) x |= 0x80000000u;
-            StageScope sc(ctx, PEDK_ST_COPY, 0);
-            PEDK_CUDA_TRY(cudaMemcpyAsync(ka.p + rows, s->h_kmer.data(), m * 8, cudaMemcpyHostToDevice, st));
-            PEDK_CUDA_TRY(cudaMemcpyAsync(va.p + rows, v.data(), m * 4, cudaMemcpyHostToDevice, st));
-            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-            ctx->stats.h2d_bytes += m * 12;
-            rows += m;
-            hist_done = false;
-            continue;
-        }
-        if (!s || !s->n_rows) continue;
-        {
-            StageScope sc(ctx, PEDK_ST_EXPAND, 1);
-            launch_copy_rows(s->row_key_ptr(), s->row_val_ptr(), s->n_rows, ka.p + rows, va.p + rows, i ? 0x80000000u : 0u,
-                             single_rank ? hist.p : nullptr, n_pass, st);
-        }
-        rows += s->n_rows;
-    }
-    if (multi) {
+    bool hist_done = false;
+    const bool device_rows = !(control && control->host_only_table) && !(target && target->host_only_table);
+    if (multi && device_rows) {
         // rows move to the rank that holds their 3-nt bucket: contiguous bucket ranges, balanced
         // on the histogram of both samples over all ranks, so every (k-1)-mer group and every
         // first-of-bucket row is local to one rank and rank order is key order
-        PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, 64 * sizeof(unsigned long long), st));
+        const uint64_t* sk[2];
+        const uint32_t* sv[2];
+        uint64_t sn[2];
+        uint32_t ob[2];
+        int n_src = 0;
         {
-            StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
-            launch_bucket_hist(ka.p, rows, k, hist.p, st);
+            StageScope sc(ctx, PEDK_ST_EXCHANGE, 2);
+            for (int i = 0; i < 2; ++i) {
+                pedk_sample* s = ss[i];
+                if (!s) continue;
+                sk[n_src] = s->row_key_ptr();
+                sv[n_src] = s->row_val_ptr();
+                sn[n_src] = s->n_rows;
+                ob[n_src] = i ? 0x80000000u : 0u;
+                launch_bucket_hist(sk[n_src], sn[n_src], k, hist.p, st);
+                ++n_src;
+            }
         }
+        uint64_t local64[64], global64[64];
+        PEDK_CUDA_TRY(cudaMemcpyAsync(local64, hist.p, sizeof local64, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));  // the local counts are on the host before they are summed in place
         comm_allreduce_sum(ctx, hist.p, 64);
-        uint64_t h64[64];
-        PEDK_CUDA_TRY(cudaMemcpyAsync(h64, hist.p, sizeof h64, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(global64, hist.p, sizeof global64, cudaMemcpyDeviceToHost, st));
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        DestSpec spec;
-        spec.mode = DEST_ROW;
-        spec.stride = 2;
-        spec.bucket_shift = 2 * k - 6;
-        plan_bucket_owners(h64, ctx->nranks, spec.owner);
-        DBuf<uint64_t> rec(ctx, 2 * rows), mine;
-        uint64_t n_mine = 0;
-        {
-            StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
-            launch_rows_pack(ka.p, va.p, rows, rec.p, st);
+        route_rows(ctx, sk, sv, sn, ob, n_src, k, local64, global64, &ka, &va, &rows);
+    } else {
+        ka = DBuf<uint64_t>(ctx, cap);
+        va = DBuf<uint32_t>(ctx, cap);
+        // one rank: the digit histograms of the row sort are taken while the rows are copied
+        hist_done = !multi;
+        for (int i = 0; i < 2; ++i) {
+            pedk_sample* s = ss[i];
+            if (s && s->host_only_table) {
+                // strand table read back from count files: upload it as rows
+                uint64_t m = s->h_kmer.size();
+                if (!m) continue;
+                std::vector<uint32_t> v(s->h_cnt);
+                if (i) for (auto& x : v) x |= 0x80000000u;
+                StageScope sc(ctx, PEDK_ST_COPY, 0);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(ka.p + rows, s->h_kmer.data(), m * 8, cudaMemcpyHostToDevice, st));
+                PEDK_CUDA_TRY(cudaMemcpyAsync(va.p + rows, v.data(), m * 4, cudaMemcpyHostToDevice, st));
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                ctx->stats.h2d_bytes += m * 12;
+                rows += m;
+                hist_done = false;
+                continue;
+            }
+            if (!s || !s->n_rows) continue;
+            {
+                StageScope sc(ctx, PEDK_ST_EXPAND, 1);
+                launch_copy_rows(s->row_key_ptr(), s->row_val_ptr(), s->n_rows, ka.p + rows, va.p + rows,
+                                 i ? 0x80000000u : 0u, hist_done ? hist.p : nullptr, n_pass, st);
+            }
+            rows += s->n_rows;
         }
-        exchange_records(ctx, rec.p, rows, spec, &mine, &n_mine);
-        rec.reset();
-        rows = n_mine;
-        ka = DBuf<uint64_t>(ctx, rows);
-        va = DBuf<uint32_t>(ctx, rows);
-        {
-            StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
-            launch_rows_unpack(mine.p, rows, ka.p, va.p, st);
+        if (multi) {
+            // (tables uploaded from count files: the staged all-to-all-v)
+            PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, 64 * sizeof(unsigned long long), st));
+            {
+                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+                launch_bucket_hist(ka.p, rows, k, hist.p, st);
+            }
+            comm_allreduce_sum(ctx, hist.p, 64);
+            uint64_t h64[64];
+            PEDK_CUDA_TRY(cudaMemcpyAsync(h64, hist.p, sizeof h64, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            DestSpec spec;
+            spec.mode = DEST_ROW;
+            spec.stride = 2;
+            spec.bucket_shift = 2 * k - 6;
+            plan_bucket_owners(h64, ctx->nranks, spec.owner);
+            DBuf<uint64_t> rec(ctx, 2 * rows), mine;
+            uint64_t n_mine = 0;
+            {
+                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+                launch_rows_pack(ka.p, va.p, rows, rec.p, st);
+            }
+            exchange_records(ctx, rec.p, rows, spec, &mine, &n_mine);
+            rec.reset();
+            rows = n_mine;
+            ka = DBuf<uint64_t>(ctx, rows);
+            va = DBuf<uint32_t>(ctx, rows);
+            {
+                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
+                launch_rows_unpack(mine.p, rows, ka.p, va.p, st);
+            }
         }
     }
     if (rows == 0) return;
