@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pedk", choices=["pedk", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of configs[1] (1.0 = 100 Mb genome, 20 M reads/sample)")
-    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=3_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2)
 }
 
 // ------------------------------------------------------------------ level B
-constexpr int SUB_TILE = 8192;  // keys per tile; a tile lies inside one level-A bin
+constexpr int SUB_TILE = 8192;  // keys per tile; a tile lies inside one segment of a level-A bin
 constexpr int SH_THREADS = 256;
 constexpr int SH_GROUP = 8;  // tiles per CTA of the histogram kernel
 constexpr int SS_THREADS = 512;
@@ -277,8 +277,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
 template <typename KT, bool WHOLE>
 __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, unsigned n, KT* __restrict__ out,
                                                  unsigned long long* __restrict__ cur, int shiftB, unsigned maskB,
-                                                 KT* stage, uint8_t* ssub, unsigned* hist, unsigned* off,
-                                                 KT** s_out) {
+                                                 KT* stage, unsigned* hist, unsigned* off, KT** s_out) {
     const unsigned tid = threadIdx.x;
     KT key[SS_ITEMS];
     uint32_t rank2[SS_ITEMS / 2];
@@ -309,20 +308,24 @@ __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, uns
         const unsigned r = (j & 1) ? rank2[j / 2] >> 16 : rank2[j / 2] & 0xffffu;
         if (WHOLE || r != 0xffffu) {
             const unsigned sub = (unsigned)(key[j] >> shiftB) & maskB;
-            const unsigned pos = off[sub] + r;
-            stage[pos] = key[j];
-            ssub[pos] = (uint8_t)sub;
+            stage[off[sub] + r] = key[j];
         }
     }
     __syncthreads();
+    // the sub-bin of a staged key is in the key itself: no side array (shared-memory wavefronts,
+    // not HBM, bound this kernel)
     if (WHOLE) {
 #pragma unroll
         for (int j = 0; j < SS_ITEMS; ++j) {
             const unsigned i = j * SS_THREADS + tid;
-            s_out[ssub[i]][i] = stage[i];
+            const KT kk = stage[i];
+            s_out[(unsigned)(kk >> shiftB) & maskB][i] = kk;
         }
     } else {
-        for (unsigned i = tid; i < n; i += SS_THREADS) s_out[ssub[i]][i] = stage[i];
+        for (unsigned i = tid; i < n; i += SS_THREADS) {
+            const KT kk = stage[i];
+            s_out[(unsigned)(kk >> shiftB) & maskB][i] = kk;
+        }
     }
 }
 
@@ -334,7 +337,6 @@ __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restr
                                                               unsigned long long* __restrict__ curB) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     KT* stage = reinterpret_cast<KT*>(ss_smem);
-    uint8_t* ssub = reinterpret_cast<uint8_t*>(stage + SUB_TILE);
     __shared__ unsigned hist[NB];
     __shared__ unsigned off[NB];
     __shared__ KT* s_out[NB];
@@ -349,11 +351,9 @@ __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restr
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
     if (n == SUB_TILE)
-        sub_scatter_tile<KT, true>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, ssub, hist, off,
-                                   s_out);
+        sub_scatter_tile<KT, true>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
     else
-        sub_scatter_tile<KT, false>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, ssub, hist, off,
-                                    s_out);
+        sub_scatter_tile<KT, false>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
 }
 
 // ------------------------------------------------------------------ buckets -> rows
@@ -835,7 +835,7 @@ void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long
     const int shiftB = 2 * k - a - b;
     const unsigned maskB = (1u << b) - 1;
     if (wide) {
-        constexpr size_t SMEM = (size_t)SUB_TILE * (sizeof(uint64_t) + 1);
+        constexpr size_t SMEM = (size_t)SUB_TILE * sizeof(uint64_t);
         static bool attr_set = false;
         if (!attr_set) {
             PEDK_CUDA_TRY(cudaFuncSetAttribute(k_sub_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -846,7 +846,7 @@ void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long
                                                                    static_cast<uint64_t*>(out), offA, tile_prefix,
                                                                    n_bins, n_tiles, shiftB, maskB, curB);
     } else {
-        constexpr size_t SMEM = (size_t)SUB_TILE * (sizeof(uint32_t) + 1);
+        constexpr size_t SMEM = (size_t)SUB_TILE * sizeof(uint32_t);
         k_sub_scatter<uint32_t><<<n_tiles, SS_THREADS, SMEM, st>>>(static_cast<const uint32_t*>(in),
                                                                    static_cast<uint32_t*>(out), offA, tile_prefix,
                                                                    n_bins, n_tiles, shiftB, maskB, curB);
