@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l); echo "gpus: $N"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/multi_rank_check.py tiny adversarial clip50 c1_40x > gpurun_out/multi18_n$N.log 2>&1; echo "multi check rc=$?"; grep -v "^\*\|^$\|OMP_NUM" gpurun_out/multi18_n$N.log | tail -8
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/multi_rank_check.py tiny adversarial clip50 c1_40x ref30k > gpurun_out/multi18_n$N.log 2>&1; echo "multi check rc=$?"; grep -v "^\*\|^$\|OMP_NUM" gpurun_out/multi18_n$N.log | tail -8
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench18_n$N.log 2>&1; echo "bench rc=$?"
 PEDK_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29536 bench.py --gpus $N --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench18_n${N}_trace.log 2>&1; echo "trace rc=$?"
 python - <<PY

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle  # noqa: E402
 from ped_b200 import api  # noqa: E402
-from tests.cases import CASES, make_inputs  # noqa: E402
+from tests.cases import CASES, REF_CASES, make_inputs, make_ref_inputs  # noqa: E402
 
 
 def slice_records(fq: bytes, rank: int, world: int) -> bytes:
@@ -46,14 +46,21 @@ def main():
     ctx.comm_init(idt.cpu().numpy().tobytes(), rank, world)
     ok = True
     for name in sys.argv[1:]:
-        case = CASES[name]
-        fc, ft = make_inputs(case)
-        clip = case.get("clipping", 0)
+        is_ref = name in REF_CASES
+        if is_ref:
+            # the control is the reference tiled into reads: every rank is fed the whole FASTA
+            # and keeps the windows it owns; the target's records are sliced as usual
+            fc, ft = make_ref_inputs(REF_CASES[name])
+            clip = 0
+        else:
+            case = CASES[name]
+            fc, ft = make_inputs(case)
+            clip = case.get("clipping", 0)
         c, t = api.Sample(ctx), api.Sample(ctx)
-        c.add_fastq(slice_records(fc, rank, world))
+        c.add_fastq(fc if is_ref else slice_records(fc, rank, world))
         t.add_fastq(slice_records(ft, rank, world))
         ti = t.ingest(clip)
-        ci = c.ingest(clip)
+        ci = c.ingest_reference() if is_ref else c.ingest(clip)
         c.count(20)
         t.count(20)
         r = ctx.join(c, t)
@@ -63,7 +70,7 @@ def main():
         dist.all_gather_object(parts, dict(text=r.text(), ck=ck, cc=cc, tk=tk, tc=tc,
                                            cu=int(ci.unique_reads), tu=int(ti.unique_reads)))
         if rank == 0:
-            oc, ot, osnp = oracle.run(fc, ft, 20, clip)
+            oc, ot, osnp = oracle.run_ref(fc, ft, 20) if is_ref else oracle.run(fc, ft, 20, clip)
             text = b"".join(p["text"] for p in parts)
             for key, cnt, o in (("ck", "cc", oc), ("tk", "tc", ot)):
                 km = np.concatenate([p[key] for p in parts])
