@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(PC_THREADS) k_part_count(const uint64_t* __res
 }
 
 // ------------------------------------------------------------------ level A: scatter
-constexpr int PT_THREADS = 512;
-constexpr int PT_WARPS = PT_THREADS / 32;
+// 512 threads x 20 keys per tile (two CTAs per SM); on several ranks 1024 x 20, one CTA per SM:
+// the runs a tile stores over NVLink are twice as long (~320 bytes per bin)
 
 template <typename KT>
 struct KeyBudget;
@@ -130,15 +130,23 @@ struct KeyBudget<uint64_t> {
     static constexpr int ITEMS = 12;
 };
 
+// a 1024-thread tile must keep its ranks in 16 bits and its staging area in shared memory
+template <typename KT, int NT>
+struct PT_BIG_OK {
+    static constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
+    static constexpr bool value = 1024 * NT * RPW <= 65536 && (size_t)1024 * NT * RPW * (sizeof(KT) + 1) <= 200 * 1024;
+};
+
 // NT = windows per lane per read (ceil((L-k+1)/32) rounded up to an instantiated value),
 // RPW = reads per warp per tile.
-template <typename KT, int NT, int RPW, bool CONTIG, int KC>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+template <typename KT, int NT, int RPW, bool CONTIG, int KC, int PT_THREADS>
+__global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
     k_part_scatter(const uint64_t* __restrict__ words, int W, int L, int k_rt, uint64_t n_reads, int a_rt, int nranks,
                    unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
                    int* __restrict__ overflow, PeerPtrs dst) {
     const int k = KC ? KC : k_rt;
     const int a = KC ? 8 : a_rt;
+    constexpr int PT_WARPS = PT_THREADS / 32;
     constexpr int ITEMS = NT * RPW;
     constexpr int TILE = PT_THREADS * ITEMS;
     static_assert(TILE <= 65536, "ranks are kept in 16 bits");
@@ -688,23 +696,39 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
     }
 }
 
-template <typename KT, int NT, bool CONTIG, int KC>
-void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
+template <typename KT, int NT, bool CONTIG, int KC, int PT_THREADS>
+void launch_part_scatter_th(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                             unsigned long long* cur, const unsigned long long* lim, int* overflow,
                             const PeerPtrs& dst, cudaStream_t st) {
+    constexpr int PT_WARPS = PT_THREADS / 32;
     constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
     constexpr int TILE = PT_THREADS * NT * RPW;
     constexpr size_t SMEM = (size_t)TILE * (sizeof(KT) + 1);
     static bool attr_set = false;
     if (!attr_set) {
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_part_scatter<KT, NT, RPW, CONTIG, KC>,
+        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
     const uint64_t tiles = (n_reads + (uint64_t)PT_WARPS * RPW - 1) / ((uint64_t)PT_WARPS * RPW);
-    const unsigned grid = (unsigned)(tiles < (uint64_t)kNumSMs * 2 ? tiles : (uint64_t)kNumSMs * 2);
-    k_part_scatter<KT, NT, RPW, CONTIG, KC>
+    const uint64_t resident = (uint64_t)kNumSMs * (PT_THREADS > 512 ? 1 : 2);
+    const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+    k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>
         <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst);
+}
+
+template <typename KT, int NT, bool CONTIG, int KC>
+void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
+                            unsigned long long* cur, const unsigned long long* lim, int* overflow,
+                            const PeerPtrs& dst, cudaStream_t st) {
+    // the k = 20 kernel with 32-bit words also comes with long tiles for several ranks
+    static const int big = getenv("PEDK_PART_BIG_TILE") ? atoi(getenv("PEDK_PART_BIG_TILE")) : 1;
+    if (KC == 20 && sizeof(KT) == 4 && nranks > 1 && big && PT_BIG_OK<KT, NT>::value)
+        launch_part_scatter_th<KT, NT, CONTIG, KC, (KC == 20 ? 1024 : 512)>(words, W, L, k, n_reads, a, nranks, cur,
+                                                                           lim, overflow, dst, st);
+    else
+        launch_part_scatter_th<KT, NT, CONTIG, KC, 512>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst,
+                                                        st);
 }
 
 // windows per lane, rounded up to an instantiated value

@@ -64,16 +64,12 @@ void launch_extract(const uint64_t* words, int W, int L, int k, uint64_t n_reads
 void launch_extract_pal(const uint64_t* words, const uint8_t* pal, int W, int L, int k, uint64_t n_reads,
                         uint64_t* out, unsigned long long* cursor, cudaStream_t st);
 
-// multi-GPU: extraction fused with owner binning and the exchange (kmer.cu).  Rank r's
-// receive buffer is dst.p[r] (peer memory over NVLink for r != me).
+// Peer memory of a multi-GPU job: rank r's receive buffer is p[r] (NVLink peer memory mapped
+// through CUDA IPC for r != me).
 constexpr int PEDK_MAX_PEERS = 8;
 struct PeerPtrs {
     uint64_t* p[PEDK_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
-void launch_extract_owner_count(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
-                                unsigned long long* counts, cudaStream_t st);  // (legacy sort path)
-void launch_extract_owner_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
-                                  unsigned long long* cursors, const PeerPtrs& dst, cudaStream_t st);
 
 // ---------------- S2-S4 bucketed: bin, bin again, count per bucket (bucket.cu) ----------------
 // a, b = bits of the two binning levels (common.cuh kmer_bits_a/_b); wide != 0: the stored

@@ -94,121 +94,6 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_pal(const uint64_t* __re
     }
 }
 
-// ---- multi-GPU: extraction fused with the owner binning and the exchange ----
-// owner of a canonical k-mer: common.cuh kmer_owner_rank (also comm.cu's DEST_KMER and
-// pedk_owner_of_kmer on the host)
-__device__ __forceinline__ int kmer_owner(uint64_t canon, int k, int nranks) { return kmer_owner_rank(canon, k, nranks); }
-
-constexpr int XO_MAX_ITEMS = 16;  // windows per lane per read: reads up to 512 bases
-
-// COUNT_ONLY: counts[r] += canonical k-mers of the local reads owned by rank r.
-// otherwise : every k-mer is stored straight into the receive buffer of its owner
-//             (dst.p[r] is rank r's buffer: local memory for r == me, NVLink peer memory
-//             mapped through CUDA IPC for the others), at the slots this rank was assigned
-//             (cursors[r], preset to the offset of this rank's run inside r's buffer).
-//             One kernel extracts, bins and exchanges; nothing is staged in between.
-template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(EX_THREADS) k_extract_owner(const uint64_t* __restrict__ words, int W, int L, int k,
-                                                             uint64_t n_reads, int nranks,
-                                                             unsigned long long* __restrict__ counts,
-                                                             unsigned long long* __restrict__ cursors,
-                                                             PeerPtrs dst) {
-    constexpr int NW = EX_THREADS / 32;
-    extern __shared__ __align__(16) unsigned char xo_smem[];
-    uint64_t* stage = reinterpret_cast<uint64_t*>(xo_smem);  // NW * nwin keys, grouped by owner
-    __shared__ unsigned w_cnt[NW][PEDK_MAX_PEERS];
-    __shared__ unsigned s_start[PEDK_MAX_PEERS + 1];         // where each owner's run starts in `stage`
-    __shared__ unsigned long long b_base[PEDK_MAX_PEERS];    // ... and in the owner's receive buffer
-    __shared__ uint64_t* s_dst[PEDK_MAX_PEERS];
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned lt = lanemask_lt();
-    const int nwin = L - k + 1;
-    const int kshift = 64 - 2 * k;
-    const int nt = (nwin + 31) >> 5;
-    if (!COUNT_ONLY && tid < PEDK_MAX_PEERS) s_dst[tid] = dst.p[tid];
-    const uint64_t n_rounds = (n_reads + NW - 1) / NW;  // one read per warp per round
-    unsigned long long total = 0;                       // COUNT_ONLY: lane r accumulates rank r
-    for (uint64_t round = blockIdx.x; round < n_rounds; round += gridDim.x) {
-        const uint64_t r = round * NW + warp;
-        const bool live = r < n_reads;
-        const uint64_t mine = (live && (int)lane < W) ? words[r * (uint64_t)W + lane] : 0ull;
-        uint64_t key[XO_MAX_ITEMS];
-        int own[XO_MAX_ITEMS];
-        unsigned cnt = 0;  // lane q: k-mers of this read that go to rank q
-#pragma unroll
-        for (int t = 0; t < XO_MAX_ITEMS; ++t) {
-            own[t] = -1;
-            if (t < nt) {
-                const uint64_t hi = __shfl_sync(0xffffffffu, mine, t);
-                const uint64_t lo = __shfl_sync(0xffffffffu, mine, t + 1);
-                const int i = 32 * t + (int)lane;
-                const uint64_t x = lane ? ((hi << (2 * lane)) | (lo >> (64 - 2 * lane))) : hi;
-                const uint64_t km = x >> kshift;
-                const uint64_t rc = revcomp_groups64(km) >> kshift;
-                key[t] = km < rc ? km : rc;
-                if (live && i < nwin) own[t] = kmer_owner(key[t], k, nranks);
-                for (int q = 0; q < nranks; ++q) {
-                    unsigned m = __ballot_sync(0xffffffffu, own[t] == q);
-                    if (lane == (unsigned)q) cnt += __popc(m);
-                }
-            }
-        }
-        if (COUNT_ONLY) {
-            total += cnt;
-            continue;
-        }
-        if ((int)lane < nranks) w_cnt[warp][lane] = cnt;
-        __syncthreads();
-        if ((int)tid < nranks) {
-            unsigned tot = 0;
-            for (int w = 0; w < NW; ++w) {
-                unsigned c = w_cnt[w][tid];
-                w_cnt[w][tid] = tot;
-                tot += c;
-            }
-            s_start[tid + 1] = tot;  // turned into a prefix below
-            b_base[tid] = tot ? atomicAdd(&cursors[tid], (unsigned long long)tot) : 0ull;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned acc = 0;
-            s_start[0] = 0;
-            for (int q = 0; q < nranks; ++q) {
-                acc += s_start[q + 1];
-                s_start[q + 1] = acc;
-            }
-        }
-        __syncthreads();
-        // stage the block's k-mers grouped by owner ...
-        unsigned running = (int)lane < nranks ? s_start[lane] + w_cnt[warp][lane] : 0u;
-#pragma unroll
-        for (int t = 0; t < XO_MAX_ITEMS; ++t) {
-            if (t < nt) {
-                unsigned mym = 0, add = 0;
-                for (int q = 0; q < nranks; ++q) {
-                    unsigned m = __ballot_sync(0xffffffffu, own[t] == q);
-                    if (own[t] == q) mym = m;
-                    if (lane == (unsigned)q) add = __popc(m);
-                }
-                const unsigned base = __shfl_sync(0xffffffffu, running, own[t] < 0 ? 0 : own[t]);
-                running += add;
-                if (own[t] >= 0) stage[base + __popc(mym & lt)] = key[t];
-            }
-        }
-        __syncthreads();
-        // ... and store each owner's run contiguously into its receive buffer: full 256-byte
-        // warp stores over NVLink instead of a few keys per store
-        const unsigned n_staged = s_start[nranks];
-        for (unsigned i = tid; i < n_staged; i += EX_THREADS) {
-            int q = 0;
-            while (q + 1 < nranks && i >= s_start[q + 1]) ++q;
-            s_dst[q][b_base[q] + (i - s_start[q])] = stage[i];
-        }
-        __syncthreads();
-    }
-    if (COUNT_ONLY && (int)lane < nranks && total) atomicAdd(&counts[lane], total);
-}
-
 constexpr int CR_THREADS = 256;
 constexpr int CR_ITEMS = 8;
 constexpr int CR_WARPS = CR_THREADS / 32;
@@ -417,29 +302,6 @@ void launch_count_rows(const uint64_t* keys, size_t n, int k, int strand, int sa
     else
         k_count_rows<false><<<grid, CR_THREADS, 0, st>>>(keys, n, k, 0u, nullptr, nullptr, 0, row_key, row_val, cap,
                                                          counters);
-    PEDK_CUDA_TRY(cudaGetLastError());
-}
-
-}  // namespace pedk
-
-namespace pedk {
-
-void launch_extract_owner_count(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
-                                unsigned long long* counts, cudaStream_t st) {
-    if (!n_reads || L < k) return;
-    uint64_t rounds = (n_reads + 7) / 8;
-    unsigned grid = (unsigned)(rounds < (uint64_t)kNumSMs * 8 ? rounds : (uint64_t)kNumSMs * 8);
-    k_extract_owner<true><<<grid, EX_THREADS, 0, st>>>(words, W, L, k, n_reads, nranks, counts, nullptr, PeerPtrs{});
-    PEDK_CUDA_TRY(cudaGetLastError());
-}
-
-void launch_extract_owner_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int nranks,
-                                  unsigned long long* cursors, const PeerPtrs& dst, cudaStream_t st) {
-    if (!n_reads || L < k) return;
-    uint64_t rounds = (n_reads + 7) / 8;
-    unsigned grid = (unsigned)(rounds < (uint64_t)kNumSMs * 8 ? rounds : (uint64_t)kNumSMs * 8);
-    const size_t smem = (size_t)(EX_THREADS / 32) * (size_t)(L - k + 1) * sizeof(uint64_t);
-    k_extract_owner<false><<<grid, EX_THREADS, smem, st>>>(words, W, L, k, n_reads, nranks, nullptr, cursors, dst);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

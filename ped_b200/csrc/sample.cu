@@ -757,58 +757,6 @@ void do_count(pedk_sample* s, int k) {
     auto extract_sort = [&](bool pal_only, uint64_t m_local, DBuf<uint64_t>& a, DBuf<uint64_t>& b, uint64_t& m_final,
                             int stage) -> int {
         PEDK_CUDA_TRY(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-        static const bool use_p2p = !(getenv("PEDK_P2P") && atoi(getenv("PEDK_P2P")) == 0);
-        if (multi && !pal_only && use_p2p) {
-            // ONE kernel extracts every k-mer, bins it by owner and stores it into the owner's
-            // receive buffer over NVLink (peer memory mapped with CUDA IPC): no staging copy,
-            // no separate all-to-all.  A counting pass over the reads (no stores) sizes the runs.
-            const int R = ctx->nranks, me = ctx->rank;
-            DBuf<unsigned long long> cbuf(ctx, (size_t)PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 2));
-            unsigned long long* my_counts = cbuf.p;
-            unsigned long long* all_counts = cbuf.p + PEDK_MAX_RANKS;
-            unsigned long long* cursors = cbuf.p + PEDK_MAX_RANKS * (PEDK_MAX_RANKS + 1);
-            std::vector<unsigned long long> h;
-            {
-                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
-                PEDK_CUDA_TRY(cudaMemsetAsync(cbuf.p, 0, cbuf.bytes(), st));
-                for (const ReadGroup& g : s->groups)
-                    if (g.L >= k && g.n) launch_extract_owner_count(g.words.p, g.W, g.L, k, g.n, R, my_counts, st);
-                comm_count_matrix(ctx, my_counts, all_counts, &h);
-            }
-            trace(ctx, "  fused exchange: counts");
-            std::vector<unsigned long long> off(R, 0);  // where my run starts inside rank d's buffer
-            m_final = 0;
-            for (int d = 0; d < R; ++d)
-                for (int src = 0; src < me; ++src) off[d] += h[(size_t)src * PEDK_MAX_RANKS + d];
-            for (int src = 0; src < R; ++src) m_final += h[(size_t)src * PEDK_MAX_RANKS + me];
-            a = DBuf<uint64_t>(ctx, m_final);
-            void* peers[PEDK_MAX_RANKS];
-            comm_peer_pointers(ctx, a.p, peers);
-            PeerPtrs dst;
-            for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
-            {
-                StageScope sc(ctx, PEDK_ST_EXCHANGE, 1);
-                PEDK_CUDA_TRY(cudaMemcpyAsync(cursors, off.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
-                // nobody may store into a buffer before its owner is done with the previous contents
-                comm_barrier(ctx);
-                for (const ReadGroup& g : s->groups)
-                    if (g.L >= k && g.n) launch_extract_owner_scatter(g.words.p, g.W, g.L, k, g.n, R, cursors, dst, st);
-                comm_barrier(ctx);  // every rank's stores have landed
-            }
-            if (ctx->trace) {
-                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-                trace(ctx, "  fused exchange: extract + bin + NVLink stores");
-            }
-            {
-                StageScope sc(ctx, PEDK_ST_EXTRACT, 1);
-                launch_digit_hist(a.p, m_final, hist.p, n_pass, st);
-            }
-            b = DBuf<uint64_t>(ctx, m_final);
-            int cur = radix_sort(ctx, a.p, b.p, nullptr, nullptr, m_final, n_pass, hist.p, stage);
-            check_err_flag(ctx, "radix sort");
-            trace(ctx, "extract + radix sort");
-            return cur;
-        }
         a = DBuf<uint64_t>(ctx, m_local);
         if (pal_only) PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 2, 0, sizeof(unsigned long long), st));
         uint64_t off = 0;
