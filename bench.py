@@ -277,8 +277,18 @@ def main():
     top_name = max(kern, key=lambda n: kern[n]["ms"])
     top = kern[top_name]
     achieved = top["bytes"] / (top["ms"] / 1000.0) / 1e9 if top["ms"] > 0 else 0.0
+    # DRAM traffic of that kernel from the committed ncu capture (profiles/r1g_traffic.json holds
+    # measured bytes / algorithmic bytes per launch), scaled to this run's launches
+    traffic = None
+    try:
+        ratio = json.load(open(os.path.join(ROOT, "profiles", "r1g_traffic.json")))["dram_traffic_over_algorithmic"]
+        if top_name in ratio:
+            traffic = ratio[top_name] * top["bytes"] / top["launches"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": KERNEL_DOC[top_name], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1g_traffic.json",
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                 "launches_in_timed_region": top["launches"], "mean_launch_ms": top["ms"] / top["launches"],
                 "share_of_step": top["ms"] / args.steps / dev_ms,
