@@ -91,6 +91,11 @@ int pedk_sample_reserve(pedk_sample *s, uint64_t fastq_bytes);
  * _add_fastq_device: memory already in HBM. */
 int pedk_sample_add_fastq(pedk_sample *s, const void *host_bytes, uint64_t n);
 int pedk_sample_add_fastq_device(pedk_sample *s, const void *device_bytes, uint64_t n);
+/* The text is already in HBM and may be read IN PLACE (no copy): `capacity` bytes from
+ * device_bytes must be addressable, at least n rounded up to 16 KiB plus 16 KiB; the bytes
+ * beyond n are overwritten with zeros, and the buffer must stay untouched until
+ * pedk_sample_ingest / _ingest_reference returns.  Only for a sample that holds no text yet. */
+int pedk_sample_borrow_fastq_device(pedk_sample *s, void *device_bytes, uint64_t n, uint64_t capacity);
 /* S0+S1 = mkSortUniq/sortUniqSub/complement/sortUniqSort (ped.pl:1365-1530,
  * 3464-3484): 4-line state machine, drop reads with N, clipping (0 = not
  * given -> fixed length, or ped.pl's automatic choice for mixed lengths),
@@ -157,7 +162,9 @@ void pedk_free(void *p);
 int pedk_result_destroy(pedk_result *r);
 
 /* Whole hot path in one call: FASTQ text of both samples -> edge list.
- * where = 0: buffers are HOST memory; 1: DEVICE memory. */
+ * where = 0: buffers are HOST memory; 1: DEVICE memory (copied); 2: DEVICE memory that is
+ * addressable up to its size rounded up to 16 KiB plus 16 KiB and may be read in place
+ * (pedk_sample_borrow_fastq_device: the padding is zeroed). */
 int pedk_kmer_edges(pedk_ctx *ctx, const void *control_fastq, uint64_t control_bytes, const void *target_fastq,
                     uint64_t target_bytes, int where, int k, int clipping, pedk_result **out);
 

@@ -98,6 +98,7 @@ SIGNATURES = {
     "pedk_sample_add_fastq": (C.c_int, [_P, _P, C.c_uint64]),
     "pedk_sample_add_fastq_device": (C.c_int, [_P, _P, C.c_uint64]),
     "pedk_sample_ingest": (C.c_int, [_P, C.c_int, C.POINTER(IngestInfo)]),
+    "pedk_sample_borrow_fastq_device": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64]),
     "pedk_sample_count": (C.c_int, [_P, C.c_int, C.POINTER(CountInfo)]),
     "pedk_sample_table": (C.c_int, [_P, _P, _P, C.c_uint64, _U64P]),
     "pedk_sample_reads": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint64, _U64P, C.POINTER(C.c_int32),
@@ -229,10 +230,13 @@ class Context:
 
     # ---- whole path ----
     def kmer_edges(self, control_fastq, control_bytes: int, target_fastq, target_bytes: int, *, device_buffers: bool,
-                   k: int = 20, clipping: int = 0) -> "Result":
+                   k: int = 20, clipping: int = 0, padded: bool = False) -> "Result":
+        """padded (device buffers only): the buffers are addressable up to fastq_padded_bytes(n) and are read
+        in place instead of being copied."""
         r = C.c_void_p()
+        where = (2 if padded else 1) if device_buffers else 0
         self.check(self.lib.pedk_kmer_edges(self.h, _ptr(control_fastq), control_bytes, _ptr(target_fastq),
-                                            target_bytes, 1 if device_buffers else 0, k, clipping, C.byref(r)))
+                                            target_bytes, where, k, clipping, C.byref(r)))
         return Result(self, r)
 
     def join(self, control: "Sample", target: "Sample") -> "Result":
@@ -397,6 +401,11 @@ class Result:
         out = np.zeros(n.value, dtype=EDGE_DTYPE)
         self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+
+def fastq_padded_bytes(n: int) -> int:
+    """Capacity a device buffer of n text bytes needs to be read in place (pedk_sample_borrow_fastq_device)."""
+    return (n + 16383) // 16384 * 16384 + 16384
 
 
 # ---- sharding plan (host side; no GPU needed) ----

@@ -375,21 +375,32 @@ extern "C" int pedk_sample_sort_uniq_text(pedk_sample* s, int tag, char** text, 
 extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_t control_bytes,
                                const void* target_fastq, uint64_t target_bytes, int where, int k, int clipping,
                                pedk_result** out) {
-    if (!ctx || !out || (where != 0 && where != 1)) return PEDK_E_INVAL;
+    if (!ctx || !out || where < 0 || where > 2) return PEDK_E_INVAL;
     *out = nullptr;
     pedk_sample *c = nullptr, *t = nullptr;
     int rc = pedk_sample_create(ctx, &c);
     if (rc == PEDK_OK) rc = pedk_sample_create(ctx, &t);
     // both copies are queued before the first kernel so the target's transfer
     // runs under the control's ingest on the copy engine
-    if (rc == PEDK_OK) rc = pedk_sample_reserve(c, control_bytes);
-    if (rc == PEDK_OK) rc = pedk_sample_reserve(t, target_bytes);
-    if (rc == PEDK_OK)
-        rc = where ? pedk_sample_add_fastq_device(t, target_fastq, target_bytes)
-                   : pedk_sample_add_fastq(t, target_fastq, target_bytes);
-    if (rc == PEDK_OK)
-        rc = where ? pedk_sample_add_fastq_device(c, control_fastq, control_bytes)
-                   : pedk_sample_add_fastq(c, control_fastq, control_bytes);
+    if (where == 2) {
+        // padded device buffers: read in place, no copy
+        const uint64_t T = 16384;
+        if (rc == PEDK_OK)
+            rc = pedk_sample_borrow_fastq_device(t, const_cast<void*>(target_fastq), target_bytes,
+                                                 (target_bytes + T - 1) / T * T + T);
+        if (rc == PEDK_OK)
+            rc = pedk_sample_borrow_fastq_device(c, const_cast<void*>(control_fastq), control_bytes,
+                                                 (control_bytes + T - 1) / T * T + T);
+    } else {
+        if (rc == PEDK_OK) rc = pedk_sample_reserve(c, control_bytes);
+        if (rc == PEDK_OK) rc = pedk_sample_reserve(t, target_bytes);
+        if (rc == PEDK_OK)
+            rc = where ? pedk_sample_add_fastq_device(t, target_fastq, target_bytes)
+                       : pedk_sample_add_fastq(t, target_fastq, target_bytes);
+        if (rc == PEDK_OK)
+            rc = where ? pedk_sample_add_fastq_device(c, control_fastq, control_bytes)
+                       : pedk_sample_add_fastq(c, control_fastq, control_bytes);
+    }
     // ped.pl:291-297 ingests the target first, and `$clipping` is a global: a value chosen
     // automatically for the target is an explicit clipping= for the control
     pedk_ingest_info ti;

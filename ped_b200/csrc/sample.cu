@@ -1070,6 +1070,28 @@ extern "C" int pedk_sample_add_fastq_device(pedk_sample* s, const void* device_b
     return add_fastq(s, device_bytes, n, cudaMemcpyDeviceToDevice);
 }
 
+extern "C" int pedk_sample_borrow_fastq_device(pedk_sample* s, void* device_bytes, uint64_t n, uint64_t capacity) {
+    if (!s || (!device_bytes && n)) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    if (s->fq_len || s->copy_pending) throw PedkError(PEDK_E_INVAL, "pedk_sample_borrow_fastq_device: the sample already holds text");
+    const uint64_t need = (n + INGEST_TILE_BYTES - 1) / INGEST_TILE_BYTES * INGEST_TILE_BYTES + INGEST_TILE_BYTES;
+    if (capacity < need)
+        throw PedkError(PEDK_E_INVAL, "pedk_sample_borrow_fastq_device: capacity must cover the text rounded up to 16 KiB plus 16 KiB");
+    if (!n) return PEDK_OK;
+    if (s->ingested) {
+        s->ingested = false;
+        s->groups.clear();
+    }
+    // a DBuf over memory the context's allocator does not know: releasing it is a no-op
+    s->fq.reset();
+    s->fq.ctx = s->ctx;
+    s->fq.p = static_cast<uint8_t*>(device_bytes);
+    s->fq.n = capacity;
+    s->fq_len = n;
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
 extern "C" int pedk_sample_ingest(pedk_sample* s, int clipping, pedk_ingest_info* info) {
     if (!s) return PEDK_E_INVAL;
     PEDK_API_BEGIN

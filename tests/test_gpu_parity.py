@@ -155,6 +155,17 @@ def test_chunked_host_feed_and_fused_call(ctx):
     r = ctx.kmer_edges(dc, len(fc), dt, len(ft), device_buffers=True)
     assert r.text() == osnp
     r.destroy()
+    # ... and with padded device buffers that are read in place (twice: the text must survive)
+    pc = torch.full((api.fastq_padded_bytes(len(fc)),), 0x41, dtype=torch.uint8, device="cuda")
+    pt = torch.full((api.fastq_padded_bytes(len(ft)),), 0x0A, dtype=torch.uint8, device="cuda")
+    pc[:len(fc)] = dc
+    pt[:len(ft)] = dt
+    torch.cuda.synchronize()
+    for _ in range(2):
+        r = ctx.kmer_edges(pc, len(fc), pt, len(ft), device_buffers=True, padded=True)
+        assert r.text() == osnp
+        r.destroy()
+    assert bytes(pc[:len(fc)].cpu().numpy().tobytes()) == fc
 
 
 def test_medium_scale_against_oracle(ctx):
