@@ -283,6 +283,17 @@ __global__ void __launch_bounds__(256) k_pack_fixed(const uint8_t* __restrict__ 
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long kept = 0, bad_reads = 0;
+    // byte masks of the eight four-byte groups of this lane's word: what lies beyond the read
+    // (the newline, the '+' line) is replaced by 'A' (code 0).  Fixed for the whole launch.
+    uint32_t bm[8];
+    {
+        const int nvalid = L - 32 * (int)g;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int nb = nvalid - 4 * i;
+            bm[i] = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (0xffffffffu >> (32 - 8 * nb));
+        }
+    }
     for (uint64_t r0 = warp * RPW; r0 < n_records; r0 += n_warps * RPW) {
         const uint64_t r = r0 + grp;
         const bool live = r < n_records;
@@ -295,17 +306,28 @@ __global__ void __launch_bounds__(256) k_pack_fixed(const uint8_t* __restrict__ 
             uint32_t u[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) u[i] = __ldg(p + i);
-            const int nvalid = L - 32 * (int)g;  // bases of this word that belong to the read
+            // the alu pipe bounds this kernel: the alphabet test is "does the 2-bit code map back to
+            // the byte" (two permutes through the table "ACGT"), settled exactly only for the rare
+            // word that fails it
+            uint32_t nonacgt = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 uint32_t x = __funnelshift_r(u[i], u[i + 1], sh);
-                const int nb = nvalid - 4 * i;  // valid bytes of this group of four
-                const uint32_t m = nb >= 4 ? 0xffffffffu : nb <= 0 ? 0u : (0xffffffffu >> (32 - 8 * nb));
-                x = (x & m) | (0x41414141u & ~m);  // beyond the read: 'A' (code 0)
-                has_n |= __vcmpeq4(x, 0x4E4E4E4Eu) != 0;
-                bad |= (acgt_bytes(x) | __vcmpeq4(x, 0x4E4E4E4Eu)) != 0xffffffffu;
+                x = (x & bm[i]) | (0x41414141u & ~bm[i]);
                 const uint32_t c = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                const uint32_t t = c | (c >> 4);
+                const uint32_t sel = __byte_perm(t, 0u, 0x4420u);  // the four codes as selector nibbles
+                nonacgt |= __byte_perm(0x54474341u, 0u, sel) ^ x;
                 mine |= (uint64_t)((c * 0x40100401u) >> 24) << (56 - 8 * i);
+            }
+            if (nonacgt) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t x = __funnelshift_r(u[i], u[i + 1], sh);
+                    x = (x & bm[i]) | (0x41414141u & ~bm[i]);
+                    has_n |= __vcmpeq4(x, 0x4E4E4E4Eu) != 0;
+                    bad |= (acgt_bytes(x) | __vcmpeq4(x, 0x4E4E4E4Eu)) != 0xffffffffu;
+                }
             }
         }
         // flags of the whole read

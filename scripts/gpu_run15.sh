@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tiny or adversarial or dup or other_k or overflow or many_instances or corner or c1_40x or fused_call" > gpurun_out/t15_parity.log 2>&1; echo "parity rc=$?"; tail -5 gpurun_out/t15_parity.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tiny or adversarial or dup or other_k or overflow or many_instances or corner or c1_40x or fused_call or alphabet or mixed or clip" > gpurun_out/t15_parity.log 2>&1; echo "parity rc=$?"; tail -5 gpurun_out/t15_parity.log
 timeout 900 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/bench15_full.log 2>&1; echo "full bench rc=$?"
 python - <<PY
 import json
