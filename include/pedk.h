@@ -114,6 +114,8 @@ int pedk_sample_ingest_reference(pedk_sample *s, int window, int step, pedk_inge
  * header line, seq the cleaned sequence (NULL: length only).  *overwritten = 1 for a sequence
  * that a later one of the same name replaced. */
 int pedk_sample_num_chromosomes(pedk_sample *s, int *n);
+/* host-only helper (no CUDA call): "chr" + the name ped.pl:1045-1050 derives from a header line */
+int pedk_chromosome_file_name(const char *header_line, char *out, uint64_t cap);
 int pedk_sample_chromosome(pedk_sample *s, int i, char *name, uint64_t name_cap, uint64_t *length,
                            int *overwritten, char *seq, uint64_t seq_cap);
 /* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer

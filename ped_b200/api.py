@@ -117,6 +117,7 @@ SIGNATURES = {
     "pedk_sample_ingest_reference": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(IngestInfo)]),
     "pedk_sample_num_chromosomes": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "pedk_sample_chromosome": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _U64P, C.POINTER(C.c_int), _P, C.c_uint64]),
+    "pedk_chromosome_file_name": (C.c_int, [C.c_char_p, _P, C.c_uint64]),
     "pedk_mk_control_read": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_mk_sort_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pedk_count_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
@@ -401,6 +402,15 @@ class Result:
         out = np.zeros(n.value, dtype=EDGE_DTYPE)
         self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+
+def chromosome_file_name(header_line: bytes) -> str:
+    """The chromosome file ped.pl's mkChrFromFile opens for a FASTA header line (host-only)."""
+    buf = C.create_string_buffer(len(header_line) + 8)
+    rc = load_library().pedk_chromosome_file_name(header_line, buf, len(header_line) + 8)
+    if rc:
+        raise PedkError(rc, "pedk_chromosome_file_name")
+    return buf.value.decode()
 
 
 def fastq_padded_bytes(n: int) -> int:

@@ -1,4 +1,10 @@
-// S2: k-mer extraction and S4: run-length count.
+// S2: k-mer extraction and S4: run-length count -- the SORT form of the counting path.
+//
+// Since round 1d the instance stream of a sample goes through bucket.cu (hash bins ->
+// buckets -> shared-memory tables) and is never sorted.  The kernels here still (a) build
+// the small correction table of the windows of palindromic reads (extract -> LSD sort ->
+// run-length), and (b) are the whole counting path under PEDK_COUNT_MODE=sort, which the
+// parity tests keep running against the bucketed path.
 //
 // S2 replaces the Perl substr loop of countKmerSub (ped.pl:909-920): one warp
 // per unique read, lane i takes windows i, i+32, ... out of the packed words

@@ -315,6 +315,15 @@ extern "C" int pedk_sample_ingest_reference(pedk_sample* s, int window, int step
     PEDK_API_END(s->ctx)
 }
 
+// host-only: the file name ped.pl gives the sequence of a FASTA header line (no CUDA call)
+extern "C" int pedk_chromosome_file_name(const char* header_line, char* out, uint64_t cap) {
+    if (!header_line || !out) return PEDK_E_INVAL;
+    const std::string name = chr_name_of(header_line);
+    if (cap < name.size() + 1) return PEDK_E_INVAL;
+    memcpy(out, name.c_str(), name.size() + 1);
+    return PEDK_OK;
+}
+
 extern "C" int pedk_sample_num_chromosomes(pedk_sample* s, int* n) {
     if (!s || !n) return PEDK_E_INVAL;
     *n = (int)s->chromosomes.size();

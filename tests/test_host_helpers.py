@@ -132,3 +132,16 @@ def test_kmer_owner_is_a_contiguous_range_of_bins(built):
                 x = rnd.getrandbits(2 * k)
                 b = api.kmer_hash(x, k) >> (2 * k - a)
                 assert api.owner_of_kmer(x, k, world) == (b * world) >> a
+
+
+def test_chromosome_file_names_match_the_oracle(built):
+    """Host logic of the reference ingest (reference.cu chr_name_of) against the oracle's
+    restatement of ped.pl:1045-1050, on header forms the golden case does not hold."""
+    from oracle import oracle
+    from ped_b200 import api
+
+    headers = [b">chr1", b">1", b">001 leading zeros", b">chrX\tdesc", b">CHR07", b">Chr_x y", b">", b"> spaced",
+               b">scaffold_12|len=5", b">chrchr2", b">0", b">000", b">12a", b">>two", b">a>b", b">chr", b">MT  mito"]
+    for h in headers:
+        want = list(oracle.ref_chromosomes(h + b"\nACGT\n").keys())
+        assert [api.chromosome_file_name(h)] == want, h
