@@ -92,7 +92,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0: float, t1: float) -> None:
+        """Only the samples that arrived inside [t0, t1] (the timed region) count; nvidia-smi is started
+        before the warm-up because it needs a few hundred ms to deliver its first line."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -103,7 +108,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.15]  # a line reports the 100 ms before it
+        for r in inside:
             if len(r) < 9:
                 continue
             try:
@@ -119,19 +126,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_arm(wl, sample_reads: int, threads: int):
-    """Oracle (CPU restatement of ped.pl) on the first `sample_reads` reads of each sample."""
-    from oracle import oracle
+def cpu_inputs(wl, sample_reads: int):
     from ped_b200 import api
 
-    if threads > 0:
-        oracle.set_threads(threads)
-    cores = oracle.get_threads()
     cfg = wl["cfg"]
     g = api.synth_genome(1000 + cfg, wl["genome"])
     t = api.synth_mutate(g, 2000 + cfg, 1000, 100)
     fc = api.synth_fastq(g, 3000 + cfg, sample_reads, read_len=L)
     ft = api.synth_fastq(t, 4000 + cfg, sample_reads, read_len=L)
+    return fc, ft
+
+
+def cpu_arm(wl, sample_reads: int, threads: int, inputs=None):
+    """Oracle (CPU restatement of ped.pl) on the first `sample_reads` reads of each sample."""
+    from oracle import oracle
+
+    if threads > 0:
+        oracle.set_threads(threads)
+    cores = oracle.get_threads()
+    fc, ft = inputs if inputs is not None else cpu_inputs(wl, sample_reads)
     t0 = time.perf_counter()
     _, _, snp = oracle.run(fc, ft, K)
     dt = time.perf_counter() - t0
@@ -142,14 +155,21 @@ def cpu_arm(wl, sample_reads: int, threads: int):
 
 
 def run_reference(args, rank: int, world: int):
+    """The CPU arm alone: every step is the oracle over a bounded sample of the workload, sized from
+    a calibration run so that warm-up + steps end within a few minutes."""
     if rank != 0:
         return
     wl = workload(args.scale)
-    n = max(10_000, min(args.cpu_sample_reads, wl["reads"]))
+    n_cal = max(10_000, min(500_000, wl["reads"]))
+    _, dt_cal = cpu_arm(wl, n_cal, 0)
+    budget_s = 150.0 / max(1, args.warmup + args.steps)
+    n = int(n_cal * budget_s / max(dt_cal, 1e-3))
+    n = max(100_000, min(n, args.cpu_sample_reads, wl["reads"]))
+    inputs = cpu_inputs(wl, n)
     times = []
     base = None
     for i in range(args.warmup + args.steps):
-        base, dt = cpu_arm(wl, n, 0)
+        base, dt = cpu_arm(wl, n, 0, inputs)
         if i >= args.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
@@ -169,7 +189,7 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pedk", choices=["pedk", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of configs[1] (1.0 = 100 Mb genome, 20 M reads/sample)")
@@ -236,16 +256,17 @@ def main():
 
     def timed(fn, steps, warmup):
         edges = None
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(warmup):
             r = fn()
             edges = r.num_edges
             r.destroy()
         barrier()
         ctx.reset_stats()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        t_start = time.time()
         w0 = time.perf_counter()
         e0.record(stream)
         for _ in range(steps):
@@ -255,6 +276,7 @@ def main():
         e1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - w0) * 1000.0
+        sampler.window(t_start, time.time())
         dev_ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
         st = ctx.stats()
