@@ -75,8 +75,8 @@ typedef struct pedk_ingest_info {
 
 typedef struct pedk_count_info {
     int32_t k;
-    int32_t sort_passes;
-    uint64_t instances;       /* canonical k-mer instances sorted (half of the reference's M) */
+    int32_t sort_passes;      /* 0 on the bucketed path (the instance stream is not sorted) */
+    uint64_t instances;       /* canonical k-mer instances counted on this rank (half of the reference's M) */
     uint64_t canonical_kmers; /* rows of the canonical table */
     uint64_t correction_rows; /* windows of palindromic reads (usually 0) */
 } pedk_count_info;
@@ -119,7 +119,7 @@ int pedk_chromosome_file_name(const char *header_line, char *out, uint64_t cap);
 int pedk_sample_chromosome(pedk_sample *s, int i, char *name, uint64_t name_cap, uint64_t *length,
                            int *overwritten, char *seq, uint64_t seq_cap);
 /* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer
- * of every unique read, sorted and counted.  4 <= k <= 32 (the reference
+ * of every unique read, brought together (hash bins, buckets) and counted.  4 <= k <= 32 (the reference
  * hard-codes 20, ped.pl:912-913).  Leaves the canonical table in HBM. */
 int pedk_sample_count(pedk_sample *s, int k, pedk_count_info *info);
 /* The count table as ped.pl's count/<s>.count.*.gz hold it (both strands,
@@ -199,9 +199,9 @@ int pedk_join_kmer(pedk_ctx *ctx, const char *wd, const char *target, const char
 enum {
     PEDK_ST_INGEST = 0,   /* newline scan, record index, pack */
     PEDK_ST_DEDUP = 1,
-    PEDK_ST_EXTRACT = 2,
-    PEDK_ST_SORT = 3,     /* radix passes over the instance stream */
-    PEDK_ST_COUNT = 4,    /* run-length count */
+    PEDK_ST_EXTRACT = 2,  /* k-mer extraction + hash + level-A binning (one rank; EXCHANGE on several) */
+    PEDK_ST_SORT = 3,     /* level-B histogram + binning (PEDK_COUNT_MODE=sort: radix passes over the instances) */
+    PEDK_ST_COUNT = 4,    /* per-bucket tables -> strand rows (sort mode: run-length count) */
     PEDK_ST_EXPAND = 5,
     PEDK_ST_ROWSORT = 6,  /* radix passes over the merged strand rows */
     PEDK_ST_EDGES = 7,
