@@ -280,6 +280,12 @@ int pedk_synth_fastq_host(const pedk_synth_params *p, const char *genome, uint64
 int pedk_synth_fastq_device(pedk_ctx *ctx, const pedk_synth_params *p, const char *genome_dev,
                             uint64_t first_read, uint64_t n_reads, char *out_dev);
 
+/* host-only (no CUDA call): pass 1 of joinKmerSub (ped.pl:720-744) as the truth table the edge
+ * kernel uses.  A (k-1)-mer group is coded in 16 bits, two per slot (control A,C,G,T = bits
+ * 0-7, target = bits 8-15): 0 = count <= 1 or absent, 1 = count 2, 2 = 3..100, 3 = > 100.
+ * bits2048[code >> 5] >> (code & 31) & 1 says whether the group passes. */
+int pedk_edge_pass1_table(uint32_t *bits2048);
+
 /* ---- raw kernels, exposed for unit tests (device pointers) ------------- */
 int pedk_test_sort_u64(pedk_ctx *ctx, uint64_t *keys_dev, uint64_t n, int key_bits);
 int pedk_test_sort_pairs(pedk_ctx *ctx, uint64_t *keys_dev, uint32_t *vals_dev, uint64_t n, int key_bits);

@@ -117,6 +117,7 @@ SIGNATURES = {
     "pedk_sample_ingest_reference": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(IngestInfo)]),
     "pedk_sample_num_chromosomes": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "pedk_sample_chromosome": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _U64P, C.POINTER(C.c_int), _P, C.c_uint64]),
+    "pedk_edge_pass1_table": (C.c_int, [_P]),
     "pedk_chromosome_file_name": (C.c_int, [C.c_char_p, _P, C.c_uint64]),
     "pedk_mk_control_read": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_mk_sort_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -402,6 +403,15 @@ class Result:
         out = np.zeros(n.value, dtype=EDGE_DTYPE)
         self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+
+def edge_pass1_table() -> np.ndarray:
+    """2048 words: bit `code` set iff a (k-1)-mer group with that class code passes pass 1 (host-only)."""
+    bits = np.zeros(2048, dtype=np.uint32)
+    rc = load_library().pedk_edge_pass1_table(_ptr(bits))
+    if rc:
+        raise PedkError(rc, "pedk_edge_pass1_table")
+    return bits
 
 
 def chromosome_file_name(header_line: bytes) -> str:

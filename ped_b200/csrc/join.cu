@@ -372,6 +372,13 @@ extern "C" int pedk_sample_sort_uniq_text(pedk_sample* s, int tag, char** text, 
     PEDK_API_END(s->ctx)
 }
 
+// host-only (no CUDA call): the 65 536-entry truth table k_edges filters (k-1)-mer groups with
+extern "C" int pedk_edge_pass1_table(uint32_t* bits2048) {
+    if (!bits2048) return PEDK_E_INVAL;
+    pedk::build_edge_pass1_table(bits2048);
+    return PEDK_OK;
+}
+
 extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_t control_bytes,
                                const void* target_fastq, uint64_t target_bytes, int where, int k, int clipping,
                                pedk_result** out) {

@@ -145,3 +145,47 @@ def test_chromosome_file_names_match_the_oracle(built):
     for h in headers:
         want = list(oracle.ref_chromosomes(h + b"\nACGT\n").keys())
         assert [api.chromosome_file_name(h)] == want, h
+
+
+def test_edge_pass1_truth_table_matches_the_rule_on_counts(built):
+    """k_edges decides pass 1 of joinKmerSub (ped.pl:720-744) from 2-bit count classes.  For every one
+    of the 65 536 class codes, pass 1 evaluated on actual counts (both ends of every class) must agree
+    with the table -- i.e. the rule really only depends on the classes."""
+    from ped_b200 import api
+
+    bits = api.edge_pass1_table()
+    reps = {0: (0, 1), 1: (2, 2), 2: (3, 100), 3: (101, 2_000_000_000)}
+
+    def pass1(c, t):  # ped.pl:720-744 with cutoff 3
+        rep = nohita = nohitb = pola = polb = 0
+        a = b = 0
+        for x in range(4):
+            cv, tv = c[x], t[x]
+            if cv > 100:
+                rep += 1
+            elif cv >= 3:
+                a |= 1 << x
+                if tv <= 1:
+                    pola += 1
+            elif cv <= 1:
+                nohita += 1
+            if tv > 100:
+                rep += 1
+            elif tv >= 3:
+                b |= 1 << x
+                if cv <= 1:
+                    polb += 1
+            elif tv <= 1:
+                nohitb += 1
+        return a != b and a and b and rep == 0 and nohita >= 2 and nohitb >= 2 and (pola == 1 or polb == 1)
+
+    rnd = random.Random(1)
+    n_pass = 0
+    for code in range(65536):
+        want = bool((int(bits[code >> 5]) >> (code & 31)) & 1)
+        n_pass += want
+        cls = [(code >> (2 * s)) & 3 for s in range(8)]
+        for trial in range(3):
+            pick = [reps[c][0] if trial == 0 else reps[c][1] if trial == 1 else rnd.choice(reps[c]) for c in cls]
+            assert bool(pass1(pick[:4], pick[4:])) == want, (code, pick)
+    assert 0 < n_pass < 65536 // 8
