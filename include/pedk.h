@@ -257,6 +257,16 @@ int pedk_owner_of_kmer(uint64_t canonical_kmer, int k, int nranks);
 uint64_t pedk_kmer_hash(uint64_t kmer, int k);
 uint64_t pedk_kmer_unhash(uint64_t hash, int k);
 int pedk_plan_bucket_owners(const uint64_t *hist64, int nranks, uint8_t *owner64);
+/* host-only (no CUDA call): the plan of the k-mer exchange for rank `rank` of `nranks` -- where this
+ * rank's run of every level-A bin starts (cur256) and, when sized optimistically, ends (lim256)
+ * inside the OWNER's buffer; the segments of this rank's own bins (seg = n_seg starts, n_seg ends,
+ * n_seg bins; room for 3 x 256 x nranks values); the elements its receive buffer needs.
+ * exact == 0: every (bin, source) segment holds m_max / bins + 1/8 + 4096 elements (counts, what
+ * every rank stored, may be NULL: no segments then); exact != 0: sizes from counts.
+ * counts[src * 257 + bin]. */
+int pedk_plan_level_a(int k, int nranks, int rank, uint64_t m_max, const uint64_t *counts, int exact,
+                      uint64_t *cur256, uint64_t *lim256, uint64_t *seg, int *n_seg, uint64_t *buffer_elems,
+                      uint64_t *segment_capacity);
 
 /* ---- synthetic reads (tests and bench.py) ---------------- */
 

@@ -133,6 +133,8 @@ SIGNATURES = {
     "pedk_kmer_hash": (C.c_uint64, [C.c_uint64, C.c_int]),
     "pedk_kmer_unhash": (C.c_uint64, [C.c_uint64, C.c_int]),
     "pedk_plan_bucket_owners": (C.c_int, [_P, C.c_int, _P]),
+    "pedk_plan_level_a": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, _P, _P, C.POINTER(C.c_int),
+                                    _U64P, _U64P]),
     "pedk_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
     "pedk_synth_mutate": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _U64P]),
     "pedk_synth_fastq_bytes": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint32]),
@@ -446,6 +448,24 @@ def kmer_hash(kmer: int, k: int) -> int:
 
 def kmer_unhash(h: int, k: int) -> int:
     return int(load_library().pedk_kmer_unhash(int(h), k))
+
+
+def plan_level_a(k: int, nranks: int, rank: int, m_max: int = 0, counts=None, exact: bool = False) -> dict:
+    """Host-side plan of the k-mer exchange (pedk_plan_level_a): cursors, limits, segments, buffer size."""
+    cur = np.zeros(256, dtype=np.uint64)
+    lim = np.zeros(256, dtype=np.uint64)
+    seg = np.zeros(3 * 256 * nranks, dtype=np.uint64)
+    n_seg = C.c_int()
+    elems = C.c_uint64()
+    cap = C.c_uint64()
+    c = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint64)
+    rc = load_library().pedk_plan_level_a(k, nranks, rank, m_max, None if c is None else _ptr(c), 1 if exact else 0,
+                                          _ptr(cur), _ptr(lim), _ptr(seg), C.byref(n_seg), C.byref(elems), C.byref(cap))
+    if rc:
+        raise PedkError(rc, "pedk_plan_level_a")
+    n = n_seg.value
+    return {"cur": cur, "lim": lim, "seg_start": seg[:n].copy(), "seg_end": seg[n:2 * n].copy(),
+            "seg_bin": seg[2 * n:3 * n].copy(), "buffer_elems": int(elems.value), "capacity": int(cap.value)}
 
 
 def plan_bucket_owners(hist64, nranks: int) -> np.ndarray:

@@ -4,6 +4,7 @@
 #include "sample.h"
 
 #include "comm.h"
+#include "plan.h"
 
 #include <string.h>
 
@@ -491,7 +492,6 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     DBuf<uint8_t> keysA;
     DBuf<unsigned long long> histA(ctx, (size_t)(NBINS_MAX + 1) * (PEDK_MAX_RANKS + 1));
     std::vector<unsigned long long> all((size_t)(NBINS_MAX + 1) * R, 0);
-    auto owner_of_bin = [&](int bin) { return (int)(((uint64_t)bin * (uint64_t)R) >> a); };
     auto scatter_all = [&](unsigned long long* d_cur, const unsigned long long* d_lim, int* d_ovf) {
         PeerPtrs dst;
         if (multi) {
@@ -524,18 +524,11 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
             PEDK_CUDA_TRY(cudaStreamSynchronize(st));
             for (int r = 0; r < R; ++r) m_max = std::max<uint64_t>(m_max, mm[(size_t)r]);
         }
-        const uint64_t C = ((m_max / nbA) + (m_max / nbA) / 8 + 4096 + 31) / 32 * 32;
-        // segment of (bin, src) inside the owner's buffer: ((bin's index among the owner's bins) * R + src) * C
-        std::vector<unsigned long long> curA(NBINS_MAX, 0), limA(NBINS_MAX, 0);
-        std::vector<int> local_index(nbA, 0), owned(R, 0);
-        for (int bin = 0; bin < nbA; ++bin) {
-            const int o = owner_of_bin(bin);
-            local_index[bin] = owned[o]++;
-            curA[bin] = ((unsigned long long)local_index[bin] * R + me) * C;
-            limA[bin] = curA[bin] + C;
-        }
-        const uint64_t seg_slots = (uint64_t)owned[me] * R;
-        keysA = DBuf<uint8_t>(ctx, seg_slots * C * ksz);
+        LevelAPlan lp;
+        plan_level_a_optimistic(a, R, me, m_max, &lp);
+        const uint64_t C = lp.C;
+        const std::vector<unsigned long long>&curA = lp.cur, &limA = lp.lim;
+        keysA = DBuf<uint8_t>(ctx, lp.buffer_elems * ksz);
         DBuf<unsigned long long> plan(ctx, (size_t)3 * NBINS_MAX + 8);
         unsigned long long* d_cur = plan.p;
         unsigned long long* d_lim = plan.p + NBINS_MAX;
@@ -561,15 +554,10 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
         trace(ctx, overflow ? "  bins: extract + hash + bin (optimistic sizes overflowed)"
                             : multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
         if (!overflow) {
-            for (int bin = 0; bin < nbA; ++bin) {
-                if (owner_of_bin(bin) != me) continue;
-                for (int src = 0; src < R; ++src) {
-                    const unsigned long long st0 = ((unsigned long long)local_index[bin] * R + src) * C;
-                    seg_start.push_back(st0);
-                    seg_end.push_back(st0 + all[(size_t)src * (NBINS_MAX + 1) + bin]);
-                    seg_bin.push_back((unsigned long long)bin);
-                }
-            }
+            level_a_segments_optimistic(a, R, me, all.data(), &lp);
+            seg_start = lp.seg_start;
+            seg_end = lp.seg_end;
+            seg_bin = lp.seg_bin;
             uint64_t sent = 0;
             for (int bin = 0; bin < nbA; ++bin) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
             if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
@@ -593,27 +581,16 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
         ctx->stats.d2h_bytes += all.size() * 8;
         trace(ctx, "  bins: counts");
-        std::vector<unsigned long long> curA(NBINS_MAX, 0), owner_fill(R, 0);
+        LevelAPlan lp;
+        plan_level_a_exact(a, R, me, all.data(), &lp);
+        seg_start = lp.seg_start;
+        seg_end = lp.seg_end;
+        seg_bin = lp.seg_bin;
+        const std::vector<unsigned long long>& curA = lp.cur;
         uint64_t sent = 0;
-        for (int bin = 0; bin < nbA; ++bin) {
-            const int owner = owner_of_bin(bin);
-            unsigned long long tot = 0, before_me = 0;
-            for (int src = 0; src < R; ++src) {
-                const unsigned long long c = all[(size_t)src * (NBINS_MAX + 1) + bin];
-                if (src < me) before_me += c;
-                tot += c;
-            }
-            curA[bin] = owner_fill[owner] + before_me;
-            if (owner == me) {
-                seg_start.push_back(owner_fill[owner]);
-                seg_end.push_back(owner_fill[owner] + tot);
-                seg_bin.push_back((unsigned long long)bin);
-            }
-            owner_fill[owner] += tot;
-            sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
-        }
+        for (int bin = 0; bin < nbA; ++bin) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
         if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
-        keysA = DBuf<uint8_t>(ctx, owner_fill[me] * ksz);
+        keysA = DBuf<uint8_t>(ctx, lp.buffer_elems * ksz);
         DBuf<unsigned long long> plan(ctx, NBINS_MAX);
         PEDK_CUDA_TRY(cudaMemcpyAsync(plan.p, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
         scatter_all(plan.p, nullptr, nullptr);

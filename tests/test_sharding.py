@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from ped_b200 import api
 
@@ -40,3 +41,52 @@ def test_two_rank_gloo_replay_matches_oracle(built):
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and "SHARDING_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("exact", [False, True])
+def test_kmer_exchange_plan_replayed_on_the_host(built, world, exact):
+    """The index arithmetic of the fused extract + bin + NVLink-store exchange (plan.cu), replayed with
+    numpy: every rank hashes its k-mers, appends each bin's run at the cursor the plan gives it inside the
+    OWNER's buffer; afterwards the segments the plan hands to the owners must hold exactly the k-mers
+    each rank owns, bin by bin, without overlap and inside the buffer."""
+    k = 20
+    rng = np.random.default_rng(world * 2 + exact)
+    per_rank = [rng.integers(0, 1 << 40, size=int(n), dtype=np.uint64) for n in rng.integers(3000, 9000, world)]
+    if world > 1:
+        per_rank[1] = per_rank[1][:0]  # a rank without reads
+    hashed = [np.array([api.kmer_hash(int(x), k) for x in keys], dtype=np.uint64) for keys in per_rank]
+    bins = [(h >> np.uint64(32)).astype(np.int64) for h in hashed]
+    counts = np.zeros((world, 257), dtype=np.uint64)
+    for r in range(world):
+        counts[r, :256] = np.bincount(bins[r], minlength=256)
+    m_max = max(len(x) for x in per_rank)
+    plans = [api.plan_level_a(k, world, r, m_max, counts, exact) for r in range(world)]
+    buffers = [np.full(p["buffer_elems"], -1, dtype=np.int64) for p in plans]
+    for r in range(world):
+        cur = plans[r]["cur"].astype(np.int64).copy()
+        for h, b in zip(hashed[r], bins[r]):
+            owner = (int(b) * world) >> 8
+            assert owner == api.owner_of_kmer(int(api.kmer_unhash(int(h), k)), k, world)
+            if not exact:
+                assert cur[b] < int(plans[r]["lim"][b])  # 1/8 + 4096 of slack: uniform keys never overflow
+            assert buffers[owner][cur[b]] == -1, "two runs overlap"
+            buffers[owner][cur[b]] = int(h) & 0xFFFFFFFF
+            cur[b] += 1
+    for r in range(world):
+        p = plans[r]
+        got = {}
+        last_end = 0
+        for s0, s1, b in zip(p["seg_start"], p["seg_end"], p["seg_bin"]):
+            assert last_end <= s0 <= s1 <= p["buffer_elems"]
+            last_end = int(s1)
+            seg = buffers[r][int(s0):int(s1)]
+            assert (seg >= 0).all()
+            got.setdefault(int(b), []).extend(seg.tolist())
+        assert sum(len(v) for v in got.values()) == int((buffers[r] >= 0).sum())  # nothing outside the segments
+        want = {}
+        for src in range(world):
+            for h, b in zip(hashed[src], bins[src]):
+                if (int(b) * world) >> 8 == r:
+                    want.setdefault(int(b), []).append(int(h) & 0xFFFFFFFF)
+        assert {b: sorted(v) for b, v in got.items() if v} == {b: sorted(v) for b, v in want.items()}
