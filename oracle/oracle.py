@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
         L.oracle_ref_seq.restype = C.c_size_t
         L.oracle_ref_seq.argtypes = [P, C.c_size_t, C.POINTER(C.c_char_p)]
         L.oracle_ref_free.argtypes = [P]
+        L.oracle_ref20_uniq_text.restype = P
+        L.oracle_ref20_uniq_text.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+        L.oracle_map_kmer_text.restype = P
+        L.oracle_map_kmer_text.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 
@@ -216,6 +220,31 @@ def run_ref(ref_fasta: bytes, target_fastq: bytes, k: int = 20, clipping: int = 
     c.count(k)
     t.count(k)
     return c, t, join_text(c, t)
+
+
+# ---- groundwork for SURVEY 8(f) f1 (next round): oracle only, nothing in the product uses it ----
+
+def ref20_uniq_text(ref_fasta: bytes, tag: int) -> bytes:
+    """`zcat <ref>/ref20_uniq.TAG.gz` (ped.pl:1162-1211 mk20mer + 1138-1160 mkUniq)."""
+    L = lib()
+    n = C.c_size_t()
+    p = L.oracle_ref20_uniq_text(ref_fasta, len(ref_fasta), tag, C.byref(n))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        L.oracle_free(p)
+
+
+def map_kmer_text(snp_tag_text: bytes, ref20_uniq_tag_text: bytes) -> bytes:
+    """`$tmpdir/<t>.map.TAG` (ped.pl:641-685 mapKmerSub) from `$tmpdir/<t>.snp.TAG` and ref20_uniq.TAG."""
+    L = lib()
+    n = C.c_size_t()
+    p = L.oracle_map_kmer_text(snp_tag_text, len(snp_tag_text), ref20_uniq_tag_text, len(ref20_uniq_tag_text),
+                               C.byref(n))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        L.oracle_free(p)
 
 
 def set_threads(n: int) -> None:

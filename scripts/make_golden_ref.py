@@ -4,6 +4,8 @@ by running the UNMODIFIED reference in the build container:
 
   perl ped.pl ref=REF,file=REF.fa,wd=WD           mkChrFromFile, mkControlRead (ped.pl:1027-1136)
   perl ped.pl target=T,control=REF,method=kmer    count / lbc / join with the tiled reference as control
+  perl ped.pl target=T,ref=REF,sub=mapKmerSub,arg=TAG   (groundwork for SURVEY 8f row f1) the edges of each
+                                                  bucket joined with REF/ref20_uniq.TAG.gz (ped.pl:641-685)
 
 The first run leaves REF/chrNAME and REF/sort_uniq/; the second REF/count, REF/lbc, T/* and
 T/T.kmer.snp (no-ref format: the edge list itself, before ped.pl's mapping stages).
@@ -68,6 +70,28 @@ def run_case(name: str) -> dict:
         out["target"] = t
         with open(os.path.join(wd, "T", "T.kmer.snp"), "rb") as f:
             out["kmer_snp"] = f.read().decode()
+        # ---- groundwork for f1: the unique-20-mer index of the reference and the edge -> position map ----
+        from scripts.make_golden import TAGS
+        r = {}
+        r["sha256"], r["rows"], r["tags"] = zcat_all(os.path.join(wd, "REF"), "ref20_uniq.{tag}.gz")
+        out["ref20_uniq"] = r
+        tmpdir = os.path.join(wd, "T", "tmp")
+        os.makedirs(tmpdir, exist_ok=True)
+        os.makedirs(os.path.join(wd, "child"), exist_ok=True)
+        by_tag = {t: [] for t in TAGS}
+        for line in out["kmer_snp"].splitlines(keepends=True):
+            by_tag[line[:3]].append(line)
+        maps = {}
+        for t in TAGS:
+            with open(os.path.join(tmpdir, f"T.snp.{t}"), "w") as f:
+                f.write("".join(by_tag[t]))
+            subprocess.run(["perl", os.path.join(REF, "ped.pl"), f"target=T,ref=REF,sub=mapKmerSub,arg={t},wd={wd}"],
+                           cwd=REF, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with open(os.path.join(tmpdir, f"T.map.{t}")) as f:
+                m = f.read()
+            if m:
+                maps[t] = m
+        out["map"] = maps
         return out
     finally:
         shutil.rmtree(wd, ignore_errors=True)

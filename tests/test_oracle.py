@@ -153,3 +153,31 @@ def test_oracle_reference_parsing_corner_cases(built):
     s = oracle.OracleSample()
     s.ingest_reference(b">a\n" + b"ACGT" * 24 + b"\n")  # 96 bases: no window
     assert s.num_reads == 0
+
+
+@pytest.mark.parametrize("name", sorted(REF_CASES))
+def test_oracle_groundwork_for_position_mapping(name, built):
+    """Groundwork for SURVEY 8(f) row f1 (next round; the product does not implement it yet): the
+    oracle's unique-20-mer index of the reference (ped.pl:1138-1211) and its edge -> position map
+    (ped.pl:641-685) against ped.pl's own ref20_uniq files and `sub=mapKmerSub` outputs."""
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    fa, ft = make_ref_inputs(REF_CASES[name])
+    h = hashlib.sha256()
+    rows = 0
+    uniq = []
+    for t in range(64):
+        b = oracle.ref20_uniq_text(fa, t)
+        uniq.append(b)
+        h.update(b)
+        rows += b.count(b"\n")
+    assert (rows, h.hexdigest()) == (g["ref20_uniq"]["rows"], g["ref20_uniq"]["sha256"])
+    by_tag = {t: b"" for t in TAGS}
+    for line in g["kmer_snp"].encode().splitlines(keepends=True):
+        by_tag[line[:3].decode()] += line
+    got = {}
+    for i, t in enumerate(TAGS):
+        m = oracle.map_kmer_text(by_tag[t], uniq[i])
+        if m:
+            got[t] = m.decode()
+    assert got == g["map"]
