@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- PED k-mer hot path on B200: read bases -> edges per second.
 
-Workload (BASELINE.json configs[1]): C. elegans-scale synthetic target +
+Default workload (BASELINE.json configs[1]): C. elegans-scale synthetic target +
 control, 100 Mb random genome, 30x of 150 bp reads (20 M reads per sample),
 0.2 % substitution errors, 0.1 % reads with an N, planted SNPs (1e-3) and
 indels (1e-4), k = 20.  One step = the whole hot path over both
 samples: FASTQ text -> strand-closed de-duplicated reads -> canonical 20-mers
--> hash bins -> buckets -> count tables -> merged strand rows (radix sort) -> edge list.
+-> hash bins -> buckets -> count tables -> strand rows -> join records binned by the
+hash of their 19-mer -> per-bucket join tables -> edge list.  `--workload` selects the other
+BASELINE configs (configs2: 135 Mb 50x, k 20 or 31; configs3: 400 Mb 30x; configs4: 250 Mb with
+the reference itself as the control), `--scale` a fraction of one.
 
   value  bases/s with the FASTQ text already resident in HBM (device-timed)
   e2e    the same through the C-ABI call with HOST (pinned) FASTQ buffers:
@@ -14,6 +17,10 @@ samples: FASTQ text -> strand-closed de-duplicated reads -> canonical 20-mers
   roofline      the dominant kernel class of the timed region (largest summed duration):
                 its algorithmic bytes / its time, vs measured HBM copy peak; all classes listed
   cpu_baseline  the oracle (CPU restatement of ped.pl) on a bounded sample, host cores
+  parity        outside the timed region: sha256 of the edge list (all ranks' edges merged by key)
+                and the order-independent digests of both count tables, compared with the oracle's
+                answers for this exact workload (tests/golden/atsize_*.json, made on the box's host
+                by scripts/make_golden_atsize.py); match = null when no golden exists for it
 
 `--impl reference` times the CPU arm alone (the oracle port with all host
 threads; the Perl reference itself cannot travel to the GPU box -- DESIGN.md).
@@ -45,15 +52,55 @@ KERNEL_DOC = {
     "sub_scatter": "k_sub_scatter (level-A bins -> buckets: 4 B/instance in, 4 B out)",
     "bucket_count": "k_bucket_count (per-bucket shared-memory hash tables -> strand rows: 4 B/instance in, 12 B/row out)",
     "pack": "k_pack_fixed (FASTQ sequence lines -> 2-bit packed canonical reads)",
+    "join_count": "k_rows_count (strand rows -> level-A' bin sizes of the 19-mer hash + first row of every lbc file: 8 B/row in)",
+    "join_scatter": "k_rows_scatter (strand rows -> join records in the bins of their 19-mer hash: 12 B/row in, 8 B out)",
+    "join_sub": "k_sub_hist + k_sub_scatter over the join records (bins -> buckets: 2 reads + 1 write of 8 B/row)",
+    "join_table": "k_join_bucket (per-bucket shared-memory join tables + joinKmerSub: 8 B/row in)",
 }
 
 
-def workload(scale: float):
-    """configs[1] scaled by `scale` (1.0 = the full configuration)."""
-    G = int(100_000_000 * scale)
-    N = int(20_000_000 * scale)
-    return dict(name="configs[1]: C. elegans-scale 100 Mb, 30x 150 bp, target+control, k=20", genome=G, reads=N,
-                read_len=L, k=K, scale=scale, cfg=2)
+WORKLOADS = {
+    # BASELINE.json configs[1..4]; cfg selects the seeds (genome 1000+cfg, variants 2000+cfg,
+    # control reads 3000+cfg, target reads 4000+cfg)
+    "configs1": dict(name="configs[1]: C. elegans-scale 100 Mb, 30x 150 bp, target+control", genome=100_000_000,
+                     reads=20_000_000, cfg=2, control="reads"),
+    "configs2": dict(name="configs[2]: Arabidopsis-scale 135 Mb, 50x 150 bp (45 M reads per sample; ped.pl "
+                          "concatenates the mate files, so mates are independent reads), target+control",
+                     genome=135_000_000, reads=45_000_000, cfg=3, control="reads"),
+    "configs3": dict(name="configs[3]: rice-scale 400 Mb, 30x 150 bp, target+control", genome=400_000_000,
+                     reads=80_000_000, cfg=4, control="reads"),
+    "configs4": dict(name="configs[4]: human-chromosome-scale 250 Mb, 30x 150 bp target, the reference tiled "
+                          "into 100-base windows every 2 bases as the control", genome=250_000_000,
+                     reads=50_000_000, cfg=5, control="reference"),
+}
+
+
+def workload(key: str, scale: float, k: int):
+    """A BASELINE config scaled by `scale` (1.0 = the full configuration)."""
+    w = dict(WORKLOADS[key])
+    w["key"] = key
+    w["genome"] = int(w["genome"] * scale)
+    w["reads"] = int(w["reads"] * scale)
+    w["read_len"] = L
+    w["k"] = k
+    w["scale"] = scale
+    w["name"] += f", k={k}" + (f" (scaled x{scale:g})" if scale != 1.0 else "")
+    return w
+
+
+def golden_path(wl) -> str:
+    return os.path.join(ROOT, "tests", "golden", f"atsize_{wl['key']}_s{wl['scale']:g}_k{wl['k']}.json")
+
+
+def edges_sha(texts) -> str:
+    """sha256 of the edge list: the lines of all ranks merged by key (a line starts with its (k-1)-mer)."""
+    import hashlib
+
+    if len(texts) == 1:
+        return hashlib.sha256(texts[0]).hexdigest()
+    lines = [ln for t in texts for ln in t.split(b"\n") if ln]
+    lines.sort()
+    return hashlib.sha256(b"".join(ln + b"\n" for ln in lines)).hexdigest()
 
 
 def peaks():
@@ -127,59 +174,89 @@ class ClockSampler:
 
 
 def cpu_inputs(wl, sample_reads: int):
-    from ped_b200 import api
+    """Host-side inputs of the CPU arm (libpedk_synth.so: the product library is not mapped)."""
+    import synth
 
     cfg = wl["cfg"]
-    g = api.synth_genome(1000 + cfg, wl["genome"])
-    t = api.synth_mutate(g, 2000 + cfg, 1000, 100)
-    fc = api.synth_fastq(g, 3000 + cfg, sample_reads, read_len=L)
-    ft = api.synth_fastq(t, 4000 + cfg, sample_reads, read_len=L)
+    g = synth.synth_genome(1000 + cfg, wl["genome"])
+    t = synth.synth_mutate(g, 2000 + cfg, 1000, 100)
+    ft = synth.synth_fastq_array(t, 4000 + cfg, sample_reads, read_len=L)
+    if wl["control"] == "reference":
+        fc = reference_fasta(g)
+    else:
+        fc = synth.synth_fastq_array(g, 3000 + cfg, sample_reads, read_len=L)
     return fc, ft
 
 
-def cpu_arm(wl, sample_reads: int, threads: int, inputs=None):
-    """Oracle (CPU restatement of ped.pl) on the first `sample_reads` reads of each sample."""
+def reference_fasta(genome):
+    """The reference of a configs[4] run as one FASTA record (60-column lines, like a genome release)."""
+    import numpy as np
+
+    G = len(genome)
+    rows = (G + 59) // 60
+    body = np.full((rows, 61), 0x0A, dtype=np.uint8)
+    flat = body.reshape(-1)
+    pad = np.full(rows * 60, 0x41, dtype=np.uint8)
+    pad[:G] = genome
+    body[:, :60] = pad.reshape(rows, 60)
+    last = G - (rows - 1) * 60
+    out = np.concatenate([np.frombuffer(b">chr1\n", dtype=np.uint8), flat[: (rows - 1) * 61 + last],
+                          np.frombuffer(b"\n", dtype=np.uint8)])
+    return out
+
+
+def cpu_arm(wl, sample_reads: int, inputs=None):
+    """Oracle (CPU restatement of ped.pl) on the first `sample_reads` reads of each sample, on ALL host
+    cores: the thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1)."""
     from oracle import oracle
 
-    if threads > 0:
-        oracle.set_threads(threads)
+    oracle.set_threads(os.cpu_count() or 1)
     cores = oracle.get_threads()
     fc, ft = inputs if inputs is not None else cpu_inputs(wl, sample_reads)
     t0 = time.perf_counter()
-    _, _, snp = oracle.run(fc, ft, K)
+    if wl["control"] == "reference":
+        _, _, snp = oracle.run_ref(fc.tobytes(), ft, wl["k"])
+    else:
+        _, _, snp = oracle.run(fc, ft, wl["k"])
     dt = time.perf_counter() - t0
-    bases = 2 * sample_reads * L
+    bases = bases_of(wl, sample_reads)
     return dict(value=bases / dt, unit=UNIT, cores=cores, kind="port",
                 sample=f"first {sample_reads} reads of each sample of the workload ({bases} bases, {dt:.1f} s, "
                        f"{snp.count(chr(10).encode())} edges); oracle/ped_oracle.c, OpenMP over ped.pl's 64 buckets"), dt
 
 
+def bases_of(wl, reads_per_sample: int) -> int:
+    """Read bases one step consumes: both samples' reads; a reference used as the control
+    counts with its own length."""
+    if wl["control"] == "reference":
+        return reads_per_sample * L + wl["genome"]
+    return 2 * reads_per_sample * L
+
+
 def run_reference(args, rank: int, world: int):
-    """The CPU arm alone: every step is the oracle over a bounded sample of the workload, sized from
-    a calibration run so that warm-up + steps end within a few minutes."""
+    """The CPU arm alone: every step is the oracle over a bounded sample of the workload -- the same
+    fixed sample at every N, all host cores."""
     if rank != 0:
         return
-    wl = workload(args.scale)
-    n_cal = max(10_000, min(500_000, wl["reads"]))
-    _, dt_cal = cpu_arm(wl, n_cal, 0)
-    budget_s = 150.0 / max(1, args.warmup + args.steps)
-    n = int(n_cal * budget_s / max(dt_cal, 1e-3))
-    n = max(100_000, min(n, args.cpu_sample_reads, wl["reads"]))
+    wl = workload(args.workload, args.scale, args.k)
+    n = max(10_000, min(args.ref_sample_reads, wl["reads"]))
     inputs = cpu_inputs(wl, n)
     times = []
     base = None
     for i in range(args.warmup + args.steps):
-        base, dt = cpu_arm(wl, n, 0, inputs)
+        base, dt = cpu_arm(wl, n, inputs)
         if i >= args.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
-    value = 2 * n * L / (ms / 1000.0)
+    value = bases_of(wl, n) / (ms / 1000.0)
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["name"], "genome": wl["genome"], "reads_per_sample": wl["reads"],
-                       "read_len": L, "k": K, "step": f"bounded sample: first {n} reads of each sample on the host CPU"},
+                       "read_len": L, "k": wl["k"],
+                       "step": f"bounded sample: first {n} reads of each sample on the host CPU, "
+                               f"{base['cores']} threads"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -192,10 +269,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pedk", choices=["pedk", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="fraction of configs[1] (1.0 = 100 Mb genome, 20 M reads/sample)")
+    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS))
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload (1.0 = the full configuration)")
     ap.add_argument("--cpu-sample-reads", type=int, default=3_000_000)
+    ap.add_argument("--ref-sample-reads", type=int, default=1_250_000,
+                    help="--impl reference: reads per sample of one step (the same at every N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,6 +287,7 @@ def main():
     if args.impl == "reference":
         from ped_b200 import build
         build.build_oracle()
+        build.build_synth()
         run_reference(args, rank, world)
         return
 
@@ -227,8 +310,10 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
-    wl = workload(args.scale)
+    wl = workload(args.workload, args.scale, args.k)
     cfg = wl["cfg"]
+    kk = wl["k"]
+    ref_control = wl["control"] == "reference"
     # strong scaling: the SAME workload on N GPUs.  Rank r ingests reads [r*N/R, (r+1)*N/R) of
     # both samples; reads, k-mers and table rows then change hands inside the library.
     N_all = wl["reads"]
@@ -238,15 +323,25 @@ def main():
     g = api.synth_genome(1000 + cfg, G)
     t = api.synth_mutate(g, 2000 + cfg, 1000, 100)
     gd, td = torch.from_numpy(g).cuda(), torch.from_numpy(t).cuda()
-    nb = api.synth_fastq_bytes(first, N, L)
+    nb_t = api.synth_fastq_bytes(first, N, L)
     # padded so that the library reads the resident text in place (no device-to-device copy)
-    dev_c = torch.empty(api.fastq_padded_bytes(nb), dtype=torch.uint8, device="cuda")
-    dev_t = torch.empty(api.fastq_padded_bytes(nb), dtype=torch.uint8, device="cuda")
+    dev_t = torch.empty(api.fastq_padded_bytes(nb_t), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
-    ctx.synth_fastq_device(api.SynthParams(3000 + cfg, len(g), L, 2000, 1000, 0), gd, first, N, dev_c)
     ctx.synth_fastq_device(api.SynthParams(4000 + cfg, len(t), L, 2000, 1000, 0), td, first, N, dev_t)
+    if ref_control:
+        # the control is the reference itself: every rank is fed the whole FASTA and keeps the windows it owns
+        fa = reference_fasta(g)
+        nb_c = len(fa)
+        dev_c = torch.empty(api.fastq_padded_bytes(nb_c), dtype=torch.uint8, device="cuda")
+        dev_c[:nb_c] = torch.from_numpy(fa).cuda()
+    else:
+        nb_c = api.synth_fastq_bytes(first, N, L)
+        dev_c = torch.empty(api.fastq_padded_bytes(nb_c), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.synth_fastq_device(api.SynthParams(3000 + cfg, len(g), L, 2000, 1000, 0), gd, first, N, dev_c)
+    torch.cuda.synchronize()
     del gd, td
-    bases_per_step = 2 * N_all * L  # whole job
+    bases_per_step = bases_of(wl, N_all)  # whole job
     stream = torch.cuda.ExternalStream(ctx.stream)
 
     def barrier():
@@ -284,12 +379,13 @@ def main():
         ne = torch.tensor([edges or 0], dtype=torch.int64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ne, op=dist.ReduceOp.SUM)  # every rank holds the edges of its bucket range
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)  # every rank holds the edges of the 19-mers whose hash it owns
         return ms[0].item() / steps, ms[1].item() / steps, st, clocks, int(ne.item())
 
     # ---- resident leg: FASTQ text already in HBM ----
     dev_ms, wall_ms, st, clocks, edges = timed(
-        lambda: ctx.kmer_edges(dev_c, nb, dev_t, nb, device_buffers=True, padded=True, k=K), args.steps, args.warmup)
+        lambda: ctx.kmer_edges(dev_c, nb_c, dev_t, nb_t, device_buffers=True, padded=True, k=kk,
+                               reference_control=ref_control), args.steps, args.warmup)
     value = bases_per_step / (dev_ms / 1000.0)
     launches = st["kernel_launches"]
 
@@ -300,18 +396,22 @@ def main():
     top_name = max(kern, key=lambda n: kern[n]["ms"])
     top = kern[top_name]
     achieved = top["bytes"] / (top["ms"] / 1000.0) / 1e9 if top["ms"] > 0 else 0.0
-    # DRAM traffic of that kernel from the committed ncu capture (profiles/r1g_traffic.json holds
-    # measured bytes / algorithmic bytes per launch), scaled to this run's launches
-    traffic = None
-    try:
-        ratio = json.load(open(os.path.join(ROOT, "profiles", "r1g_traffic.json")))["dram_traffic_over_algorithmic"]
+    # DRAM traffic of that kernel: NOT measured in this run -- the ratio (ncu dram bytes read + written) /
+    # (algorithmic bytes) of the committed capture of the same kernel, times this run's algorithmic bytes
+    traffic, traffic_src = None, None
+    for tf in ("r2_traffic.json", "r1g_traffic.json"):
+        try:
+            ratio = json.load(open(os.path.join(ROOT, "profiles", tf)))["dram_traffic_over_algorithmic"]
+        except Exception:
+            continue
         if top_name in ratio:
             traffic = ratio[top_name] * top["bytes"] / top["launches"]
-    except Exception:
-        traffic = None
+            traffic_src = (f"committed ncu capture profiles/{tf} (dram__bytes_read.sum + dram__bytes_write.sum per "
+                           f"launch over algorithmic bytes = {ratio[top_name]:.3f}) x this run's algorithmic bytes; "
+                           f"not measured in this run")
+            break
     roofline = {"bound": "hbm", "kernel": KERNEL_DOC[top_name], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1g_traffic.json",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                 "launches_in_timed_region": top["launches"], "mean_launch_ms": top["ms"] / top["launches"],
                 "share_of_step": top["ms"] / args.steps / dev_ms,
@@ -321,19 +421,55 @@ def main():
                                 for n, v in kern.items()}}
     stage_ms = {k: v / args.steps for k, v in st["stage_ms"].items()}
 
+    # ---- parity (outside the timed region): edge list + both count tables against the oracle's answers ----
+    parity = None
+    if not args.no_parity:
+        c, tt = api.Sample(ctx), api.Sample(ctx)
+        tt.borrow_fastq_device(dev_t, nb_t)
+        c.borrow_fastq_device(dev_c, nb_c)
+        tt.ingest()
+        tt.count(kk)
+        if ref_control:
+            c.ingest_reference()
+        else:
+            c.ingest()
+        c.count(kk)
+        r = ctx.join(c, tt)
+        dig = [c.table_digest(), tt.table_digest()]
+        text = r.text()
+        r.destroy(); c.destroy(); tt.destroy()
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, dict(text=text, dig=dig))
+        else:
+            parts = [dict(text=text, dig=dig)]
+        if rank == 0:
+            tab = [[sum(p["dig"][i][0] for p in parts), sum(p["dig"][i][1] for p in parts) % 2**64] for i in (0, 1)]
+            parity = {"edges_sha": edges_sha([p["text"] for p in parts]),
+                      "edges": sum(p["text"].count(b"\n") for p in parts),
+                      "table_sum": {"control": {"rows": tab[0][0], "digest": f"{tab[0][1]:016x}"},
+                                    "target": {"rows": tab[1][0], "digest": f"{tab[1][1]:016x}"}},
+                      "golden": None, "match": None}
+            gp = golden_path(wl)
+            if os.path.exists(gp):
+                gold = json.load(open(gp))
+                parity["golden"] = os.path.relpath(gp, ROOT)
+                parity["match"] = bool(gold["edges_sha"] == parity["edges_sha"] and gold["edges"] == parity["edges"]
+                                       and gold["table_sum"] == parity["table_sum"])
+
     # ---- e2e leg: host (pinned) FASTQ -> edge list on the host ----
     e2e = None
     if not args.no_e2e:
-        host_c = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
-        host_t = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
-        host_c.copy_(dev_c[:nb])
-        host_t.copy_(dev_t[:nb])
+        host_c = torch.empty(nb_c, dtype=torch.uint8, pin_memory=True)
+        host_t = torch.empty(nb_t, dtype=torch.uint8, pin_memory=True)
+        host_c.copy_(dev_c[:nb_c])
+        host_t.copy_(dev_t[:nb_t])
         torch.cuda.synchronize()
         del dev_c, dev_t
         torch.cuda.empty_cache()
 
         def step_e2e():
-            r = ctx.kmer_edges(host_c, nb, host_t, nb, device_buffers=False, k=K)
+            r = ctx.kmer_edges(host_c, nb_c, host_t, nb_t, device_buffers=False, k=kk, reference_control=ref_control)
             r.text()  # the edge list is host memory here
             return r
 
@@ -347,19 +483,21 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from ped_b200 import build
         build.build_oracle()
-        cpu, _ = cpu_arm(wl, max(10_000, min(args.cpu_sample_reads, N_all)), 0)
+        cpu, _ = cpu_arm(wl, max(10_000, min(args.cpu_sample_reads, N_all)))
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": wl["name"], "genome": G, "reads_per_sample": N_all, "read_len": L, "k": K,
+                "config": {"workload": wl["name"], "genome": G, "reads_per_sample": N_all, "read_len": L, "k": kk,
                            "bases_per_step": bases_per_step, "edges": edges,
                            "l2": "inputs larger than L2 (FASTQ text and k-mer stream are GBs)",
-                           "parallelism": (f"{world} ranks: reads and canonical k-mers to their hash owner, table rows to "
-                                           f"their 3-nt bucket owner (NCCL all-to-all-v)") if world > 1 else "1 GPU"},
+                           "parallelism": (f"{world} ranks, one per GPU: packed reads to their hash owner (NCCL send/recv); "
+                                           f"canonical k-mers and join records stored by the binning kernels straight "
+                                           f"into the owner's HBM over NVLink (CUDA-IPC peer memory); NCCL only for "
+                                           f"the small count/plan collectives") if world > 1 else "1 GPU"},
                 "wall_ms_per_step": wall_ms, "stage_ms_per_step": stage_ms, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "clocks": clocks,
                 "peak_device_bytes": st["peak_device_bytes"]}
         print(json.dumps(line), flush=True)
     ctx.close()

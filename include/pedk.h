@@ -126,6 +126,11 @@ int pedk_sample_count(pedk_sample *s, int k, pedk_count_info *info);
  * ascending; bucket TAG = the rows whose first three bases are TAG).  Call
  * with kmers == NULL to get *n only. */
 int pedk_sample_table(pedk_sample *s, uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n);
+/* Order-independent digest of the count table on this rank: *rows = its rows (both strands), *digest =
+ * the sum over rows of mix64(kmer * 0x9E3779B97F4A7C15 + count) modulo 2^64 (mix64 = the splitmix64
+ * finaliser).  Sums over ranks give the digest of the whole table; no sort and no copy is made, so it
+ * checks a table of any size against a known answer (bench.py "parity"). */
+int pedk_sample_table_digest(pedk_sample *s, uint64_t *rows, uint64_t *digest);
 /* Unique reads of length group g as packed canonical representatives
  * (words_per_read u64 each, first base in the top bits of word 0) plus the
  * palindrome flag; the sort_uniq/ lines are these and their reverse
@@ -170,6 +175,12 @@ int pedk_result_destroy(pedk_result *r);
 int pedk_kmer_edges(pedk_ctx *ctx, const void *control_fastq, uint64_t control_bytes, const void *target_fastq,
                     uint64_t target_bytes, int where, int k, int clipping, pedk_result **out);
 
+/* The same with the reference itself as the control (`ped.pl target=T,ref=R`: $control = $ref,
+ * ped.pl:193): ref_fasta is the text of the reference FASTA, tiled like mkControlRead does
+ * (pedk_sample_ingest_reference). */
+int pedk_kmer_edges_ref(pedk_ctx *ctx, const void *ref_fasta, uint64_t ref_bytes, const void *target_fastq,
+                        uint64_t target_bytes, int where, int k, int clipping, pedk_result **out);
+
 /* ---- file level: what ped.pl calls ------------------- */
 
 /* mkSortUniq (ped.pl:1365-1410): reads <wd>/<subject>/read/ (gz, bz2, xz and
@@ -202,9 +213,9 @@ enum {
     PEDK_ST_EXTRACT = 2,  /* k-mer extraction + hash + level-A binning (one rank; EXCHANGE on several) */
     PEDK_ST_SORT = 3,     /* level-B histogram + binning (PEDK_COUNT_MODE=sort: radix passes over the instances) */
     PEDK_ST_COUNT = 4,    /* per-bucket tables -> strand rows (sort mode: run-length count) */
-    PEDK_ST_EXPAND = 5,
-    PEDK_ST_ROWSORT = 6,  /* radix passes over the merged strand rows */
-    PEDK_ST_EDGES = 7,
+    PEDK_ST_EXPAND = 5,   /* (table emission only) strand rows copied for the sort */
+    PEDK_ST_ROWSORT = 6,  /* join: rows -> join records -> bins -> buckets; tables: radix passes over the rows */
+    PEDK_ST_EDGES = 7,    /* join: per-bucket tables + joinKmerSub */
     PEDK_ST_COPY = 8,     /* host<->device copies issued by the library */
     PEDK_ST_EXCHANGE = 9, /* multi-GPU all-to-all */
     PEDK_N_STAGES = 10
@@ -220,9 +231,9 @@ typedef struct pedk_stats {
     uint64_t peak_device_bytes;
     /* per kernel class (PEDK_KC_*): launches, summed duration and the ALGORITHMIC bytes
      * (what the kernel must read and write) of those launches */
-    double kc_ms[8];
-    uint64_t kc_bytes[8];
-    uint64_t kc_launches[8];
+    double kc_ms[16];
+    uint64_t kc_bytes[16];
+    uint64_t kc_launches[16];
 } pedk_stats;
 enum {
     PEDK_KC_RADIX_KEYS = 0,   /* k_radix_pass over 8-byte keys: 16 B/key */
@@ -233,7 +244,11 @@ enum {
     PEDK_KC_BUCKET_COUNT = 5, /* k_bucket_count: one read + 12 B per row */
     PEDK_KC_PACK = 6,         /* k_pack_fixed: FASTQ text in, packed reads out */
     PEDK_KC_PART_COUNT = 7,   /* k_part_count: packed reads in */
-    PEDK_N_KC = 8
+    PEDK_KC_JOIN_COUNT = 8,   /* k_rows_count: the keys of the strand rows in (8 B/row) */
+    PEDK_KC_JOIN_SCATTER = 9, /* k_rows_scatter: rows in (12 B), join records out (8 B) */
+    PEDK_KC_JOIN_SUB = 10,    /* k_sub_hist + k_sub_scatter over the join records: 2 reads + 1 write of 8 B */
+    PEDK_KC_JOIN_TABLE = 11,  /* k_join_bucket: join records in (8 B/row) */
+    PEDK_N_KC = 12
 };
 int pedk_get_stats(pedk_ctx *ctx, pedk_stats *out);   /* synchronises the stream */
 int pedk_reset_stats(pedk_ctx *ctx);
@@ -270,6 +285,8 @@ int pedk_plan_level_a(int k, int nranks, int rank, uint64_t m_max, const uint64_
 
 /* ---- synthetic reads (tests and bench.py) ---------------- */
 
+#ifndef PEDK_SYNTH_PARAMS_DEFINED
+#define PEDK_SYNTH_PARAMS_DEFINED
 typedef struct pedk_synth_params {
     uint64_t seed;
     uint64_t genome_len;
@@ -278,15 +295,10 @@ typedef struct pedk_synth_params {
     uint32_t n_ppm;     /* reads with one N per million reads */
     uint32_t dup_ppm;   /* reads re-using the placement of the previous read, per million */
 } pedk_synth_params;
+#endif
 
-/* host-only helpers (no CUDA call) */
-int pedk_synth_genome(uint64_t seed, uint64_t genome_len, char *out);
-int pedk_synth_mutate(const char *genome, uint64_t genome_len, uint64_t seed, uint32_t snp_ppm, uint32_t indel_ppm,
-                      char *out, uint64_t cap, uint64_t *out_len);
-uint64_t pedk_synth_fastq_bytes(uint64_t first_read, uint64_t n_reads, uint32_t read_len);
-int pedk_synth_fastq_host(const pedk_synth_params *p, const char *genome, uint64_t first_read, uint64_t n_reads,
-                          char *out);
-/* same bytes, generated in HBM: genome_dev and out_dev are device pointers */
+/* The bytes libpedk_synth.so's host generator writes (include/pedk_synth.h), generated in HBM:
+ * genome_dev and out_dev are device pointers. */
 int pedk_synth_fastq_device(pedk_ctx *ctx, const pedk_synth_params *p, const char *genome_dev,
                             uint64_t first_read, uint64_t n_reads, char *out_dev);
 

@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
         L.oracle_error.argtypes = [P]
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_get_threads.restype = C.c_int
-        L.oracle_ingest.argtypes = [P, C.c_char_p, C.c_size_t, C.c_int]
+        L.oracle_ingest.argtypes = [P, C.c_void_p, C.c_size_t, C.c_int]
         L.oracle_clipping_used.argtypes = [P]
         L.oracle_auto_clipped.argtypes = [P]
         L.oracle_dedup.argtypes = [P]
@@ -86,11 +86,11 @@ TAGS = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT"]
 class OracleSample:
     """CPU restatement of ped.pl's per-sample stages (see ped_oracle.c header)."""
 
-    def __init__(self, fastq: bytes = b"", clipping: int = 0):
+    def __init__(self, fastq=b"", clipping: int = 0):
         self.L = lib()
         self.h = self.L.oracle_sample_new()
         self.k = 0
-        if fastq:
+        if len(fastq):
             self.ingest(fastq, clipping)
 
     def __del__(self):
@@ -101,8 +101,13 @@ class OracleSample:
         except Exception:
             pass
 
-    def ingest(self, fastq: bytes, clipping: int = 0) -> None:
-        rc = self.L.oracle_ingest(self.h, fastq, len(fastq), clipping)
+    def ingest(self, fastq, clipping: int = 0) -> None:
+        """fastq: bytes, or a numpy uint8 array (no copy: at-size inputs are many GB)."""
+        if isinstance(fastq, np.ndarray):
+            ptr, n = C.c_void_p(fastq.ctypes.data), fastq.size
+        else:
+            ptr, n = C.cast(C.c_char_p(fastq), C.c_void_p), len(fastq)
+        rc = self.L.oracle_ingest(self.h, ptr, n, clipping)
         if rc:
             raise RuntimeError(self.L.oracle_error(self.h).decode())
         self.L.oracle_dedup(self.h)
@@ -148,13 +153,14 @@ class OracleSample:
     def num_instances(self) -> int:
         return self.L.oracle_num_instances(self.h)
 
-    def table(self) -> Tuple[np.ndarray, np.ndarray]:
+    def table(self, copy: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+        """copy=False: views into the oracle's own arrays (valid until the next count / free)."""
         n = self.L.oracle_num_kmers(self.h)
         if n == 0:
             return np.empty(0, np.uint64), np.empty(0, np.uint32)
-        km = np.ctypeslib.as_array(self.L.oracle_kmers(self.h), shape=(n,)).copy()
-        ct = np.ctypeslib.as_array(self.L.oracle_counts(self.h), shape=(n,)).copy()
-        return km, ct
+        km = np.ctypeslib.as_array(self.L.oracle_kmers(self.h), shape=(n,))
+        ct = np.ctypeslib.as_array(self.L.oracle_counts(self.h), shape=(n,))
+        return (km.copy(), ct.copy()) if copy else (km, ct)
 
     def _text(self, fn, tag: int) -> bytes:
         n = C.c_size_t()

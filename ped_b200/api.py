@@ -19,10 +19,18 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpedk.so")
 
+# synthetic inputs (tests and bench.py): the host generator is test infrastructure outside this package
+# (synth/, its own libpedk_synth.so); re-exported here so that test code reads api.synth_*
+import sys as _sys  # noqa: E402
+
+if os.path.dirname(_HERE) not in _sys.path:
+    _sys.path.insert(0, os.path.dirname(_HERE))
+from synth import SynthParams, synth_fastq, synth_fastq_bytes, synth_genome, synth_mutate  # noqa: E402,F401
+
 PEDK_N_STAGES = 10
 STAGES = ["ingest", "dedup", "extract", "sort", "count", "expand", "rowsort", "edges", "copy", "exchange"]
 KERNEL_CLASSES = ["radix_keys", "radix_pairs", "part_scatter", "sub_hist", "sub_scatter", "bucket_count", "pack",
-                  "part_count"]
+                  "part_count", "join_count", "join_scatter", "join_sub", "join_table"]
 COMM_ID_BYTES = 128
 
 
@@ -57,8 +65,8 @@ class Stats(C.Structure):
     _fields_ = [("stage_ms", C.c_double * PEDK_N_STAGES), ("stage_launches", C.c_uint64 * PEDK_N_STAGES),
                 ("kernel_launches", C.c_uint64), ("sort_pass_launches", C.c_uint64), ("sort_pass_keys", C.c_uint64),
                 ("sort_pass_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("peak_device_bytes", C.c_uint64), ("kc_ms", C.c_double * 8), ("kc_bytes", C.c_uint64 * 8),
-                ("kc_launches", C.c_uint64 * 8)]
+                ("peak_device_bytes", C.c_uint64), ("kc_ms", C.c_double * 16), ("kc_bytes", C.c_uint64 * 16),
+                ("kc_launches", C.c_uint64 * 16)]
 
     def as_dict(self) -> dict:
         return {
@@ -72,13 +80,10 @@ class Stats(C.Structure):
             "d2h_bytes": int(self.d2h_bytes),
             "peak_device_bytes": int(self.peak_device_bytes),
             "kernels": {KERNEL_CLASSES[i]: {"ms": float(self.kc_ms[i]), "bytes": int(self.kc_bytes[i]),
-                                            "launches": int(self.kc_launches[i])} for i in range(8)},
+                                            "launches": int(self.kc_launches[i])} for i in range(len(KERNEL_CLASSES))},
         }
 
 
-class SynthParams(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32), ("err_ppm", C.c_uint32),
-                ("n_ppm", C.c_uint32), ("dup_ppm", C.c_uint32)]
 
 
 # every symbol include/pedk.h declares: (restype, argtypes)
@@ -101,6 +106,7 @@ SIGNATURES = {
     "pedk_sample_borrow_fastq_device": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64]),
     "pedk_sample_count": (C.c_int, [_P, C.c_int, C.POINTER(CountInfo)]),
     "pedk_sample_table": (C.c_int, [_P, _P, _P, C.c_uint64, _U64P]),
+    "pedk_sample_table_digest": (C.c_int, [_P, _U64P, _U64P]),
     "pedk_sample_reads": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint64, _U64P, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32)]),
     "pedk_sample_release_reads": (C.c_int, [_P]),
@@ -114,6 +120,7 @@ SIGNATURES = {
     "pedk_free": (None, [_P]),
     "pedk_result_destroy": (C.c_int, [_P]),
     "pedk_kmer_edges": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _PP]),
+    "pedk_kmer_edges_ref": (C.c_int, [_P, _P, C.c_uint64, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, _PP]),
     "pedk_sample_ingest_reference": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(IngestInfo)]),
     "pedk_sample_num_chromosomes": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "pedk_sample_chromosome": (C.c_int, [_P, C.c_int, _P, C.c_uint64, _U64P, C.POINTER(C.c_int), _P, C.c_uint64]),
@@ -135,10 +142,6 @@ SIGNATURES = {
     "pedk_plan_bucket_owners": (C.c_int, [_P, C.c_int, _P]),
     "pedk_plan_level_a": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, _P, _P, C.POINTER(C.c_int),
                                     _U64P, _U64P]),
-    "pedk_synth_genome": (C.c_int, [C.c_uint64, C.c_uint64, _P]),
-    "pedk_synth_mutate": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P, C.c_uint64, _U64P]),
-    "pedk_synth_fastq_bytes": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint32]),
-    "pedk_synth_fastq_host": (C.c_int, [C.POINTER(SynthParams), _P, C.c_uint64, C.c_uint64, _P]),
     "pedk_synth_fastq_device": (C.c_int, [_P, C.POINTER(SynthParams), _P, C.c_uint64, C.c_uint64, _P]),
     "pedk_test_sort_u64": (C.c_int, [_P, _P, C.c_uint64, C.c_int]),
     "pedk_test_sort_pairs": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
@@ -234,13 +237,15 @@ class Context:
 
     # ---- whole path ----
     def kmer_edges(self, control_fastq, control_bytes: int, target_fastq, target_bytes: int, *, device_buffers: bool,
-                   k: int = 20, clipping: int = 0, padded: bool = False) -> "Result":
+                   k: int = 20, clipping: int = 0, padded: bool = False, reference_control: bool = False) -> "Result":
         """padded (device buffers only): the buffers are addressable up to fastq_padded_bytes(n) and are read
-        in place instead of being copied."""
+        in place instead of being copied.  reference_control: control_fastq is the text of a reference FASTA
+        that is tiled into reads like `ped.pl ref=` does (pedk_kmer_edges_ref)."""
         r = C.c_void_p()
         where = (2 if padded else 1) if device_buffers else 0
-        self.check(self.lib.pedk_kmer_edges(self.h, _ptr(control_fastq), control_bytes, _ptr(target_fastq),
-                                            target_bytes, where, k, clipping, C.byref(r)))
+        fn = self.lib.pedk_kmer_edges_ref if reference_control else self.lib.pedk_kmer_edges
+        self.check(fn(self.h, _ptr(control_fastq), control_bytes, _ptr(target_fastq), target_bytes, where, k, clipping,
+                      C.byref(r)))
         return Result(self, r)
 
     def join(self, control: "Sample", target: "Sample") -> "Result":
@@ -292,6 +297,11 @@ class Sample:
     def add_fastq_device(self, dev_ptr, nbytes: int) -> None:
         self.ctx.check(self.ctx.lib.pedk_sample_add_fastq_device(self.h, _ptr(dev_ptr), nbytes))
 
+    def borrow_fastq_device(self, dev_buf, nbytes: int) -> None:
+        """Text already in HBM, read in place: dev_buf must be addressable up to fastq_padded_bytes(nbytes)."""
+        self.ctx.check(self.ctx.lib.pedk_sample_borrow_fastq_device(self.h, _ptr(dev_buf), nbytes,
+                                                                    fastq_padded_bytes(nbytes)))
+
     def ingest(self, clipping: int = 0) -> IngestInfo:
         """mkSortUniq (ped.pl:1365-1530)."""
         info = IngestInfo()
@@ -338,6 +348,13 @@ class Sample:
         ct = np.empty(n.value, dtype=np.uint32)
         self.ctx.check(self.ctx.lib.pedk_sample_table(self.h, _ptr(km), _ptr(ct), n.value, C.byref(n)))
         return km, ct
+
+    def table_digest(self) -> Tuple[int, int]:
+        """(rows, digest) of this rank's part of the count table (pedk_sample_table_digest)."""
+        n = C.c_uint64()
+        d = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_sample_table_digest(self.h, C.byref(n), C.byref(d)))
+        return int(n.value), int(d.value)
 
     def reads(self, group: int = 0) -> Tuple[np.ndarray, np.ndarray, int]:
         """Unique canonical packed reads of a length group: (words [n, W] u64, pal [n] u8, read_len)."""
@@ -405,6 +422,18 @@ class Result:
         out = np.zeros(n.value, dtype=EDGE_DTYPE)
         self.ctx.check(self.ctx.lib.pedk_result_edges(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+
+def table_digest(kmers: np.ndarray, counts: np.ndarray) -> Tuple[int, int]:
+    """The same digest computed with numpy from a (kmers, counts) table, e.g. the oracle's."""
+    M = np.uint64
+    with np.errstate(over="ignore"):
+        x = kmers.astype(M) * M(0x9E3779B97F4A7C15) + counts.astype(M)
+        x = x + M(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> M(30))) * M(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> M(27))) * M(0x94D049BB133111EB)
+        x = x ^ (x >> M(31))
+        return int(len(kmers)), int(x.sum(dtype=M))
 
 
 def edge_pass1_table() -> np.ndarray:
@@ -478,39 +507,3 @@ def plan_bucket_owners(hist64, nranks: int) -> np.ndarray:
     return out
 
 
-# ---- synthetic inputs (host side; no GPU needed) ----
-
-def synth_genome(seed: int, length: int) -> np.ndarray:
-    lib = load_library()
-    g = np.empty(length, dtype=np.uint8)
-    rc = lib.pedk_synth_genome(seed, length, _ptr(g))
-    if rc:
-        raise PedkError(rc, "pedk_synth_genome")
-    return g
-
-
-def synth_mutate(genome: np.ndarray, seed: int, snp_ppm: int = 1000, indel_ppm: int = 100) -> np.ndarray:
-    lib = load_library()
-    cap = len(genome) + len(genome) // 8 + 64
-    out = np.empty(cap, dtype=np.uint8)
-    n = C.c_uint64()
-    rc = lib.pedk_synth_mutate(_ptr(genome), len(genome), seed, snp_ppm, indel_ppm, _ptr(out), cap, C.byref(n))
-    if rc:
-        raise PedkError(rc, "pedk_synth_mutate")
-    return out[: n.value].copy()
-
-
-def synth_fastq_bytes(first: int, n_reads: int, read_len: int) -> int:
-    return int(load_library().pedk_synth_fastq_bytes(first, n_reads, read_len))
-
-
-def synth_fastq(genome: np.ndarray, seed: int, n_reads: int, read_len: int = 150, err_ppm: int = 2000,
-                n_ppm: int = 1000, dup_ppm: int = 0, first: int = 0) -> bytes:
-    lib = load_library()
-    p = SynthParams(seed, len(genome), read_len, err_ppm, n_ppm, dup_ppm)
-    nb = synth_fastq_bytes(first, n_reads, read_len)
-    out = np.empty(nb, dtype=np.uint8)
-    rc = lib.pedk_synth_fastq_host(C.byref(p), _ptr(genome), first, n_reads, _ptr(out))
-    if rc:
-        raise PedkError(rc, "pedk_synth_fastq_host")
-    return out.tobytes()

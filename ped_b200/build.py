@@ -14,6 +14,8 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "ped_b200", "csrc")
 LIB = os.path.join(CSRC, "libpedk.so")
+SYNTH_SRC = os.path.join(ROOT, "synth", "synth_host.cc")
+SYNTH_LIB = os.path.join(ROOT, "synth", "libpedk_synth.so")
 ORACLE_SRC = os.path.join(ROOT, "oracle", "ped_oracle.c")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libped_oracle.so")
 
@@ -69,6 +71,16 @@ def build_libpedk(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_synth(force: bool = False) -> str:
+    """libpedk_synth.so: the host-side synthetic generator (plain C++, no CUDA; include/pedk_synth.h)."""
+    deps = [SYNTH_SRC, os.path.join(CSRC, "synth.h"), os.path.join(CSRC, "common.cuh"),
+            os.path.join(ROOT, "include", "pedk_synth.h")]
+    if force or not _newer(SYNTH_LIB, deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-shared", "-fPIC", "-Wall",
+                               "-Wno-unused-function", "-o", SYNTH_LIB, SYNTH_SRC])
+    return SYNTH_LIB
+
+
 def build_oracle(force: bool = False) -> str:
     if force or not _newer(ORACLE_LIB, [ORACLE_SRC]):
         subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-Wall", "-o", ORACLE_LIB, ORACLE_SRC])
@@ -78,4 +90,5 @@ def build_oracle(force: bool = False) -> str:
 if __name__ == "__main__":
     v = "-v" in sys.argv
     print(build_libpedk(force="-f" in sys.argv, verbose=v))
+    print(build_synth(force="-f" in sys.argv))
     print(build_oracle(force="-f" in sys.argv))

@@ -704,12 +704,7 @@ void launch_part_scatter_th(const uint64_t* words, int W, int L, int k, uint64_t
     constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
     constexpr int TILE = PT_THREADS * NT * RPW;
     constexpr size_t SMEM = (size_t)TILE * (sizeof(KT) + 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        attr_set = true;
-    }
+    ensure_dyn_smem(k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>, SMEM);
     const uint64_t tiles = (n_reads + (uint64_t)PT_WARPS * RPW - 1) / ((uint64_t)PT_WARPS * RPW);
     const uint64_t resident = (uint64_t)kNumSMs * (PT_THREADS > 512 ? 1 : 2);
     const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
@@ -833,13 +828,11 @@ void launch_cursor_counts(const unsigned long long* cur, const unsigned long lon
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
-                     int n_seg, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st) {
+void launch_sub_hist_bits(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
+                          int n_seg, unsigned n_tiles, int shiftB, unsigned maskB, unsigned* histB, cudaStream_t st) {
     const unsigned long long* offA = seg;
     const int n_bins = n_seg;
     if (!n_tiles) return;
-    const int shiftB = 2 * k - a - b;
-    const unsigned maskB = (1u << b) - 1;
     const unsigned grid = (n_tiles + SH_GROUP - 1) / SH_GROUP;
     if (wide)
         k_sub_hist<uint64_t><<<grid, SH_THREADS, 0, st>>>(static_cast<const uint64_t*>(keys), offA, tile_prefix,
@@ -850,22 +843,20 @@ void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, 
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* seg,
-                        const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int k, int a, int b,
-                        unsigned long long* curB, cudaStream_t st) {
+void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
+                     int n_seg, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st) {
+    launch_sub_hist_bits(keys, wide, seg, tile_prefix, n_seg, n_tiles, 2 * k - a - b, (1u << b) - 1, histB, st);
+}
+
+void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned long long* seg,
+                             const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int shiftB, unsigned maskB,
+                             unsigned long long* curB, cudaStream_t st) {
     const unsigned long long* offA = seg;
     const int n_bins = n_seg;
     if (!n_tiles) return;
-    const int shiftB = 2 * k - a - b;
-    const unsigned maskB = (1u << b) - 1;
     if (wide) {
         constexpr size_t SMEM = (size_t)SUB_TILE * sizeof(uint64_t);
-        static bool attr_set = false;
-        if (!attr_set) {
-            PEDK_CUDA_TRY(cudaFuncSetAttribute(k_sub_scatter<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)SMEM));
-            attr_set = true;
-        }
+        ensure_dyn_smem(k_sub_scatter<uint64_t>, SMEM);
         k_sub_scatter<uint64_t><<<n_tiles, SS_THREADS, SMEM, st>>>(static_cast<const uint64_t*>(in),
                                                                    static_cast<uint64_t*>(out), offA, tile_prefix,
                                                                    n_bins, n_tiles, shiftB, maskB, curB);
@@ -876,6 +867,12 @@ void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long
                                                                    n_bins, n_tiles, shiftB, maskB, curB);
     }
     PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* seg,
+                        const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int k, int a, int b,
+                        unsigned long long* curB, cudaStream_t st) {
+    launch_sub_scatter_bits(in, out, wide, seg, tile_prefix, n_seg, n_tiles, 2 * k - a - b, (1u << b) - 1, curB, st);
 }
 
 void launch_bucket_count(const void* keys, int wide, const unsigned long long* offB, unsigned n_buckets, int k, int a,
@@ -892,22 +889,12 @@ void launch_bucket_count(const void* keys, int wide, const unsigned long long* o
     unsigned grid = kNumSMs * (smem > 100 * 1024 ? 1 : 2);
     if (grid > n_buckets) grid = n_buckets;
     if (wide) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            PEDK_CUDA_TRY(cudaFuncSetAttribute(k_bucket_count<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(((size_t)1 << 13) * 14)));
-            attr_set = true;
-        }
+        ensure_dyn_smem(k_bucket_count<uint64_t>, ((size_t)1 << 13) * 14);
         k_bucket_count<uint64_t><<<grid, BC_THREADS, smem, st>>>(static_cast<const uint64_t*>(keys), offB, n_buckets,
                                                                  k, a, b, log_slots, strand, corr_key, corr_cnt,
                                                                  n_corr, row_key, row_val, cap, counters, ticket, err);
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
-            PEDK_CUDA_TRY(cudaFuncSetAttribute(k_bucket_count<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(((size_t)1 << 13) * 10)));
-            attr_set = true;
-        }
+        ensure_dyn_smem(k_bucket_count<uint32_t>, ((size_t)1 << 13) * 10);
         k_bucket_count<uint32_t><<<grid, BC_THREADS, smem, st>>>(static_cast<const uint32_t*>(keys), offB, n_buckets,
                                                                  k, a, b, log_slots, strand, corr_key, corr_cnt,
                                                                  n_corr, row_key, row_val, cap, counters, ticket, err);

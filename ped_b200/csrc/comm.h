@@ -23,6 +23,15 @@ void comm_destroy(pedk_ctx* ctx);
 void comm_ipc_destroy(pedk_ctx* ctx);
 // in-place sum over ranks of n u64 words in device memory (no-op on one rank)
 void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n);
+void comm_allreduce_min(pedk_ctx* ctx, unsigned long long* dev, size_t n);
+// Elements to allocate for a block of `elems` 8-byte words that peers map through CUDA IPC: IPC
+// shares whole driver allocations, so such a block is its own cudaMalloc of a multiple of 2 MiB
+// (blocks under 1 MiB would otherwise be carved out of a shared slab).
+inline size_t peer_block_elems(size_t elems, bool shared, size_t elem_bytes = 8) {
+    if (!shared) return elems;
+    const size_t g = (size_t(2) << 20) / elem_bytes;
+    return elems < g ? g : (elems + g - 1) / g * g;
+}
 uint64_t comm_allreduce_sum_host(pedk_ctx* ctx, uint64_t v);
 void plan_bucket_owners(const uint64_t* hist64, int nranks, uint8_t* owner64);
 // all-to-all-v of n records; *recv holds the *n_recv records this rank owns, grouped by source rank

@@ -6,10 +6,25 @@
 #include <time.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 using namespace pedk;
 
 namespace pedk {
+
+void set_max_dyn_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;  // (kernel, device) -> bytes granted
+    int dev = 0;
+    PEDK_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return;
+    PEDK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
+}
 
 cudaStream_t ctx_stream(pedk_ctx* ctx) { return ctx->stream; }
 

@@ -14,6 +14,8 @@ namespace pedk {
 
 namespace {
 
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
 __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* a, uint64_t n, uint64_t key) {
     uint64_t lo = 0, hi = n;
     while (lo < hi) {
@@ -204,6 +206,306 @@ __global__ void k_lookup_groups(const uint64_t* __restrict__ row_key, const uint
     out[q] = g;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Hash join (the pedk_join path).  The reference sorts both lbc tables only so that `join` sees
+// equal 19-mers next to each other (ped.pl:709); what the test needs is that the <= 8 rows of a
+// (k-1)-mer P = K >> 2 (4 last bases x 2 samples) MEET.  So the strand rows are not sorted:
+//   k_rows_count    rows -> 2^a-bin histogram of the top bits of kmer_hash(P), plus the smallest
+//                   k-mer of every (sample, 3-nt bucket): the first lbc row of that file (F7)
+//   k_rows_scatter  rows -> 8-byte join records, appended to the level-A' bin of hash(P) (in the
+//                   owner rank's buffer, peer memory over NVLink on several GPUs)
+//   k_sub_hist / k_sub_scatter (bucket.cu)   the same second binning level as the instances
+//   k_join_bucket   one CTA per bucket: a shared-memory table keyed by the remaining hash bits
+//                   ORs every row's 7-bit count into its (sample, base) field; a pass over the
+//                   occupied slots applies joinKmerSub (pass-1 truth table, then the counts)
+// A join record: (low bits of hash(P)) << 10 | last base << 8 | sample << 7 | min(count, 127).
+// Counts above 100 only ever mean "repeat" (ped.pl:721, 732), and a row that is printed has
+// none, so saturating at 127 loses nothing.
+constexpr int JR_PAYLOAD_BITS = 10;
+
+__global__ void __launch_bounds__(256) k_rows_count(const uint64_t* __restrict__ key, uint64_t n, unsigned sample,
+                                                   int k, int nbitsP, int shiftA,
+                                                   unsigned long long* __restrict__ hist,
+                                                   unsigned long long* __restrict__ first) {
+    __shared__ unsigned h[256];
+    __shared__ unsigned long long smin[64];
+    const unsigned tid = threadIdx.x;
+    h[tid] = 0;
+    if (tid < 64) smin[tid] = ~0ull;
+    __syncthreads();
+    const int tag_shift = 2 * k - 6;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + tid; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t K = key[i];
+        atomicAdd(&h[(unsigned)(kmer_hash(K >> 2, nbitsP) >> shiftA)], 1u);
+        const unsigned tag = (unsigned)(K >> tag_shift) & 63u;
+        // most rows are not the smallest of their bucket: look before paying for the atomic
+        if (K < *(volatile unsigned long long*)&smin[tag]) atomicMin(&smin[tag], (unsigned long long)K);
+    }
+    __syncthreads();
+    if (h[tid]) atomicAdd(&hist[tid], (unsigned long long)h[tid]);
+    if (tid < 64 && smin[tid] != ~0ull) atomicMin(&first[sample * 64 + tid], smin[tid]);
+}
+
+constexpr int JS_THREADS = 512;
+constexpr int JS_ITEMS = 8;
+constexpr int JS_TILE = JS_THREADS * JS_ITEMS;
+
+__global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* __restrict__ key,
+                                                               const uint32_t* __restrict__ val, uint64_t n,
+                                                               unsigned sample, int nbitsP, int a, int nranks,
+                                                               unsigned long long* __restrict__ cur, PeerPtrs dst) {
+    __shared__ uint64_t stage[JS_TILE];
+    __shared__ uint8_t sbin[JS_TILE];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned off[256];
+    __shared__ uint64_t* s_out[256];
+    const unsigned tid = threadIdx.x;
+    const int shiftA = nbitsP - a;
+    const uint64_t maskS = (1ull << shiftA) - 1;
+    const uint64_t n_tiles = (n + JS_TILE - 1) / JS_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        uint64_t rec[JS_ITEMS];
+        uint32_t meta[JS_ITEMS];  // bin << 16 | rank inside (tile, bin); ~0: no row
+#pragma unroll
+        for (int j = 0; j < JS_ITEMS; ++j) {
+            const uint64_t i = tile * JS_TILE + (uint64_t)j * JS_THREADS + tid;
+            meta[j] = 0xffffffffu;
+            rec[j] = 0;
+            if (i < n) {
+                const uint64_t K = key[i];
+                const uint32_t c = val[i] & 0x7fffffffu;
+                const uint64_t hp = kmer_hash(K >> 2, nbitsP);
+                const unsigned bin = (unsigned)(hp >> shiftA);
+                rec[j] = ((hp & maskS) << JR_PAYLOAD_BITS) | ((K & 3) << 8) | ((uint64_t)sample << 7) |
+                         (c > 127u ? 127u : c);
+                meta[j] = (bin << 16) | atomicAdd(&hist[bin], 1u);
+            }
+        }
+        __syncthreads();
+        const unsigned c = tid < 256 ? hist[tid] : 0u;
+        uint64_t total;
+        const uint64_t ex = block_exclusive_scan<JS_THREADS>(c, &total);
+        if (tid < 256) {
+            const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
+            off[tid] = (unsigned)ex;
+            const int owner = (int)tid < (1 << a) ? (int)((tid * (unsigned)nranks) >> a) : 0;
+            s_out[tid] = dst.p[owner] + (g - ex);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < JS_ITEMS; ++j) {
+            if (meta[j] != 0xffffffffu) {
+                const unsigned bin = meta[j] >> 16;
+                const unsigned pos = off[bin] + (meta[j] & 0xffffu);
+                stage[pos] = rec[j];
+                sbin[pos] = (uint8_t)bin;
+            }
+        }
+        __syncthreads();
+        const unsigned n_staged = (unsigned)total;
+        for (unsigned i = tid; i < n_staged; i += JS_THREADS) s_out[sbin[i]][i] = stage[i];
+        __syncthreads();
+    }
+}
+
+constexpr int JB_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t jb_fold(uint32_t x) { return x; }
+__device__ __forceinline__ uint32_t jb_fold(uint64_t x) { return (uint32_t)x ^ ((uint32_t)(x >> 32) * 0x9E3779B1u); }
+__device__ __forceinline__ uint32_t jb_cas(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+__device__ __forceinline__ uint64_t jb_cas(uint64_t* p, uint64_t cmp, uint64_t v) {
+    return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)cmp, (unsigned long long)v);
+}
+
+// KT: type of the table key = the r = 2(k-1) - a - b hash bits a bucket does not fix (u32 while
+// r <= 31, so that ~0 is free to mean "empty").  tc/tt: four 7-bit counts of the control / target.
+// A bucket whose groups do not fit the table is processed in rounds of a secondary hash, like
+// k_bucket_count (bucket.cu).
+template <typename KT>
+__global__ void __launch_bounds__(JB_THREADS, 1) k_join_bucket(const uint64_t* __restrict__ recs,
+                                                              const unsigned long long* __restrict__ offB,
+                                                              unsigned n_buckets, int kp, int a, int b,
+                                                              int log_slots,
+                                                              const unsigned long long* __restrict__ first,
+                                                              const uint32_t* __restrict__ pass1_bits,
+                                                              EdgeRec* __restrict__ edges, uint64_t cap,
+                                                              unsigned long long* __restrict__ n_edges,
+                                                              unsigned* __restrict__ ticket, int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char jb_smem[];
+    const unsigned slots = 1u << log_slots;
+    KT* tkey = reinterpret_cast<KT*>(jb_smem);
+    uint32_t* tc = reinterpret_cast<uint32_t*>(tkey + slots);
+    uint32_t* tt = tc + slots;
+    __shared__ unsigned s_bucket, s_distinct, s_overflow;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const int nbitsP = 2 * kp, rs = nbitsP - a, r = rs - b;
+    const KT EMPTY = ~KT(0);
+    const KT maskR = r ? (KT)((((uint64_t)1) << r) - 1) : KT(0);
+    const unsigned smask = slots - 1;
+    const unsigned limit = slots - (slots >> 2);
+    const int hshift = 32 - log_slots;
+    for (;;) {
+        if (tid == 0) s_bucket = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const unsigned bk = s_bucket;
+        if (bk >= n_buckets) break;
+        const unsigned long long lo = offB[bk], hi = offB[bk + 1];
+        if (hi == lo) {
+            __syncthreads();
+            continue;
+        }
+        const uint64_t hbase = ((uint64_t)(bk >> 8) << rs) | ((uint64_t)(bk & 255u) << r);
+        unsigned R = 1, rd = 0;
+        for (;;) {
+            for (unsigned i = tid; i < slots; i += JB_THREADS) {
+                tkey[i] = EMPTY;
+                tc[i] = 0;
+                tt[i] = 0;
+            }
+            if (tid == 0) {
+                s_distinct = 0;
+                s_overflow = 0;
+            }
+            __syncthreads();
+            // ---- every row ORs its count into the (sample, base) field of its group ----
+            unsigned my_new = 0;
+            for (unsigned long long i0 = lo; i0 < hi; i0 += JB_THREADS) {
+                if (__any_sync(FULL_MASK, *(volatile unsigned*)&s_overflow != 0)) break;
+                const unsigned long long i = i0 + tid;
+                if (i < hi) {
+                    const uint64_t rec = recs[i];
+                    const KT x = (KT)((KT)(rec >> JR_PAYLOAD_BITS) & maskR);
+                    bool want = true;
+                    if (R > 1) want = (((jb_fold(x) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
+                    if (want) {
+                        unsigned h = hshift < 32 ? (jb_fold(x) * 0x9E3779B1u) >> hshift : 0u;
+                        unsigned probes = 0;
+                        for (;;) {
+                            KT q = *(volatile KT*)&tkey[h];
+                            if (q == EMPTY) {
+                                const KT old = jb_cas(&tkey[h], EMPTY, x);
+                                if (old == EMPTY) {
+                                    ++my_new;
+                                    q = x;
+                                } else {
+                                    q = old;
+                                }
+                            }
+                            if (q == x) {
+                                const unsigned cnt = (unsigned)rec & 127u, base = (unsigned)(rec >> 8) & 3u;
+                                atomicOr(((rec >> 7) & 1u) ? &tt[h] : &tc[h], cnt << (7 * base));
+                                break;
+                            }
+                            h = (h + 1) & smask;
+                            if (++probes > slots) {
+                                s_overflow = 1;
+                                break;
+                            }
+                        }
+                    }
+                }
+                const unsigned wn = __reduce_add_sync(FULL_MASK, my_new);
+                my_new = 0;
+                if (wn && lane == 0 && atomicAdd(&s_distinct, wn) + wn > limit) s_overflow = 1;
+            }
+            __syncthreads();
+            if (s_overflow) {
+                __syncthreads();  // everybody has seen the flag before it is cleared again
+                if (R >= (1u << 20)) {
+                    if (tid == 0) atomicExch(err, 3);
+                    break;
+                }
+                R <<= 1;
+                continue;
+            }
+            // ---- joinKmerSub (ped.pl:703-782) on every group ----
+            for (unsigned sl = tid; sl < slots; sl += JB_THREADS) {
+                const KT q = tkey[sl];
+                if (q == EMPTY) continue;
+                const uint32_t pc = tc[sl], pt = tt[sl];
+                if (!pc || !pt) continue;  // `join` is an inner join (ped.pl:709); a count is never 0
+                uint32_t c[4], t[4];
+                unsigned code = 0;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    c[x] = (pc >> (7 * x)) & 127u;
+                    t[x] = (pt >> (7 * x)) & 127u;
+                    code |= count_class(c[x]) << (2 * x);
+                    code |= count_class(t[x]) << (2 * (4 + x));
+                }
+                if (!((__ldg(pass1_bits + (code >> 5)) >> (code & 31u)) & 1u)) continue;
+                // ---- rare from here on ----
+                const uint64_t P = kmer_unhash(hbase | (uint64_t)q, nbitsP);
+                const unsigned tag = (unsigned)(P >> (nbitsP - 6)) & 63u;
+                const unsigned long long fc = first[tag], ft = first[64 + tag];
+                if ((fc != ~0ull && (fc >> 2) == P) || (ft != ~0ull && (ft >> 2) == P)) continue;  // F7 rows: host
+                uint8_t cont, alt;
+                if (!edge_test(c, t, &cont, &alt)) continue;
+                const unsigned long long o = atomicAdd(n_edges, 1ull);
+                if (o < cap) {
+                    EdgeRec e;
+                    e.p = P;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) { e.c[x] = c[x]; e.t[x] = t[x]; }
+                    e.cont = cont;
+                    e.alt = alt;
+#pragma unroll
+                    for (int x = 0; x < 6; ++x) e.pad[x] = 0;
+                    edges[o] = e;
+                }
+            }
+            __syncthreads();  // the table is cleared next
+            while (R > 1 && rd >= (R >> 1)) {
+                rd -= R >> 1;
+                R >>= 1;
+            }
+            if (R == 1) break;
+            rd += R >> 1;
+        }
+    }
+}
+
+// The groups of n_p given (k-1)-mers, read from their buckets (host-side F7 rows).  One CTA per P.
+__global__ void __launch_bounds__(256) k_join_lookup(const uint64_t* __restrict__ recs,
+                                                    const unsigned long long* __restrict__ offB, int kp, int a, int b,
+                                                    const uint64_t* __restrict__ p_list, GroupRec* __restrict__ out) {
+    __shared__ GroupRec g;
+    const int nbitsP = 2 * kp, rs = nbitsP - a, r = rs - b;
+    const uint64_t P = p_list[blockIdx.x];
+    const uint64_t h = kmer_hash(P, nbitsP);
+    const unsigned bk = (unsigned)(h >> rs) * 256u + ((unsigned)(h >> r) & ((1u << b) - 1));
+    const uint64_t want = h & ((1ull << rs) - 1);
+    if (threadIdx.x == 0) {
+        g.p = P;
+        for (int x = 0; x < 4; ++x) { g.c[x] = g.t[x] = 0; g.hasc[x] = g.hast[x] = 0; }
+    }
+    __syncthreads();
+    for (unsigned long long i = offB[bk] + threadIdx.x; i < offB[bk + 1]; i += blockDim.x) {
+        const uint64_t rec = recs[i];
+        if ((rec >> JR_PAYLOAD_BITS) != want) continue;
+        const unsigned x = (unsigned)(rec >> 8) & 3u, cnt = (unsigned)rec & 127u;
+        if ((rec >> 7) & 1u) { g.t[x] = cnt; g.hast[x] = 1; }
+        else { g.c[x] = cnt; g.hasc[x] = 1; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = g;
+}
+
+
+// Order-independent digest of a strand table: sum over rows of mix64(K * phi + count) modulo 2^64.
+__global__ void __launch_bounds__(256) k_rows_digest(const uint64_t* __restrict__ key, const uint32_t* __restrict__ val,
+                                                    uint64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        acc += mix64(key[i] * 0x9E3779B97F4A7C15ull + (uint64_t)(val[i] & 0x7fffffffu));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, d);
+    if ((threadIdx.x & 31u) == 0 && acc) atomicAdd(out, acc);
+}
+
 }  // namespace
 
 void launch_copy_rows(const uint64_t* src_key, const uint32_t* src_val, uint64_t n, uint64_t* dst_key,
@@ -262,6 +564,76 @@ void launch_lookup_groups(const uint64_t* row_key, const uint32_t* row_val, uint
                           int n_p, GroupRec* out, cudaStream_t st) {
     if (!n_p) return;
     k_lookup_groups<<<(n_p + 127) / 128, 128, 0, st>>>(row_key, row_val, n, p_list, n_p, out);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+
+void launch_rows_count(const uint64_t* row_key, uint64_t n, int sample, int k, unsigned long long* hist256,
+                       unsigned long long* first, cudaStream_t st) {
+    if (!n) return;
+    const int kp = k - 1, a = kmer_bits_a(kp);
+    const uint64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    const unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_rows_count<<<grid, 256, 0, st>>>(row_key, n, (unsigned)sample, k, 2 * kp, 2 * kp - a, hist256, first);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_rows_scatter(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int sample, int k, int nranks,
+                         unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st) {
+    if (!n) return;
+    const int kp = k - 1, a = kmer_bits_a(kp);
+    const uint64_t tiles = (n + JS_TILE - 1) / JS_TILE;
+    const unsigned grid = (unsigned)(tiles < (uint64_t)kNumSMs * 2 ? tiles : (uint64_t)kNumSMs * 2);
+    k_rows_scatter<<<grid, JS_THREADS, 0, st>>>(row_key, row_val, n, (unsigned)sample, 2 * kp, a, nranks, cur, dst);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+int join_record_shift_b(int k, int b) {
+    const int kp = k - 1, a = kmer_bits_a(kp);
+    return 2 * kp - a - b + JR_PAYLOAD_BITS;
+}
+
+void launch_join_bucket(const uint64_t* recs, const unsigned long long* offB, unsigned n_buckets, int k, int b,
+                        int log_slots,
+                        const unsigned long long* first, const uint32_t* pass1_bits, EdgeRec* edges, uint64_t cap,
+                        unsigned long long* n_edges, unsigned* ticket, int* err, cudaStream_t st) {
+    if (!n_buckets) return;
+    const int kp = k - 1, a = kmer_bits_a(kp);
+    const int r = 2 * kp - a - b;
+    if (log_slots < 10) log_slots = 10;
+    if (log_slots > 14) log_slots = 14;
+    const bool wide = r > 31;
+    if (wide && log_slots > 13) log_slots = 13;
+    const size_t smem = ((size_t)1 << log_slots) * ((wide ? 8 : 4) + 8);
+    PEDK_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    unsigned grid = kNumSMs * (smem <= 100 * 1024 ? 2 : 1);
+    if (grid > n_buckets) grid = n_buckets;
+    if (wide) {
+        ensure_dyn_smem(k_join_bucket<uint64_t>, ((size_t)1 << 13) * 16);
+        k_join_bucket<uint64_t><<<grid, JB_THREADS, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first,
+                                                                pass1_bits, edges, cap, n_edges, ticket, err);
+    } else {
+        ensure_dyn_smem(k_join_bucket<uint32_t>, ((size_t)1 << 14) * 12);
+        k_join_bucket<uint32_t><<<grid, JB_THREADS, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first,
+                                                                pass1_bits, edges, cap, n_edges, ticket, err);
+    }
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_join_lookup(const uint64_t* recs, const unsigned long long* offB, int k, int b, const uint64_t* p_list,
+                        int n_p, GroupRec* out, cudaStream_t st) {
+    if (!n_p) return;
+    const int kp = k - 1;
+    k_join_lookup<<<n_p, 256, 0, st>>>(recs, offB, kp, kmer_bits_a(kp), b, p_list, out);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_rows_digest(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, unsigned long long* out,
+                        cudaStream_t st) {
+    if (!n) return;
+    const uint64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    const unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_rows_digest<<<grid, 256, 0, st>>>(row_key, row_val, n, out);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

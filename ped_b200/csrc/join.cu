@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <string>
 
+#include "comm.h"
+#include "plan.h"
 #include "sample.h"
 
 using namespace pedk;
@@ -99,6 +101,10 @@ bool quirk_row(const GroupRec& g, bool first_c, bool first_t, int k, pedk_edge* 
     return true;
 }
 
+// joinKmer without a sort (edges.cu "Hash join"): the strand rows of both samples become 8-byte
+// join records binned twice by the hash of their (k-1)-mer -- on several ranks the first level
+// stores straight into the owner's buffer over NVLink, like the k-mer instances -- and one CTA
+// per bucket applies joinKmerSub to the groups that met in its shared-memory table.
 void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_result* res) {
     cudaStream_t st = ctx->stream;
     PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -107,61 +113,197 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         throw PedkError(PEDK_E_INVAL, "pedk_join: samples not counted with the same k");
     const int k = control->k;
     res->k = k;
-    RowTable rows;
-    build_rows(ctx, control, target, &rows);
-    if (!rows.n) return;
+    const bool multi = ctx->nranks > 1;
+    const int R = ctx->nranks, me = ctx->rank;
+    const int kp = k - 1, a = kmer_bits_a(kp);
+    // PEDK_JOIN_B (tests): fewer second-level bits -> larger buckets, so that the tables overflow
+    const int b = [&]() {
+        const int full = kmer_bits_b(kp);
+        const char* v = getenv("PEDK_JOIN_B");
+        const int x = v && *v ? atoi(v) : full;
+        return x < 1 ? 1 : x > full ? full : x;
+    }();
+    constexpr int NB = 256;
 
-    DBuf<unsigned long long> first(ctx, 128);
-    uint64_t cap = rows.n / 16;
-    if (cap < (1u << 16)) cap = 1u << 16;
-    if (cap > rows.n) cap = rows.n;
-    DBuf<EdgeRec> edges(ctx, cap);
-    uint64_t E = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        {
-            StageScope sc(ctx, PEDK_ST_EDGES, 2);
-            PEDK_CUDA_TRY(cudaMemsetAsync(first.p, 0xFF, first.bytes(), st));
-            PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 4, 0, sizeof(unsigned long long), st));
-            launch_first_of_bucket(rows.key.p, rows.val.p, rows.n, k, first.p, st);
-            launch_edges(rows.key.p, rows.val.p, rows.n, k, first.p, ctx->edge_pass1, edges.p, cap, ctx->scalars + 4, st);
+    // ---- the rows of both samples (tables read back from count files are uploaded first) ----
+    struct Src {
+        const uint64_t* key = nullptr;
+        const uint32_t* val = nullptr;
+        uint64_t n = 0;
+        DBuf<uint64_t> up_key;
+        DBuf<uint32_t> up_val;
+    } src[2];
+    pedk_sample* ss[2] = {control, target};
+    uint64_t rows_local = 0;
+    for (int i = 0; i < 2; ++i) {
+        pedk_sample* s = ss[i];
+        if (s->host_only_table) {
+            const uint64_t m = s->h_kmer.size();
+            src[i].up_key = DBuf<uint64_t>(ctx, m);
+            src[i].up_val = DBuf<uint32_t>(ctx, m);
+            if (m) {
+                StageScope sc(ctx, PEDK_ST_COPY, 0);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(src[i].up_key.p, s->h_kmer.data(), m * 8, cudaMemcpyHostToDevice, st));
+                PEDK_CUDA_TRY(cudaMemcpyAsync(src[i].up_val.p, s->h_cnt.data(), m * 4, cudaMemcpyHostToDevice, st));
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                ctx->stats.h2d_bytes += m * 12;
+            }
+            src[i].key = src[i].up_key.p;
+            src[i].val = src[i].up_val.p;
+            src[i].n = m;
+        } else {
+            src[i].key = s->row_key_ptr();
+            src[i].val = s->row_val_ptr();
+            src[i].n = s->n_rows;
         }
-        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->scalars + 4, 8, cudaMemcpyDeviceToHost, st));
-        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        E = ctx->h_scalars[0];
-        if (E <= cap) break;
-        cap = E;  // rare: more edges than one row in sixteen
-        edges = DBuf<EdgeRec>(ctx, cap);
+        rows_local += src[i].n;
     }
-    // EdgeRec and pedk_edge share one layout (quirk = first pad byte = 0): the records go through
-    // a pinned staging buffer of the context straight into the result
-    static_assert(sizeof(EdgeRec) == sizeof(pedk_edge), "edge record layout");
-    unsigned char* stage = static_cast<unsigned char*>(host_stage(ctx, E * sizeof(EdgeRec) + 1024));
-    unsigned long long* h_first = reinterpret_cast<unsigned long long*>(stage + E * sizeof(EdgeRec));
-    {
-        StageScope sc(ctx, PEDK_ST_COPY, 0);
-        if (E) PEDK_CUDA_TRY(cudaMemcpyAsync(stage, edges.p, E * sizeof(EdgeRec), cudaMemcpyDeviceToHost, st));
-        PEDK_CUDA_TRY(cudaMemcpyAsync(h_first, first.p, 128 * 8, cudaMemcpyDeviceToHost, st));
-    }
-    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-    ctx->stats.d2h_bytes += E * sizeof(EdgeRec) + 1024;
-    trace(ctx, "edges kernel + D2H");
+    if (rows_local == 0 && !multi) return;
 
-    // ---- first-of-bucket rows: look the groups up and evaluate their text on the host ----
+    // ---- (1) level-A' bin sizes and the first k-mer of every (sample, 3-nt bucket) ----
+    DBuf<unsigned long long> counts(ctx, (size_t)(NB + 1) * (PEDK_MAX_RANKS + 1) + 128);
+    unsigned long long* d_hist = counts.p;                             // [257]
+    unsigned long long* d_all = counts.p + (NB + 1);                   // [R][257]
+    unsigned long long* d_first = counts.p + (size_t)(NB + 1) * (PEDK_MAX_RANKS + 1);  // [128]
+    {
+        StageScope sc(ctx, PEDK_ST_ROWSORT, 2, 0, 0, PEDK_KC_JOIN_COUNT, rows_local * 8);
+        PEDK_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)(NB + 1) * 8, st));
+        PEDK_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, 128 * 8, st));
+        for (int i = 0; i < 2; ++i) launch_rows_count(src[i].key, src[i].n, i, k, d_hist, d_first, st);
+    }
+    std::vector<unsigned long long> all((size_t)(NB + 1) * R, 0);
+    unsigned char* hstage = static_cast<unsigned char*>(host_stage(ctx, 1 << 16));
+    unsigned long long* h_first = reinterpret_cast<unsigned long long*>(hstage);
+    if (multi) {
+        comm_allgather_u64(ctx, d_hist, d_all, NB + 1);
+        comm_allreduce_min(ctx, d_first, 128);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), d_hist, (size_t)(NB + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PEDK_CUDA_TRY(cudaMemcpyAsync(h_first, d_first, 128 * 8, cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->stats.d2h_bytes += all.size() * 8 + 1024;
+    trace(ctx, "  join: row counts");
+    LevelAPlan lp;
+    plan_level_a_exact(a, R, me, all.data(), &lp);
+    const uint64_t m = lp.buffer_elems;  // join records this rank owns
+    uint64_t rows_all = 0;
+    for (size_t i = 0; i < all.size(); ++i) rows_all += all[i];
+    if (rows_all == 0) return;
+
+    // ---- (2) rows -> join records in the level-A' bins (of their owner rank) ----
+    DBuf<uint64_t> recA(ctx, peer_block_elems(m, multi));
+    DBuf<unsigned long long> d_cur(ctx, NB);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_cur.p, lp.cur.data(), (size_t)NB * 8, cudaMemcpyHostToDevice, st));
+    {
+        PeerPtrs dst;
+        if (multi) {
+            void* peers[PEDK_MAX_RANKS];
+            comm_peer_pointers(ctx, recA.p, peers);
+            for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
+        } else {
+            dst.p[0] = recA.p;
+        }
+        StageScope sc(ctx, multi ? PEDK_ST_EXCHANGE : PEDK_ST_ROWSORT, 2, 0, 0, PEDK_KC_JOIN_SCATTER, rows_local * 20);
+        if (multi) comm_barrier(ctx);  // nobody stores into a buffer its owner still reads
+        for (int i = 0; i < 2; ++i) launch_rows_scatter(src[i].key, src[i].val, src[i].n, i, k, R, d_cur.p, dst, st);
+        if (multi) comm_barrier(ctx);  // every rank's stores have landed
+    }
+    std::vector<GroupRec> groups;
     std::vector<uint64_t> plist;
     for (int i = 0; i < 128; ++i)
         if (h_first[i] != ~0ull) plist.push_back(h_first[i] >> 2);
     std::sort(plist.begin(), plist.end());
     plist.erase(std::unique(plist.begin(), plist.end()), plist.end());
-    std::vector<GroupRec> groups(plist.size());
-    if (!plist.empty()) {
-        DBuf<uint64_t> d_p(ctx, plist.size());
-        DBuf<GroupRec> d_g(ctx, plist.size());
-        StageScope sc(ctx, PEDK_ST_EDGES, 1);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(d_p.p, plist.data(), plist.size() * 8, cudaMemcpyHostToDevice, st));
-        launch_lookup_groups(rows.key.p, rows.val.p, rows.n, d_p.p, (int)plist.size(), d_g.p, st);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(groups.data(), d_g.p, plist.size() * sizeof(GroupRec), cudaMemcpyDeviceToHost, st));
+    uint64_t E = 0;
+    unsigned char* stage = nullptr;
+    if (m) {
+        // ---- (3) second binning level: exact bucket sizes, offsets, scatter ----
+        const unsigned TILE = sub_tile_keys();
+        const int n_seg = (int)lp.seg_start.size();
+        std::vector<unsigned> tile_prefix((size_t)n_seg + 1, 0);
+        for (int sg = 0; sg < n_seg; ++sg) {
+            const unsigned long long len = lp.seg_end[(size_t)sg] - lp.seg_start[(size_t)sg];
+            const unsigned long long tiles = (len + TILE - 1) / TILE;
+            if ((unsigned long long)tile_prefix[(size_t)sg] + tiles > 0xfffffff0ull)
+                throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^45 table rows on one GPU");
+            tile_prefix[(size_t)sg + 1] = tile_prefix[(size_t)sg] + (unsigned)tiles;
+        }
+        const unsigned n_tiles = tile_prefix[(size_t)n_seg];
+        DBuf<unsigned long long> d_seg(ctx, (size_t)3 * n_seg);
+        DBuf<unsigned> tprefix(ctx, (size_t)n_seg + 1);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p, lp.seg_start.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + n_seg, lp.seg_end.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + 2 * n_seg, lp.seg_bin.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
+        const size_t n_buckets = ((size_t)1 << a) * NB;
+        const int shiftB = join_record_shift_b(k, b);
+        const unsigned maskB = (1u << b) - 1;
+        DBuf<unsigned> histB(ctx, n_buckets);
+        DBuf<unsigned long long> offB(ctx, n_buckets + 1), curB(ctx, n_buckets);
+        DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
+        DBuf<uint64_t> recB(ctx, m);
+        {
+            StageScope sc(ctx, PEDK_ST_ROWSORT, 6, 0, 0, PEDK_KC_JOIN_SUB, m * 24);
+            PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
+            launch_sub_hist_bits(recA.p, 1, d_seg.p, tprefix.p, n_seg, n_tiles, shiftB, maskB, histB.p, st);
+            exclusive_scan_u32(histB.p, reinterpret_cast<uint64_t*>(offB.p), n_buckets, ctx->scalars + 3, ws.p, st);
+            const unsigned long long total = m;
+            PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
+            launch_sub_scatter_bits(recA.p, recB.p, 1, d_seg.p, tprefix.p, n_seg, n_tiles, shiftB, maskB, curB.p, st);
+        }
+        // ---- (4) one CTA per bucket: groups meet in a shared-memory table, joinKmerSub on each ----
+        const int log_slots = []() {
+            const char* v = getenv("PEDK_JOIN_SLOTS_LOG2");
+            const int x = v && *v ? atoi(v) : 14;
+            return x < 10 ? 10 : x > 14 ? 14 : x;
+        }();
+        uint64_t cap = m / 16;
+        if (cap < (1u << 16)) cap = 1u << 16;
+        DBuf<EdgeRec> edges(ctx, cap);
+        DBuf<uint64_t> d_p(ctx, plist.size() ? plist.size() : 1);
+        DBuf<GroupRec> d_g(ctx, plist.size() ? plist.size() : 1);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            {
+                StageScope sc(ctx, PEDK_ST_EDGES, 1, 0, 0, PEDK_KC_JOIN_TABLE, m * 8);
+                PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 4, 0, sizeof(unsigned long long), st));
+                launch_join_bucket(recB.p, offB.p, (unsigned)n_buckets, k, b, log_slots, d_first, ctx->edge_pass1, edges.p, cap,
+                                   ctx->scalars + 4, ctx->tile_ctr, ctx->err_flag, st);
+            }
+            PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->scalars + 4, 8, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            E = ctx->h_scalars[0];
+            if (E <= cap) break;
+            cap = E;  // rare: more edges than one row in sixteen
+            edges = DBuf<EdgeRec>(ctx, cap);
+        }
+        check_err_flag(ctx, "join buckets");
+        // EdgeRec and pedk_edge share one layout (quirk = first pad byte = 0): the records go through
+        // a pinned staging buffer of the context straight into the result
+        static_assert(sizeof(EdgeRec) == sizeof(pedk_edge), "edge record layout");
+        stage = static_cast<unsigned char*>(host_stage(ctx, E * sizeof(EdgeRec) + 2048));
+        groups.resize(plist.size());
+        {
+            StageScope sc(ctx, PEDK_ST_COPY, 0);
+            if (E) PEDK_CUDA_TRY(cudaMemcpyAsync(stage, edges.p, E * sizeof(EdgeRec), cudaMemcpyDeviceToHost, st));
+        }
+        // ---- first-of-bucket rows: look the groups up and evaluate their text on the host ----
+        if (!plist.empty()) {
+            StageScope sc(ctx, PEDK_ST_EDGES, 1);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(d_p.p, plist.data(), plist.size() * 8, cudaMemcpyHostToDevice, st));
+            launch_join_lookup(recB.p, offB.p, k, b, d_p.p, (int)plist.size(), d_g.p, st);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(groups.data(), d_g.p, plist.size() * sizeof(GroupRec), cudaMemcpyDeviceToHost, st));
+        }
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += E * sizeof(EdgeRec) + plist.size() * sizeof(GroupRec);
+        trace(ctx, "join: bins + buckets + edges + D2H");
     }
+    // h_first lives in the same pinned buffer host_stage may have re-allocated: take it again
+    std::vector<unsigned long long> first(128);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(first.data(), d_first, 128 * 8, cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
 
     res->edges.resize(E);
     if (E) memcpy(static_cast<void*>(res->edges.data()), stage, E * sizeof(pedk_edge));
@@ -169,10 +311,10 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     for (const GroupRec& g : groups) {
         bool pc = g.hasc[0] | g.hasc[1] | g.hasc[2] | g.hasc[3];
         bool pt = g.hast[0] | g.hast[1] | g.hast[2] | g.hast[3];
-        if (!(pc && pt)) continue;  // inner join
+        if (!(pc && pt)) continue;  // inner join (on several ranks: only the owner of the bucket sees the group)
         unsigned tag = (unsigned)(g.p >> (2 * (k - 1) - 6));
-        bool first_c = h_first[tag] != ~0ull && (h_first[tag] >> 2) == g.p;
-        bool first_t = h_first[64 + tag] != ~0ull && (h_first[64 + tag] >> 2) == g.p;
+        bool first_c = first[tag] != ~0ull && (first[tag] >> 2) == g.p;
+        bool first_t = first[64 + tag] != ~0ull && (first[64 + tag] >> 2) == g.p;
         pedk_edge e;
         std::string line;
         if (quirk_row(g, first_c, first_t, k, &e, &line)) {
@@ -379,9 +521,9 @@ extern "C" int pedk_edge_pass1_table(uint32_t* bits2048) {
     return PEDK_OK;
 }
 
-extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_t control_bytes,
-                               const void* target_fastq, uint64_t target_bytes, int where, int k, int clipping,
-                               pedk_result** out) {
+static int kmer_edges_impl(pedk_ctx* ctx, const void* control_text, uint64_t control_bytes, const void* target_fastq,
+                           uint64_t target_bytes, int where, int k, int clipping, bool ref_control,
+                           pedk_result** out) {
     if (!ctx || !out || where < 0 || where > 2) return PEDK_E_INVAL;
     *out = nullptr;
     pedk_sample *c = nullptr, *t = nullptr;
@@ -396,7 +538,7 @@ extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_
             rc = pedk_sample_borrow_fastq_device(t, const_cast<void*>(target_fastq), target_bytes,
                                                  (target_bytes + T - 1) / T * T + T);
         if (rc == PEDK_OK)
-            rc = pedk_sample_borrow_fastq_device(c, const_cast<void*>(control_fastq), control_bytes,
+            rc = pedk_sample_borrow_fastq_device(c, const_cast<void*>(control_text), control_bytes,
                                                  (control_bytes + T - 1) / T * T + T);
     } else {
         if (rc == PEDK_OK) rc = pedk_sample_reserve(c, control_bytes);
@@ -405,8 +547,8 @@ extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_
             rc = where ? pedk_sample_add_fastq_device(t, target_fastq, target_bytes)
                        : pedk_sample_add_fastq(t, target_fastq, target_bytes);
         if (rc == PEDK_OK)
-            rc = where ? pedk_sample_add_fastq_device(c, control_fastq, control_bytes)
-                       : pedk_sample_add_fastq(c, control_fastq, control_bytes);
+            rc = where ? pedk_sample_add_fastq_device(c, control_text, control_bytes)
+                       : pedk_sample_add_fastq(c, control_text, control_bytes);
     }
     // ped.pl:291-297 ingests the target first, and `$clipping` is a global: a value chosen
     // automatically for the target is an explicit clipping= for the control
@@ -415,7 +557,7 @@ extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_
     if (rc == PEDK_OK && ti.auto_clipped) clipping = ti.clipping_used;
     if (rc == PEDK_OK) rc = pedk_sample_count(t, k, nullptr);
     if (rc == PEDK_OK) rc = pedk_sample_release_reads(t);
-    if (rc == PEDK_OK) rc = pedk_sample_ingest(c, clipping, nullptr);
+    if (rc == PEDK_OK) rc = ref_control ? pedk_sample_ingest_reference(c, 0, 0, nullptr) : pedk_sample_ingest(c, clipping, nullptr);
     if (rc == PEDK_OK) rc = pedk_sample_count(c, k, nullptr);
     if (rc == PEDK_OK) rc = pedk_sample_release_reads(c);
     if (rc == PEDK_OK) rc = pedk_join(ctx, c, t, out);
@@ -423,4 +565,15 @@ extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_
     pedk_sample_destroy(t);
     pedk::trace(ctx, "samples destroyed (step end)");
     return rc;
+}
+
+extern "C" int pedk_kmer_edges(pedk_ctx* ctx, const void* control_fastq, uint64_t control_bytes,
+                               const void* target_fastq, uint64_t target_bytes, int where, int k, int clipping,
+                               pedk_result** out) {
+    return kmer_edges_impl(ctx, control_fastq, control_bytes, target_fastq, target_bytes, where, k, clipping, false, out);
+}
+
+extern "C" int pedk_kmer_edges_ref(pedk_ctx* ctx, const void* ref_fasta, uint64_t ref_bytes, const void* target_fastq,
+                                   uint64_t target_bytes, int where, int k, int clipping, pedk_result** out) {
+    return kmer_edges_impl(ctx, ref_fasta, ref_bytes, target_fastq, target_bytes, where, k, clipping, true, out);
 }

@@ -167,6 +167,34 @@ struct GroupRec {
 // look up the groups of n_p given (k-1)-mers (host-side quirk rows)
 void launch_lookup_groups(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, const uint64_t* p_list,
                           int n_p, GroupRec* out, cudaStream_t st);
+// ---- hash join (edges.cu): rows -> join records binned by kmer_hash(K >> 2) -> per-bucket tables ----
+// a' = kmer_bits_a(k-1), b' = kmer_bits_b(k-1) bits for the two binning levels of the (k-1)-mer hash
+// hist256[bin] += rows of that level-A' bin; first[sample * 64 + tag] = min(K) (preset ~0)
+void launch_rows_count(const uint64_t* row_key, uint64_t n, int sample, int k, unsigned long long* hist256,
+                       unsigned long long* first, cudaStream_t st);
+// rows -> 8-byte join records appended at cur[bin] inside dst.p[owner of bin]
+void launch_rows_scatter(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, int sample, int k, int nranks,
+                         unsigned long long* cur, const PeerPtrs& dst, cudaStream_t st);
+// bit position of the level-B' digit inside a join record (for launch_sub_hist_bits / _scatter_bits)
+int join_record_shift_b(int k, int b);
+void launch_sub_hist_bits(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
+                          int n_seg, unsigned n_tiles, int shiftB, unsigned maskB, unsigned* histB, cudaStream_t st);
+void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned long long* seg,
+                             const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int shiftB, unsigned maskB,
+                             unsigned long long* curB, cudaStream_t st);
+// buckets of join records (offB[n_buckets + 1]) -> edges; groups that are the first of a 3-nt
+// bucket in either sample (first[128]) are left to the host (F7)
+void launch_join_bucket(const uint64_t* recs, const unsigned long long* offB, unsigned n_buckets, int k, int b,
+                        int log_slots,
+                        const unsigned long long* first, const uint32_t* pass1_bits, EdgeRec* edges, uint64_t cap,
+                        unsigned long long* n_edges, unsigned* ticket, int* err, cudaStream_t st);
+void launch_join_lookup(const uint64_t* recs, const unsigned long long* offB, int k, int b, const uint64_t* p_list,
+                        int n_p, GroupRec* out, cudaStream_t st);
+
+// *out += sum over rows of mix64(K * 0x9E3779B97F4A7C15 + count): order-independent table digest
+void launch_rows_digest(const uint64_t* row_key, const uint32_t* row_val, uint64_t n, unsigned long long* out,
+                        cudaStream_t st);
+
 // ---------------- synthetic reads (synth.cu) ----------------
 struct SynthParams;
 void launch_synth_fastq(const SynthParams& p, const char* genome_dev, uint64_t first, uint64_t n, char* out_dev,

@@ -273,12 +273,7 @@ __global__ void __launch_bounds__(256) k_hist_to_base(unsigned long long* __rest
 template <bool PAIRS, int SHIFT>
 void launch_pass_variant(const uint64_t* in, uint64_t* out, const uint32_t* vin, uint32_t* vout, size_t pn,
                          unsigned long long* bin_base, RadixWorkspace ws, unsigned tiles, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        PEDK_CUDA_TRY(cudaFuncSetAttribute(k_radix_pass<PAIRS, SHIFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(RadixSmem<PAIRS>)));
-        attr_set = true;
-    }
+    ensure_dyn_smem(k_radix_pass<PAIRS, SHIFT>, sizeof(RadixSmem<PAIRS>));
     k_radix_pass<PAIRS, SHIFT><<<tiles, RS_THREADS, sizeof(RadixSmem<PAIRS>), st>>>(
         in, out, vin, vout, pn, bin_base, reinterpret_cast<uint32_t*>(ws.lookback), ws.tile_ctr, tiles, ws.err);
 }

@@ -239,7 +239,10 @@ void do_ingest_reference(pedk_sample* s, int window, int step) {
         }
     }
     for (uint64_t c = 0; c < H; ++c) {
-        const uint64_t nw = (live[c] && chr_len[c] >= (uint64_t)window) ? (chr_len[c] - window) / step + 1 : 0;
+        // mkControlRead skips a chromosome called NOP (ped.pl:1069); its chrNOP file is still written
+        const bool nop = s->chromosomes[c].name == "chrNOP";
+        const uint64_t nw =
+            (live[c] && !nop && chr_len[c] >= (uint64_t)window) ? (chr_len[c] - window) / step + 1 : 0;
         win_base[c + 1] = win_base[c] + nw;
         s->chromosomes[c].live = live[c] != 0;
     }

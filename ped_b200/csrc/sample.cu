@@ -56,9 +56,12 @@ void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8
                  const uint8_t* valid) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    if (n_c >= 0xFFFFFFF0ull) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^32 reads in one sample on one GPU");
-    uint32_t cap = 1024;
-    while ((uint64_t)cap < 2 * n_c) cap <<= 1;
+    // the table holds 32-bit read indices and its capacity (a power of two >= 2 n) must fit 32 bits
+    if (n_c > (1ull << 30))
+        throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^30 packed reads in one length group on one GPU");
+    uint64_t cap64 = 1024;
+    while (cap64 < 2 * n_c) cap64 <<= 1;
+    const uint32_t cap = (uint32_t)cap64;
     DBuf<uint32_t> table(ctx, cap);
     DBuf<uint8_t> uniq(ctx, n_c);
     DBuf<uint64_t> pos(ctx, n_c);
@@ -528,7 +531,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
         plan_level_a_optimistic(a, R, me, m_max, &lp);
         const uint64_t C = lp.C;
         const std::vector<unsigned long long>&curA = lp.cur, &limA = lp.lim;
-        keysA = DBuf<uint8_t>(ctx, lp.buffer_elems * ksz);
+        keysA = DBuf<uint8_t>(ctx, peer_block_elems(lp.buffer_elems * ksz, multi, 1));
         DBuf<unsigned long long> plan(ctx, (size_t)3 * NBINS_MAX + 8);
         unsigned long long* d_cur = plan.p;
         unsigned long long* d_lim = plan.p + NBINS_MAX;
@@ -590,7 +593,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
         uint64_t sent = 0;
         for (int bin = 0; bin < nbA; ++bin) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
         if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
-        keysA = DBuf<uint8_t>(ctx, lp.buffer_elems * ksz);
+        keysA = DBuf<uint8_t>(ctx, peer_block_elems(lp.buffer_elems * ksz, multi, 1));
         DBuf<unsigned long long> plan(ctx, NBINS_MAX);
         PEDK_CUDA_TRY(cudaMemcpyAsync(plan.p, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
         scatter_all(plan.p, nullptr, nullptr);
@@ -1098,6 +1101,33 @@ extern "C" int pedk_sample_table(pedk_sample* s, uint64_t* kmers, uint32_t* coun
         memcpy(kmers, s->h_kmer.data(), *n * 8);
         memcpy(counts, s->h_cnt.data(), *n * 4);
     }
+    return PEDK_OK;
+    PEDK_API_END(s->ctx)
+}
+
+extern "C" int pedk_sample_table_digest(pedk_sample* s, uint64_t* rows, uint64_t* digest) {
+    if (!s || !rows || !digest) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    pedk_ctx* ctx = s->ctx;
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (s->host_only_table) {
+        uint64_t acc = 0;
+        for (size_t i = 0; i < s->h_kmer.size(); ++i)
+            acc += mix64(s->h_kmer[i] * 0x9E3779B97F4A7C15ull + (uint64_t)s->h_cnt[i]);
+        *rows = s->h_kmer.size();
+        *digest = acc;
+        return PEDK_OK;
+    }
+    if (!s->counted) throw PedkError(PEDK_E_INVAL, "sample has not been counted");
+    PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 10, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        StageScope sc(ctx, PEDK_ST_EDGES, 1);
+        launch_rows_digest(s->row_key_ptr(), s->row_val_ptr(), s->n_rows, ctx->scalars + 10, ctx->stream);
+    }
+    PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 10, ctx->scalars + 10, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *rows = s->n_rows;
+    *digest = ctx->h_scalars[10];
     return PEDK_OK;
     PEDK_API_END(s->ctx)
 }

@@ -38,6 +38,15 @@ struct PedkError {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Opt a kernel in to `bytes` of dynamic shared memory (> 48 KB needs it).  The attribute belongs to
+// the CURRENT device's context, so it is remembered per (kernel, device) -- a process may hold
+// contexts on several GPUs (ctx.cu).
+void set_max_dyn_smem(const void* kernel, size_t bytes);
+template <typename F>
+inline void ensure_dyn_smem(F* kernel, size_t bytes) {
+    set_max_dyn_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

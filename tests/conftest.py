@@ -36,6 +36,7 @@ def built():
     from ped_b200 import build
 
     build.build_libpedk()
+    build.build_synth()
     build.build_oracle()
     return True
 

@@ -1,8 +1,10 @@
 """Launched by torchrun (one rank per GPU): the sharded path must reproduce the oracle.
 
 Rank r ingests a contiguous slice of the records of both samples; reads, canonical k-mers
-and table rows change hands inside libpedk (NCCL).  Rank order is key order, so the
-concatenation over ranks of the tables / edge texts must equal the single-process oracle.
+and table rows change hands inside libpedk (peer stores over NVLink, NCCL for the small
+collectives).  The tables come back in rank order = key order, so their concatenation over the
+ranks must equal the single-process oracle; every rank holds the edges of the (k-1)-mers whose
+hash it owns, sorted, so the merged edge lines must equal the oracle's edge list.
 usage: torchrun --nproc-per-node N tests/multi_rank_check.py case [case ...]
 """
 import os
@@ -67,16 +69,19 @@ def main():
         ck, cc = c.table()
         tk, tc = t.table()
         parts = [None] * world
-        dist.all_gather_object(parts, dict(text=r.text(), ck=ck, cc=cc, tk=tk, tc=tc,
-                                           cu=int(ci.unique_reads), tu=int(ti.unique_reads)))
+        dist.all_gather_object(parts, dict(text=r.text(), ck=ck, cc=cc, tk=tk, tc=tc, cd=c.table_digest(),
+                                           td=t.table_digest(), cu=int(ci.unique_reads), tu=int(ti.unique_reads)))
         if rank == 0:
             oc, ot, osnp = oracle.run_ref(fc, ft, 20) if is_ref else oracle.run(fc, ft, 20, clip)
-            text = b"".join(p["text"] for p in parts)
+            lines = [ln for p in parts for ln in p["text"].split(b"\n") if ln]
+            text = b"".join(ln + b"\n" for ln in sorted(lines))  # a line starts with its (k-1)-mer: sorted = key order
             for key, cnt, o in (("ck", "cc", oc), ("tk", "tc", ot)):
                 km = np.concatenate([p[key] for p in parts])
                 ct = np.concatenate([p[cnt] for p in parts])
                 okm, oct_ = o.table()
                 good = km.shape == okm.shape and (km == okm).all() and (ct == oct_).all()
+                dg = [p[key[0] + "d"] for p in parts]  # (rows, digest) of every rank's unsorted rows
+                good = good and (sum(d[0] for d in dg), sum(d[1] for d in dg) % 2**64) == api.table_digest(okm, oct_)
                 print(f"[{name}] {key[0]} table rows {len(km)} vs oracle {len(okm)}: {'ok' if good else 'MISMATCH'}")
                 ok &= bool(good)
             uc = sum(p["cu"] for p in parts), sum(p["tu"] for p in parts)

@@ -10,8 +10,8 @@ from ped_b200 import api
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "pedk.h")).read()
+def declared_functions(header="pedk.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b(pedk_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
@@ -27,6 +27,21 @@ def test_header_symbols_exported(built):
 
 def test_python_mirror_covers_header(built):
     assert sorted(api.SIGNATURES) == declared_functions()
+
+
+def test_synth_library_is_separate(built):
+    """The host generator lives in libpedk_synth.so (include/pedk_synth.h): a CPU arm that makes its
+    inputs with it never maps the product library."""
+    import synth
+
+    lib = synth.load_library()
+    names = declared_functions("pedk_synth.h")
+    assert sorted(synth.SIGNATURES) == names
+    for n in names:
+        assert hasattr(lib, n)
+    product = api.load_library()
+    for n in names:
+        assert not hasattr(product, n), f"libpedk.so still exports {n}"
 
 
 def test_struct_layouts_match_header(built):

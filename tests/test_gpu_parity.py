@@ -36,6 +36,8 @@ def check_sample(gs: api.Sample, info, os_: oracle.OracleSample, texts=True):
     okm, oct_ = os_.table()
     assert km.shape == okm.shape and (km == okm).all()
     assert (ct == oct_).all()
+    # the order-independent digest bench.py's parity check relies on, taken from the unsorted rows
+    assert gs.table_digest() == api.table_digest(okm, oct_)
     if texts:
         for tag in range(64):
             assert gs.sort_uniq_text(tag) == os_.sort_uniq_text(tag), ("sort_uniq", tag)
@@ -168,13 +170,15 @@ def test_chunked_host_feed_and_fused_call(ctx):
     assert bytes(pc[:len(fc)].cpu().numpy().tobytes()) == fc
 
 
-def test_medium_scale_against_oracle(ctx):
-    """5 Mb genome, 30x (the survey's config-2 cut-down): table and edges vs the oracle."""
+@pytest.mark.parametrize("k", [20, 31])
+def test_medium_scale_against_oracle(ctx, k):
+    """5 Mb genome, 30x, 2 x 1 M reads = 300 Mbases (the survey's config-2 cut-down): table and edges vs
+    the oracle, at the reference's k and at k = 31 (BASELINE config 3's other point: 64-bit instances)."""
     case = dict(kind="synth", cfg=12, genome=5_000_000, reads=1_000_000, L=150, snp_ppm=1000, indel_ppm=100,
                 err_ppm=2000, n_ppm=1000, dup_ppm=0)
     fc, ft = make_inputs(case)
-    oc, ot, osnp = oracle.run(fc, ft, 20)
-    c, t, ci, ti, r = gpu_run(ctx, fc, ft, 20)
+    oc, ot, osnp = oracle.run(fc, ft, k)
+    c, t, ci, ti, r = gpu_run(ctx, fc, ft, k)
     try:
         check_sample(c, ci, oc, texts=False)
         check_sample(t, ti, ot, texts=False)
@@ -218,11 +222,13 @@ def test_full_size_properties(ctx, k, G, N):
 
 
 @pytest.mark.parametrize("env", [{"PEDK_BUCKET_SLOTS_LOG2": "10"}, {"PEDK_BUCKET_SLOTS_LOG2": "10", "PEDK_BUCKET_B": "1"},
-                                 {"PEDK_BUCKET_B": "2"}, {"PEDK_BUCKET_EXACT": "1"}, {"PEDK_COUNT_MODE": "sort"}])
+                                 {"PEDK_BUCKET_B": "2"}, {"PEDK_BUCKET_EXACT": "1"}, {"PEDK_COUNT_MODE": "sort"},
+                                 {"PEDK_JOIN_SLOTS_LOG2": "10", "PEDK_JOIN_B": "1"}, {"PEDK_JOIN_B": "3"}])
 @pytest.mark.parametrize("k", [20, 31])
 def test_bucket_table_overflow_and_legacy_path(ctx, env, k):
     """The per-bucket hash table is forced to overflow (1024 slots, buckets 128x larger) so that
-    buckets are split by further hash bits and re-read; PEDK_BUCKET_EXACT=1 sizes the level-A bins
+    buckets are split by further hash bits and re-read (PEDK_JOIN_*: the same for the tables of the
+    hash join, whose groups then meet in several rounds); PEDK_BUCKET_EXACT=1 sizes the level-A bins
     with a counting pass instead of optimistically; PEDK_COUNT_MODE=sort is the extract +
     LSD radix sort + run-length path the buckets replaced.  All must give the reference's table."""
     case = dict(kind="synth", cfg=13, genome=300_000, reads=60_000, L=150, snp_ppm=1000, indel_ppm=100,
