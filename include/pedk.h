@@ -79,6 +79,9 @@ typedef struct pedk_count_info {
     uint64_t instances;       /* canonical k-mer instances counted on this rank (half of the reference's M) */
     uint64_t canonical_kmers; /* rows of the canonical table */
     uint64_t correction_rows; /* windows of palindromic reads (usually 0) */
+    int32_t count_passes;     /* > 1: the instances did not fit HBM at once and were counted in this many
+                                 groups of hash bins (the reference spills to disk instead: sort -T, ped.pl:89) */
+    int32_t pad;
 } pedk_count_info;
 
 int pedk_sample_create(pedk_ctx *ctx, pedk_sample **s);
@@ -118,6 +121,19 @@ int pedk_sample_num_chromosomes(pedk_sample *s, int *n);
 int pedk_chromosome_file_name(const char *header_line, char *out, uint64_t cap);
 int pedk_sample_chromosome(pedk_sample *s, int i, char *name, uint64_t name_cap, uint64_t *length,
                            int *overwritten, char *seq, uint64_t seq_cap);
+/* f1, mk20mer + mkUniq (ped.pl:1162-1211, 1138-1160) on a sample that went through
+ * pedk_sample_ingest_reference: every k-base window without N of every chromosome (a chromosome
+ * called NOP is skipped, ped.pl:1217) on both strands; the k-mers that occur on exactly one of those
+ * lines stay.  *rows = lines of all ref20_uniq files together.  The reference hard-codes k = 20.
+ * The reference must be shorter than 2^31 bases. */
+int pedk_sample_ref20_uniq(pedk_sample *ref, int k, uint64_t *rows);
+/* `zcat <ref>/ref20_uniq.TAG.gz`: lines `KMER\tCHR\tPOS\tf|r`, ascending.  Caller frees with pedk_free. */
+int pedk_sample_ref20_uniq_text(pedk_sample *ref, int tag, char **text, uint64_t *len);
+/* f1, mapKmerSub (ped.pl:641-685): snp_text = lines of <tmpdir>/<t>.snp.TAG (the edge list; any tags,
+ * in key order).  Every edge whose control allele is one base is looked up as (k-1)-mer + that base
+ * in the unique k-mer index; the result is the text of the <tmpdir>/<t>.map.TAG files, in the same
+ * order.  Caller frees with pedk_free. */
+int pedk_sample_map_kmer_text(pedk_sample *ref, const char *snp_text, uint64_t snp_len, char **text, uint64_t *len);
 /* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer
  * of every unique read, brought together (hash bins, buckets) and counted.  4 <= k <= 32 (the reference
  * hard-codes 20, ped.pl:912-913).  Leaves the canonical table in HBM. */
@@ -196,6 +212,13 @@ int pedk_mk_sort_uniq(pedk_ctx *ctx, const char *wd, const char *subject, int cl
  * <wd>/<ref>/sort_uniq/<ref>.sort_uniq.TAG.gz.  The reference stays resident as a sample, so
  * pedk_count_kmer(wd, ref) continues from HBM. */
 int pedk_mk_control_read(pedk_ctx *ctx, const char *wd, const char *ref, const char *file);
+/* mk20 (ped.pl:1213-1249): writes <wd>/<ref>/ref20_uniq.TAG.gz.  The reference is taken from this
+ * process's pedk_mk_control_read when it is still resident, else parsed again from <wd>/<ref>/<file>
+ * (file may be NULL when it is resident).  k = 20 in the reference. */
+int pedk_mk_ref20_uniq(pedk_ctx *ctx, const char *wd, const char *ref, const char *file, int k);
+/* mapKmer (ped.pl:625-685): reads <tmpdir>/<target>.snp.TAG (pedk_join_kmer with have_ref) and the
+ * unique k-mer index (resident, or <wd>/<ref>/ref20_uniq.TAG.gz), writes <tmpdir>/<target>.map.TAG */
+int pedk_map_kmer(pedk_ctx *ctx, const char *wd, const char *target, const char *ref, const char *tmpdir);
 /* countKmer (ped.pl:784-815): writes <wd>/<subject>/count/<subject>.count.TAG.gz */
 int pedk_count_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
 /* lbcKmer (ped.pl:817-831): writes <wd>/<subject>/lbc/<subject>.lbc.TAG.gz */
@@ -282,6 +305,12 @@ int pedk_plan_bucket_owners(const uint64_t *hist64, int nranks, uint8_t *owner64
 int pedk_plan_level_a(int k, int nranks, int rank, uint64_t m_max, const uint64_t *counts, int exact,
                       uint64_t *cur256, uint64_t *lim256, uint64_t *seg, int *n_seg, uint64_t *buffer_elems,
                       uint64_t *segment_capacity);
+
+/* the same for pass `pass` of n_pass (a power of two): a sample whose instances do not fit HBM at once is
+ * counted in n_pass groups of bins, bin % n_pass == pass; the other bins get no room and no segment */
+int pedk_plan_level_a_pass(int k, int nranks, int rank, uint64_t m_max, const uint64_t *counts, int exact,
+                           int n_pass, int pass, uint64_t *cur256, uint64_t *lim256, uint64_t *seg, int *n_seg,
+                           uint64_t *buffer_elems, uint64_t *segment_capacity);
 
 /* ---- synthetic reads (tests and bench.py) ---------------- */
 

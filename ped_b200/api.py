@@ -49,7 +49,8 @@ class IngestInfo(C.Structure):
 
 class CountInfo(C.Structure):
     _fields_ = [("k", C.c_int32), ("sort_passes", C.c_int32), ("instances", C.c_uint64),
-                ("canonical_kmers", C.c_uint64), ("correction_rows", C.c_uint64)]
+                ("canonical_kmers", C.c_uint64), ("correction_rows", C.c_uint64), ("count_passes", C.c_int32),
+                ("pad", C.c_int32)]
 
 
 class Edge(C.Structure):
@@ -106,6 +107,11 @@ SIGNATURES = {
     "pedk_sample_borrow_fastq_device": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64]),
     "pedk_sample_count": (C.c_int, [_P, C.c_int, C.POINTER(CountInfo)]),
     "pedk_sample_table": (C.c_int, [_P, _P, _P, C.c_uint64, _U64P]),
+    "pedk_sample_ref20_uniq": (C.c_int, [_P, C.c_int, _U64P]),
+    "pedk_sample_ref20_uniq_text": (C.c_int, [_P, C.c_int, _PP, _U64P]),
+    "pedk_sample_map_kmer_text": (C.c_int, [_P, C.c_char_p, C.c_uint64, _PP, _U64P]),
+    "pedk_mk_ref20_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "pedk_map_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_sample_table_digest": (C.c_int, [_P, _U64P, _U64P]),
     "pedk_sample_reads": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint64, _U64P, C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32)]),
@@ -143,6 +149,8 @@ SIGNATURES = {
     "pedk_plan_level_a": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, _P, _P, _P, C.POINTER(C.c_int),
                                     _U64P, _U64P]),
     "pedk_synth_fastq_device": (C.c_int, [_P, C.POINTER(SynthParams), _P, C.c_uint64, C.c_uint64, _P]),
+    "pedk_plan_level_a_pass": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P,
+                                         C.POINTER(C.c_int), _U64P, _U64P]),
     "pedk_test_sort_u64": (C.c_int, [_P, _P, C.c_uint64, C.c_int]),
     "pedk_test_sort_pairs": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int]),
     "pedk_test_rle": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _U64P]),
@@ -334,10 +342,30 @@ class Sample:
             out.append((name.value.decode(), seq, bool(ow.value)))
         return out
 
+    def ref20_uniq(self, k: int = 20) -> int:
+        """mk20mer + mkUniq (ped.pl:1138-1211) on an ingested reference: lines of all ref20_uniq files."""
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_sample_ref20_uniq(self.h, k, C.byref(n)))
+        return int(n.value)
+
+    def ref20_uniq_text(self, tag: int) -> bytes:
+        return self._text(self.ctx.lib.pedk_sample_ref20_uniq_text, tag)
+
+    def map_kmer_text(self, snp_text: bytes) -> bytes:
+        """mapKmerSub (ped.pl:641-685): edge lines -> `<tmpdir>/<t>.map.TAG` lines."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_sample_map_kmer_text(self.h, snp_text, len(snp_text), C.byref(p), C.byref(n)))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            self.ctx.lib.pedk_free(p)
+
     def count(self, k: int = 20) -> CountInfo:
         """countKmer (ped.pl:784-932)."""
         info = CountInfo()
         self.ctx.check(self.ctx.lib.pedk_sample_count(self.h, k, C.byref(info)))
+        self.last_count = info
         return info
 
     def table(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -479,8 +507,9 @@ def kmer_unhash(h: int, k: int) -> int:
     return int(load_library().pedk_kmer_unhash(int(h), k))
 
 
-def plan_level_a(k: int, nranks: int, rank: int, m_max: int = 0, counts=None, exact: bool = False) -> dict:
-    """Host-side plan of the k-mer exchange (pedk_plan_level_a): cursors, limits, segments, buffer size."""
+def plan_level_a(k: int, nranks: int, rank: int, m_max: int = 0, counts=None, exact: bool = False, n_pass: int = 1,
+                 pass_: int = 0) -> dict:
+    """Host-side plan of the k-mer exchange (pedk_plan_level_a_pass): cursors, limits, segments, buffer size."""
     cur = np.zeros(256, dtype=np.uint64)
     lim = np.zeros(256, dtype=np.uint64)
     seg = np.zeros(3 * 256 * nranks, dtype=np.uint64)
@@ -488,8 +517,9 @@ def plan_level_a(k: int, nranks: int, rank: int, m_max: int = 0, counts=None, ex
     elems = C.c_uint64()
     cap = C.c_uint64()
     c = None if counts is None else np.ascontiguousarray(counts, dtype=np.uint64)
-    rc = load_library().pedk_plan_level_a(k, nranks, rank, m_max, None if c is None else _ptr(c), 1 if exact else 0,
-                                          _ptr(cur), _ptr(lim), _ptr(seg), C.byref(n_seg), C.byref(elems), C.byref(cap))
+    rc = load_library().pedk_plan_level_a_pass(k, nranks, rank, m_max, None if c is None else _ptr(c),
+                                               1 if exact else 0, n_pass, pass_, _ptr(cur), _ptr(lim), _ptr(seg),
+                                               C.byref(n_seg), C.byref(elems), C.byref(cap))
     if rc:
         raise PedkError(rc, "pedk_plan_level_a")
     n = n_seg.value

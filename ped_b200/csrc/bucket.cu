@@ -31,6 +31,8 @@
 // extract + LSD sort + run-length path it replaces (radix.cu keeps sorting the rows).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "util.cuh"
 
@@ -143,7 +145,7 @@ template <typename KT, int NT, int RPW, bool CONTIG, int KC, int PT_THREADS>
 __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
     k_part_scatter(const uint64_t* __restrict__ words, int W, int L, int k_rt, uint64_t n_reads, int a_rt, int nranks,
                    unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
-                   int* __restrict__ overflow, PeerPtrs dst) {
+                   int* __restrict__ overflow, PeerPtrs dst, unsigned pass_mask, unsigned pass_id) {
     const int k = KC ? KC : k_rt;
     const int a = KC ? 8 : a_rt;
     constexpr int PT_WARPS = PT_THREADS / 32;
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
                 const unsigned bin = (unsigned)(h >> shiftA);
                 keyv[idx] = (KT)(h & maskS);
                 meta[idx] = 0xffffffffu;
-                if (valid[t]) meta[idx] = (bin << 16) | atomicAdd(&hist[bin], 1u);
+                // counting in several passes (HBM capacity): only the bins of this pass are kept
+                if (valid[t] && (bin & pass_mask) == pass_id) meta[idx] = (bin << 16) | atomicAdd(&hist[bin], 1u);
             }
         }
         __syncthreads();
@@ -226,11 +229,17 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
 }
 
 // ------------------------------------------------------------------ level B
-constexpr int SUB_TILE = 8192;  // keys per tile; a tile lies inside one segment of a level-A bin
+// keys per tile of the level-B passes (a tile lies inside one segment of a level-A bin) and the CTA
+// shape of the scatter: 512 threads x 16 keys (two CTAs per SM: 64 registers) or 256 x 16 (four
+// CTAs per SM: the same threads per SM, but twice as many independent barrier domains -- the
+// kernel is bound by shared-memory latency between its barriers, not by issue slots or HBM)
+constexpr int SS_ITEMS = 16;
 constexpr int SH_THREADS = 256;
-constexpr int SH_GROUP = 8;  // tiles per CTA of the histogram kernel
-constexpr int SS_THREADS = 512;
-constexpr int SS_ITEMS = SUB_TILE / SS_THREADS;
+constexpr int SH_GROUP_KEYS = 65536;  // keys per CTA of the histogram kernel
+int sub_scatter_threads() {
+    const int t = getenv("PEDK_SUB_THREADS") ? atoi(getenv("PEDK_SUB_THREADS")) : 256;
+    return t >= 512 ? 512 : 256;
+}
 
 // A level-A bin arrives as one or more SEGMENTS (one per source rank, or one per bin when the
 // bins were sized exactly): seg[0][s] = first element, seg[1][s] = end, seg[2][s] = bin.
@@ -248,15 +257,16 @@ template <typename KT>
 __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ keys,
                                                         const unsigned long long* __restrict__ seg,
                                                         const unsigned* __restrict__ tile_prefix, int n_bins,
-                                                        unsigned n_tiles, int shiftB, unsigned maskB,
-                                                        unsigned* __restrict__ histB) {
+                                                        unsigned n_tiles, unsigned sub_tile, int shiftB,
+                                                        unsigned maskB, unsigned* __restrict__ histB) {
     __shared__ unsigned h[NB];
     const unsigned tid = threadIdx.x;
     h[tid] = 0;
     __syncthreads();
     int cur_bin = -1;
-    const unsigned t0 = blockIdx.x * SH_GROUP;
-    const unsigned t1 = t0 + SH_GROUP < n_tiles ? t0 + SH_GROUP : n_tiles;
+    const unsigned group = SH_GROUP_KEYS / sub_tile;
+    const unsigned t0 = blockIdx.x * group;
+    const unsigned t1 = t0 + group < n_tiles ? t0 + group : n_tiles;
     for (unsigned t = t0; t < t1; ++t) {
         const int sg = bin_of_tile(tile_prefix, n_bins, t);
         const int bin = (int)seg[2 * (size_t)n_bins + sg];
@@ -269,9 +279,9 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
             }
             cur_bin = bin;
         }
-        const unsigned long long start = seg[sg] + (unsigned long long)(t - tile_prefix[sg]) * SUB_TILE;
+        const unsigned long long start = seg[sg] + (unsigned long long)(t - tile_prefix[sg]) * sub_tile;
         const unsigned long long lim = seg[(size_t)n_bins + sg];
-        const unsigned long long end = start + SUB_TILE < lim ? start + SUB_TILE : lim;
+        const unsigned long long end = start + sub_tile < lim ? start + sub_tile : lim;
         for (unsigned long long i = start + tid; i < end; i += SH_THREADS)
             atomicAdd(&h[(unsigned)(keys[i] >> shiftB) & maskB], 1u);
     }
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
 // One tile of a level-A bin -> its 2^b sub-bins.  WHOLE: the tile holds SUB_TILE keys (all but
 // the last tile of a bin), so no index is tested.  A thread keeps its 16 keys and their ranks
 // (two 16-bit ranks per register; the sub-bin is recomputed from the key) between the phases.
-template <typename KT, bool WHOLE>
+template <typename KT, bool WHOLE, int SS_THREADS>
 __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, unsigned n, KT* __restrict__ out,
                                                  unsigned long long* __restrict__ cur, int shiftB, unsigned maskB,
                                                  KT* stage, unsigned* hist, unsigned* off, KT** s_out) {
@@ -337,8 +347,8 @@ __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, uns
     }
 }
 
-template <typename KT>
-__global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restrict__ in, KT* __restrict__ out,
+template <typename KT, int SS_THREADS>
+__global__ void __launch_bounds__(SS_THREADS, 1024 / SS_THREADS) k_sub_scatter(const KT* __restrict__ in, KT* __restrict__ out,
                                                               const unsigned long long* __restrict__ seg,
                                                               const unsigned* __restrict__ tile_prefix, int n_bins,
                                                               unsigned n_tiles, int shiftB, unsigned maskB,
@@ -353,20 +363,22 @@ __global__ void __launch_bounds__(SS_THREADS, 2) k_sub_scatter(const KT* __restr
     if (t >= n_tiles) return;
     const int sg = bin_of_tile(tile_prefix, n_bins, t);
     const int bin = (int)seg[2 * (size_t)n_bins + sg];
+    constexpr unsigned SUB_TILE = SS_THREADS * SS_ITEMS;
     const unsigned long long start = seg[sg] + (unsigned long long)(t - tile_prefix[sg]) * SUB_TILE;
     const unsigned long long lim = seg[(size_t)n_bins + sg];
     const unsigned n = (unsigned)(start + SUB_TILE < lim ? SUB_TILE : lim - start);
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
     if (n == SUB_TILE)
-        sub_scatter_tile<KT, true>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
+        sub_scatter_tile<KT, true, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
     else
-        sub_scatter_tile<KT, false>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
+        sub_scatter_tile<KT, false, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
 }
 
 // ------------------------------------------------------------------ buckets -> rows
-constexpr int BC_THREADS = 1024;
-constexpr int BC_WARPS = BC_THREADS / 32;
+// CTA shapes of k_bucket_count: 1024 threads x 2 CTAs per SM (32 registers per thread) or
+// 512 x 2 (64 registers: fewer re-computed loop invariants, half the warps); PEDK_BC_THREADS picks
+constexpr int BC_MAX_WARPS = 32;
 constexpr int BC_UNROLL = 4;  // (the slow path of k_bucket_count selects among exactly four keys)
 
 __device__ __forceinline__ uint32_t fold32(uint32_t x) { return x; }
@@ -400,108 +412,182 @@ __device__ __forceinline__ uint64_t lower_bound_u64(const uint64_t* a, uint64_t 
     return lo;
 }
 
-// Insert the n keys at bkeys into the table (round rd of R, see k_bucket_count).
-//  (1) dense: every lane looks at the home group of each of its four keys: a k-mer that is
-//      already there (~25 of 26 instances at 30x) costs a vector load, four compares and one
-//      fire-and-forget add, without a divergent loop;
-//  (2) the rest (first instance of a k-mer, or a home group full of other k-mers) probes
-//      group by group, one pending key per lane and turn.
-// A slot only ever goes EMPTY -> key, so plain loads are safe for hits, and everybody agrees
-// on the first free slot of a group.  New k-mers are counted per thread and added up once
-// per iteration; beyond `limit` of them the round is abandoned (s_overflow).
-template <typename KT, bool MULTI>
-__device__ __forceinline__ void bucket_insert(const KT* __restrict__ bkeys, unsigned n, KT* tkey, uint32_t* tcnt,
-                                              int log_slots, KT maskR, unsigned R, unsigned rd, unsigned limit,
-                                              unsigned* s_distinct, unsigned* s_overflow) {
-    constexpr int GS = 16 / sizeof(KT);  // slots per 16-byte group
+// 16 bytes of keys in one load (the instance stream is read with 128-bit loads)
+__device__ __forceinline__ void load_keys16(const uint32_t* p, uint32_t (&x)[4]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+__device__ __forceinline__ void load_keys16(const uint64_t* p, uint64_t (&x)[2]) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    x[0] = v.x; x[1] = v.y;
+}
+
+// tcnt[slot] += 1 if p: one predicated shared-memory reduction, no branch
+__device__ __forceinline__ void red_add_if(uint32_t* addr, bool p) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "@q red.shared.add.u32 [%0], 1;\n\t"
+        "}"
+        :
+        : "r"((unsigned)__cvta_generic_to_shared(addr)), "r"((unsigned)p)
+        : "memory");
+}
+
+constexpr int BC_QUEUE = 32 + 128;  // per warp: < 32 left over + at most 4 x 32 pushed per iteration
+
+// One key that is not in its home group yet (the first instance of a k-mer, or a home group full
+// of other k-mers): probe group by group.  A slot only ever goes EMPTY -> key, so everybody
+// agrees on the first free slot of a group.  Returns 1 if the key opened a new slot.
+template <typename KT>
+__device__ __forceinline__ unsigned slow_insert(KT xs, unsigned add, KT* tkey, uint32_t* tcnt, int gshift,
+                                                unsigned gmask, unsigned n_groups, unsigned* s_overflow) {
+    constexpr int GS = 16 / sizeof(KT);
+    const KT EMPTY = ~KT(0);
+    unsigned g = ((fold32(xs) * 0x9E3779B1u) >> gshift) & gmask;
+    unsigned probes = 0;
+    for (;;) {
+        KT q[GS];
+        load_group(tkey + g * GS, q);
+        int hit = -1, free_slot = -1;
+#pragma unroll
+        for (int j = GS - 1; j >= 0; --j) {
+            if (q[j] == EMPTY) free_slot = j;
+            if (q[j] == xs) hit = j;
+        }
+        unsigned is_new = 0;
+        if (hit < 0 && free_slot >= 0) {
+            // not here yet and the group has room: claim its FIRST free slot
+            const KT old = cas_key(&tkey[g * GS + free_slot], EMPTY, xs);
+            if (old == EMPTY) {
+                is_new = 1;
+                hit = free_slot;
+            } else if (old == xs) {
+                hit = free_slot;
+            } else {
+                continue;  // another k-mer took it: look at the group again
+            }
+        }
+        if (hit >= 0) {
+            atomicAdd(&tcnt[g * GS + hit], add);
+            return is_new;
+        }
+        g = (g + 1) & gmask;  // group full of other k-mers
+        if (++probes > n_groups) {
+            *s_overflow = 1;
+            return 0;
+        }
+    }
+}
+
+// Insert the keys [lo, hi) of `keys` into the table (round rd of R, see k_bucket_count).
+//  (1) dense: every lane looks at the home group of each key of its 16-byte load: a k-mer that is
+//      already there (~25 of 26 instances at 30x) costs a vector load of the group, GS compares
+//      and one predicated fire-and-forget add -- no divergent loop, no branch per key;
+//  (2) the rest goes to the warp's queue in shared memory and is inserted 32 keys at a time, every
+//      lane busy (slow_insert).  Handling them where they occur made the whole warp walk the
+//      probe loop for one or two lanes: as many instructions again as the dense part.
+// New k-mers are counted when a queue is drained; beyond `limit` of them the round is abandoned
+// (s_overflow).  wq: this warp's queue (BC_QUEUE keys).
+template <typename KT, bool MULTI, int BC_THREADS>
+__device__ __forceinline__ void bucket_insert(const KT* __restrict__ keys, unsigned long long lo,
+                                              unsigned long long hi, KT* tkey, uint32_t* tcnt, KT* wq, int log_slots,
+                                              KT maskR, unsigned R, unsigned rd, unsigned limit, unsigned* s_distinct,
+                                              unsigned* s_overflow) {
+    constexpr int GS = 16 / sizeof(KT);  // slots per 16-byte group = keys per 16-byte load
     constexpr int GS_LOG = sizeof(KT) == 4 ? 2 : 1;
     const KT EMPTY = ~KT(0);
     const unsigned n_groups = (1u << log_slots) >> GS_LOG;
     const unsigned gmask = n_groups - 1;
     const int gshift = 32 - log_slots + GS_LOG;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const unsigned lt = lanemask_lt();
+    // the loads are aligned to 16 bytes: the first and the last vector may reach outside [lo, hi)
+    const unsigned long long a0 = lo & ~(unsigned long long)(GS - 1);
+    const unsigned long long n_vec = (hi - a0 + GS - 1) / GS;
+    unsigned n_q = 0;  // keys in this warp's queue (the same in every lane)
     unsigned my_new = 0;
-    for (unsigned base = 0; base < n; base += BC_THREADS * BC_UNROLL) {
-        if (__any_sync(FULL, *(volatile unsigned*)s_overflow != 0)) break;
-        KT x[BC_UNROLL];
-#pragma unroll
-        for (int u = 0; u < BC_UNROLL; ++u) {
-            const unsigned i = base + u * BC_THREADS + tid;
-            x[u] = i < n ? (KT)(bkeys[i] & maskR) : EMPTY;  // keys are <= maskR < EMPTY
-        }
-        unsigned want = 0;
-#pragma unroll
-        for (int u = 0; u < BC_UNROLL; ++u) {
-            bool w = x[u] != EMPTY;
-            if (MULTI) w = w && (((fold32(x[u]) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
-            want |= (w ? 1u : 0u) << u;
-        }
-        // a warp full of ONE k-mer (repeats, low-complexity sequence): a single update
-        const KT s0 = __shfl_sync(FULL, x[0], 0);
-        unsigned add = 1;
-        if (__all_sync(FULL, want == 15u && x[0] == s0 && x[1] == s0 && x[2] == s0 && x[3] == s0)) {
-            want = lane == 0 ? 1u : 0u;
-            add = 32 * BC_UNROLL;
-        }
-        unsigned pend = 0;
-#pragma unroll
-        for (int u = 0; u < BC_UNROLL; ++u) {
-            const unsigned g = ((fold32(x[u]) * 0x9E3779B1u) >> gshift) & gmask;
-            KT q[GS];
-            load_group(tkey + g * GS, q);
-            int hit = -1;
-#pragma unroll
-            for (int j = GS - 1; j >= 0; --j)
-                if (q[j] == x[u]) hit = j;
-            if ((want >> u) & 1u) {
-                if (hit >= 0) atomicAdd(&tcnt[g * GS + hit], add);
-                else pend |= 1u << u;
-            }
-        }
-        while (__any_sync(FULL, pend != 0)) {
-            if (pend) {
-                const int u = __ffs(pend) - 1;
-                pend &= pend - 1;
-                const KT xs = u == 0 ? x[0] : u == 1 ? x[1] : u == 2 ? x[2] : x[3];
-                unsigned g = ((fold32(xs) * 0x9E3779B1u) >> gshift) & gmask;
-                unsigned probes = 0;
-                for (;;) {
-                    KT q[GS];
-                    load_group(tkey + g * GS, q);
-                    int hit = -1, free_slot = -1;
-#pragma unroll
-                    for (int j = GS - 1; j >= 0; --j) {
-                        if (q[j] == EMPTY) free_slot = j;
-                        if (q[j] == xs) hit = j;
-                    }
-                    if (hit < 0 && free_slot >= 0) {
-                        // not here yet and the group has room: claim its FIRST free slot
-                        const KT old = cas_key(&tkey[g * GS + free_slot], EMPTY, xs);
-                        if (old == EMPTY) {
-                            ++my_new;
-                            hit = free_slot;
-                        } else if (old == xs) {
-                            hit = free_slot;
-                        } else {
-                            continue;  // another k-mer took it: look at the group again
-                        }
-                    }
-                    if (hit >= 0) {
-                        atomicAdd(&tcnt[g * GS + hit], add);
-                        break;
-                    }
-                    g = (g + 1) & gmask;  // group full of other k-mers
-                    if (++probes > n_groups) {
-                        *s_overflow = 1;
-                        break;
-                    }
-                }
-            }
-        }
+    auto drain = [&](unsigned n_take) {
+        // the last n_take (<= 32) keys of the queue, one per lane
+        n_q -= n_take;
+        __syncwarp();
+        if (lane < n_take) my_new += slow_insert<KT>(wq[n_q + lane], 1u, tkey, tcnt, gshift, gmask, n_groups, s_overflow);
         const unsigned wn = __reduce_add_sync(FULL, my_new);
         my_new = 0;
         if (wn && lane == 0 && atomicAdd(s_distinct, wn) + wn > limit) *s_overflow = 1;
+        __syncwarp();
+    };
+    for (unsigned long long v0 = 0; v0 < n_vec; v0 += BC_THREADS) {
+        if (__any_sync(FULL, *(volatile unsigned*)s_overflow != 0)) break;
+        const unsigned long long v = v0 + tid;
+        KT x[GS];
+        if (v < n_vec) {
+            load_keys16(keys + a0 + v * GS, x);
+            if (v == 0 || v + 1 == n_vec) {
+#pragma unroll
+                for (int j = 0; j < GS; ++j) {
+                    const unsigned long long i = a0 + v * GS + j;
+                    x[j] = (i >= lo && i < hi) ? (KT)(x[j] & maskR) : EMPTY;  // keys are <= maskR < EMPTY
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < GS; ++j) x[j] = (KT)(x[j] & maskR);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < GS; ++j) x[j] = EMPTY;
+        }
+        // a warp full of ONE k-mer (repeats, low-complexity sequence): a single update
+        {
+            const KT s0 = __shfl_sync(FULL, x[0], 0);
+            bool same = x[0] == s0 && s0 != EMPTY;
+#pragma unroll
+            for (int j = 1; j < GS; ++j) same = same && x[j] == s0;
+            if (__all_sync(FULL, same)) {
+                bool mine = lane == 0;
+                if (MULTI) mine = mine && (((fold32(s0) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
+                if (mine) my_new += slow_insert<KT>(s0, 32u * GS, tkey, tcnt, gshift, gmask, n_groups, s_overflow);
+                continue;
+            }
+        }
+        unsigned pm[GS];  // per key: the lanes whose key goes to the queue
+#pragma unroll
+        for (int j = 0; j < GS; ++j) {
+            bool want = x[j] != EMPTY;
+            if (MULTI) want = want && (((fold32(x[j]) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
+            const unsigned g = ((fold32(x[j]) * 0x9E3779B1u) >> gshift) & gmask;
+            KT q[GS];
+            load_group(tkey + g * GS, q);
+            // the slot of the group that holds the key, if any: selects and ONE predicated add,
+            // no branch (a branch per slot cost more instructions than the compares)
+            unsigned off = 0;
+            bool hit = q[0] == x[j];
+#pragma unroll
+            for (int jj = 1; jj < GS; ++jj) {
+                const bool h = q[jj] == x[j];
+                off = h ? (unsigned)jj : off;
+                hit = hit || h;
+            }
+            hit = hit && want;
+            red_add_if(&tcnt[g * GS + off], hit);
+            pm[j] = __ballot_sync(FULL, want && !hit);
+        }
+        // pending keys -> the warp's queue (positions from the ballots: no atomics, no branches)
+        {
+            unsigned at = n_q;
+#pragma unroll
+            for (int j = 0; j < GS; ++j) {
+                if ((pm[j] >> lane) & 1u) wq[at + __popc(pm[j] & lt)] = x[j];
+                at += __popc(pm[j]);
+            }
+            n_q = at;
+        }
+        while (n_q >= 32u) drain(32u);
     }
+    if (n_q) drain(n_q);
+    const unsigned wn = __reduce_add_sync(FULL, my_new);
+    if (wn && lane == 0 && atomicAdd(s_distinct, wn) + wn > limit) *s_overflow = 1;
 }
 
 // strand != 0: rows (K, c) and (revcomp K, c), c = the reference's count (SURVEY.md Appendix
@@ -511,11 +597,12 @@ __device__ __forceinline__ void bucket_insert(const KT* __restrict__ bkeys, unsi
 // counters[0] = rows appended (keeps counting past cap so the caller can retry with room),
 // counters[1] += distinct canonical k-mers.  err is raised if a bucket cannot be split further.
 //
-// Shared memory: tkey[slots], tcnt[slots], list[slots] (u16: the occupied slots, compacted).
+// Shared memory: tkey[slots], tcnt[slots], then one area that holds the warps' queues of pending
+// keys while a round inserts and list[slots] (u16: the occupied slots, compacted) afterwards.
 // A slot only ever goes EMPTY -> key, so the common case (the k-mer is already in the table:
 // ~25 of 26 instances at 30x) is a plain load, a compare and one fire-and-forget atomic add;
 // only the first instance of a k-mer pays for a compare-and-swap.
-template <typename KT>
+template <typename KT, int BC_THREADS>
 __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __restrict__ keys,
                                                                const unsigned long long* __restrict__ offB,
                                                                unsigned n_buckets, int k, int a, int b,
@@ -532,8 +619,10 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
     KT* tkey = reinterpret_cast<KT*>(bc_smem);
     uint32_t* tcnt = reinterpret_cast<uint32_t*>(tkey + slots);
     uint16_t* list = reinterpret_cast<uint16_t*>(tcnt + slots);
+    KT* wq = reinterpret_cast<KT*>(tcnt + slots) + (threadIdx.x >> 5) * BC_QUEUE;  // aliases list
     __shared__ unsigned s_bucket, s_distinct, s_overflow, s_nh, s_nr, s_rcur;
-    __shared__ unsigned w_cnt[BC_WARPS];
+    constexpr int BC_WARPS = BC_THREADS / 32;
+    __shared__ unsigned w_cnt[BC_MAX_WARPS];
     __shared__ unsigned long long s_base;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned lt = lanemask_lt();
@@ -570,16 +659,13 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
                 s_rcur = 0;  // reverse rows placed so far (only used when there is a palindrome)
             }
             __syncthreads();
-            // ---- insert (in pieces of < 2^30 keys so that the inner indices are 32 bit) ----
-            for (unsigned long long seg = lo; seg < hi; seg += 1ull << 30) {
-                const unsigned seg_n = hi - seg < (1ull << 30) ? (unsigned)(hi - seg) : 1u << 30;
-                if (R == 1)
-                    bucket_insert<KT, false>(keys + seg, seg_n, tkey, tcnt, log_slots, maskR, R, rd, limit, &s_distinct,
-                                             &s_overflow);
-                else
-                    bucket_insert<KT, true>(keys + seg, seg_n, tkey, tcnt, log_slots, maskR, R, rd, limit, &s_distinct,
-                                            &s_overflow);
-            }
+            // ---- insert ----
+            if (R == 1)
+                bucket_insert<KT, false, BC_THREADS>(keys, lo, hi, tkey, tcnt, wq, log_slots, maskR, R, rd, limit, &s_distinct,
+                                         &s_overflow);
+            else
+                bucket_insert<KT, true, BC_THREADS>(keys, lo, hi, tkey, tcnt, wq, log_slots, maskR, R, rd, limit, &s_distinct,
+                                        &s_overflow);
             __syncthreads();
             if (s_overflow) {
                 __syncthreads();  // everybody has seen the flag before it is cleared again
@@ -597,14 +683,14 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
             if (lane == 0) w_cnt[warp] = nh_w;
             __syncthreads();
             if (warp == 0) {
-                const unsigned c = w_cnt[lane];
+                const unsigned c = lane < (unsigned)BC_WARPS ? w_cnt[lane] : 0u;
                 unsigned inc = c;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const unsigned o = __shfl_up_sync(FULL, inc, d);
                     if (lane >= (unsigned)d) inc += o;
                 }
-                w_cnt[lane] = inc - c;
+                if (lane < (unsigned)BC_WARPS) w_cnt[lane] = inc - c;
                 if (lane == 31) s_nh = inc;
             }
             __syncthreads();
@@ -699,7 +785,7 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
 template <typename KT, int NT, bool CONTIG, int KC, int PT_THREADS>
 void launch_part_scatter_th(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                             unsigned long long* cur, const unsigned long long* lim, int* overflow,
-                            const PeerPtrs& dst, cudaStream_t st) {
+                            const PeerPtrs& dst, unsigned pass_mask, unsigned pass_id, cudaStream_t st) {
     constexpr int PT_WARPS = PT_THREADS / 32;
     constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
     constexpr int TILE = PT_THREADS * NT * RPW;
@@ -709,21 +795,21 @@ void launch_part_scatter_th(const uint64_t* words, int W, int L, int k, uint64_t
     const uint64_t resident = (uint64_t)kNumSMs * (PT_THREADS > 512 ? 1 : 2);
     const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
     k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>
-        <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst);
+        <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id);
 }
 
 template <typename KT, int NT, bool CONTIG, int KC>
 void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                             unsigned long long* cur, const unsigned long long* lim, int* overflow,
-                            const PeerPtrs& dst, cudaStream_t st) {
+                            const PeerPtrs& dst, unsigned pass_mask, unsigned pass_id, cudaStream_t st) {
     // the k = 20 kernel with 32-bit words also comes with long tiles for several ranks
     static const int big = getenv("PEDK_PART_BIG_TILE") ? atoi(getenv("PEDK_PART_BIG_TILE")) : 1;
     if (KC == 20 && sizeof(KT) == 4 && (nranks > 1 || big == 2) && big && PT_BIG_OK<KT, NT>::value)
         launch_part_scatter_th<KT, NT, CONTIG, KC, (KC == 20 ? 1024 : 512)>(words, W, L, k, n_reads, a, nranks, cur,
-                                                                           lim, overflow, dst, st);
+                                                                           lim, overflow, dst, pass_mask, pass_id, st);
     else
         launch_part_scatter_th<KT, NT, CONTIG, KC, 512>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst,
-                                                        st);
+                                                        pass_mask, pass_id, st);
 }
 
 // windows per lane, rounded up to an instantiated value
@@ -737,29 +823,29 @@ bool contiguous_ok(int nt, int k) { return nt - 1 + k <= 32; }
 template <typename KT>
 void launch_part_scatter_t(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                            unsigned long long* cur, const unsigned long long* lim, int* overflow, const PeerPtrs& dst,
-                           cudaStream_t st) {
+                           unsigned pass_mask, unsigned pass_id, cudaStream_t st) {
     const int nt = nt_of(L, k);
     const bool contig = contiguous_ok(nt, k);
     if (k == 20 && sizeof(KT) == 4 && contig && nt >= 2 && nt <= 6) {
         // the reference's k, short reads: k folded into the kernel
         switch (nt) {
-        case 2: launch_part_scatter_nt<KT, 2, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
-        case 3: launch_part_scatter_nt<KT, 3, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
-        case 4: launch_part_scatter_nt<KT, 4, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
-        case 5: launch_part_scatter_nt<KT, 5, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
-        default: launch_part_scatter_nt<KT, 6, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); break;
+        case 2: launch_part_scatter_nt<KT, 2, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st); break;
+        case 3: launch_part_scatter_nt<KT, 3, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st); break;
+        case 4: launch_part_scatter_nt<KT, 4, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st); break;
+        case 5: launch_part_scatter_nt<KT, 5, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st); break;
+        default: launch_part_scatter_nt<KT, 6, true, 20>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st); break;
         }
         return;
     }
 #define PEDK_PS(N)                                                                                        \
     case N:                                                                                               \
-        if (contig) launch_part_scatter_nt<KT, N, true, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st); \
-        else launch_part_scatter_nt<KT, N, false, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);   \
+        if (contig) launch_part_scatter_nt<KT, N, true, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st); \
+        else launch_part_scatter_nt<KT, N, false, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st);   \
         break;
     switch (nt) {
         PEDK_PS(1) PEDK_PS(2) PEDK_PS(3) PEDK_PS(4) PEDK_PS(5) PEDK_PS(6) PEDK_PS(8) PEDK_PS(12)
     default:
-        launch_part_scatter_nt<KT, 16, false, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);
+        launch_part_scatter_nt<KT, 16, false, 0>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st);
     }
 #undef PEDK_PS
 }
@@ -800,22 +886,27 @@ void launch_part_count(const uint64_t* words, int W, int L, int k, uint64_t n_re
 
 void launch_part_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks, int wide,
                          unsigned long long* cur, const unsigned long long* lim, int* overflow, const PeerPtrs& dst,
-                         cudaStream_t st) {
+                         int n_pass, int pass, cudaStream_t st) {
     if (!n_reads || L < k) return;
+    const unsigned pass_mask = (unsigned)n_pass - 1u, pass_id = (unsigned)pass;  // n_pass is a power of two
     if (wide)
-        launch_part_scatter_t<uint64_t>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);
+        launch_part_scatter_t<uint64_t>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st);
     else
-        launch_part_scatter_t<uint32_t>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, st);
+        launch_part_scatter_t<uint32_t>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id, st);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-unsigned sub_tile_keys() { return SUB_TILE; }
+unsigned sub_tile_keys() { return (unsigned)(sub_scatter_threads() * SS_ITEMS); }
 
 namespace {
 __global__ void k_cursor_counts(const unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
                                 unsigned long long cap, int n, unsigned long long* __restrict__ cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (lim[i] == 0) {  // a bin outside this pass: no segment, nothing stored
+        cnt[i] = 0;
+        return;
+    }
     const unsigned long long start = lim[i] - cap;
     const unsigned long long c = cur[i] - start;
     cnt[i] = c > cap ? cap : c;  // beyond cap only after an overflow (the flag is raised then)
@@ -833,13 +924,15 @@ void launch_sub_hist_bits(const void* keys, int wide, const unsigned long long* 
     const unsigned long long* offA = seg;
     const int n_bins = n_seg;
     if (!n_tiles) return;
-    const unsigned grid = (n_tiles + SH_GROUP - 1) / SH_GROUP;
+    const unsigned sub_tile = sub_tile_keys();
+    const unsigned group = SH_GROUP_KEYS / sub_tile;
+    const unsigned grid = (n_tiles + group - 1) / group;
     if (wide)
         k_sub_hist<uint64_t><<<grid, SH_THREADS, 0, st>>>(static_cast<const uint64_t*>(keys), offA, tile_prefix,
-                                                          n_bins, n_tiles, shiftB, maskB, histB);
+                                                          n_bins, n_tiles, sub_tile, shiftB, maskB, histB);
     else
         k_sub_hist<uint32_t><<<grid, SH_THREADS, 0, st>>>(static_cast<const uint32_t*>(keys), offA, tile_prefix,
-                                                          n_bins, n_tiles, shiftB, maskB, histB);
+                                                          n_bins, n_tiles, sub_tile, shiftB, maskB, histB);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
@@ -854,18 +947,22 @@ void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned
     const unsigned long long* offA = seg;
     const int n_bins = n_seg;
     if (!n_tiles) return;
+    const int threads = sub_scatter_threads();
+    const size_t smem = (size_t)threads * SS_ITEMS * (wide ? sizeof(uint64_t) : sizeof(uint32_t));
+#define PEDK_SS(KT, TH)                                                                                          \
+    do {                                                                                                         \
+        ensure_dyn_smem(k_sub_scatter<KT, TH>, smem);                                                            \
+        k_sub_scatter<KT, TH><<<n_tiles, TH, smem, st>>>(static_cast<const KT*>(in), static_cast<KT*>(out), offA, \
+                                                         tile_prefix, n_bins, n_tiles, shiftB, maskB, curB);     \
+    } while (0)
     if (wide) {
-        constexpr size_t SMEM = (size_t)SUB_TILE * sizeof(uint64_t);
-        ensure_dyn_smem(k_sub_scatter<uint64_t>, SMEM);
-        k_sub_scatter<uint64_t><<<n_tiles, SS_THREADS, SMEM, st>>>(static_cast<const uint64_t*>(in),
-                                                                   static_cast<uint64_t*>(out), offA, tile_prefix,
-                                                                   n_bins, n_tiles, shiftB, maskB, curB);
+        if (threads == 512) PEDK_SS(uint64_t, 512);
+        else PEDK_SS(uint64_t, 256);
     } else {
-        constexpr size_t SMEM = (size_t)SUB_TILE * sizeof(uint32_t);
-        k_sub_scatter<uint32_t><<<n_tiles, SS_THREADS, SMEM, st>>>(static_cast<const uint32_t*>(in),
-                                                                   static_cast<uint32_t*>(out), offA, tile_prefix,
-                                                                   n_bins, n_tiles, shiftB, maskB, curB);
+        if (threads == 512) PEDK_SS(uint32_t, 512);
+        else PEDK_SS(uint32_t, 256);
     }
+#undef PEDK_SS
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
@@ -882,23 +979,30 @@ void launch_bucket_count(const void* keys, int wide, const unsigned long long* o
     if (!n_buckets) return;
     if (log_slots < 10) log_slots = 10;
     if (log_slots > 13) log_slots = 13;
-    const size_t per_slot = (wide ? sizeof(uint64_t) : sizeof(uint32_t)) + sizeof(uint32_t) + sizeof(uint16_t);
-    const size_t smem = ((size_t)1 << log_slots) * per_slot;
+    const size_t ksz = wide ? sizeof(uint64_t) : sizeof(uint32_t);
+    const int threads_env = getenv("PEDK_BC_THREADS") ? atoi(getenv("PEDK_BC_THREADS")) : 1024;
+    const int threads = threads_env <= 512 ? 512 : 1024;
+    const size_t area = std::max(((size_t)1 << log_slots) * sizeof(uint16_t), (size_t)(threads / 32) * BC_QUEUE * ksz);
+    const size_t smem = ((size_t)1 << log_slots) * (ksz + sizeof(uint32_t)) + area;
     PEDK_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-    // two resident CTAs of 1024 threads per SM; buckets are handed out by ticket
+    // two resident CTAs per SM while two tables fit its shared memory; buckets are handed out by ticket
     unsigned grid = kNumSMs * (smem > 100 * 1024 ? 1 : 2);
     if (grid > n_buckets) grid = n_buckets;
+#define PEDK_BC(KT, TH)                                                                                            \
+    do {                                                                                                           \
+        ensure_dyn_smem(k_bucket_count<KT, TH>, smem);                                                             \
+        k_bucket_count<KT, TH><<<grid, TH, smem, st>>>(static_cast<const KT*>(keys), offB, n_buckets, k, a, b, log_slots, \
+                                                       strand, corr_key, corr_cnt, n_corr, row_key, row_val, cap,  \
+                                                       counters, ticket, err);                                     \
+    } while (0)
     if (wide) {
-        ensure_dyn_smem(k_bucket_count<uint64_t>, ((size_t)1 << 13) * 14);
-        k_bucket_count<uint64_t><<<grid, BC_THREADS, smem, st>>>(static_cast<const uint64_t*>(keys), offB, n_buckets,
-                                                                 k, a, b, log_slots, strand, corr_key, corr_cnt,
-                                                                 n_corr, row_key, row_val, cap, counters, ticket, err);
+        if (threads == 512) PEDK_BC(uint64_t, 512);
+        else PEDK_BC(uint64_t, 1024);
     } else {
-        ensure_dyn_smem(k_bucket_count<uint32_t>, ((size_t)1 << 13) * 10);
-        k_bucket_count<uint32_t><<<grid, BC_THREADS, smem, st>>>(static_cast<const uint32_t*>(keys), offB, n_buckets,
-                                                                 k, a, b, log_slots, strand, corr_key, corr_cnt,
-                                                                 n_corr, row_key, row_val, cap, counters, ticket, err);
+        if (threads == 512) PEDK_BC(uint32_t, 512);
+        else PEDK_BC(uint32_t, 1024);
     }
+#undef PEDK_BC
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

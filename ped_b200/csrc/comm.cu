@@ -306,6 +306,12 @@ void comm_allreduce_min(pedk_ctx* ctx, unsigned long long* dev, size_t n) {
     nccl_check(nccl()->AllReduce(dev, dev, n, ncclUint64, ncclMin, comm_of(ctx), ctx->stream), "ncclAllReduce (min)");
 }
 
+void comm_allreduce_max(pedk_ctx* ctx, unsigned long long* dev, size_t n) {
+    if (ctx->nranks <= 1 || !n) return;
+    StageScope sc(ctx, PEDK_ST_EXCHANGE, 0);
+    nccl_check(nccl()->AllReduce(dev, dev, n, ncclUint64, ncclMax, comm_of(ctx), ctx->stream), "ncclAllReduce (max)");
+}
+
 uint64_t comm_allreduce_sum_host(pedk_ctx* ctx, uint64_t v) {
     if (ctx->nranks <= 1) return v;
     unsigned long long x = v;

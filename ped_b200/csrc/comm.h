@@ -24,6 +24,7 @@ void comm_ipc_destroy(pedk_ctx* ctx);
 // in-place sum over ranks of n u64 words in device memory (no-op on one rank)
 void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n);
 void comm_allreduce_min(pedk_ctx* ctx, unsigned long long* dev, size_t n);
+void comm_allreduce_max(pedk_ctx* ctx, unsigned long long* dev, size_t n);
 // Elements to allocate for a block of `elems` 8-byte words that peers map through CUDA IPC: IPC
 // shares whole driver allocations, so such a block is its own cudaMalloc of a multiple of 2 MiB
 // (blocks under 1 MiB would otherwise be carved out of a shared slab).

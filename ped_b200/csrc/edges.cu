@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* 
     }
 }
 
-constexpr int JB_THREADS = 1024;
+constexpr int JB_UNROLL = 4;  // records a thread has in flight
 
 __device__ __forceinline__ uint32_t jb_fold(uint32_t x) { return x; }
 __device__ __forceinline__ uint32_t jb_fold(uint64_t x) { return (uint32_t)x ^ ((uint32_t)(x >> 32) * 0x9E3779B1u); }
@@ -322,18 +322,16 @@ __device__ __forceinline__ uint64_t jb_cas(uint64_t* p, uint64_t cmp, uint64_t v
 
 // KT: type of the table key = the r = 2(k-1) - a - b hash bits a bucket does not fix (u32 while
 // r <= 31, so that ~0 is free to mean "empty").  tc/tt: four 7-bit counts of the control / target.
-// A bucket whose groups do not fit the table is processed in rounds of a secondary hash, like
-// k_bucket_count (bucket.cu).
-template <typename KT>
-__global__ void __launch_bounds__(JB_THREADS, 1) k_join_bucket(const uint64_t* __restrict__ recs,
-                                                              const unsigned long long* __restrict__ offB,
-                                                              unsigned n_buckets, int kp, int a, int b,
-                                                              int log_slots,
-                                                              const unsigned long long* __restrict__ first,
-                                                              const uint32_t* __restrict__ pass1_bits,
-                                                              EdgeRec* __restrict__ edges, uint64_t cap,
-                                                              unsigned long long* __restrict__ n_edges,
-                                                              unsigned* __restrict__ ticket, int* __restrict__ err) {
+// Linear probing; about half of the records open a new group (a group is mostly one row per
+// sample), so there is no separate fast path.  The pass over the slots that applies the test also
+// resets them, so a bucket costs one sweep of the table, not two.  A bucket whose groups do not
+// fit the table is processed in rounds of a secondary hash, like k_bucket_count (bucket.cu).
+template <typename KT, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
+    k_join_bucket(const uint64_t* __restrict__ recs, const unsigned long long* __restrict__ offB, unsigned n_buckets,
+                  int kp, int a, int b, int log_slots, const unsigned long long* __restrict__ first,
+                  const uint32_t* __restrict__ pass1_bits, EdgeRec* __restrict__ edges, uint64_t cap,
+                  unsigned long long* __restrict__ n_edges, unsigned* __restrict__ ticket, int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char jb_smem[];
     const unsigned slots = 1u << log_slots;
     KT* tkey = reinterpret_cast<KT*>(jb_smem);
@@ -347,8 +345,17 @@ __global__ void __launch_bounds__(JB_THREADS, 1) k_join_bucket(const uint64_t* _
     const unsigned smask = slots - 1;
     const unsigned limit = slots - (slots >> 2);
     const int hshift = 32 - log_slots;
+    for (unsigned i = tid; i < slots; i += THREADS) {
+        tkey[i] = EMPTY;
+        tc[i] = 0;
+        tt[i] = 0;
+    }
     for (;;) {
-        if (tid == 0) s_bucket = atomicAdd(ticket, 1u);
+        if (tid == 0) {
+            s_bucket = atomicAdd(ticket, 1u);
+            s_distinct = 0;
+            s_overflow = 0;
+        }
         __syncthreads();
         const unsigned bk = s_bucket;
         if (bk >= n_buckets) break;
@@ -360,60 +367,61 @@ __global__ void __launch_bounds__(JB_THREADS, 1) k_join_bucket(const uint64_t* _
         const uint64_t hbase = ((uint64_t)(bk >> 8) << rs) | ((uint64_t)(bk & 255u) << r);
         unsigned R = 1, rd = 0;
         for (;;) {
-            for (unsigned i = tid; i < slots; i += JB_THREADS) {
-                tkey[i] = EMPTY;
-                tc[i] = 0;
-                tt[i] = 0;
-            }
-            if (tid == 0) {
-                s_distinct = 0;
-                s_overflow = 0;
-            }
-            __syncthreads();
             // ---- every row ORs its count into the (sample, base) field of its group ----
             unsigned my_new = 0;
-            for (unsigned long long i0 = lo; i0 < hi; i0 += JB_THREADS) {
-                if (__any_sync(FULL_MASK, *(volatile unsigned*)&s_overflow != 0)) break;
-                const unsigned long long i = i0 + tid;
-                if (i < hi) {
-                    const uint64_t rec = recs[i];
-                    const KT x = (KT)((KT)(rec >> JR_PAYLOAD_BITS) & maskR);
-                    bool want = true;
-                    if (R > 1) want = (((jb_fold(x) * 0x85EBCA77u) >> 10) & (R - 1)) == rd;
-                    if (want) {
-                        unsigned h = hshift < 32 ? (jb_fold(x) * 0x9E3779B1u) >> hshift : 0u;
-                        unsigned probes = 0;
-                        for (;;) {
-                            KT q = *(volatile KT*)&tkey[h];
+            bool stuck = false;
+            for (unsigned long long i0 = lo; i0 < hi; i0 += (unsigned long long)THREADS * JB_UNROLL) {
+                uint64_t rec[JB_UNROLL];
+#pragma unroll
+                for (int u = 0; u < JB_UNROLL; ++u) {
+                    const unsigned long long i = i0 + (unsigned long long)u * THREADS + tid;
+                    rec[u] = i < hi ? recs[i] : ~0ull;  // a record never has all bits set (count <= 127)
+                }
+#pragma unroll
+                for (int u = 0; u < JB_UNROLL; ++u) {
+                    if (rec[u] == ~0ull) continue;
+                    const KT x = (KT)((KT)(rec[u] >> JR_PAYLOAD_BITS) & maskR);
+                    if (R > 1 && (((jb_fold(x) * 0x85EBCA77u) >> 10) & (R - 1)) != rd) continue;
+                    unsigned h = (jb_fold(x) * 0x9E3779B1u) >> hshift;
+                    unsigned probes = 0;
+                    for (;;) {
+                        KT q = *(volatile KT*)&tkey[h];
+                        if (q == EMPTY) {
+                            q = jb_cas(&tkey[h], EMPTY, x);
                             if (q == EMPTY) {
-                                const KT old = jb_cas(&tkey[h], EMPTY, x);
-                                if (old == EMPTY) {
-                                    ++my_new;
-                                    q = x;
-                                } else {
-                                    q = old;
-                                }
+                                ++my_new;
+                                q = x;
                             }
-                            if (q == x) {
-                                const unsigned cnt = (unsigned)rec & 127u, base = (unsigned)(rec >> 8) & 3u;
-                                atomicOr(((rec >> 7) & 1u) ? &tt[h] : &tc[h], cnt << (7 * base));
-                                break;
-                            }
-                            h = (h + 1) & smask;
-                            if (++probes > slots) {
-                                s_overflow = 1;
-                                break;
-                            }
+                        }
+                        if (q == x) {
+                            const unsigned cnt = (unsigned)rec[u] & 127u, base = (unsigned)(rec[u] >> 8) & 3u;
+                            atomicOr(((rec[u] >> 7) & 1u) ? &tt[h] : &tc[h], cnt << (7 * base));
+                            break;
+                        }
+                        h = (h + 1) & smask;
+                        if (++probes > 512u) {  // a table this crowded is abandoned (rounds below)
+                            stuck = true;
+                            break;
                         }
                     }
                 }
-                const unsigned wn = __reduce_add_sync(FULL_MASK, my_new);
-                my_new = 0;
-                if (wn && lane == 0 && atomicAdd(&s_distinct, wn) + wn > limit) s_overflow = 1;
             }
+            const unsigned wn = __reduce_add_sync(FULL_MASK, my_new);
+            if (lane == 0 && wn) atomicAdd(&s_distinct, wn);
+            if (stuck) s_overflow = 1;
             __syncthreads();
-            if (s_overflow) {
-                __syncthreads();  // everybody has seen the flag before it is cleared again
+            if (s_overflow || s_distinct > limit) {
+                __syncthreads();  // everybody has seen the flags before they are cleared again
+                for (unsigned i = tid; i < slots; i += THREADS) {
+                    tkey[i] = EMPTY;
+                    tc[i] = 0;
+                    tt[i] = 0;
+                }
+                if (tid == 0) {
+                    s_distinct = 0;
+                    s_overflow = 0;
+                }
+                __syncthreads();
                 if (R >= (1u << 20)) {
                     if (tid == 0) atomicExch(err, 3);
                     break;
@@ -421,11 +429,14 @@ __global__ void __launch_bounds__(JB_THREADS, 1) k_join_bucket(const uint64_t* _
                 R <<= 1;
                 continue;
             }
-            // ---- joinKmerSub (ped.pl:703-782) on every group ----
-            for (unsigned sl = tid; sl < slots; sl += JB_THREADS) {
+            // ---- joinKmerSub (ped.pl:703-782) on every group; the slot is empty again afterwards ----
+            for (unsigned sl = tid; sl < slots; sl += THREADS) {
                 const KT q = tkey[sl];
                 if (q == EMPTY) continue;
                 const uint32_t pc = tc[sl], pt = tt[sl];
+                tkey[sl] = EMPTY;
+                tc[sl] = 0;
+                tt[sl] = 0;
                 if (!pc || !pt) continue;  // `join` is an inner join (ped.pl:709); a count is never 0
                 uint32_t c[4], t[4];
                 unsigned code = 0;
@@ -457,7 +468,8 @@ __global__ void __launch_bounds__(JB_THREADS, 1) k_join_bucket(const uint64_t* _
                     edges[o] = e;
                 }
             }
-            __syncthreads();  // the table is cleared next
+            if (tid == 0) s_distinct = 0;
+            __syncthreads();  // the table is empty again
             while (R > 1 && rd >= (R >> 1)) {
                 rd -= R >> 1;
                 R >>= 1;
@@ -594,9 +606,8 @@ int join_record_shift_b(int k, int b) {
 }
 
 void launch_join_bucket(const uint64_t* recs, const unsigned long long* offB, unsigned n_buckets, int k, int b,
-                        int log_slots,
-                        const unsigned long long* first, const uint32_t* pass1_bits, EdgeRec* edges, uint64_t cap,
-                        unsigned long long* n_edges, unsigned* ticket, int* err, cudaStream_t st) {
+                        int log_slots, const unsigned long long* first, const uint32_t* pass1_bits, EdgeRec* edges,
+                        uint64_t cap, unsigned long long* n_edges, unsigned* ticket, int* err, cudaStream_t st) {
     if (!n_buckets) return;
     const int kp = k - 1, a = kmer_bits_a(kp);
     const int r = 2 * kp - a - b;
@@ -605,18 +616,26 @@ void launch_join_bucket(const uint64_t* recs, const unsigned long long* offB, un
     const bool wide = r > 31;
     if (wide && log_slots > 13) log_slots = 13;
     const size_t smem = ((size_t)1 << log_slots) * ((wide ? 8 : 4) + 8);
+    const int threads_env = getenv("PEDK_JOIN_THREADS") ? atoi(getenv("PEDK_JOIN_THREADS")) : 0;
+    // two CTAs of 512 threads per SM while two tables fit its shared memory, else one of 1024
+    const bool small = threads_env ? threads_env <= 512 : smem <= 100 * 1024;
     PEDK_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
-    unsigned grid = kNumSMs * (smem <= 100 * 1024 ? 2 : 1);
+    unsigned grid = kNumSMs * ((small && smem <= 100 * 1024) ? 2 : 1);
     if (grid > n_buckets) grid = n_buckets;
+#define PEDK_JB(KT, TH)                                                                                        \
+    do {                                                                                                       \
+        ensure_dyn_smem(k_join_bucket<KT, TH>, smem);                                                          \
+        k_join_bucket<KT, TH><<<grid, TH, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first, pass1_bits, \
+                                                      edges, cap, n_edges, ticket, err);                       \
+    } while (0)
     if (wide) {
-        ensure_dyn_smem(k_join_bucket<uint64_t>, ((size_t)1 << 13) * 16);
-        k_join_bucket<uint64_t><<<grid, JB_THREADS, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first,
-                                                                pass1_bits, edges, cap, n_edges, ticket, err);
+        if (small) PEDK_JB(uint64_t, 512);
+        else PEDK_JB(uint64_t, 1024);
     } else {
-        ensure_dyn_smem(k_join_bucket<uint32_t>, ((size_t)1 << 14) * 12);
-        k_join_bucket<uint32_t><<<grid, JB_THREADS, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first,
-                                                                pass1_bits, edges, cap, n_edges, ticket, err);
+        if (small) PEDK_JB(uint32_t, 512);
+        else PEDK_JB(uint32_t, 1024);
     }
+#undef PEDK_JB
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

@@ -509,6 +509,75 @@ void do_join_kmer(pedk_ctx* ctx, const std::string& wd, const std::string& targe
     pedk_result_destroy(r);
 }
 
+std::string read_plain(const std::string& path) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return std::string();  // ped.pl reads a missing file as an empty one
+    std::string out;
+    std::vector<char> buf(1 << 20);
+    for (;;) {
+        size_t n = fread(buf.data(), 1, buf.size(), f);
+        if (!n) break;
+        out.append(buf.data(), n);
+    }
+    fclose(f);
+    return out;
+}
+
+// the reference as a resident sample: from this process's mkControlRead, or parsed again from the FASTA
+pedk_sample* reference_sample(pedk_ctx* ctx, const std::string& wd, const std::string& ref, const std::string& file) {
+    pedk_sample* s = cached(ctx, wd + "/" + ref);
+    if (s && s->ref_clean.p) return s;
+    if (file.empty()) return nullptr;
+    const std::string path = wd + "/" + ref + "/" + file;
+    if (!exists(path)) throw PedkError(PEDK_E_IO, file + " is not found in " + wd + "/" + ref);
+    s = fresh_sample(ctx, wd + "/" + ref);
+    {
+        Feeder feed(s);
+        if (ends_with(file, "gz")) feed.feed_gz(path);
+        else if (ends_with(file, "bz2")) feed.feed_pipe("bzcat " + shell_quote(path));
+        else feed.feed_plain(path);
+        feed.flush();
+    }
+    must(ctx, pedk_sample_ingest_reference(s, 0, 0, nullptr));
+    return s;
+}
+
+// mk20 (ped.pl:1213-1249): mk20mer per chromosome + mkUniq per tag -> <ref>/ref20_uniq.TAG.gz
+void do_mk_ref20_uniq(pedk_ctx* ctx, const std::string& wd, const std::string& ref, const std::string& file, int k) {
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    pedk_sample* s = reference_sample(ctx, wd, ref, file);
+    if (!s) throw PedkError(PEDK_E_INVAL, "pedk_mk_ref20_uniq: the reference is not resident and no FASTA file was named");
+    must(ctx, pedk_sample_ref20_uniq(s, k, nullptr));
+    if (!s->ref20.any_chromosome) return;  // no mk20mer ran: no tmp files, no mkUniq (ped.pl:1238)
+    const std::string dir = wd + "/" + ref;
+    for_each_tag([&](int t) {
+        const std::string text = ref20_text(s, t);
+        write_gz_atomic(dir + "/ref20_uniq." + tag_name(t) + ".gz", text.data(), text.size());
+    });
+}
+
+// mapKmer (ped.pl:625-685): <tmpdir>/<t>.snp.TAG x <ref>/ref20_uniq.TAG.gz -> <tmpdir>/<t>.map.TAG
+void do_map_kmer(pedk_ctx* ctx, const std::string& wd, const std::string& target, const std::string& ref,
+                 const std::string& tmpdir) {
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    pedk_sample* s = cached(ctx, wd + "/" + ref);
+    if (!s || !s->ref20.built) {
+        // a fresh process: the index comes back from the ref20_uniq files
+        if (!s) s = fresh_sample(ctx, wd + "/" + ref);
+        s->ref20 = pedk_sample::Ref20{};
+        for (int t = 0; t < 64; ++t) {
+            const std::string p = wd + "/" + ref + "/ref20_uniq." + tag_name(t) + ".gz";
+            ref20_append_text(s, t, exists(p) ? read_gz(p) : std::string());
+        }
+        s->ref20.built = true;
+    }
+    for (int t = 0; t < 64; ++t) {
+        const std::string snp = read_plain(tmpdir + "/" + target + ".snp." + tag_name(t));
+        const std::string m = map_kmer_text(s, snp.data(), snp.size());
+        write_plain_atomic(tmpdir + "/" + target + ".map." + tag_name(t), m.data(), m.size());
+    }
+}
+
 }  // namespace
 
 namespace pedk {
@@ -525,6 +594,22 @@ extern "C" int pedk_mk_control_read(pedk_ctx* ctx, const char* wd, const char* r
     if (!ctx || !wd || !ref || !file) return PEDK_E_INVAL;
     PEDK_API_BEGIN
     do_mk_control_read(ctx, wd, ref, file);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_mk_ref20_uniq(pedk_ctx* ctx, const char* wd, const char* ref, const char* file, int k) {
+    if (!ctx || !wd || !ref) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_mk_ref20_uniq(ctx, wd, ref, file ? file : "", k);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_map_kmer(pedk_ctx* ctx, const char* wd, const char* target, const char* ref, const char* tmpdir) {
+    if (!ctx || !wd || !target || !ref || !tmpdir) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_map_kmer(ctx, wd, target, ref, tmpdir);
     return PEDK_OK;
     PEDK_API_END(ctx)
 }

@@ -81,10 +81,11 @@ void launch_part_count(const uint64_t* words, int W, int L, int k, uint64_t n_re
 // cur[bin] = next free element of that bin inside the buffer of the rank that owns it
 // (dst.p[owner], owner = bin * nranks >> a; peer memory over NVLink for owner != me).
 // lim != null (optimistic sizing): lim[bin] = end of the segment this rank may fill; a run that
-// does not fit is dropped and *overflow set.
+// does not fit is dropped and *overflow set.  n_pass (a power of two) > 1: only the k-mers of the
+// bins with bin % n_pass == pass are kept (a sample whose instances do not fit HBM at once).
 void launch_part_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks, int wide,
                          unsigned long long* cur, const unsigned long long* lim, int* overflow, const PeerPtrs& dst,
-                         cudaStream_t st);
+                         int n_pass, int pass, cudaStream_t st);
 unsigned sub_tile_keys();
 // optimistic sizing: cnt[i] = cur[i] - (lim[i] - cap), what really went into segment i
 void launch_cursor_counts(const unsigned long long* cur, const unsigned long long* lim, unsigned long long cap, int n,

@@ -11,15 +11,16 @@ namespace pedk {
 
 static int owner_of_bin(int bin, int R, int a) { return (int)(((uint64_t)bin * (uint64_t)R) >> a); }
 
-void plan_level_a_optimistic(int a, int R, int me, uint64_t m_max, LevelAPlan* p) {
+void plan_level_a_optimistic(int a, int R, int me, uint64_t m_max, LevelAPlan* p, int n_pass, int pass) {
     const int nbA = 1 << a;
     // expected size of a (bin, source) run + 1/8 + 4096, a multiple of 32 elements
     p->C = ((m_max / nbA) + (m_max / nbA) / 8 + 4096 + 31) / 32 * 32;
     p->cur.assign(LEVEL_A_BINS, 0);
     p->lim.assign(LEVEL_A_BINS, 0);
-    p->local_index.assign(nbA, 0);
+    p->local_index.assign(nbA, -1);
     std::vector<int> owned(R, 0);
     for (int bin = 0; bin < nbA; ++bin) {
+        if (bin % n_pass != pass) continue;  // not in this pass: cur == lim == 0, nothing fits, nothing is stored
         const int o = owner_of_bin(bin, R, a);
         p->local_index[bin] = owned[o]++;
         // segment of (bin, src) inside the owner's buffer: ((bin's index among the owner's bins) * R + src) * C
@@ -38,7 +39,7 @@ void level_a_segments_optimistic(int a, int R, int me, const unsigned long long*
     p->seg_end.clear();
     p->seg_bin.clear();
     for (int bin = 0; bin < nbA; ++bin) {
-        if (owner_of_bin(bin, R, a) != me) continue;
+        if (owner_of_bin(bin, R, a) != me || p->local_index[bin] < 0) continue;
         for (int src = 0; src < R; ++src) {
             const unsigned long long st0 = ((unsigned long long)p->local_index[bin] * R + src) * p->C;
             p->seg_start.push_back(st0);
@@ -48,7 +49,7 @@ void level_a_segments_optimistic(int a, int R, int me, const unsigned long long*
     }
 }
 
-void plan_level_a_exact(int a, int R, int me, const unsigned long long* counts, LevelAPlan* p) {
+void plan_level_a_exact(int a, int R, int me, const unsigned long long* counts, LevelAPlan* p, int n_pass, int pass) {
     const int nbA = 1 << a;
     p->C = 0;
     p->cur.assign(LEVEL_A_BINS, 0);
@@ -58,6 +59,7 @@ void plan_level_a_exact(int a, int R, int me, const unsigned long long* counts, 
     p->seg_bin.clear();
     std::vector<unsigned long long> owner_fill(R, 0);
     for (int bin = 0; bin < nbA; ++bin) {
+        if (bin % n_pass != pass) continue;
         const int owner = owner_of_bin(bin, R, a);
         unsigned long long tot = 0, before_me = 0;
         for (int src = 0; src < R; ++src) {
@@ -84,15 +86,23 @@ void plan_level_a_exact(int a, int R, int me, const unsigned long long* counts, 
 extern "C" int pedk_plan_level_a(int k, int nranks, int rank, uint64_t m_max, const uint64_t* counts, int exact,
                                  uint64_t* cur256, uint64_t* lim256, uint64_t* seg, int* n_seg,
                                  uint64_t* buffer_elems, uint64_t* segment_capacity) {
+    return pedk_plan_level_a_pass(k, nranks, rank, m_max, counts, exact, 1, 0, cur256, lim256, seg, n_seg, buffer_elems,
+                                  segment_capacity);
+}
+
+extern "C" int pedk_plan_level_a_pass(int k, int nranks, int rank, uint64_t m_max, const uint64_t* counts, int exact,
+                                      int n_pass, int pass, uint64_t* cur256, uint64_t* lim256, uint64_t* seg,
+                                      int* n_seg, uint64_t* buffer_elems, uint64_t* segment_capacity) {
     if (k < 4 || k > 32 || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks || !cur256 || !n_seg) return PEDK_E_INVAL;
+    if (n_pass < 1 || (n_pass & (n_pass - 1)) || pass < 0 || pass >= n_pass) return PEDK_E_INVAL;
     if (exact && !counts) return PEDK_E_INVAL;
     const int a = pedk::kmer_bits_a(k);
     pedk::LevelAPlan p;
     const unsigned long long* c = reinterpret_cast<const unsigned long long*>(counts);
     if (exact) {
-        pedk::plan_level_a_exact(a, nranks, rank, c, &p);
+        pedk::plan_level_a_exact(a, nranks, rank, c, &p, n_pass, pass);
     } else {
-        pedk::plan_level_a_optimistic(a, nranks, rank, m_max, &p);
+        pedk::plan_level_a_optimistic(a, nranks, rank, m_max, &p, n_pass, pass);
         if (c) pedk::level_a_segments_optimistic(a, nranks, rank, c, &p);
     }
     for (int i = 0; i < pedk::LEVEL_A_BINS; ++i) {

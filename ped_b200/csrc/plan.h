@@ -18,11 +18,15 @@ struct LevelAPlan {
     std::vector<unsigned long long> seg_start, seg_end, seg_bin;
 };
 
+// A sample whose instances do not fit HBM at once is counted in n_pass passes (a power of two):
+// pass `pass` takes the level-A bins with bin % n_pass == pass, so every rank owns an equal share
+// of every pass.  Bins outside the pass get no room (local_index -1) and no segment.
 // every (bin, source) run gets a segment of the expected size + 1/8 + 4096
-void plan_level_a_optimistic(int a, int R, int me, uint64_t m_max, LevelAPlan* p);
+void plan_level_a_optimistic(int a, int R, int me, uint64_t m_max, LevelAPlan* p, int n_pass = 1, int pass = 0);
 // counts[src * 257 + bin] = what rank src stored into bin -> the segments of my bins
 void level_a_segments_optimistic(int a, int R, int me, const unsigned long long* counts, LevelAPlan* p);
 // exact sizes known up front: bins back to back, inside a bin the sources in rank order
-void plan_level_a_exact(int a, int R, int me, const unsigned long long* counts, LevelAPlan* p);
+void plan_level_a_exact(int a, int R, int me, const unsigned long long* counts, LevelAPlan* p, int n_pass = 1,
+                        int pass = 0);
 
 }  // namespace pedk

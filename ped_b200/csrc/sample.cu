@@ -469,6 +469,47 @@ int env_int(const char* name, int dflt, int lo, int hi) {
     return x < lo ? lo : x > hi ? hi : x;
 }
 
+// How many passes the instance stream of this sample is counted in (SURVEY.md 7.4 / 5 "prefix-range
+// chunking"; the reference's equivalent is `sort -S 1M -T`, ped.pl:89, behind the 64-way fan-out of
+// ped.pl:790-812).  One pass needs the level-A bins (+1/8) and the buckets at once; when that exceeds
+// what the device has free, the bins are split into 2, 4, ... groups and the (small) packed reads are
+// sliced once per group.  Collective on several ranks (the largest need decides).
+int choose_count_passes(pedk_ctx* ctx, uint64_t m_max, size_t ksz, int nbA) {
+    const int R = ctx->nranks;
+    int max_pass = nbA / R;  // every rank keeps at least one bin per pass
+    if (max_pass < 1) max_pass = 1;
+    int forced = env_int("PEDK_COUNT_PASSES", 0, 0, 256);
+    int P = 1;
+    if (forced > 0) {
+        while (P < forced) P <<= 1;
+    } else {
+        size_t free_b = 0, total_b = 0;
+        PEDK_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        // blocks the context's allocator holds but nobody uses count as free
+        const size_t cached = ctx->reserved_bytes > ctx->cur_bytes ? ctx->reserved_bytes - ctx->cur_bytes : 0;
+        const char* cap_env = getenv("PEDK_DEVICE_BUDGET_MB");  // tests: pretend the device is small
+        double budget = (double)(free_b + cached) * 0.90;
+        if (cap_env && *cap_env) budget = std::min(budget, atof(cap_env) * 1048576.0);
+        // level-A segments (expected + 1/8 + slack per (bin, source)) + buckets + the rows that come out
+        auto need = [&](int passes) {
+            const double inst = (double)m_max * R / passes;  // what a rank receives per pass (even hash)
+            return inst * ksz * (1.125 + 1.0) + (double)nbA / passes * R * 4096 * ksz + inst * 0.25 * 12;
+        };
+        while (P < max_pass && need(P) > budget) P <<= 1;
+    }
+    if (P > max_pass) P = max_pass;
+    if (R > 1) {
+        // all ranks must agree: take the largest
+        unsigned long long v = (unsigned long long)P;
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 14, &v, 8, cudaMemcpyHostToDevice, ctx->stream));
+        comm_allreduce_max(ctx, ctx->scalars + 14, 1);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(&v, ctx->scalars + 14, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        P = (int)v;
+    }
+    return P;
+}
+
 void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     pedk_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
@@ -490,209 +531,256 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
             m_local += g.n * (uint64_t)(g.L - k + 1);
         }
     const unsigned TILE = sub_tile_keys();
-    // what the level-A pass leaves for the level-B passes: the segments of this rank's bins
-    std::vector<unsigned long long> seg_start, seg_end, seg_bin;
-    DBuf<uint8_t> keysA;
     DBuf<unsigned long long> histA(ctx, (size_t)(NBINS_MAX + 1) * (PEDK_MAX_RANKS + 1));
     std::vector<unsigned long long> all((size_t)(NBINS_MAX + 1) * R, 0);
-    auto scatter_all = [&](unsigned long long* d_cur, const unsigned long long* d_lim, int* d_ovf) {
-        PeerPtrs dst;
-        if (multi) {
-            void* peers[PEDK_MAX_RANKS];
-            comm_peer_pointers(ctx, keysA.p, peers);
-            for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
-        } else {
-            dst.p[0] = reinterpret_cast<uint64_t*>(keysA.p);
-        }
-        StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART, packed_bytes + m_local * ksz);
-        // nobody may store into a buffer before its owner is done with the previous contents
-        if (multi) comm_barrier(ctx);
-        for (const ReadGroup& g : s->groups)
-            if (g.L >= k && g.n)
-                launch_part_scatter(g.words.p, g.W, g.L, k, g.n, a, R, wide, d_cur, d_lim, d_ovf, dst, st);
-    };
-
-    // (1) OPTIMISTIC: the hash spreads the k-mers evenly over the bins, so every (source rank,
-    // bin) run gets a segment of the expected size plus 1/8 (+4096) and the reads are sliced
-    // ONCE.  If a run does not fit (a k-mer with millions of instances), fall through to (2).
-    bool done = false;
-    const bool force_exact = getenv("PEDK_BUCKET_EXACT") && atoi(getenv("PEDK_BUCKET_EXACT")) != 0;
-    if (!force_exact) {
-        uint64_t m_max = m_local;
-        if (multi) {
-            PEDK_CUDA_TRY(cudaMemcpyAsync(histA.p, &m_local, 8, cudaMemcpyHostToDevice, st));
-            comm_allgather_u64(ctx, histA.p, histA.p + 8, 1);
-            std::vector<unsigned long long> mm((size_t)R);
-            PEDK_CUDA_TRY(cudaMemcpyAsync(mm.data(), histA.p + 8, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
-            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-            for (int r = 0; r < R; ++r) m_max = std::max<uint64_t>(m_max, mm[(size_t)r]);
-        }
-        LevelAPlan lp;
-        plan_level_a_optimistic(a, R, me, m_max, &lp);
-        const uint64_t C = lp.C;
-        const std::vector<unsigned long long>&curA = lp.cur, &limA = lp.lim;
-        keysA = DBuf<uint8_t>(ctx, peer_block_elems(lp.buffer_elems * ksz, multi, 1));
-        DBuf<unsigned long long> plan(ctx, (size_t)3 * NBINS_MAX + 8);
-        unsigned long long* d_cur = plan.p;
-        unsigned long long* d_lim = plan.p + NBINS_MAX;
-        unsigned long long* d_cnt = plan.p + 2 * NBINS_MAX;  // [NBINS_MAX] counts, then the overflow flag
-        PEDK_CUDA_TRY(cudaMemcpyAsync(d_cur, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
-        PEDK_CUDA_TRY(cudaMemcpyAsync(d_lim, limA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
-        PEDK_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, ((size_t)NBINS_MAX + 8) * 8, st));
-        int* d_ovf = reinterpret_cast<int*>(d_cnt + NBINS_MAX);
-        scatter_all(d_cur, d_lim, d_ovf);
-        // what every rank really stored: cursor - start per bin (+ the flag), to all ranks.  On
-        // several ranks this all-gather is also the fence "every rank's stores have landed".
-        launch_cursor_counts(d_cur, d_lim, C, NBINS_MAX, d_cnt, st);
-        if (multi) {
-            comm_allgather_u64(ctx, d_cnt, histA.p, NBINS_MAX + 1);
-            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
-        } else {
-            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), d_cnt, ((size_t)NBINS_MAX + 1) * 8, cudaMemcpyDeviceToHost, st));
-        }
+    uint64_t m_max = m_local;
+    if (multi) {
+        PEDK_CUDA_TRY(cudaMemcpyAsync(histA.p, &m_local, 8, cudaMemcpyHostToDevice, st));
+        comm_allgather_u64(ctx, histA.p, histA.p + 8, 1);
+        std::vector<unsigned long long> mm((size_t)R);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(mm.data(), histA.p + 8, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        ctx->stats.d2h_bytes += all.size() * 8;
-        bool overflow = false;
-        for (int r = 0; r < R; ++r) overflow |= all[(size_t)r * (NBINS_MAX + 1) + NBINS_MAX] != 0;
-        trace(ctx, overflow ? "  bins: extract + hash + bin (optimistic sizes overflowed)"
-                            : multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
-        if (!overflow) {
-            level_a_segments_optimistic(a, R, me, all.data(), &lp);
+        for (int r = 0; r < R; ++r) m_max = std::max<uint64_t>(m_max, mm[(size_t)r]);
+    }
+    const int P = choose_count_passes(ctx, m_max, ksz, nbA);
+    s->cinfo.count_passes = P;
+    const bool force_exact = getenv("PEDK_BUCKET_EXACT") && atoi(getenv("PEDK_BUCKET_EXACT")) != 0;
+    uint64_t m_total = 0;
+    s->n_rows = 0;
+    s->D = 0;
+    uint64_t row_cap = 0;  // several passes: the rows of all passes are collected in s->rkey / s->rval
+
+    for (int pass = 0; pass < P; ++pass) {
+        // what the level-A pass leaves for the level-B passes: the segments of this rank's bins
+        std::vector<unsigned long long> seg_start, seg_end, seg_bin;
+        DBuf<uint8_t> keysA;
+        auto scatter_all = [&](unsigned long long* d_cur, const unsigned long long* d_lim, int* d_ovf) {
+            PeerPtrs dst;
+            if (multi) {
+                void* peers[PEDK_MAX_RANKS];
+                comm_peer_pointers(ctx, keysA.p, peers);
+                for (int d = 0; d < R; ++d) dst.p[d] = static_cast<uint64_t*>(peers[d]);
+            } else {
+                dst.p[0] = reinterpret_cast<uint64_t*>(keysA.p);
+            }
+            StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART, packed_bytes + m_local / P * ksz);
+            // nobody may store into a buffer before its owner is done with the previous contents
+            if (multi) comm_barrier(ctx);
+            for (const ReadGroup& g : s->groups)
+                if (g.L >= k && g.n)
+                    launch_part_scatter(g.words.p, g.W, g.L, k, g.n, a, R, wide, d_cur, d_lim, d_ovf, dst, P, pass, st);
+        };
+        auto sent_by_me = [&]() {
+            uint64_t sent = 0;
+            for (int bin = 0; bin < nbA; ++bin)
+                if (bin % P == pass) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
+            return sent;
+        };
+
+        // (1) OPTIMISTIC: the hash spreads the k-mers evenly over the bins, so every (source rank,
+        // bin) run gets a segment of the expected size plus 1/8 (+4096) and the reads are sliced
+        // ONCE.  If a run does not fit (a k-mer with millions of instances), fall through to (2).
+        bool done = false;
+        uint64_t sent_expected = 0;  // P > 1: known only after the pass (the filter drops the other bins)
+        if (!force_exact) {
+            LevelAPlan lp;
+            plan_level_a_optimistic(a, R, me, m_max, &lp, P, pass);
+            const uint64_t C = lp.C;
+            keysA = DBuf<uint8_t>(ctx, peer_block_elems(lp.buffer_elems * ksz, multi, 1));
+            DBuf<unsigned long long> plan(ctx, (size_t)3 * NBINS_MAX + 8);
+            unsigned long long* d_cur = plan.p;
+            unsigned long long* d_lim = plan.p + NBINS_MAX;
+            unsigned long long* d_cnt = plan.p + 2 * NBINS_MAX;  // [NBINS_MAX] counts, then the overflow flag
+            PEDK_CUDA_TRY(cudaMemcpyAsync(d_cur, lp.cur.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaMemcpyAsync(d_lim, lp.lim.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, ((size_t)NBINS_MAX + 8) * 8, st));
+            int* d_ovf = reinterpret_cast<int*>(d_cnt + NBINS_MAX);
+            scatter_all(d_cur, d_lim, d_ovf);
+            // what every rank really stored: cursor - start per bin (+ the flag), to all ranks.  On
+            // several ranks this all-gather is also the fence "every rank's stores have landed".
+            launch_cursor_counts(d_cur, d_lim, C, NBINS_MAX, d_cnt, st);
+            if (multi) {
+                comm_allgather_u64(ctx, d_cnt, histA.p, NBINS_MAX + 1);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
+            } else {
+                PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), d_cnt, ((size_t)NBINS_MAX + 1) * 8, cudaMemcpyDeviceToHost, st));
+            }
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->stats.d2h_bytes += all.size() * 8;
+            bool overflow = false;
+            for (int r = 0; r < R; ++r) overflow |= all[(size_t)r * (NBINS_MAX + 1) + NBINS_MAX] != 0;
+            trace(ctx, overflow ? "  bins: extract + hash + bin (optimistic sizes overflowed)"
+                                : multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+            if (!overflow) {
+                level_a_segments_optimistic(a, R, me, all.data(), &lp);
+                seg_start = lp.seg_start;
+                seg_end = lp.seg_end;
+                seg_bin = lp.seg_bin;
+                sent_expected = sent_by_me();
+                if (P == 1 && sent_expected != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
+                done = true;
+            }
+        }
+        if (!done) {
+            // (2) EXACT: size the bins with a pass over the packed reads (no stores), then slice again
+            {
+                StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART_COUNT, packed_bytes);
+                PEDK_CUDA_TRY(cudaMemsetAsync(histA.p, 0, histA.bytes(), st));
+                for (const ReadGroup& g : s->groups)
+                    if (g.L >= k && g.n) launch_part_count(g.words.p, g.W, g.L, k, g.n, a, histA.p, st);
+            }
+            if (multi) {
+                comm_allgather_u64(ctx, histA.p, histA.p + NBINS_MAX + 1, NBINS_MAX + 1);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p + NBINS_MAX + 1, all.size() * 8, cudaMemcpyDeviceToHost, st));
+            } else {
+                PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, ((size_t)NBINS_MAX + 1) * 8, cudaMemcpyDeviceToHost, st));
+            }
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->stats.d2h_bytes += all.size() * 8;
+            trace(ctx, "  bins: counts");
+            uint64_t counted = 0;
+            for (int bin = 0; bin < nbA; ++bin) counted += all[(size_t)me * (NBINS_MAX + 1) + bin];
+            if (counted != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
+            LevelAPlan lp;
+            plan_level_a_exact(a, R, me, all.data(), &lp, P, pass);
             seg_start = lp.seg_start;
             seg_end = lp.seg_end;
             seg_bin = lp.seg_bin;
-            uint64_t sent = 0;
-            for (int bin = 0; bin < nbA; ++bin) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
-            if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
-            done = true;
+            keysA.reset();
+            keysA = DBuf<uint8_t>(ctx, peer_block_elems(lp.buffer_elems * ksz, multi, 1));
+            DBuf<unsigned long long> plan(ctx, NBINS_MAX);
+            PEDK_CUDA_TRY(cudaMemcpyAsync(plan.p, lp.cur.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
+            scatter_all(plan.p, nullptr, nullptr);
+            if (multi) comm_barrier(ctx);  // every rank's stores have landed
+            if (ctx->trace) {
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                trace(ctx, multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+            }
         }
-    }
-    if (!done) {
-        // (2) EXACT: size the bins with a pass over the packed reads (no stores), then slice again
+        // the segments of this rank's bins, their tiles
+        const int n_seg = (int)seg_start.size();
+        std::vector<unsigned> tile_prefix((size_t)n_seg + 1, 0);
+        uint64_t m = 0;
+        for (int sg = 0; sg < n_seg; ++sg) {
+            const unsigned long long len = seg_end[(size_t)sg] - seg_start[(size_t)sg];
+            const unsigned long long tiles = (len + TILE - 1) / TILE;
+            if ((unsigned long long)tile_prefix[(size_t)sg] + tiles > 0xfffffff0ull)
+                throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^45 k-mer instances on one GPU");
+            tile_prefix[(size_t)sg + 1] = tile_prefix[(size_t)sg] + (unsigned)tiles;
+            m += len;
+        }
+        const unsigned n_tiles = tile_prefix[(size_t)n_seg];
+        m_total += m;
+        if (m == 0) continue;
+        DBuf<unsigned long long> d_seg(ctx, (size_t)3 * n_seg);
+        DBuf<unsigned> tprefix(ctx, (size_t)n_seg + 1);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p, seg_start.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + n_seg, seg_end.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + 2 * n_seg, seg_bin.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
+
+        // (4) exact bucket sizes, (5) their offsets
+        const size_t n_buckets = (size_t)nbA * NBINS_MAX;
+        DBuf<unsigned> histB(ctx, n_buckets);
+        DBuf<unsigned long long> offB(ctx, n_buckets + 1), curB(ctx, n_buckets);
+        DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
         {
-            StageScope sc(ctx, exch_stage, 1, 0, 0, PEDK_KC_PART_COUNT, packed_bytes);
-            PEDK_CUDA_TRY(cudaMemsetAsync(histA.p, 0, histA.bytes(), st));
-            for (const ReadGroup& g : s->groups)
-                if (g.L >= k && g.n) launch_part_count(g.words.p, g.W, g.L, k, g.n, a, histA.p, st);
+            StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_HIST, m * ksz);
+            PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
+            launch_sub_hist(keysA.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, histB.p, st);
         }
-        if (multi) {
-            comm_allgather_u64(ctx, histA.p, histA.p + NBINS_MAX + 1, NBINS_MAX + 1);
-            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p + NBINS_MAX + 1, all.size() * 8, cudaMemcpyDeviceToHost, st));
-        } else {
-            PEDK_CUDA_TRY(cudaMemcpyAsync(all.data(), histA.p, ((size_t)NBINS_MAX + 1) * 8, cudaMemcpyDeviceToHost, st));
+        {
+            StageScope sc(ctx, PEDK_ST_SORT, 3);
+            exclusive_scan_u32(histB.p, reinterpret_cast<uint64_t*>(offB.p), n_buckets, ctx->scalars + 3, ws.p, st);
+            const unsigned long long total = m;
+            PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
+            PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
         }
-        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        ctx->stats.d2h_bytes += all.size() * 8;
-        trace(ctx, "  bins: counts");
-        LevelAPlan lp;
-        plan_level_a_exact(a, R, me, all.data(), &lp);
-        seg_start = lp.seg_start;
-        seg_end = lp.seg_end;
-        seg_bin = lp.seg_bin;
-        const std::vector<unsigned long long>& curA = lp.cur;
-        uint64_t sent = 0;
-        for (int bin = 0; bin < nbA; ++bin) sent += all[(size_t)me * (NBINS_MAX + 1) + bin];
-        if (sent != m_local) throw PedkError(PEDK_E_INTERNAL, "level-A bin counts do not add up");
-        keysA = DBuf<uint8_t>(ctx, peer_block_elems(lp.buffer_elems * ksz, multi, 1));
-        DBuf<unsigned long long> plan(ctx, NBINS_MAX);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(plan.p, curA.data(), (size_t)NBINS_MAX * 8, cudaMemcpyHostToDevice, st));
-        scatter_all(plan.p, nullptr, nullptr);
-        if (multi) comm_barrier(ctx);  // every rank's stores have landed
+        // (6) second binning level
+        DBuf<uint8_t> keysB(ctx, m * ksz + 64);  // the count kernel reads it with aligned 16-byte loads
+        {
+            StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
+            launch_sub_scatter(keysA.p, keysB.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, curB.p, st);
+        }
         if (ctx->trace) {
             PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-            trace(ctx, multi ? "  bins: extract + hash + bin + NVLink stores" : "  bins: extract + hash + bin");
+            trace(ctx, "  buckets: histogram + scan + scatter");
+        }
+        // (7) one CTA per bucket: count, rows.  The rows first land in the level-A buffer (free
+        // now: room for a row per three 4-byte instances); with one pass they stay there, with
+        // several they are collected in the sample's own arrays.
+        uint64_t cap = keysA.n / 12;
+        uint64_t* tmp_key = reinterpret_cast<uint64_t*>(keysA.p);
+        uint32_t* tmp_val = reinterpret_cast<uint32_t*>(tmp_key + cap);
+        DBuf<uint64_t> big_key;
+        DBuf<uint32_t> big_val;
+        uint64_t rows_pass = 0, heads_pass = 0;
+        for (int attempt = 0;; ++attempt) {
+            {
+                StageScope sc(ctx, PEDK_ST_COUNT, 1, 0, 0, PEDK_KC_BUCKET_COUNT, m * ksz);
+                PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), st));
+                launch_bucket_count(keysB.p, wide, offB.p, (unsigned)n_buckets, k, a, b, log_slots, 1, s->ckey.p, s->ccnt.p,
+                                    s->n_corr, tmp_key, tmp_val, cap, ctx->scalars + 8, ctx->tile_ctr, ctx->err_flag, st);
+            }
+            PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 2 * sizeof(unsigned long long),
+                                          cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->stats.d2h_bytes += 16;
+            trace(ctx, "  buckets: count -> rows");
+            rows_pass = ctx->h_scalars[8];
+            heads_pass = ctx->h_scalars[9];
+            if (rows_pass <= cap) break;
+            if (attempt) throw PedkError(PEDK_E_INTERNAL, "row count changed between two passes");
+            // mostly distinct k-mers (very low coverage): run again into arrays of the exact size
+            cap = rows_pass;
+            big_key = DBuf<uint64_t>(ctx, cap);
+            big_val = DBuf<uint32_t>(ctx, cap);
+            tmp_key = big_key.p;
+            tmp_val = big_val.p;
+        }
+        check_err_flag(ctx, "bucket count");
+        ctx->stats.kc_bytes[PEDK_KC_BUCKET_COUNT] += rows_pass * 12;
+        keysB.reset();
+        if (P == 1) {
+            s->n_rows = rows_pass;
+            s->D = heads_pass;
+            if (big_key.p) {
+                s->rkey = std::move(big_key);
+                s->rval = std::move(big_val);
+            } else {
+                // the rows stay in the level-A buffer: no copy to exact-size arrays
+                s->row_key_in_store = tmp_key;
+                s->row_val_in_store = tmp_val;
+                s->row_store = std::move(keysA);
+            }
+        } else {
+            if (s->n_rows + rows_pass > row_cap) {
+                // grow: what the passes so far produced, extrapolated to all passes, plus a margin
+                uint64_t want = (s->n_rows + rows_pass) * (uint64_t)P / (uint64_t)(pass + 1);
+                want += want / 16 + 1024;
+                DBuf<uint64_t> nk(ctx, want);
+                DBuf<uint32_t> nv(ctx, want);
+                if (s->n_rows) {
+                    StageScope sc(ctx, PEDK_ST_COUNT, 0);
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(nk.p, s->rkey.p, s->n_rows * 8, cudaMemcpyDeviceToDevice, st));
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(nv.p, s->rval.p, s->n_rows * 4, cudaMemcpyDeviceToDevice, st));
+                }
+                s->rkey = std::move(nk);
+                s->rval = std::move(nv);
+                row_cap = want;
+            }
+            if (rows_pass) {
+                StageScope sc(ctx, PEDK_ST_COUNT, 0);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(s->rkey.p + s->n_rows, tmp_key, rows_pass * 8, cudaMemcpyDeviceToDevice, st));
+                PEDK_CUDA_TRY(cudaMemcpyAsync(s->rval.p + s->n_rows, tmp_val, rows_pass * 4, cudaMemcpyDeviceToDevice, st));
+            }
+            s->n_rows += rows_pass;
+            s->D += heads_pass;
         }
     }
-    // the segments of this rank's bins, their tiles
-    const int n_seg = (int)seg_start.size();
-    std::vector<unsigned> tile_prefix((size_t)n_seg + 1, 0);
-    uint64_t m = 0;
-    for (int sg = 0; sg < n_seg; ++sg) {
-        const unsigned long long len = seg_end[(size_t)sg] - seg_start[(size_t)sg];
-        const unsigned long long tiles = (len + TILE - 1) / TILE;
-        if ((unsigned long long)tile_prefix[(size_t)sg] + tiles > 0xfffffff0ull)
-            throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^45 k-mer instances on one GPU");
-        tile_prefix[(size_t)sg + 1] = tile_prefix[(size_t)sg] + (unsigned)tiles;
-        m += len;
-    }
-    const unsigned n_tiles = tile_prefix[(size_t)n_seg];
-    *m_out = m;
-    if (m == 0) return;
-    DBuf<unsigned long long> d_seg(ctx, (size_t)3 * n_seg);
-    DBuf<unsigned> tprefix(ctx, (size_t)n_seg + 1);
-    PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p, seg_start.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
-    PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + n_seg, seg_end.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
-    PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + 2 * n_seg, seg_bin.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
-    PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
-
-    // (4) exact bucket sizes, (5) their offsets
-    const size_t n_buckets = (size_t)nbA * NBINS_MAX;
-    DBuf<unsigned> histB(ctx, n_buckets);
-    DBuf<unsigned long long> offB(ctx, n_buckets + 1), curB(ctx, n_buckets);
-    DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
-    {
-        StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_HIST, m * ksz);
-        PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
-        launch_sub_hist(keysA.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, histB.p, st);
-    }
-    {
-        StageScope sc(ctx, PEDK_ST_SORT, 3);
-        exclusive_scan_u32(histB.p, reinterpret_cast<uint64_t*>(offB.p), n_buckets, ctx->scalars + 3, ws.p, st);
-        const unsigned long long total = m;
-        PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
-        PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
-    }
-    // (6) second binning level
-    DBuf<uint8_t> keysB(ctx, m * ksz);
-    {
-        StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
-        launch_sub_scatter(keysA.p, keysB.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, curB.p, st);
-    }
-    if (ctx->trace) {
-        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        trace(ctx, "  buckets: histogram + scan + scatter");
-    }
-    // (7) one CTA per bucket: count, rows.  The rows first land in the level-A buffer (free
-    // now: room for a row per three 4-byte instances), then move to exact-size arrays.
-    uint64_t cap = keysA.n / 12;
-    uint64_t* tmp_key = reinterpret_cast<uint64_t*>(keysA.p);
-    uint32_t* tmp_val = reinterpret_cast<uint32_t*>(tmp_key + cap);
-    DBuf<uint64_t> big_key;
-    DBuf<uint32_t> big_val;
-    for (int attempt = 0;; ++attempt) {
-        {
-            StageScope sc(ctx, PEDK_ST_COUNT, 1, 0, 0, PEDK_KC_BUCKET_COUNT, m * ksz);
-            PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), st));
-            launch_bucket_count(keysB.p, wide, offB.p, (unsigned)n_buckets, k, a, b, log_slots, 1, s->ckey.p, s->ccnt.p,
-                                s->n_corr, tmp_key, tmp_val, cap, ctx->scalars + 8, ctx->tile_ctr, ctx->err_flag, st);
-        }
-        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 2 * sizeof(unsigned long long),
-                                      cudaMemcpyDeviceToHost, st));
-        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        ctx->stats.d2h_bytes += 16;
-        trace(ctx, "  buckets: count -> rows");
-        s->n_rows = ctx->h_scalars[8];
-        s->D = ctx->h_scalars[9];
-        if (s->n_rows <= cap) break;
-        if (attempt) throw PedkError(PEDK_E_INTERNAL, "row count changed between two passes");
-        // mostly distinct k-mers (very low coverage): run again into arrays of the exact size
-        cap = s->n_rows;
-        big_key = DBuf<uint64_t>(ctx, cap);
-        big_val = DBuf<uint32_t>(ctx, cap);
-        tmp_key = big_key.p;
-        tmp_val = big_val.p;
-    }
-    check_err_flag(ctx, "bucket count");
-    ctx->stats.kc_bytes[PEDK_KC_BUCKET_COUNT] += s->n_rows * 12;
-    if (big_key.p) {
-        s->rkey = std::move(big_key);
-        s->rval = std::move(big_val);
-    } else {
-        // the rows stay in the level-A buffer: no copy to exact-size arrays
-        s->row_key_in_store = tmp_key;
-        s->row_val_in_store = tmp_val;
-        s->row_store = std::move(keysA);
-    }
+    // every instance of every rank was stored in exactly one pass
+    if (!multi && m_total != m_local) throw PedkError(PEDK_E_INTERNAL, "passes do not add up to the sample's instances");
+    *m_out = m_total;
 }
 
 void do_count(pedk_sample* s, int k) {

@@ -59,6 +59,19 @@ struct pedk_sample {
     std::vector<Chromosome> chromosomes;
     pedk::DBuf<uint8_t> ref_clean;
     uint64_t ref_clean_len = 0;
+    // f1: the unique-k-mer index of the reference (refindex.cu), in the order of the ref20_uniq files
+    struct Ref20 {
+        bool built = false;
+        bool any_chromosome = false;   // mk20 wrote its 64 files (there was a chromosome to process)
+        int k = 0;
+        std::vector<uint64_t> kmer;    // ascending
+        std::vector<uint32_t> chr;     // index into names
+        std::vector<uint64_t> pos;     // 1-based: first base (strand f) or last base (strand r) of the k-mer
+        std::vector<uint8_t> strand;   // 0 = f, 1 = r
+        std::vector<std::string> names;  // chromosome names as mk20mer prints them (no "chr" prefix)
+        uint64_t tag_start[65] = {0};
+        pedk::DBuf<uint64_t> d_kmer;   // the keys in HBM, for the edge look-ups
+    } ref20;
 };
 
 namespace pedk {
@@ -77,5 +90,9 @@ void dedup_group(pedk_sample* s, int L, int W, DBuf<uint64_t>& words, DBuf<uint8
 // reads the sequence read_scalar-style helpers of sample.cu rely on
 
 void ensure_host_reads(pedk_sample* s);
+// f1 (refindex.cu)
+void ref20_append_text(pedk_sample* s, int tag, const std::string& text);
+std::string ref20_text(pedk_sample* s, int tag);
+std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len);
 std::string kmer_string(uint64_t v, int k);
 }  // namespace pedk

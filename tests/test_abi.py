@@ -49,7 +49,7 @@ def test_struct_layouts_match_header(built):
 
     assert C.sizeof(api.Edge) == 48 and api.EDGE_DTYPE.itemsize == 48
     assert C.sizeof(api.IngestInfo) == 64
-    assert C.sizeof(api.CountInfo) == 32
+    assert C.sizeof(api.CountInfo) == 40
     assert C.sizeof(api.SynthParams) == 32
 
 

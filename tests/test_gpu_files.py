@@ -130,10 +130,32 @@ def test_reference_as_control_file_contract(built, tmp_path, gz):
     for s in (b"T", b"REF"):
         ctx.check(lib.pedk_count_kmer(ctx.h, wd.encode(), s, 20))
         ctx.check(lib.pedk_lbc_kmer(ctx.h, wd.encode(), s, 20))
+    # mkRef's order (ped.pl:1018-1023): chromosome files, then mk20, then mkControlRead; here the
+    # reference is resident after pedk_mk_control_read, so mk20 needs no second parse
+    ctx.check(lib.pedk_mk_ref20_uniq(ctx.h, wd.encode(), b"REF", None, 20))
     tmpdir = f"{wd}/T/tmp"
     ctx.check(lib.pedk_join_kmer(ctx.h, wd.encode(), b"T", b"REF", 20, tmpdir.encode(), 1))
+    ctx.check(lib.pedk_map_kmer(ctx.h, wd.encode(), b"T", b"REF", tmpdir.encode()))
     assert lib.pedk_mk_control_read(ctx.h, wd.encode(), b"REF", b"nosuch.fa") == -4
     ctx.close()
+    # f1: <ref>/ref20_uniq.TAG.gz and <tmpdir>/<t>.map.TAG as ped.pl leaves them
+    g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
+    for i, tag in enumerate(TAGS):
+        assert _zcat(f"{wd}/REF/ref20_uniq.{tag}.gz") == oracle.ref20_uniq_text(fa, i)
+        assert open(f"{tmpdir}/T.map.{tag}").read() == g["map"].get(tag, "")
+    # ... and again in a fresh process that only has the files (FASTA named: parsed again; map from gz)
+    for tag in TAGS:
+        os.unlink(f"{wd}/REF/ref20_uniq.{tag}.gz")
+        os.unlink(f"{tmpdir}/T.map.{tag}")
+    ctx = api.Context(0)
+    ctx.check(ctx.lib.pedk_mk_ref20_uniq(ctx.h, wd.encode(), b"REF", name.encode(), 20))
+    ctx.close()
+    ctx = api.Context(0)
+    ctx.check(ctx.lib.pedk_map_kmer(ctx.h, wd.encode(), b"T", b"REF", tmpdir.encode()))
+    ctx.close()
+    for i, tag in enumerate(TAGS):
+        assert _zcat(f"{wd}/REF/ref20_uniq.{tag}.gz") == oracle.ref20_uniq_text(fa, i)
+        assert open(f"{tmpdir}/T.map.{tag}").read() == g["map"].get(tag, "")
     for fn, seq in oracle.ref_chromosomes(fa).items():
         assert open(f"{wd}/REF/{fn}", "rb").read() == seq
     for s, o in (("REF", oc), ("T", ot)):
@@ -142,5 +164,4 @@ def test_reference_as_control_file_contract(built, tmp_path, gz):
             assert _zcat(f"{wd}/{s}/count/{s}.count.{tag}.gz") == o.count_text(i)
             assert _zcat(f"{wd}/{s}/lbc/{s}.lbc.{tag}.gz") == o.lbc_text(i)
     assert b"".join(open(f"{tmpdir}/T.snp.{t}", "rb").read() for t in TAGS) == osnp
-    g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
     assert osnp.decode() == g["kmer_snp"]

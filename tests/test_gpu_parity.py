@@ -223,12 +223,17 @@ def test_full_size_properties(ctx, k, G, N):
 
 @pytest.mark.parametrize("env", [{"PEDK_BUCKET_SLOTS_LOG2": "10"}, {"PEDK_BUCKET_SLOTS_LOG2": "10", "PEDK_BUCKET_B": "1"},
                                  {"PEDK_BUCKET_B": "2"}, {"PEDK_BUCKET_EXACT": "1"}, {"PEDK_COUNT_MODE": "sort"},
-                                 {"PEDK_JOIN_SLOTS_LOG2": "10", "PEDK_JOIN_B": "1"}, {"PEDK_JOIN_B": "3"}])
+                                 {"PEDK_JOIN_SLOTS_LOG2": "10", "PEDK_JOIN_B": "1"}, {"PEDK_JOIN_B": "3"},
+                                 {"PEDK_COUNT_PASSES": "4"}, {"PEDK_COUNT_PASSES": "2", "PEDK_BUCKET_EXACT": "1"},
+                                 {"PEDK_DEVICE_BUDGET_MB": "8"}, {"PEDK_BC_THREADS": "512"},
+                                 {"PEDK_SUB_THREADS": "512"}])
 @pytest.mark.parametrize("k", [20, 31])
 def test_bucket_table_overflow_and_legacy_path(ctx, env, k):
     """The per-bucket hash table is forced to overflow (1024 slots, buckets 128x larger) so that
     buckets are split by further hash bits and re-read (PEDK_JOIN_*: the same for the tables of the
-    hash join, whose groups then meet in several rounds); PEDK_BUCKET_EXACT=1 sizes the level-A bins
+    hash join, whose groups then meet in several rounds); PEDK_COUNT_PASSES / PEDK_DEVICE_BUDGET_MB
+    count the instances in several groups of hash bins, as a sample that does not fit HBM is
+    (the reference's `sort -T` spill); PEDK_BUCKET_EXACT=1 sizes the level-A bins
     with a counting pass instead of optimistically; PEDK_COUNT_MODE=sort is the extract +
     LSD radix sort + run-length path the buckets replaced.  All must give the reference's table."""
     case = dict(kind="synth", cfg=13, genome=300_000, reads=60_000, L=150, snp_ppm=1000, indel_ppm=100,
@@ -239,6 +244,10 @@ def test_bucket_table_overflow_and_legacy_path(ctx, env, k):
     os.environ.update(env)
     try:
         c, t, ci, ti, r = gpu_run(ctx, fc, ft, k)
+        if "PEDK_COUNT_PASSES" in env:
+            assert c.last_count.count_passes == int(env["PEDK_COUNT_PASSES"])
+        if "PEDK_DEVICE_BUDGET_MB" in env:
+            assert c.last_count.count_passes > 1
     finally:
         for n, v in old.items():
             if v is None:
@@ -358,3 +367,58 @@ def test_reference_tiling_properties_at_scale(ctx):
     idx = np.searchsorted(km, rc)
     assert (km[idx] == rc).all() and (ct[idx] == ct).all()
     s.destroy()
+
+
+def test_reference_unique_kmer_index_and_position_map(ctx):
+    """f1: mk20mer + mkUniq (ped.pl:1138-1211) and mapKmerSub (ped.pl:641-685) against
+    ped.pl's own ref20_uniq files and `sub=mapKmerSub` outputs (tests/golden/ref30k.json) and the oracle."""
+    g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
+    fa, ft = make_ref_inputs(REF_CASES["ref30k"])
+    c, t = api.Sample(ctx), api.Sample(ctx)
+    c.add_fastq(fa)
+    t.add_fastq(ft)
+    t.ingest()
+    c.ingest_reference()
+    rows = c.ref20_uniq(20)
+    c.count(20)
+    t.count(20)
+    r = ctx.join(c, t)
+    try:
+        h = hashlib.sha256()
+        for tag in range(64):
+            b = c.ref20_uniq_text(tag)
+            assert b == oracle.ref20_uniq_text(fa, tag), tag
+            h.update(b)
+        assert (rows, h.hexdigest()) == (g["ref20_uniq"]["rows"], g["ref20_uniq"]["sha256"])
+        snp = r.text()
+        assert snp.decode() == g["kmer_snp"]
+        by_tag = {tg: b"" for tg in oracle.TAGS}
+        for line in snp.splitlines(keepends=True):
+            by_tag[line[:3].decode()] += line
+        got = {}
+        for tg in oracle.TAGS:
+            m = c.map_kmer_text(by_tag[tg])
+            if m:
+                got[tg] = m.decode()
+        assert got == g["map"]
+        # the whole edge list at once maps to the concatenation of the per-tag files
+        assert c.map_kmer_text(snp).decode() == "".join(g["map"].get(tg, "") for tg in oracle.TAGS)
+    finally:
+        r.destroy(); c.destroy(); t.destroy()
+
+
+@pytest.mark.parametrize("fa", [b"", b">only\n", b">a\n" + b"ACGT" * 4 + b"\n", b">NOP\n" + b"ACGTTGCA" * 9 + b"\n",
+                                b">a\n" + b"ACGTTGCAAT" * 7 + b"\n>b x\n" + b"GATTACAGATTACCA" * 5 + b"N" + b"ACGTTGCAAT" * 3,
+                                b">p\nACGTTGCAATATTGCAACGT" + b"GGATC" * 9 + b"\n"])
+def test_reference_unique_kmer_index_corner_inputs(ctx, fa):
+    """Empty reference, a sequence shorter than k, a chromosome called NOP (skipped, ped.pl:1217), repeats
+    within and between chromosomes, an N, a palindromic 20-mer (both of its lines carry the same k-mer)."""
+    s = api.Sample(ctx)
+    s.add_fastq(fa)
+    s.ingest_reference()
+    s.ref20_uniq(20)
+    try:
+        for tag in range(64):
+            assert s.ref20_uniq_text(tag) == oracle.ref20_uniq_text(fa, tag), tag
+    finally:
+        s.destroy()
