@@ -134,6 +134,11 @@ int pedk_sample_ref20_uniq_text(pedk_sample *ref, int tag, char **text, uint64_t
  * in the unique k-mer index; the result is the text of the <tmpdir>/<t>.map.TAG files, in the same
  * order.  Caller frees with pedk_free. */
 int pedk_sample_map_kmer_text(pedk_sample *ref, const char *snp_text, uint64_t snp_len, char **text, uint64_t *len);
+/* f3, cnvJoin + cnvJoinSub (ped.pl:934-989): the full outer join of the two count tables, for the
+ * k-mers of the unique k-mer index of `ref`: lines `chr\tpos\tstrand\ttarget_count\tcontrol_count`
+ * (a k-mer one sample does not have counts 0 there), ordered like `sort -k 1 -n -k 2 -n` -- the text
+ * of <target>/<target>.<control>.cnv.  One rank.  Caller frees with pedk_free. */
+int pedk_cnv_text(pedk_sample *ref, pedk_sample *control, pedk_sample *target, char **text, uint64_t *len);
 /* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer
  * of every unique read, brought together (hash bins, buckets) and counted.  4 <= k <= 32 (the reference
  * hard-codes 20, ped.pl:912-913).  Leaves the canonical table in HBM. */
@@ -219,6 +224,10 @@ int pedk_mk_ref20_uniq(pedk_ctx *ctx, const char *wd, const char *ref, const cha
 /* mapKmer (ped.pl:625-685): reads <tmpdir>/<target>.snp.TAG (pedk_join_kmer with have_ref) and the
  * unique k-mer index (resident, or <wd>/<ref>/ref20_uniq.TAG.gz), writes <tmpdir>/<target>.map.TAG */
 int pedk_map_kmer(pedk_ctx *ctx, const char *wd, const char *target, const char *ref, const char *tmpdir);
+/* cnvJoin (ped.pl:934-947) after both countKmer calls of `cnv` (ped.pl:362-366): writes
+ * <wd>/<target>/<target>.<control>.cnv from the count tables (resident or count files) and the unique
+ * k-mer index (resident or ref20_uniq files) */
+int pedk_cnv(pedk_ctx *ctx, const char *wd, const char *target, const char *control, const char *ref, int k);
 /* countKmer (ped.pl:784-815): writes <wd>/<subject>/count/<subject>.count.TAG.gz */
 int pedk_count_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
 /* lbcKmer (ped.pl:817-831): writes <wd>/<subject>/lbc/<subject>.lbc.TAG.gz */

@@ -110,6 +110,8 @@ SIGNATURES = {
     "pedk_sample_ref20_uniq": (C.c_int, [_P, C.c_int, _U64P]),
     "pedk_sample_ref20_uniq_text": (C.c_int, [_P, C.c_int, _PP, _U64P]),
     "pedk_sample_map_kmer_text": (C.c_int, [_P, C.c_char_p, C.c_uint64, _PP, _U64P]),
+    "pedk_cnv_text": (C.c_int, [_P, _P, _P, _PP, _U64P]),
+    "pedk_cnv": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_mk_ref20_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_map_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_sample_table_digest": (C.c_int, [_P, _U64P, _U64P]),
@@ -356,6 +358,16 @@ class Sample:
         p = C.c_void_p()
         n = C.c_uint64()
         self.ctx.check(self.ctx.lib.pedk_sample_map_kmer_text(self.h, snp_text, len(snp_text), C.byref(p), C.byref(n)))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            self.ctx.lib.pedk_free(p)
+
+    def cnv_text(self, control: "Sample", target: "Sample") -> bytes:
+        """cnvJoin (ped.pl:934-989) with this sample as the indexed reference: `<t>.<c>.cnv`."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_cnv_text(self.h, control.h, target.h, C.byref(p), C.byref(n)))
         try:
             return C.string_at(p, n.value)
         finally:

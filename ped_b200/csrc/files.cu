@@ -556,26 +556,41 @@ void do_mk_ref20_uniq(pedk_ctx* ctx, const std::string& wd, const std::string& r
     });
 }
 
+// the unique k-mer index of the reference: resident, or read back from <ref>/ref20_uniq.TAG.gz
+pedk_sample* indexed_reference(pedk_ctx* ctx, const std::string& wd, const std::string& ref) {
+    pedk_sample* s = cached(ctx, wd + "/" + ref);
+    if (s && s->ref20.built) return s;
+    if (!s) s = fresh_sample(ctx, wd + "/" + ref);
+    s->ref20 = pedk_sample::Ref20{};
+    for (int t = 0; t < 64; ++t) {
+        const std::string p = wd + "/" + ref + "/ref20_uniq." + tag_name(t) + ".gz";
+        ref20_append_text(s, t, exists(p) ? read_gz(p) : std::string());
+    }
+    s->ref20.built = true;
+    return s;
+}
+
 // mapKmer (ped.pl:625-685): <tmpdir>/<t>.snp.TAG x <ref>/ref20_uniq.TAG.gz -> <tmpdir>/<t>.map.TAG
 void do_map_kmer(pedk_ctx* ctx, const std::string& wd, const std::string& target, const std::string& ref,
                  const std::string& tmpdir) {
     PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
-    pedk_sample* s = cached(ctx, wd + "/" + ref);
-    if (!s || !s->ref20.built) {
-        // a fresh process: the index comes back from the ref20_uniq files
-        if (!s) s = fresh_sample(ctx, wd + "/" + ref);
-        s->ref20 = pedk_sample::Ref20{};
-        for (int t = 0; t < 64; ++t) {
-            const std::string p = wd + "/" + ref + "/ref20_uniq." + tag_name(t) + ".gz";
-            ref20_append_text(s, t, exists(p) ? read_gz(p) : std::string());
-        }
-        s->ref20.built = true;
-    }
+    pedk_sample* s = indexed_reference(ctx, wd, ref);  // resident, or back from the ref20_uniq files
     for (int t = 0; t < 64; ++t) {
         const std::string snp = read_plain(tmpdir + "/" + target + ".snp." + tag_name(t));
         const std::string m = map_kmer_text(s, snp.data(), snp.size());
         write_plain_atomic(tmpdir + "/" + target + ".map." + tag_name(t), m.data(), m.size());
     }
+}
+
+// cnv (ped.pl:362-366) after the count tables: cnvJoin (ped.pl:934-947) -> <wd>/<target>/<target>.<control>.cnv
+void do_cnv(pedk_ctx* ctx, const std::string& wd, const std::string& target, const std::string& control,
+            const std::string& ref, int k) {
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    pedk_sample* r = indexed_reference(ctx, wd, ref);
+    pedk_sample* c = counted_sample(ctx, wd, control, k);
+    pedk_sample* t = counted_sample(ctx, wd, target, k);
+    const std::string text = cnv_text(r, c, t);
+    write_plain_atomic(wd + "/" + target + "/" + target + "." + control + ".cnv", text.data(), text.size());
 }
 
 }  // namespace
@@ -610,6 +625,14 @@ extern "C" int pedk_map_kmer(pedk_ctx* ctx, const char* wd, const char* target, 
     if (!ctx || !wd || !target || !ref || !tmpdir) return PEDK_E_INVAL;
     PEDK_API_BEGIN
     do_map_kmer(ctx, wd, target, ref, tmpdir);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_cnv(pedk_ctx* ctx, const char* wd, const char* target, const char* control, const char* ref, int k) {
+    if (!ctx || !wd || !target || !control || !ref) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_cnv(ctx, wd, target, control, ref, k);
     return PEDK_OK;
     PEDK_API_END(ctx)
 }

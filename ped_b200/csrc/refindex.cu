@@ -102,6 +102,29 @@ __global__ void __launch_bounds__(128) k_lookup_sorted(const uint64_t* __restric
     out[i] = (lo < n && key[lo] == want) ? (long long)lo : -1ll;
 }
 
+// f3, cnvJoinSub (ped.pl:949-989): every unique reference k-mer looked up in the two sorted count tables
+__global__ void __launch_bounds__(256) k_cnv_lookup(const uint64_t* __restrict__ ukey, uint64_t n,
+                                                   const uint64_t* __restrict__ tkey, const uint32_t* __restrict__ tval,
+                                                   uint64_t nt, uint32_t* __restrict__ out_t,
+                                                   uint32_t* __restrict__ out_c) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t want = ukey[i];
+    uint64_t lo = 0, hi = nt;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (tkey[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    // the merged table of build_rows holds both samples: bit 31 of the value marks the target
+    uint32_t t = 0, c = 0;
+    for (; lo < nt && tkey[lo] == want; ++lo) {
+        const uint32_t v = tval[lo];
+        if (v >> 31) t = v & 0x7fffffffu; else c = v;
+    }
+    out_t[i] = t;
+    out_c[i] = c;
+}
+
 void append_u(std::string& s, uint64_t v) {
     char b[24];
     int n = 0;
@@ -402,6 +425,95 @@ std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len) {
     return out;
 }
 
+// the number GNU `sort -n` reads at the start of a key: blanks, an optional '-', digits, an optional
+// fraction; anything else ends it (no exponent, no hex), nothing at all counts as 0
+static double sort_n_value(const std::string& s) {
+    size_t i = 0;
+    while (i < s.size() && (s[i] == ' ' || s[i] == '\t')) ++i;
+    bool neg = false;
+    if (i < s.size() && s[i] == '-') { neg = true; ++i; }
+    double v = 0;
+    while (i < s.size() && s[i] >= '0' && s[i] <= '9') v = v * 10 + (s[i++] - '0');
+    if (i < s.size() && s[i] == '.') {
+        double f = 0.1;
+        for (++i; i < s.size() && s[i] >= '0' && s[i] <= '9'; ++i, f *= 0.1) v += (s[i] - '0') * f;
+    }
+    return neg ? -v : v;
+}
+
+// cnvJoin + cnvJoinSub (ped.pl:934-989): the full outer join of the two count tables, restricted to
+// the unique reference k-mers: `chr pos strand target_count control_count`, a count a sample does
+// not have printed as 0, sorted like `sort -k 1 -n -k 2 -n` under LANG=C.
+std::string cnv_text(pedk_sample* ref, pedk_sample* control, pedk_sample* target) {
+    pedk_ctx* ctx = ref->ctx;
+    cudaStream_t st = ctx->stream;
+    pedk_sample::Ref20& idx = ref->ref20;
+    if (!idx.built) throw PedkError(PEDK_E_INVAL, "pedk_cnv_text: no unique k-mer index (pedk_sample_ref20_uniq first)");
+    if (!control->k || control->k != target->k || control->k != idx.k)
+        throw PedkError(PEDK_E_INVAL, "pedk_cnv_text: the samples and the index must use the same k");
+    if (ctx->nranks > 1) throw PedkError(PEDK_E_UNSUPPORTED, "pedk_cnv_text runs on one rank");
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t U = idx.kmer.size();
+    std::string out;
+    if (!U) return out;
+    if (!idx.d_kmer.p) {
+        idx.d_kmer = DBuf<uint64_t>(ctx, U);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(idx.d_kmer.p, idx.kmer.data(), U * 8, cudaMemcpyHostToDevice, st));
+        ctx->stats.h2d_bytes += U * 8;
+    }
+    RowTable rows;  // both tables in one array sorted by k-mer
+    build_rows(ctx, control, target, &rows);
+    std::vector<uint32_t> ht(U, 0), hc(U, 0);
+    if (rows.n) {
+        DBuf<uint32_t> d_t(ctx, U), d_c(ctx, U);
+        {
+            StageScope sc(ctx, PEDK_ST_EDGES, 1);
+            k_cnv_lookup<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(idx.d_kmer.p, U, rows.key.p, rows.val.p, rows.n,
+                                                                      d_t.p, d_c.p);
+            PEDK_CUDA_TRY(cudaGetLastError());
+        }
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ht.data(), d_t.p, U * 4, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaMemcpyAsync(hc.data(), d_c.p, U * 4, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->stats.d2h_bytes += U * 8;
+    }
+    // `sort -k 1 -n -k 2 -n`: the numeric value of the leading number of the chromosome name (a name
+    // that is not a number counts as 0), then of the position, then the whole line bytewise
+    struct Line {
+        double chr_num;
+        uint64_t pos;
+        std::string text;
+    };
+    std::vector<double> name_num(idx.names.size(), 0.0);
+    for (size_t c = 0; c < idx.names.size(); ++c) name_num[c] = sort_n_value(idx.names[c]);
+    std::vector<Line> lines;
+    for (uint64_t i = 0; i < U; ++i) {
+        if (!ht[i] && !hc[i]) continue;  // in neither table: the outer join has no such line
+        Line l;
+        l.chr_num = name_num[idx.chr[i]];
+        l.pos = idx.pos[i];
+        l.text = idx.names[idx.chr[i]];
+        l.text += '\t';
+        append_u(l.text, idx.pos[i]);
+        l.text += idx.strand[i] ? "\tr\t" : "\tf\t";
+        append_u(l.text, ht[i]);
+        l.text += '\t';
+        append_u(l.text, hc[i]);
+        l.text += '\n';
+        lines.push_back(std::move(l));
+    }
+    std::sort(lines.begin(), lines.end(), [](const Line& a, const Line& b) {
+        if (a.chr_num != b.chr_num) return a.chr_num < b.chr_num;
+        if (a.pos != b.pos) return a.pos < b.pos;
+        return a.text < b.text;
+    });
+    size_t bytes = 0;
+    for (const Line& l : lines) bytes += l.text.size();
+    out.reserve(bytes);
+    for (const Line& l : lines) out += l.text;
+    return out;
+}
+
 }  // namespace pedk
 
 static char* dup_text(const std::string& s, uint64_t* len) {
@@ -436,6 +548,14 @@ extern "C" int pedk_sample_map_kmer_text(pedk_sample* ref, const char* snp_text,
     if (!ref || (!snp_text && snp_len) || !text || !len) return PEDK_E_INVAL;
     PEDK_API_BEGIN
     *text = dup_text(map_kmer_text(ref, snp_text, snp_len), len);
+    return PEDK_OK;
+    PEDK_API_END(ref->ctx)
+}
+
+extern "C" int pedk_cnv_text(pedk_sample* ref, pedk_sample* control, pedk_sample* target, char** text, uint64_t* len) {
+    if (!ref || !control || !target || !text || !len) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    *text = dup_text(cnv_text(ref, control, target), len);
     return PEDK_OK;
     PEDK_API_END(ref->ctx)
 }

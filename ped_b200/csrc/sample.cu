@@ -474,7 +474,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 // ped.pl:790-812).  One pass needs the level-A bins (+1/8) and the buckets at once; when that exceeds
 // what the device has free, the bins are split into 2, 4, ... groups and the (small) packed reads are
 // sliced once per group.  Collective on several ranks (the largest need decides).
-int choose_count_passes(pedk_ctx* ctx, uint64_t m_max, size_t ksz, int nbA) {
+int choose_count_passes(pedk_ctx* ctx, uint64_t m_rank, size_t ksz, int nbA) {
     const int R = ctx->nranks;
     int max_pass = nbA / R;  // every rank keeps at least one bin per pass
     if (max_pass < 1) max_pass = 1;
@@ -490,24 +490,15 @@ int choose_count_passes(pedk_ctx* ctx, uint64_t m_max, size_t ksz, int nbA) {
         const char* cap_env = getenv("PEDK_DEVICE_BUDGET_MB");  // tests: pretend the device is small
         double budget = (double)(free_b + cached) * 0.90;
         if (cap_env && *cap_env) budget = std::min(budget, atof(cap_env) * 1048576.0);
-        // level-A segments (expected + 1/8 + slack per (bin, source)) + buckets + the rows that come out
+        // level-A segments (expected + 1/8 + slack per (bin, source)) + buckets + the rows that come out;
+        // a rank receives about what it sends (the hash spreads the k-mers evenly)
         auto need = [&](int passes) {
-            const double inst = (double)m_max * R / passes;  // what a rank receives per pass (even hash)
-            return inst * ksz * (1.125 + 1.0) + (double)nbA / passes * R * 4096 * ksz + inst * 0.25 * 12;
+            const double inst = (double)m_rank * 1.05 / passes;
+            return inst * ksz * (1.125 + 1.0) + (double)nbA / passes * 4096 * ksz + inst * 0.25 * 12;
         };
         while (P < max_pass && need(P) > budget) P <<= 1;
     }
-    if (P > max_pass) P = max_pass;
-    if (R > 1) {
-        // all ranks must agree: take the largest
-        unsigned long long v = (unsigned long long)P;
-        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 14, &v, 8, cudaMemcpyHostToDevice, ctx->stream));
-        comm_allreduce_max(ctx, ctx->scalars + 14, 1);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(&v, ctx->scalars + 14, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        P = (int)v;
-    }
-    return P;
+    return P > max_pass ? max_pass : P;
 }
 
 void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
@@ -534,15 +525,20 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
     DBuf<unsigned long long> histA(ctx, (size_t)(NBINS_MAX + 1) * (PEDK_MAX_RANKS + 1));
     std::vector<unsigned long long> all((size_t)(NBINS_MAX + 1) * R, 0);
     uint64_t m_max = m_local;
+    int P = choose_count_passes(ctx, m_local, ksz, nbA);
     if (multi) {
-        PEDK_CUDA_TRY(cudaMemcpyAsync(histA.p, &m_local, 8, cudaMemcpyHostToDevice, st));
-        comm_allgather_u64(ctx, histA.p, histA.p + 8, 1);
-        std::vector<unsigned long long> mm((size_t)R);
-        PEDK_CUDA_TRY(cudaMemcpyAsync(mm.data(), histA.p + 8, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+        // one all-gather: what every rank slices (sizes the segments) and the passes it needs (the largest decides)
+        const unsigned long long mine[2] = {m_local, (unsigned long long)P};
+        PEDK_CUDA_TRY(cudaMemcpyAsync(histA.p, mine, 16, cudaMemcpyHostToDevice, st));
+        comm_allgather_u64(ctx, histA.p, histA.p + 8, 2);
+        std::vector<unsigned long long> mm((size_t)2 * R);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(mm.data(), histA.p + 8, mm.size() * 8, cudaMemcpyDeviceToHost, st));
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-        for (int r = 0; r < R; ++r) m_max = std::max<uint64_t>(m_max, mm[(size_t)r]);
+        for (int r = 0; r < R; ++r) {
+            m_max = std::max<uint64_t>(m_max, mm[(size_t)2 * r]);
+            P = std::max(P, (int)mm[(size_t)2 * r + 1]);
+        }
     }
-    const int P = choose_count_passes(ctx, m_max, ksz, nbA);
     s->cinfo.count_passes = P;
     const bool force_exact = getenv("PEDK_BUCKET_EXACT") && atoi(getenv("PEDK_BUCKET_EXACT")) != 0;
     uint64_t m_total = 0;
@@ -815,8 +811,16 @@ void do_count(pedk_sample* s, int k) {
     s->counted = true;
     const bool multi = ctx->nranks > 1;
     // multi-GPU: the decisions below are collective, so they use the totals over all ranks
-    const uint64_t M_all = multi ? comm_allreduce_sum_host(ctx, M) : M;
-    const uint64_t Mpal_all = multi ? comm_allreduce_sum_host(ctx, Mpal) : Mpal;
+    uint64_t M_all = M, Mpal_all = Mpal;
+    if (multi) {
+        unsigned long long v[2] = {M, Mpal};
+        PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->scalars + 12, v, sizeof v, cudaMemcpyHostToDevice, st));
+        comm_allreduce_sum(ctx, ctx->scalars + 12, 2);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(v, ctx->scalars + 12, sizeof v, cudaMemcpyDeviceToHost, st));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        M_all = v[0];
+        Mpal_all = v[1];
+    }
     if (M_all == 0) return;
 
     DBuf<unsigned long long> hist(ctx, 8 * 256);

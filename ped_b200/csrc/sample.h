@@ -94,5 +94,6 @@ void ensure_host_reads(pedk_sample* s);
 void ref20_append_text(pedk_sample* s, int tag, const std::string& text);
 std::string ref20_text(pedk_sample* s, int tag);
 std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len);
+std::string cnv_text(pedk_sample* ref, pedk_sample* control, pedk_sample* target);
 std::string kmer_string(uint64_t v, int k);
 }  // namespace pedk

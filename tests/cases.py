@@ -140,3 +140,14 @@ def make_ref_inputs(case):
     text = (b"ACGTACGT stray line before any header\n" + fa(b"chr01 first sequence", c1, crlf_at=7) +
             fa(b"scaffoldX", gb[100:160]) + fa(b"Chr2\tsecond", gb[200:900], width=70) + fa(b"2 again", c2, width=80))
     return text[:-1], ft  # no newline after the last sequence line
+
+
+def make_cnv_inputs(case):
+    """-> (reference FASTA, control FASTQ, target FASTQ) for `method=cnv` (ped.pl:362-366, 934-989): the
+    reference of make_ref_inputs, control reads from the reference genome, target reads from the mutated one."""
+    fa, ft = make_ref_inputs(case)
+    c = case["cfg"]
+    g = api.synth_genome(1000 + c, case["genome"])
+    fc = api.synth_fastq(g, 3000 + c, case["reads"], read_len=case["L"], err_ppm=case["err_ppm"], n_ppm=case["n_ppm"],
+                         dup_ppm=case["dup_ppm"])
+    return fa, fc, ft

@@ -4,6 +4,8 @@ It mirrors the Perl line by line (strings, dicts, the same split/join semantics)
 and shares no code with the oracle or the CUDA path."""
 from __future__ import annotations
 
+import re
+
 from collections import Counter
 
 NUC = "ACGT"
@@ -213,3 +215,37 @@ def run(control_fastq: str, target_fastq: str, k: int = 20, clipping: int = 0):
     # join needs the inputs sorted; the rows already are.  Unpaired keys are dropped.
     res["kmer_snp"] = "".join(join_text(res["control"]["lbc"][t], res["target"]["lbc"][t]) for t in TAGS)
     return res
+
+
+def cnv_text(ref20_uniq_text: bytes, control_table, target_table, k: int = 20) -> bytes:
+    """cnvJoin + cnvJoinSub (ped.pl:934-989), line by line: the full outer join of the two count tables
+    (a missing count is 0), inner-joined with the unique reference k-mers, `chr pos strand t c`, then
+    `sort -k 1 -n -k 2 -n` under LANG=C (numeric prefix of the chromosome name, position, whole line).
+    control_table / target_table: (kmers u64 array, counts u32 array)."""
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+    def enc(s):
+        v = 0
+        for ch in s:
+            v = (v << 2) | code[ch]
+        return v
+
+    ct = dict(zip((int(x) for x in control_table[0]), (int(x) for x in control_table[1])))
+    tt = dict(zip((int(x) for x in target_table[0]), (int(x) for x in target_table[1])))
+
+    def num(s):
+        m = re.match(r"[ \t]*(-?[0-9]*\.?[0-9]*)", s)
+        try:
+            return float(m.group(1))
+        except ValueError:
+            return 0.0
+
+    out = []
+    for line in ref20_uniq_text.decode().splitlines():
+        km, chr_, pos, strand = line.split()
+        key = enc(km)
+        if key not in ct and key not in tt:
+            continue
+        out.append(f"{chr_}\t{pos}\t{strand}\t{tt.get(key, 0)}\t{ct.get(key, 0)}\n")
+    out.sort(key=lambda ln: (num(ln.split("\t")[0]), num(ln.split("\t")[1]), ln.encode()))
+    return "".join(out).encode()

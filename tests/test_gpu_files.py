@@ -165,3 +165,37 @@ def test_reference_as_control_file_contract(built, tmp_path, gz):
             assert _zcat(f"{wd}/{s}/lbc/{s}.lbc.{tag}.gz") == o.lbc_text(i)
     assert b"".join(open(f"{tmpdir}/T.snp.{t}", "rb").read() for t in TAGS) == osnp
     assert osnp.decode() == g["kmer_snp"]
+
+
+def test_cnv_file_contract(built, tmp_path):
+    """`perl ped.pl ref=REF,file=REF.fa` then `target=T,control=C,ref=REF,method=cnv` (ped.pl:362-366, 934-989):
+    <wd>/T/T.C.cnv as the reference leaves it (tests/golden/ref30k_cnv.json), once with everything resident
+    and once in a fresh process that only has the count files and the ref20_uniq files."""
+    import hashlib
+
+    from tests.cases import make_cnv_inputs
+
+    g = json.load(open(os.path.join(GOLDEN, "ref30k_cnv.json")))
+    fa, fc, ft = make_cnv_inputs(REF_CASES["ref30k"])
+    wd = str(tmp_path)
+    os.makedirs(f"{wd}/REF")
+    open(f"{wd}/REF/REF.fa", "wb").write(fa)
+    for s, fq in (("T", ft), ("C", fc)):
+        os.makedirs(f"{wd}/{s}/read")
+        open(f"{wd}/{s}/read/{s}.fastq", "wb").write(fq)
+    ctx = api.Context(0)
+    lib = ctx.lib
+    ctx.check(lib.pedk_mk_control_read(ctx.h, wd.encode(), b"REF", b"REF.fa"))
+    ctx.check(lib.pedk_mk_ref20_uniq(ctx.h, wd.encode(), b"REF", None, 20))
+    for s in (b"T", b"C"):
+        ctx.check(lib.pedk_mk_sort_uniq(ctx.h, wd.encode(), s, 0, None, None))
+        ctx.check(lib.pedk_count_kmer(ctx.h, wd.encode(), s, 20))
+    ctx.check(lib.pedk_cnv(ctx.h, wd.encode(), b"T", b"C", b"REF", 20))
+    ctx.close()
+    b = open(f"{wd}/T/T.C.cnv", "rb").read()
+    assert (b.count(b"\n"), hashlib.sha256(b).hexdigest()) == (g["cnv_rows"], g["cnv_sha256"])
+    os.unlink(f"{wd}/T/T.C.cnv")
+    ctx = api.Context(0)
+    ctx.check(ctx.lib.pedk_cnv(ctx.h, wd.encode(), b"T", b"C", b"REF", 20))
+    ctx.close()
+    assert open(f"{wd}/T/T.C.cnv", "rb").read() == b

@@ -422,3 +422,38 @@ def test_reference_unique_kmer_index_corner_inputs(ctx, fa):
             assert s.ref20_uniq_text(tag) == oracle.ref20_uniq_text(fa, tag), tag
     finally:
         s.destroy()
+
+
+def test_cnv_against_the_reference(ctx):
+    """f3: `method=cnv` (ped.pl:362-366, 934-989) -- the full outer join of the two count
+    tables mapped through the unique 20-mers of the reference -- against ped.pl's own <t>.<c>.cnv
+    (tests/golden/ref30k_cnv.json, scripts/make_golden_cnv.py) and a line-by-line restatement."""
+    from tests import pyref
+    from tests.cases import make_cnv_inputs
+
+    g = json.load(open(os.path.join(GOLDEN, "ref30k_cnv.json")))
+    fa, fc, ft = make_cnv_inputs(REF_CASES["ref30k"])
+    r, c, t = api.Sample(ctx), api.Sample(ctx), api.Sample(ctx)
+    try:
+        r.add_fastq(fa)
+        r.ingest_reference()
+        r.ref20_uniq(20)
+        for s, fq in ((t, ft), (c, fc)):
+            s.add_fastq(fq)
+            s.ingest()
+            s.count(20)
+        text = r.cnv_text(c, t)
+        assert (text.count(b"\n"), hashlib.sha256(text).hexdigest()) == (g["cnv_rows"], g["cnv_sha256"])
+        assert text.decode().startswith(g["cnv_head"]) and text.decode().endswith(g["cnv_tail"])
+        ref20 = b"".join(r.ref20_uniq_text(tag) for tag in range(64))
+        assert text == pyref.cnv_text(ref20, c.table(), t.table())
+        # a k-mer only one sample has counts 0 in the other: the control against an empty sample
+        e = api.Sample(ctx)
+        e.add_fastq(b"")
+        e.ingest()
+        e.count(20)
+        km, ct = c.table()
+        assert r.cnv_text(c, e) == pyref.cnv_text(ref20, (km, ct), (km[:0], ct[:0]))
+        e.destroy()
+    finally:
+        r.destroy(); c.destroy(); t.destroy()

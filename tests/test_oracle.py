@@ -181,3 +181,19 @@ def test_oracle_groundwork_for_position_mapping(name, built):
         if m:
             got[t] = m.decode()
     assert got == g["map"]
+
+
+def test_cnv_restatement_against_the_reference(built):
+    """f3: the line-by-line restatement of cnvJoin/cnvJoinSub (tests/pyref.py, ped.pl:934-989) over the
+    oracle's count tables and unique-20-mer index reproduces ped.pl's own <t>.<c>.cnv
+    (tests/golden/ref30k_cnv.json, made by scripts/make_golden_cnv.py from the unmodified reference)."""
+    from tests import pyref
+    from tests.cases import make_cnv_inputs
+
+    with open(os.path.join(GOLDEN, "ref30k_cnv.json")) as f:
+        g = json.load(f)
+    fa, fc, ft = make_cnv_inputs(REF_CASES["ref30k"])
+    oc, ot, _ = oracle.run(fc, ft, 20)
+    ref20 = b"".join(oracle.ref20_uniq_text(fa, t) for t in range(64))
+    text = pyref.cnv_text(ref20, oc.table(), ot.table())
+    assert (text.count(b"\n"), hashlib.sha256(text).hexdigest()) == (g["cnv_rows"], g["cnv_sha256"])
