@@ -980,7 +980,7 @@ void launch_bucket_count(const void* keys, int wide, const unsigned long long* o
     if (log_slots < 10) log_slots = 10;
     if (log_slots > 13) log_slots = 13;
     const size_t ksz = wide ? sizeof(uint64_t) : sizeof(uint32_t);
-    const int threads_env = getenv("PEDK_BC_THREADS") ? atoi(getenv("PEDK_BC_THREADS")) : 1024;
+    const int threads_env = getenv("PEDK_BC_THREADS") ? atoi(getenv("PEDK_BC_THREADS")) : 512;
     const int threads = threads_env <= 512 ? 512 : 1024;
     const size_t area = std::max(((size_t)1 << log_slots) * sizeof(uint16_t), (size_t)(threads / 32) * BC_QUEUE * ksz);
     const size_t smem = ((size_t)1 << log_slots) * (ksz + sizeof(uint32_t)) + area;

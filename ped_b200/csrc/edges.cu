@@ -321,23 +321,27 @@ __device__ __forceinline__ uint64_t jb_cas(uint64_t* p, uint64_t cmp, uint64_t v
 }
 
 // KT: type of the table key = the r = 2(k-1) - a - b hash bits a bucket does not fix (u32 while
-// r <= 31, so that ~0 is free to mean "empty").  tc/tt: four 7-bit counts of the control / target.
+// r <= 31, so that ~0 is free to mean "empty").  tc/tt: the four counts of the control / target,
+// one byte each (a count is at most 127), so that pass 1 of joinKmerSub (ped.pl:720-744) is a few
+// byte-parallel adds: (x + 0x7E) & 0x80 per byte says "count >= 2", + 0x7D ">= 3", + 0x1B "> 100".
 // Linear probing; about half of the records open a new group (a group is mostly one row per
 // sample), so there is no separate fast path.  The pass over the slots that applies the test also
-// resets them, so a bucket costs one sweep of the table, not two.  A bucket whose groups do not
-// fit the table is processed in rounds of a secondary hash, like k_bucket_count (bucket.cu).
+// resets them, so a bucket costs one sweep of the table, not two.  Buckets are dealt round-robin
+// and the first records of the next bucket are requested before the sweep of the current one.
+// A bucket whose groups do not fit the table is processed in rounds of a secondary hash, like
+// k_bucket_count (bucket.cu).
 template <typename KT, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
     k_join_bucket(const uint64_t* __restrict__ recs, const unsigned long long* __restrict__ offB, unsigned n_buckets,
                   int kp, int a, int b, int log_slots, const unsigned long long* __restrict__ first,
-                  const uint32_t* __restrict__ pass1_bits, EdgeRec* __restrict__ edges, uint64_t cap,
-                  unsigned long long* __restrict__ n_edges, unsigned* __restrict__ ticket, int* __restrict__ err) {
+                  EdgeRec* __restrict__ edges, uint64_t cap, unsigned long long* __restrict__ n_edges,
+                  int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char jb_smem[];
     const unsigned slots = 1u << log_slots;
     KT* tkey = reinterpret_cast<KT*>(jb_smem);
     uint32_t* tc = reinterpret_cast<uint32_t*>(tkey + slots);
     uint32_t* tt = tc + slots;
-    __shared__ unsigned s_bucket, s_distinct, s_overflow;
+    __shared__ unsigned s_distinct, s_overflow;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const int nbitsP = 2 * kp, rs = nbitsP - a, r = rs - b;
     const KT EMPTY = ~KT(0);
@@ -345,37 +349,56 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
     const unsigned smask = slots - 1;
     const unsigned limit = slots - (slots >> 2);
     const int hshift = 32 - log_slots;
+    constexpr unsigned long long STEP = (unsigned long long)THREADS * JB_UNROLL;
     for (unsigned i = tid; i < slots; i += THREADS) {
         tkey[i] = EMPTY;
         tc[i] = 0;
         tt[i] = 0;
     }
-    for (;;) {
-        if (tid == 0) {
-            s_bucket = atomicAdd(ticket, 1u);
-            s_distinct = 0;
-            s_overflow = 0;
+    if (tid == 0) {
+        s_distinct = 0;
+        s_overflow = 0;
+    }
+    __syncthreads();
+    auto load_recs = [&](unsigned long long i0, unsigned long long hi, uint64_t (&rec)[JB_UNROLL]) {
+#pragma unroll
+        for (int u = 0; u < JB_UNROLL; ++u) {
+            const unsigned long long i = i0 + (unsigned long long)u * THREADS + tid;
+            rec[u] = i < hi ? recs[i] : ~0ull;  // a record never has all bits set (count <= 127)
         }
-        __syncthreads();
-        const unsigned bk = s_bucket;
-        if (bk >= n_buckets) break;
-        const unsigned long long lo = offB[bk], hi = offB[bk + 1];
-        if (hi == lo) {
-            __syncthreads();
-            continue;
+    };
+    unsigned bk = blockIdx.x;
+    unsigned long long lo = 0, hi = 0;
+    uint64_t pre[JB_UNROLL];  // the first records of the bucket that comes next
+    bool pre_ok = false;
+    if (bk < n_buckets) {
+        lo = offB[bk];
+        hi = offB[bk + 1];
+        load_recs(lo, hi, pre);
+        pre_ok = true;
+    }
+    while (bk < n_buckets) {
+        const unsigned nbk = bk + gridDim.x;
+        unsigned long long nlo = 0, nhi = 0;
+        if (nbk < n_buckets) {
+            nlo = offB[nbk];
+            nhi = offB[nbk + 1];
         }
         const uint64_t hbase = ((uint64_t)(bk >> 8) << rs) | ((uint64_t)(bk & 255u) << r);
         unsigned R = 1, rd = 0;
-        for (;;) {
-            // ---- every row ORs its count into the (sample, base) field of its group ----
+        bool use_pre = pre_ok;
+        pre_ok = false;
+        while (hi > lo) {
+            // ---- every row ORs its count into the (sample, base) byte of its group ----
             unsigned my_new = 0;
             bool stuck = false;
-            for (unsigned long long i0 = lo; i0 < hi; i0 += (unsigned long long)THREADS * JB_UNROLL) {
+            for (unsigned long long i0 = lo; i0 < hi; i0 += STEP) {
                 uint64_t rec[JB_UNROLL];
+                if (use_pre && i0 == lo) {
 #pragma unroll
-                for (int u = 0; u < JB_UNROLL; ++u) {
-                    const unsigned long long i = i0 + (unsigned long long)u * THREADS + tid;
-                    rec[u] = i < hi ? recs[i] : ~0ull;  // a record never has all bits set (count <= 127)
+                    for (int u = 0; u < JB_UNROLL; ++u) rec[u] = pre[u];
+                } else {
+                    load_recs(i0, hi, rec);
                 }
 #pragma unroll
                 for (int u = 0; u < JB_UNROLL; ++u) {
@@ -395,7 +418,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
                         }
                         if (q == x) {
                             const unsigned cnt = (unsigned)rec[u] & 127u, base = (unsigned)(rec[u] >> 8) & 3u;
-                            atomicOr(((rec[u] >> 7) & 1u) ? &tt[h] : &tc[h], cnt << (7 * base));
+                            atomicOr(((rec[u] >> 7) & 1u) ? &tt[h] : &tc[h], cnt << (8 * base));
                             break;
                         }
                         h = (h + 1) & smask;
@@ -406,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
                     }
                 }
             }
+            use_pre = false;
             const unsigned wn = __reduce_add_sync(FULL_MASK, my_new);
             if (lane == 0 && wn) atomicAdd(&s_distinct, wn);
             if (stuck) s_overflow = 1;
@@ -429,6 +453,11 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
                 R <<= 1;
                 continue;
             }
+            const bool last_round = R == 1 || rd == R - 1;
+            if (last_round && nhi > nlo) {  // in flight during the sweep below
+                load_recs(nlo, nhi, pre);
+                pre_ok = true;
+            }
             // ---- joinKmerSub (ped.pl:703-782) on every group; the slot is empty again afterwards ----
             for (unsigned sl = tid; sl < slots; sl += THREADS) {
                 const KT q = tkey[sl];
@@ -437,18 +466,24 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
                 tkey[sl] = EMPTY;
                 tc[sl] = 0;
                 tt[sl] = 0;
-                if (!pc || !pt) continue;  // `join` is an inner join (ped.pl:709); a count is never 0
+                // pass 1, bytewise (bit 7 of a byte = the condition for that base)
+                const uint32_t HI = 0x80808080u;
+                const uint32_t ge3c = (pc + 0x7D7D7D7Du) & HI, ge3t = (pt + 0x7D7D7D7Du) & HI;
+                const uint32_t repc = (pc + 0x1B1B1B1Bu) & HI, rept = (pt + 0x1B1B1B1Bu) & HI;
+                const uint32_t sa = ge3c & ~repc, sb = ge3t & ~rept;  // allele sets: 3 <= count <= 100
+                // an absent sample has no allele, so this also makes `join` an inner join (ped.pl:709)
+                if (sa == sb || !sa || !sb) continue;
+                if (repc | rept) continue;  // a count above 100 anywhere: repeat
+                const uint32_t ge2c = (pc + 0x7E7E7E7Eu) & HI, ge2t = (pt + 0x7E7E7E7Eu) & HI;
+                if (__popc(ge2c) > 2 || __popc(ge2t) > 2) continue;  // fewer than two bases with count <= 1
+                if (__popc(sa & ~ge2t) != 1 && __popc(sb & ~ge2c) != 1) continue;
+                // ---- rare from here on: pass 2 on the counts ----
                 uint32_t c[4], t[4];
-                unsigned code = 0;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
-                    c[x] = (pc >> (7 * x)) & 127u;
-                    t[x] = (pt >> (7 * x)) & 127u;
-                    code |= count_class(c[x]) << (2 * x);
-                    code |= count_class(t[x]) << (2 * (4 + x));
+                    c[x] = (pc >> (8 * x)) & 255u;
+                    t[x] = (pt >> (8 * x)) & 255u;
                 }
-                if (!((__ldg(pass1_bits + (code >> 5)) >> (code & 31u)) & 1u)) continue;
-                // ---- rare from here on ----
                 const uint64_t P = kmer_unhash(hbase | (uint64_t)q, nbitsP);
                 const unsigned tag = (unsigned)(P >> (nbitsP - 6)) & 63u;
                 const unsigned long long fc = first[tag], ft = first[64 + tag];
@@ -477,6 +512,13 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
             if (R == 1) break;
             rd += R >> 1;
         }
+        if (hi == lo && nhi > nlo) {  // an empty bucket: nothing was swept
+            load_recs(nlo, nhi, pre);
+            pre_ok = true;
+        }
+        bk = nbk;
+        lo = nlo;
+        hi = nhi;
     }
 }
 
@@ -619,14 +661,15 @@ void launch_join_bucket(const uint64_t* recs, const unsigned long long* offB, un
     const int threads_env = getenv("PEDK_JOIN_THREADS") ? atoi(getenv("PEDK_JOIN_THREADS")) : 0;
     // two CTAs of 512 threads per SM while two tables fit its shared memory, else one of 1024
     const bool small = threads_env ? threads_env <= 512 : smem <= 100 * 1024;
-    PEDK_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    (void)pass1_bits;  // the kernel evaluates pass 1 on the packed counts; the table serves k_edges
+    (void)ticket;
     unsigned grid = kNumSMs * ((small && smem <= 100 * 1024) ? 2 : 1);
     if (grid > n_buckets) grid = n_buckets;
 #define PEDK_JB(KT, TH)                                                                                        \
     do {                                                                                                       \
         ensure_dyn_smem(k_join_bucket<KT, TH>, smem);                                                          \
-        k_join_bucket<KT, TH><<<grid, TH, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first, pass1_bits, \
-                                                      edges, cap, n_edges, ticket, err);                       \
+        k_join_bucket<KT, TH><<<grid, TH, smem, st>>>(recs, offB, n_buckets, kp, a, b, log_slots, first, edges, cap, \
+                                                      n_edges, err);                                           \
     } while (0)
     if (wide) {
         if (small) PEDK_JB(uint64_t, 512);

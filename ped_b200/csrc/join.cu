@@ -257,7 +257,7 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         // ---- (4) one CTA per bucket: groups meet in a shared-memory table, joinKmerSub on each ----
         const int log_slots = []() {
             const char* v = getenv("PEDK_JOIN_SLOTS_LOG2");
-            const int x = v && *v ? atoi(v) : 13;
+            const int x = v && *v ? atoi(v) : 14;
             return x < 10 ? 10 : x > 14 ? 14 : x;
         }();
         uint64_t cap = m / 16;
