@@ -9,7 +9,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 
 #include "comm.h"
 #include "plan.h"
@@ -35,6 +37,12 @@ void append_u(std::string& s, uint64_t v) {
         v /= 10;
     } while (v);
     while (n) s.push_back(b[--n]);
+}
+
+void append_kmer(std::string& s, uint64_t v, int k) {
+    char b[32];
+    for (int j = 0; j < k; ++j) b[j] = "ACGT"[(v >> (2 * (k - 1 - j))) & 3];
+    s.append(b, (size_t)k);
 }
 
 std::string mask_string(unsigned m) {
@@ -305,8 +313,10 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     PEDK_CUDA_TRY(cudaMemcpyAsync(first.data(), d_first, 128 * 8, cudaMemcpyDeviceToHost, st));
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
 
+    trace(ctx, "  join: first rows back");
     res->edges.resize(E);
     if (E) memcpy(static_cast<void*>(res->edges.data()), stage, E * sizeof(pedk_edge));
+    trace(ctx, "  join: edges copied");
     auto& quirks = res->quirks;
     for (const GroupRec& g : groups) {
         bool pc = g.hasc[0] | g.hasc[1] | g.hasc[2] | g.hasc[3];
@@ -370,10 +380,15 @@ char* dup_text(const std::string& s, uint64_t* len) {
 }  // namespace
 
 namespace pedk {
+// The sort_uniq/ lines of a sample on the host: every unique read and (unless it is a palindrome) its
+// reverse complement, per 3-nt bucket, sorted (ped.pl:1416).  Decoding and the 64 sorts run on host
+// threads: this is the text side of the drop-in path (scope B), not of the kernel path.
 void ensure_host_reads(pedk_sample* s) {
     if (s->have_reads) return;
     pedk_ctx* ctx = s->ctx;
     for (auto& v : s->h_reads) v.clear();
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : nt > 32 ? 32 : nt;
     for (const ReadGroup& g : s->groups) {
         if (!g.n) continue;
         if (!g.words.p) throw PedkError(PEDK_E_INVAL, "packed reads were released");
@@ -383,24 +398,58 @@ void ensure_host_reads(pedk_sample* s) {
         PEDK_CUDA_TRY(cudaMemcpyAsync(pal.data(), g.pal.p, g.n, cudaMemcpyDeviceToHost, ctx->stream));
         PEDK_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->stats.d2h_bytes += w.size() * 8 + g.n;
-        std::string fwd((size_t)g.L, 'A'), rev((size_t)g.L, 'A');
-        for (uint64_t r = 0; r < g.n; ++r) {
-            const uint64_t* rw = w.data() + r * g.W;
-            for (int i = 0; i < g.L; ++i) {
-                unsigned c = (unsigned)(rw[i >> 5] >> (62 - 2 * (i & 31))) & 3u;
-                fwd[(size_t)i] = "ACGT"[c];
-                rev[(size_t)(g.L - 1 - i)] = "ACGT"[c ^ 3u];
-            }
-            unsigned tf = (unsigned)(rw[0] >> 58);
-            s->h_reads[tf].push_back(fwd);
-            if (!pal[r]) {
-                unsigned tr = (unsigned)((base_code((unsigned char)rev[0]) << 4) | (base_code((unsigned char)rev[1]) << 2) |
-                                         base_code((unsigned char)rev[2]));
-                s->h_reads[tr].push_back(rev);
-            }
-        }
+        // every thread decodes a slice of the reads into its own 64 buckets
+        std::vector<std::vector<std::string>> part((size_t)nt * 64);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t]() {
+                const uint64_t lo = g.n * t / nt, hi = g.n * (t + 1) / nt;
+                std::string fwd((size_t)g.L, 'A'), rev((size_t)g.L, 'A');
+                for (uint64_t r = lo; r < hi; ++r) {
+                    const uint64_t* rw = w.data() + r * g.W;
+                    for (int i = 0; i < g.L; ++i) {
+                        unsigned c = (unsigned)(rw[i >> 5] >> (62 - 2 * (i & 31))) & 3u;
+                        fwd[(size_t)i] = "ACGT"[c];
+                        rev[(size_t)(g.L - 1 - i)] = "ACGT"[c ^ 3u];
+                    }
+                    unsigned tf = (unsigned)(rw[0] >> 58);
+                    part[(size_t)t * 64 + tf].push_back(fwd);
+                    if (!pal[r]) {
+                        unsigned tr = (unsigned)((base_code((unsigned char)rev[0]) << 4) |
+                                                 (base_code((unsigned char)rev[1]) << 2) | base_code((unsigned char)rev[2]));
+                        part[(size_t)t * 64 + tr].push_back(rev);
+                    }
+                }
+            });
+        for (auto& x : th) x.join();
+        th.clear();
+        std::atomic<int> next(0);
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&]() {
+                for (int tag = next.fetch_add(1); tag < 64; tag = next.fetch_add(1)) {
+                    auto& dst = s->h_reads[tag];
+                    size_t add = 0;
+                    for (unsigned p = 0; p < nt; ++p) add += part[(size_t)p * 64 + tag].size();
+                    dst.reserve(dst.size() + add);
+                    for (unsigned p = 0; p < nt; ++p) {
+                        auto& src = part[(size_t)p * 64 + tag];
+                        for (auto& x : src) dst.push_back(std::move(x));
+                        std::vector<std::string>().swap(src);
+                    }
+                }
+            });
+        for (auto& x : th) x.join();
     }
-    for (auto& v : s->h_reads) std::sort(v.begin(), v.end());
+    {
+        std::atomic<int> next(0);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&]() {
+                for (int tag = next.fetch_add(1); tag < 64; tag = next.fetch_add(1))
+                    std::sort(s->h_reads[tag].begin(), s->h_reads[tag].end());
+            });
+        for (auto& x : th) x.join();
+    }
     s->have_reads = true;
 }
 
@@ -454,8 +503,9 @@ extern "C" int pedk_sample_count_text(pedk_sample* s, int tag, char** text, uint
     PEDK_CUDA_TRY(cudaSetDevice(s->ctx->device));
     ensure_host_table(s);
     std::string t;
+    t.reserve((s->tag_start[tag + 1] - s->tag_start[tag]) * (size_t)(s->k + 8));
     for (uint64_t i = s->tag_start[tag]; i < s->tag_start[tag + 1]; ++i) {
-        t += kmer_string(s->h_kmer[i], s->k);
+        append_kmer(t, s->h_kmer[i], s->k);
         t += '\t';
         append_u(t, s->h_cnt[i]);
         t += '\n';
@@ -474,6 +524,7 @@ extern "C" int pedk_sample_lbc_text(pedk_sample* s, int tag, char** text, uint64
     ensure_host_table(s);
     std::string t;
     uint64_t lo = s->tag_start[tag], hi = s->tag_start[tag + 1];
+    t.reserve((hi - lo) * (size_t)(s->k + 12));
     if (lo == hi) t = "\t\t\t\t\n";  // ped.pl:856 with nothing read
     bool first = true;
     for (uint64_t i = lo; i < hi;) {
@@ -485,7 +536,7 @@ extern "C" int pedk_sample_lbc_text(pedk_sample* s, int tag, char** text, uint64
             c[s->h_kmer[j] & 3] = s->h_cnt[j];
             has[s->h_kmer[j] & 3] = true;
         }
-        t += kmer_string(p, s->k - 1);
+        append_kmer(t, p, s->k - 1);
         for (int x = 0; x < 4; ++x) {
             t += '\t';
             if (!first || has[x]) append_u(t, c[x]);
