@@ -101,6 +101,37 @@ join_kmer(wd, target, control, k, tmpdir, have_ref)
   CODE:
     check(aTHX_ pedk_join_kmer(ctx_or_croak(aTHX), wd, target, control, k, tmpdir, have_ref), "join_kmer");
 
+void
+mk_ref20_uniq(wd, ref, file, k)
+    const char *wd
+    const char *ref
+    SV *file
+    int k
+  CODE:
+    /* mk20 = mk20mer + mkUniq (ped.pl:1138-1249); file may be undef when the reference is still resident */
+    check(aTHX_ pedk_mk_ref20_uniq(ctx_or_croak(aTHX), wd, ref, SvOK(file) ? SvPV_nolen(file) : NULL, k), "mk_ref20_uniq");
+
+void
+map_kmer(wd, target, ref, tmpdir)
+    const char *wd
+    const char *target
+    const char *ref
+    const char *tmpdir
+  CODE:
+    /* mapKmer + mapKmerSub (ped.pl:625-685) */
+    check(aTHX_ pedk_map_kmer(ctx_or_croak(aTHX), wd, target, ref, tmpdir), "map_kmer");
+
+void
+cnv(wd, target, control, ref, k)
+    const char *wd
+    const char *target
+    const char *control
+    const char *ref
+    int k
+  CODE:
+    /* cnvJoin + cnvJoinSub (ped.pl:934-989) */
+    check(aTHX_ pedk_cnv(ctx_or_croak(aTHX), wd, target, control, ref, k), "cnv");
+
 SV *
 stage_ms()
   CODE:

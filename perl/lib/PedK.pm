@@ -5,6 +5,10 @@ package PedK;
 #   PedK::count_kmer($wd, $subject, $k)            -> ped.pl countKmer   (784-815)
 #   PedK::lbc_kmer($wd, $subject, $k)              -> ped.pl lbcKmer     (817-831)
 #   PedK::join_kmer($wd, $t, $c, $k, $tmpdir, $ref)-> ped.pl joinKmer    (687-701) + 374-378
+#   PedK::mk_control_read($wd, $ref, $file)        -> ped.pl mkChrFromFile + mkControlRead (1027-1136)
+#   PedK::mk_ref20_uniq($wd, $ref, $file, $k)      -> ped.pl mk20        (1213-1249: mk20mer + mkUniq)
+#   PedK::map_kmer($wd, $t, $ref, $tmpdir)         -> ped.pl mapKmer     (625-685)
+#   PedK::cnv($wd, $t, $c, $ref, $k)               -> ped.pl cnvJoin     (934-989)
 # Every sub dies with the library's message on failure; there is no CPU fallback.
 use strict;
 use warnings;

@@ -10,9 +10,12 @@
 # is skipped when its TTT file exists (ped.pl:291-297, 369-372).  The heavy
 # subs are calls into libpedk.so through PedK.xs; nothing here forks.
 #
-# `ref=REF,file=REF.fa` (no target) builds the control reads of a reference like
-# ped.pl's mkRef does (ped.pl:1027-1136: <wd>/REF/chrNAME and REF/sort_uniq/); a
-# later `target=T,control=REF` then compares T with the tiled reference.
+# `ref=REF,file=REF.fa` (no target) builds a reference like ped.pl's mkRef does
+# (ped.pl:1017-1025: <wd>/REF/chrNAME, REF/ref20_uniq.TAG.gz and the control reads in
+# REF/sort_uniq/); a later `target=T,control=REF` then compares T with the tiled reference.
+# With `ref=REF` the per-tag edge files go to tmpdir and are mapped to positions
+# (<tmpdir>/<t>.map.TAG, ped.pl:625-685); the read-level stages after that stay ped.pl's.
+# `method=cnv` writes <wd>/<t>/<t>.<c>.cnv (ped.pl:362-366, 934-989).
 #
 use strict;
 use warnings;
@@ -43,15 +46,18 @@ if (defined $opt{ref} && $opt{ref} ne "" && defined $opt{file} && $opt{file} ne 
     # mkRef for a local FASTA (ped.pl:1017-1025): chromosome files + control reads
     my $wd = (defined $opt{wd} && $opt{wd} ne "") ? $opt{wd} : getcwd();
     PedK::open_device();
-    PedK::mk_control_read($wd, $opt{ref}, $opt{file});
+    PedK::mk_control_read($wd, $opt{ref}, $opt{file});     # mkChrFromFile + mkControlRead
+    PedK::mk_ref20_uniq($wd, $opt{ref}, undef, 20);        # mk20 (the reference is still resident)
     PedK::close_device();
-    print "control reads of $opt{ref} written to $wd/$opt{ref}/sort_uniq\n";
+    print "reference $opt{ref}: chromosome files, ref20_uniq and control reads written to $wd/$opt{ref}\n";
     exit 0;
 }
-die "ped_kmer.pl runs the k-mer comparison itself; with ref= the mapping stages of ped.pl follow: use ped.pl with the PedK patch of INTEGRATION.md\n"
-    if defined $opt{ref} && $opt{ref} ne "";
-die "method must be kmer\n" if defined $opt{method} && $opt{method} ne "kmer";
+my $ref = (defined $opt{ref} && $opt{ref} ne "") ? $opt{ref} : "";
+my $method = (defined $opt{method} && $opt{method} ne "") ? $opt{method} : "kmer";
+die "method must be kmer or cnv\n" if $method ne "kmer" && $method ne "cnv";
+die "method=cnv needs ref=\n" if $method eq "cnv" && $ref eq "";
 my ($target, $control) = ($opt{target}, $opt{control});
+$control = $ref if (!defined $control || $control eq "") && $ref ne "";    # ped.pl:193
 die "target= and control= are required\n" unless defined $target && $target ne "" && defined $control && $control ne "";
 my $wd = (defined $opt{wd} && $opt{wd} ne "") ? $opt{wd} : getcwd();
 my $tmpdir = (defined $opt{tmpdir} && $opt{tmpdir} ne "") ? $opt{tmpdir} : "$wd/$target/tmp";
@@ -62,7 +68,7 @@ my $start = time;
 my $start_stamp = localtime;
 open(my $REPORT, ">", "$wd/$target/$target.report") or die "cannot write $wd/$target/$target.report: $!\n";
 open(my $LOG, ">", "$wd/$target/$target.log") or die "cannot write $wd/$target/$target.log: $!\n";
-print $LOG $log, "method : kmer\n";
+print $LOG $log, "method : $method\n";
 
 sub report {
     my $m = shift;
@@ -73,10 +79,11 @@ sub report {
     print $REPORT $m;
 }
 
-report("Job started: kmer method (B200)");
+report("Job started: $method method (B200)");
 PedK::open_device();
 foreach my $s ($target, $control) {
     next if -e "$wd/$s/sort_uniq/$s.sort_uniq.TTT.gz";
+    next if $s eq $ref;    # the reference's control reads come from `ref=,file=` (ped.pl:295)
     report("Generating sort_uniq files for $s");
     my ($used, $automatic) = PedK::mk_sort_uniq($wd, $s, $clipping);
     print $LOG "clipping : $used\n";
@@ -87,18 +94,28 @@ foreach my $s ($target, $control) {
     report("Generating k-mers for $s");
     PedK::count_kmer($wd, $s, $k);
 }
-foreach my $s ($target, $control) {
-    next if -e "$wd/$s/lbc/$s.lbc.TTT.gz";
-    report("Joining k-mers for $s");
-    PedK::lbc_kmer($wd, $s, $k);
+if ($method eq "cnv") {
+    report("Joining k-mers between $target and $control (cnv)");
+    PedK::cnv($wd, $target, $control, $ref, $k);
+} else {
+    foreach my $s ($target, $control) {
+        next if -e "$wd/$s/lbc/$s.lbc.TTT.gz";
+        report("Joining k-mers for $s");
+        PedK::lbc_kmer($wd, $s, $k);
+    }
+    report("Detecting SNPs between $target and $control");
+    mkdir $tmpdir if $ref ne "" && !-e $tmpdir;
+    PedK::join_kmer($wd, $target, $control, $k, $tmpdir, $ref ne "" ? 1 : 0);
+    if ($ref ne "") {
+        report("Mapping SNPs between $target and $control");
+        PedK::map_kmer($wd, $target, $ref, $tmpdir);
+    }
 }
-report("Detecting SNPs between $target and $control");
-PedK::join_kmer($wd, $target, $control, $k, $tmpdir, 0);
 my $ms = PedK::stage_ms();
 report("GPU stage times (ms): " . join(" ", map { "$PedK::STAGES[$_]=" . sprintf("%.1f", $ms->[$_]) } 0 .. $#PedK::STAGES));
 PedK::close_device();
 my $elapsed = time - $start;
-report("Job finished: kmer method.\n$elapsed seconds elapsed.");
+report("Job finished: $method method.\n$elapsed seconds elapsed.");
 print $LOG "start : $start_stamp\nend : " . localtime() . "\nseconds : $elapsed\n";
 close($LOG);
 close($REPORT);

@@ -86,3 +86,19 @@ def test_synth_slices_are_independent(built):
     assert len(whole) == api.synth_fastq_bytes(0, 230, 100)
     t = api.synth_mutate(g, 3, 5000, 1000)
     assert len(t) != 0 and bytes(t) != bytes(g)
+
+
+def test_perl_binding_builds_and_loads(built):
+    """perl/PedK.xs compiles against include/pedk.h and the module loads (no device call: abi_version only)."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("xsubpp"):
+        pytest.skip("no xsubpp")
+    subprocess.run(["sh", os.path.join(ROOT, "perl", "build.sh")], check=True)
+    r = subprocess.run(["perl", "-I" + os.path.join(ROOT, "perl", "lib"), "-MPedK", "-e",
+                        "print PedK::abi_version(), ' ', join(',', map { defined &{\"PedK::$_\"} ? 1 : 0 } "
+                        "qw(mk_sort_uniq mk_control_read mk_ref20_uniq count_kmer lbc_kmer join_kmer map_kmer cnv))"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split()[0] == "1" and r.stdout.split()[1] == "1,1,1,1,1,1,1,1"

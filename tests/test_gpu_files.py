@@ -199,3 +199,38 @@ def test_cnv_file_contract(built, tmp_path):
     ctx.check(ctx.lib.pedk_cnv(ctx.h, wd.encode(), b"T", b"C", b"REF", 20))
     ctx.close()
     assert open(f"{wd}/T/T.C.cnv", "rb").read() == b
+
+
+def test_perl_drop_in_command_line(built, tmp_path):
+    """The XS binding (perl/PedK.xs -> perl/lib/auto/PedK/PedK.so) and ped.pl's command line on top of it:
+    `perl perl/ped_kmer.pl target=T,control=C,wd=WD` leaves every file ped.pl leaves (zcat-identical), and the
+    ref= forms leave ref20_uniq, the per-tag edge files and the position map."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["sh", os.path.join(root, "perl", "build.sh")], check=True)
+    case = CASES["c1_40x"]
+    fc, ft = make_inputs(case)
+    oc, ot, osnp = oracle.run(fc, ft, 20)
+    wd = _layout(tmp_path, fc, ft)
+    r = subprocess.run(["perl", os.path.join(root, "perl", "ped_kmer.pl"), f"target=T,control=C,wd={wd}"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_files(wd, oc, ot, osnp)
+    assert "clipping : 150" in open(f"{wd}/T/T.log").read()
+    # reference mode: `ref=REF,file=REF.fa`, then `target=T,ref=REF`
+    fa, ft2 = make_ref_inputs(REF_CASES["ref30k"])
+    g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
+    wd2 = os.path.join(str(tmp_path), "refmode")
+    os.makedirs(f"{wd2}/REF")
+    os.makedirs(f"{wd2}/T/read")
+    open(f"{wd2}/REF/REF.fa", "wb").write(fa)
+    open(f"{wd2}/T/read/T.fastq", "wb").write(ft2)
+    for args in (f"ref=REF,file=REF.fa,wd={wd2}", f"target=T,ref=REF,wd={wd2}"):
+        r = subprocess.run(["perl", os.path.join(root, "perl", "ped_kmer.pl"), args], capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for i, tag in enumerate(TAGS):
+        assert _zcat(f"{wd2}/REF/ref20_uniq.{tag}.gz") == oracle.ref20_uniq_text(fa, i)
+        assert open(f"{wd2}/T/tmp/T.map.{tag}").read() == g["map"].get(tag, "")
+    assert "".join(open(f"{wd2}/T/tmp/T.snp.{t}").read() for t in TAGS) == g["kmer_snp"]
