@@ -631,6 +631,7 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
     const KT maskR = (KT)(((KT)1 << r) - 1);
     const unsigned limit = slots - (slots >> 2);
     const unsigned per_warp = slots / BC_WARPS;  // >= 32: log_slots >= 10
+    unsigned r_hint = 1;  // rounds the previous bucket of this CTA needed
 
     for (;;) {
         if (tid == 0) s_bucket = atomicAdd(ticket, 1u);
@@ -645,9 +646,13 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
         const uint64_t hbase = ((uint64_t)(bk >> 8) << rs) | ((uint64_t)(bk & 255u) << r);
         // The keys of the bucket are processed in `R` rounds, round `rd` taking the keys whose
         // round hash is rd modulo R.  R is 1 unless the table overflows; an overflowing round
-        // (R, rd) is replaced by (2R, rd) and (2R, rd + R).
-        unsigned R = 1, rd = 0;
+        // (R, rd) is replaced by (2R, rd) and (2R, rd + R).  Buckets of one run are alike (the hash
+        // spreads the k-mers evenly), so a bucket starts with the split the last one needed
+        // instead of finding it again by overflowing (a genome several times the size the 2^16
+        // buckets were laid out for: every bucket needs the same few rounds).
+        unsigned R = 1, rd = 0, r_used = 1, d_max = 0;
         for (;;) {
+            while (R < r_hint) R <<= 1;  // descend to the first half, as an overflow would
             for (unsigned i = tid; i < slots; i += BC_THREADS) {
                 tkey[i] = EMPTY;
                 tcnt[i] = 0;
@@ -676,6 +681,8 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
                 R <<= 1;  // rd stays: the first half of the round that overflowed
                 continue;
             }
+            r_used = R > r_used ? R : r_used;
+            d_max = s_distinct > d_max ? s_distinct : d_max;
             // ---- compact the occupied slots: count per warp, offsets, write the slot list ----
             const unsigned s_lo = warp * per_warp, s_hi = s_lo + per_warp;
             unsigned nh_w = 0;
@@ -779,6 +786,8 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
             if (R == 1) break;
             rd += R >> 1;
         }
+        // (one odd bucket must not tax the rest of the run: halve the split again when it was roomy)
+        r_hint = (r_used > 1 && 2 * d_max <= limit) ? r_used >> 1 : r_used;
     }
 }
 

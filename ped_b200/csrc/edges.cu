@@ -385,14 +385,22 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
             nhi = offB[nbk + 1];
         }
         const uint64_t hbase = ((uint64_t)(bk >> 8) << rs) | ((uint64_t)(bk & 255u) << r);
+        // a group is one to eight rows, mostly two: a bucket with more rows than twice what the table
+        // takes is split into rounds of a secondary hash from the start (a genome several times the
+        // size the 2^16 buckets were laid out for); an overflowing round is split again
         unsigned R = 1, rd = 0;
+        while ((hi - lo) / 2 > (unsigned long long)limit * R && R < (1u << 20)) R <<= 1;
+        const unsigned r_start = R;
         bool use_pre = pre_ok;
         pre_ok = false;
         while (hi > lo) {
+            while (R < r_start) R <<= 1;  // descend to the first half, as an overflow would
             // ---- every row ORs its count into the (sample, base) byte of its group ----
             unsigned my_new = 0;
             bool stuck = false;
             for (unsigned long long i0 = lo; i0 < hi; i0 += STEP) {
+                // a round that has outgrown the table is abandoned at once, not after filling it
+                if (__any_sync(FULL_MASK, *(volatile unsigned*)&s_overflow != 0)) break;
                 uint64_t rec[JB_UNROLL];
                 if (use_pre && i0 == lo) {
 #pragma unroll
@@ -428,11 +436,12 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
                         }
                     }
                 }
+                const unsigned wn = __reduce_add_sync(FULL_MASK, my_new);
+                my_new = 0;
+                if (lane == 0 && wn && atomicAdd(&s_distinct, wn) + wn > limit) s_overflow = 1;
+                if (stuck) s_overflow = 1;
             }
             use_pre = false;
-            const unsigned wn = __reduce_add_sync(FULL_MASK, my_new);
-            if (lane == 0 && wn) atomicAdd(&s_distinct, wn);
-            if (stuck) s_overflow = 1;
             __syncthreads();
             if (s_overflow || s_distinct > limit) {
                 __syncthreads();  // everybody has seen the flags before they are cleared again
