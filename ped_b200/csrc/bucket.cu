@@ -141,7 +141,24 @@ struct PT_BIG_OK {
 
 // NT = windows per lane per read (ceil((L-k+1)/32) rounded up to an instantiated value),
 // RPW = reads per warp per tile.
-template <typename KT, int NT, int RPW, bool CONTIG, int KC, int PT_THREADS>
+// BULK: a bin's run leaves shared memory as ONE bulk copy (cp.async.bulk shared::cta -> global, the
+// TMA unit) issued by one thread instead of element-wise stores by all: the copy-out costs no issue
+// slots, needs no per-element bin array, and drains -- to the owner's HBM over NVLink on several
+// ranks -- while the CTA already extracts and hashes its next tile (the staging area is only
+// written again after the rank phase, so one buffer is enough).  Bulk copies want 16-byte aligned
+// source, destination and size: a run is staged at the same misalignment as its destination, its
+// aligned body goes by bulk copy, the <= 3 elements before and after by plain stores.
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename KT, int NT, int RPW, bool CONTIG, int KC, int PT_THREADS, bool BULK>
 __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
     k_part_scatter(const uint64_t* __restrict__ words, int W, int L, int k_rt, uint64_t n_reads, int a_rt, int nranks,
                    unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
@@ -151,10 +168,11 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
     constexpr int PT_WARPS = PT_THREADS / 32;
     constexpr int ITEMS = NT * RPW;
     constexpr int TILE = PT_THREADS * ITEMS;
+    constexpr unsigned E16 = 16 / sizeof(KT);  // elements per 16 bytes
     static_assert(TILE <= 65536, "ranks are kept in 16 bits");
     extern __shared__ __align__(16) unsigned char pt_smem[];
     KT* stage = reinterpret_cast<KT*>(pt_smem);
-    uint8_t* sbin = reinterpret_cast<uint8_t*>(stage + TILE);
+    uint8_t* sbin = reinterpret_cast<uint8_t*>(stage + TILE);  // (!BULK)
     __shared__ unsigned hist[NB];
     __shared__ unsigned off[NB];
     __shared__ KT* s_out[NB];  // per tile: where stage[0] would go if the whole tile were this bin's run
@@ -197,35 +215,70 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
         __syncthreads();
         // ---- bin offsets inside the tile; one global atomic per (tile, bin) ----
         const unsigned c = tid < NB ? hist[tid] : 0u;
-        uint64_t total;
-        const uint64_t ex = block_exclusive_scan<PT_THREADS>(c, &total);
-        if (tid < NB) {
-            const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
-            off[tid] = (unsigned)ex;
-            // optimistic sizing (lim != null): a run that does not fit its segment is dropped and
-            // the flag raised -- the caller then sizes the bins exactly and runs again
-            const bool fits = !lim || g + c <= lim[tid];
-            if (!fits) *overflow = 1;
-            s_out[tid] = fits ? s_ptr[tid] + (g - ex) : nullptr;
-        }
-        __syncthreads();
+        if (BULK) {
+            unsigned long long g = 0;
+            bool fits = true;
+            if (c) {
+                g = atomicAdd(&cur[tid], (unsigned long long)c);
+                // optimistic sizing (lim != null): a run that does not fit its segment is dropped and
+                // the flag raised -- the caller then sizes the bins exactly and runs again
+                fits = !lim || g + c <= lim[tid];
+                if (!fits) *overflow = 1;
+            }
+            const unsigned mis = (unsigned)g & (E16 - 1);  // the run starts this far into a 16-byte line of its destination
+            const unsigned need = c ? (mis + c + E16 - 1) & ~(E16 - 1) : 0u;
+            const uint64_t ex = block_exclusive_scan<PT_THREADS>(need, nullptr);
+            if (tid < NB) {
+                off[tid] = (unsigned)ex + mis;
+                s_out[tid] = (fits && c) ? s_ptr[tid] + g : nullptr;
+                bulk_wait_read();  // the copies of the previous tile have read the staging area
+            }
+            __syncthreads();
 #pragma unroll
-        for (int idx = 0; idx < ITEMS; ++idx) {
-            if (meta[idx] != 0xffffffffu) {
-                const unsigned bin = meta[idx] >> 16;
-                const unsigned pos = off[bin] + (meta[idx] & 0xffffu);
-                stage[pos] = keyv[idx];
-                sbin[pos] = (uint8_t)bin;
+            for (int idx = 0; idx < ITEMS; ++idx)
+                if (meta[idx] != 0xffffffffu) stage[off[meta[idx] >> 16] + (meta[idx] & 0xffffu)] = keyv[idx];
+            fence_async_smem();  // the staged keys are visible to the bulk-copy engine
+            __syncthreads();
+            if (tid < NB && s_out[tid]) {
+                KT* p = s_out[tid];
+                const KT* sp = stage + off[tid];
+                const unsigned head = c < ((E16 - mis) & (E16 - 1)) ? c : ((E16 - mis) & (E16 - 1));
+                const unsigned body = (c - head) & ~(E16 - 1);
+                for (unsigned i = 0; i < head; ++i) p[i] = sp[i];
+                if (body) bulk_store(p + head, sp + head, body * (unsigned)sizeof(KT));
+                for (unsigned i = head + body; i < c; ++i) p[i] = sp[i];
+                bulk_commit();
+            }
+        } else {
+            uint64_t total;
+            const uint64_t ex = block_exclusive_scan<PT_THREADS>(c, &total);
+            if (tid < NB) {
+                const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
+                off[tid] = (unsigned)ex;
+                const bool fits = !lim || g + c <= lim[tid];
+                if (!fits) *overflow = 1;
+                s_out[tid] = fits ? s_ptr[tid] + (g - ex) : nullptr;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int idx = 0; idx < ITEMS; ++idx) {
+                if (meta[idx] != 0xffffffffu) {
+                    const unsigned bin = meta[idx] >> 16;
+                    const unsigned pos = off[bin] + (meta[idx] & 0xffffu);
+                    stage[pos] = keyv[idx];
+                    sbin[pos] = (uint8_t)bin;
+                }
+            }
+            __syncthreads();
+            // ---- every bin's run goes out contiguously (to the owner's memory) ----
+            const unsigned n_staged = (unsigned)total;
+            for (unsigned i = tid; i < n_staged; i += PT_THREADS) {
+                KT* p = s_out[sbin[i]];
+                if (p) p[i] = stage[i];
             }
         }
-        __syncthreads();
-        // ---- every bin's run goes out contiguously (to the owner's memory) ----
-        const unsigned n_staged = (unsigned)total;
-        for (unsigned i = tid; i < n_staged; i += PT_THREADS) {
-            KT* p = s_out[sbin[i]];
-            if (p) p[i] = stage[i];
-        }
     }
+    if (BULK && tid < NB) bulk_wait_all();  // shared memory must outlive the copies that read it
 }
 
 // ------------------------------------------------------------------ level B
@@ -791,6 +844,11 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
     }
 }
 
+int part_scatter_bulk() {
+    const char* v = getenv("PEDK_PART_BULK");
+    return v && *v ? atoi(v) : 0;
+}
+
 template <typename KT, int NT, bool CONTIG, int KC, int PT_THREADS>
 void launch_part_scatter_th(const uint64_t* words, int W, int L, int k, uint64_t n_reads, int a, int nranks,
                             unsigned long long* cur, const unsigned long long* lim, int* overflow,
@@ -798,13 +856,22 @@ void launch_part_scatter_th(const uint64_t* words, int W, int L, int k, uint64_t
     constexpr int PT_WARPS = PT_THREADS / 32;
     constexpr int RPW = KeyBudget<KT>::ITEMS / NT > 0 ? KeyBudget<KT>::ITEMS / NT : 1;
     constexpr int TILE = PT_THREADS * NT * RPW;
-    constexpr size_t SMEM = (size_t)TILE * (sizeof(KT) + 1);
-    ensure_dyn_smem(k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>, SMEM);
     const uint64_t tiles = (n_reads + (uint64_t)PT_WARPS * RPW - 1) / ((uint64_t)PT_WARPS * RPW);
     const uint64_t resident = (uint64_t)kNumSMs * (PT_THREADS > 512 ? 1 : 2);
     const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
-    k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS>
-        <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id);
+    if (part_scatter_bulk()) {
+        // every run is staged at the misalignment of its destination and ends on a 16-byte line:
+        // up to 2 x (16 - sizeof(KT)) bytes of padding per bin
+        constexpr size_t SMEM = (size_t)TILE * sizeof(KT) + (size_t)NB * 32 + 16;
+        ensure_dyn_smem(k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS, true>, SMEM);
+        k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS, true>
+            <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id);
+    } else {
+        constexpr size_t SMEM = (size_t)TILE * (sizeof(KT) + 1);
+        ensure_dyn_smem(k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS, false>, SMEM);
+        k_part_scatter<KT, NT, RPW, CONTIG, KC, PT_THREADS, false>
+            <<<grid, PT_THREADS, SMEM, st>>>(words, W, L, k, n_reads, a, nranks, cur, lim, overflow, dst, pass_mask, pass_id);
+    }
 }
 
 template <typename KT, int NT, bool CONTIG, int KC>

@@ -251,12 +251,22 @@ constexpr int JS_THREADS = 512;
 constexpr int JS_ITEMS = 8;
 constexpr int JS_TILE = JS_THREADS * JS_ITEMS;
 
+// BULK: a bin's run leaves shared memory as one bulk copy (cp.async.bulk, the TMA unit), as in
+// k_part_scatter (bucket.cu): staged at the misalignment of its destination, the aligned body by
+// bulk copy, at most one record before and after it by plain stores.
+__device__ __forceinline__ void js_bulk_store(void* dst, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"((unsigned)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+                 : "memory");
+}
+
+template <bool BULK>
 __global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* __restrict__ key,
                                                                const uint32_t* __restrict__ val, uint64_t n,
                                                                unsigned sample, int nbitsP, int a, int nranks,
                                                                unsigned long long* __restrict__ cur, PeerPtrs dst) {
-    __shared__ uint64_t stage[JS_TILE];
-    __shared__ uint8_t sbin[JS_TILE];
+    __shared__ __align__(16) uint64_t stage[JS_TILE + 512];  // BULK: up to two records of padding per bin
+    __shared__ uint8_t sbin[BULK ? 16 : JS_TILE];
     __shared__ unsigned hist[256];
     __shared__ unsigned off[256];
     __shared__ uint64_t* s_out[256];
@@ -286,29 +296,60 @@ __global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* 
         }
         __syncthreads();
         const unsigned c = tid < 256 ? hist[tid] : 0u;
-        uint64_t total;
-        const uint64_t ex = block_exclusive_scan<JS_THREADS>(c, &total);
-        if (tid < 256) {
-            const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
-            off[tid] = (unsigned)ex;
-            const int owner = (int)tid < (1 << a) ? (int)((tid * (unsigned)nranks) >> a) : 0;
-            s_out[tid] = dst.p[owner] + (g - ex);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < JS_ITEMS; ++j) {
-            if (meta[j] != 0xffffffffu) {
-                const unsigned bin = meta[j] >> 16;
-                const unsigned pos = off[bin] + (meta[j] & 0xffffu);
-                stage[pos] = rec[j];
-                sbin[pos] = (uint8_t)bin;
+        if (BULK) {
+            unsigned long long g = 0;
+            if (c) g = atomicAdd(&cur[tid], (unsigned long long)c);
+            const unsigned mis = (unsigned)g & 1u;  // two records per 16 bytes
+            const unsigned need = c ? (mis + c + 1u) & ~1u : 0u;
+            const uint64_t ex = block_exclusive_scan<JS_THREADS>(need, nullptr);
+            if (tid < 256) {
+                off[tid] = (unsigned)ex + mis;
+                const int owner = (int)tid < (1 << a) ? (int)((tid * (unsigned)nranks) >> a) : 0;
+                s_out[tid] = c ? dst.p[owner] + g : nullptr;
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile's copies have read the staging area
             }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < JS_ITEMS; ++j)
+                if (meta[j] != 0xffffffffu) stage[off[meta[j] >> 16] + (meta[j] & 0xffffu)] = rec[j];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid < 256 && s_out[tid]) {
+                uint64_t* p = s_out[tid];
+                const uint64_t* sp = stage + off[tid];
+                const unsigned head = c < mis ? c : mis;
+                const unsigned body = (c - head) & ~1u;
+                if (head) p[0] = sp[0];
+                if (body) js_bulk_store(p + head, sp + head, body * 8u);
+                if (head + body < c) p[c - 1] = sp[c - 1];
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            uint64_t total;
+            const uint64_t ex = block_exclusive_scan<JS_THREADS>(c, &total);
+            if (tid < 256) {
+                const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
+                off[tid] = (unsigned)ex;
+                const int owner = (int)tid < (1 << a) ? (int)((tid * (unsigned)nranks) >> a) : 0;
+                s_out[tid] = dst.p[owner] + (g - ex);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < JS_ITEMS; ++j) {
+                if (meta[j] != 0xffffffffu) {
+                    const unsigned bin = meta[j] >> 16;
+                    const unsigned pos = off[bin] + (meta[j] & 0xffffu);
+                    stage[pos] = rec[j];
+                    sbin[pos] = (uint8_t)bin;
+                }
+            }
+            __syncthreads();
+            const unsigned n_staged = (unsigned)total;
+            for (unsigned i = tid; i < n_staged; i += JS_THREADS) s_out[sbin[i]][i] = stage[i];
+            __syncthreads();
         }
-        __syncthreads();
-        const unsigned n_staged = (unsigned)total;
-        for (unsigned i = tid; i < n_staged; i += JS_THREADS) s_out[sbin[i]][i] = stage[i];
-        __syncthreads();
     }
+    if (BULK && tid < 256) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 constexpr int JB_UNROLL = 4;  // records a thread has in flight
@@ -647,7 +688,11 @@ void launch_rows_scatter(const uint64_t* row_key, const uint32_t* row_val, uint6
     const int kp = k - 1, a = kmer_bits_a(kp);
     const uint64_t tiles = (n + JS_TILE - 1) / JS_TILE;
     const unsigned grid = (unsigned)(tiles < (uint64_t)kNumSMs * 2 ? tiles : (uint64_t)kNumSMs * 2);
-    k_rows_scatter<<<grid, JS_THREADS, 0, st>>>(row_key, row_val, n, (unsigned)sample, 2 * kp, a, nranks, cur, dst);
+    const char* bulk = getenv("PEDK_PART_BULK");
+    if (bulk && atoi(bulk))
+        k_rows_scatter<true><<<grid, JS_THREADS, 0, st>>>(row_key, row_val, n, (unsigned)sample, 2 * kp, a, nranks, cur, dst);
+    else
+        k_rows_scatter<false><<<grid, JS_THREADS, 0, st>>>(row_key, row_val, n, (unsigned)sample, 2 * kp, a, nranks, cur, dst);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
