@@ -426,11 +426,13 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? 2 : 1)
             nhi = offB[nbk + 1];
         }
         const uint64_t hbase = ((uint64_t)(bk >> 8) << rs) | ((uint64_t)(bk & 255u) << r);
-        // a group is one to eight rows, mostly two: a bucket with more rows than twice what the table
-        // takes is split into rounds of a secondary hash from the start (a genome several times the
-        // size the 2^16 buckets were laid out for); an overflowing round is split again
+        // a group is one to eight rows, mostly two: a bucket with more rows than the table takes
+        // groups -- twice the expected number of groups, so that a round rarely outgrows the table
+        // and has to be done again -- is split into rounds of a secondary hash from the start (a
+        // genome several times the size the 2^16 buckets were laid out for); an overflowing round
+        // is split again
         unsigned R = 1, rd = 0;
-        while ((hi - lo) / 2 > (unsigned long long)limit * R && R < (1u << 20)) R <<= 1;
+        while ((hi - lo) > (unsigned long long)limit * R && R < (1u << 20)) R <<= 1;
         const unsigned r_start = R;
         bool use_pre = pre_ok;
         pre_ok = false;

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
 N=$(nvidia-smi -L | wc -l)
 for tool in memcheck racecheck synccheck; do
-  timeout 1500 $CS --tool $tool --print-limit 20 --error-exitcode 9 python scripts/sanitize_case.py tiny c1_40x ref30k > gpurun_out/r2_sanitizer_${tool}_n1.log 2>&1
+  timeout 1500 $CS --tool $tool --print-limit 20 python scripts/sanitize_case.py tiny c1_40x ref30k > gpurun_out/r2_sanitizer_${tool}_n1.log 2>&1
   echo "$tool n1 rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|SANITIZE_CASE|edges" gpurun_out/r2_sanitizer_${tool}_n1.log | tail -6
 done
 if [ "$N" -ge 2 ]; then
