@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
 // (two 16-bit ranks per register; the sub-bin is recomputed from the key) between the phases.
 template <typename KT, bool WHOLE, int SS_THREADS>
 __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, unsigned n, KT* __restrict__ out,
-                                                 unsigned long long* __restrict__ cur, int shiftB, unsigned maskB,
-                                                 KT* stage, unsigned* hist, unsigned* off, KT** s_out) {
+                                                 unsigned long long* __restrict__ cur,
+                                                 const unsigned long long* __restrict__ lim, int* __restrict__ overflow,
+                                                 int shiftB, unsigned maskB, KT* stage, unsigned* hist, unsigned* off,
+                                                 KT** s_out) {
     const unsigned tid = threadIdx.x;
     KT key[SS_ITEMS];
     uint32_t rank2[SS_ITEMS / 2];
@@ -371,7 +373,11 @@ __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, uns
     if (tid < NB) {
         const unsigned long long g = c ? atomicAdd(&cur[tid], (unsigned long long)c) : 0ull;
         off[tid] = (unsigned)ex;
-        s_out[tid] = out + (g - ex);
+        // buckets sized optimistically (lim != null): a run that does not fit is dropped and the flag
+        // raised -- the caller then sizes the buckets exactly (k_sub_hist) and scatters again
+        const bool fits = !lim || g + c <= lim[tid];
+        if (!fits) *overflow = 1;
+        s_out[tid] = fits ? out + (g - ex) : nullptr;
     }
     __syncthreads();
 #pragma unroll
@@ -390,12 +396,14 @@ __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, uns
         for (int j = 0; j < SS_ITEMS; ++j) {
             const unsigned i = j * SS_THREADS + tid;
             const KT kk = stage[i];
-            s_out[(unsigned)(kk >> shiftB) & maskB][i] = kk;
+            KT* p = s_out[(unsigned)(kk >> shiftB) & maskB];
+            if (p) p[i] = kk;
         }
     } else {
         for (unsigned i = tid; i < n; i += SS_THREADS) {
             const KT kk = stage[i];
-            s_out[(unsigned)(kk >> shiftB) & maskB][i] = kk;
+            KT* p = s_out[(unsigned)(kk >> shiftB) & maskB];
+            if (p) p[i] = kk;
         }
     }
 }
@@ -405,7 +413,9 @@ __global__ void __launch_bounds__(SS_THREADS, 1024 / SS_THREADS) k_sub_scatter(c
                                                               const unsigned long long* __restrict__ seg,
                                                               const unsigned* __restrict__ tile_prefix, int n_bins,
                                                               unsigned n_tiles, int shiftB, unsigned maskB,
-                                                              unsigned long long* __restrict__ curB) {
+                                                              unsigned long long* __restrict__ curB,
+                                                              const unsigned long long* __restrict__ limB,
+                                                              int* __restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     KT* stage = reinterpret_cast<KT*>(ss_smem);
     __shared__ unsigned hist[NB];
@@ -423,9 +433,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1024 / SS_THREADS) k_sub_scatter(c
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
     if (n == SUB_TILE)
-        sub_scatter_tile<KT, true, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
+        sub_scatter_tile<KT, true, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB,
+                                               limB ? limB + (size_t)bin * NB : nullptr, overflow, shiftB, maskB, stage,
+                                               hist, off, s_out);
     else
-        sub_scatter_tile<KT, false, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB, shiftB, maskB, stage, hist, off, s_out);
+        sub_scatter_tile<KT, false, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB,
+                                                limB ? limB + (size_t)bin * NB : nullptr, overflow, shiftB, maskB, stage,
+                                                hist, off, s_out);
 }
 
 // ------------------------------------------------------------------ buckets -> rows
@@ -658,6 +672,7 @@ __device__ __forceinline__ void bucket_insert(const KT* __restrict__ keys, unsig
 template <typename KT, int BC_THREADS>
 __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __restrict__ keys,
                                                                const unsigned long long* __restrict__ offB,
+                                                               const unsigned long long* __restrict__ endB,
                                                                unsigned n_buckets, int k, int a, int b,
                                                                int log_slots, int strand,
                                                                const uint64_t* __restrict__ corr_key,
@@ -691,8 +706,8 @@ __global__ void __launch_bounds__(BC_THREADS, 2) k_bucket_count(const KT* __rest
         __syncthreads();
         const unsigned bk = s_bucket;
         if (bk >= n_buckets) break;
-        const unsigned long long lo = offB[bk], hi = offB[bk + 1];
-        if (hi == lo) {
+        const unsigned long long lo = offB[bk], hi = endB[bk];  // (exact sizes: endB = offB + 1)
+        if (hi <= lo) {
             __syncthreads();
             continue;
         }
@@ -1019,7 +1034,8 @@ void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, 
 
 void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned long long* seg,
                              const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int shiftB, unsigned maskB,
-                             unsigned long long* curB, cudaStream_t st) {
+                             unsigned long long* curB, const unsigned long long* limB, int* overflow,
+                             cudaStream_t st) {
     const unsigned long long* offA = seg;
     const int n_bins = n_seg;
     if (!n_tiles) return;
@@ -1029,7 +1045,8 @@ void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned
     do {                                                                                                         \
         ensure_dyn_smem(k_sub_scatter<KT, TH>, smem);                                                            \
         k_sub_scatter<KT, TH><<<n_tiles, TH, smem, st>>>(static_cast<const KT*>(in), static_cast<KT*>(out), offA, \
-                                                         tile_prefix, n_bins, n_tiles, shiftB, maskB, curB);     \
+                                                         tile_prefix, n_bins, n_tiles, shiftB, maskB, curB, limB, \
+                                                         overflow);                                              \
     } while (0)
     if (wide) {
         if (threads == 512) PEDK_SS(uint64_t, 512);
@@ -1044,11 +1061,33 @@ void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned
 
 void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* seg,
                         const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int k, int a, int b,
-                        unsigned long long* curB, cudaStream_t st) {
-    launch_sub_scatter_bits(in, out, wide, seg, tile_prefix, n_seg, n_tiles, 2 * k - a - b, (1u << b) - 1, curB, st);
+                        unsigned long long* curB, const unsigned long long* limB, int* overflow, cudaStream_t st) {
+    launch_sub_scatter_bits(in, out, wide, seg, tile_prefix, n_seg, n_tiles, 2 * k - a - b, (1u << b) - 1, curB, limB,
+                            overflow, st);
 }
 
-void launch_bucket_count(const void* keys, int wide, const unsigned long long* offB, unsigned n_buckets, int k, int a,
+namespace {
+// optimistic bucket layout: bucket (bin, sub) of an owned bin starts at (index of the bin among this
+// rank's bins of the pass * 256 + sub) * cap; the other bins get empty buckets at 0
+__global__ void k_bucket_layout(const int* __restrict__ bin_index, unsigned n_buckets, unsigned long long cap,
+                                unsigned long long* __restrict__ offB, unsigned long long* __restrict__ limB) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_buckets) return;
+    const int bi = bin_index[i >> 8];
+    const unsigned long long o = bi < 0 ? 0ull : ((unsigned long long)bi * NB + (i & 255u)) * cap;
+    offB[i] = o;
+    limB[i] = bi < 0 ? 0ull : o + cap;
+}
+}  // namespace
+
+void launch_bucket_layout(const int* bin_index, unsigned n_buckets, unsigned long long cap, unsigned long long* offB,
+                          unsigned long long* limB, cudaStream_t st) {
+    k_bucket_layout<<<(n_buckets + 255) / 256, 256, 0, st>>>(bin_index, n_buckets, cap, offB, limB);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_bucket_count(const void* keys, int wide, const unsigned long long* offB, const unsigned long long* endB,
+                         unsigned n_buckets, int k, int a,
                          int b, int log_slots, int strand, const uint64_t* corr_key, const uint32_t* corr_cnt,
                          uint64_t n_corr, uint64_t* row_key, uint32_t* row_val, uint64_t cap,
                          unsigned long long* counters, unsigned* ticket, int* err, cudaStream_t st) {
@@ -1067,7 +1106,7 @@ void launch_bucket_count(const void* keys, int wide, const unsigned long long* o
 #define PEDK_BC(KT, TH)                                                                                            \
     do {                                                                                                           \
         ensure_dyn_smem(k_bucket_count<KT, TH>, smem);                                                             \
-        k_bucket_count<KT, TH><<<grid, TH, smem, st>>>(static_cast<const KT*>(keys), offB, n_buckets, k, a, b, log_slots, \
+        k_bucket_count<KT, TH><<<grid, TH, smem, st>>>(static_cast<const KT*>(keys), offB, endB, n_buckets, k, a, b, log_slots, \
                                                        strand, corr_key, corr_cnt, n_corr, row_key, row_val, cap,  \
                                                        counters, ticket, err);                                     \
     } while (0)

@@ -260,7 +260,8 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
             const unsigned long long total = m;
             PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
             PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
-            launch_sub_scatter_bits(recA.p, recB.p, 1, d_seg.p, tprefix.p, n_seg, n_tiles, shiftB, maskB, curB.p, st);
+            launch_sub_scatter_bits(recA.p, recB.p, 1, d_seg.p, tprefix.p, n_seg, n_tiles, shiftB, maskB, curB.p, nullptr,
+                                    nullptr, st);
         }
         // ---- (4) one CTA per bucket: groups meet in a shared-memory table, joinKmerSub on each ----
         const int log_slots = []() {
@@ -336,35 +337,66 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
 }
 
 // Sort the edges by their (k-1)-mer and lay out <target>.kmer.snp: done on first access, so a
-// caller that only wants the count does not pay for the text.
+// caller that only wants the count does not pay for the text.  The lines are formatted by a few
+// host threads, each over a contiguous range of the sorted edges (the edge list of configs[1] is
+// 221 k lines; one thread took longer over it than the join kernels).
+void format_edges(const pedk_result* res, size_t lo, size_t hi, std::string* out) {
+    const int k = res->k;
+    const auto& quirks = res->quirks;
+    out->reserve((hi - lo) * 72);
+    char buf[128];
+    for (size_t i = lo; i < hi; ++i) {
+        const pedk_edge& e = res->edges[i];
+        if (e.quirk) {
+            auto it = std::lower_bound(quirks.begin(), quirks.end(), e.prefix,
+                                       [](const std::pair<uint64_t, std::string>& q, uint64_t p) { return q.first < p; });
+            if (it != quirks.end() && it->first == e.prefix) *out += it->second;
+            continue;
+        }
+        int n = 0;
+        for (int j = 0; j < k - 1; ++j) buf[n++] = "ACGT"[(e.prefix >> (2 * (k - 2 - j))) & 3];
+        buf[n++] = '\t';
+        for (int x = 0; x < 4; ++x)
+            if (e.cont_mask & (1u << x)) buf[n++] = "ACGT"[x];
+        buf[n++] = '\t';
+        for (int x = 0; x < 4; ++x)
+            if (e.alt_mask & (1u << x)) buf[n++] = "ACGT"[x];
+        for (int x = 0; x < 8; ++x) {
+            buf[n++] = '\t';
+            uint32_t v = x < 4 ? e.control[x] : e.target[x - 4];
+            char d[12];
+            int m = 0;
+            do {
+                d[m++] = (char)('0' + v % 10);
+                v /= 10;
+            } while (v);
+            while (m) buf[n++] = d[--m];
+        }
+        buf[n++] = '\n';
+        out->append(buf, (size_t)n);
+    }
+}
+
 void finalise(pedk_result* res) {
     if (res->finalised) return;
-    const int k = res->k;
     auto& quirks = res->quirks;
     std::sort(res->edges.begin(), res->edges.end(),
               [](const pedk_edge& x, const pedk_edge& y) { return x.prefix < y.prefix; });
     std::sort(quirks.begin(), quirks.end());
     // ---- <target>.kmer.snp ----
-    std::string& t = res->text;
-    t.reserve(res->edges.size() * 64);
-    size_t qi = 0;
-    for (const pedk_edge& e : res->edges) {
-        if (e.quirk) {
-            while (qi < quirks.size() && quirks[qi].first != e.prefix) ++qi;
-            t += quirks[qi].second;
-            continue;
-        }
-        for (int j = 0; j < k - 1; ++j) t.push_back("ACGT"[(e.prefix >> (2 * (k - 2 - j))) & 3]);
-        t += '\t';
-        for (int x = 0; x < 4; ++x)
-            if (e.cont_mask & (1u << x)) t.push_back("ACGT"[x]);
-        t += '\t';
-        for (int x = 0; x < 4; ++x)
-            if (e.alt_mask & (1u << x)) t.push_back("ACGT"[x]);
-        for (int x = 0; x < 4; ++x) { t += '\t'; append_u(t, e.control[x]); }
-        for (int x = 0; x < 4; ++x) { t += '\t'; append_u(t, e.target[x]); }
-        t += '\n';
-    }
+    const size_t E = res->edges.size();
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : nt > 16 ? 16 : nt;
+    if (E < 4096) nt = 1;
+    std::vector<std::string> part(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(format_edges, res, E * t / nt, E * (t + 1) / nt, &part[t]);
+    format_edges(res, 0, E / nt, &part[0]);
+    for (auto& x : th) x.join();
+    size_t bytes = 0;
+    for (const std::string& p : part) bytes += p.size();
+    res->text.reserve(bytes);
+    for (const std::string& p : part) res->text += p;
     res->finalised = true;
 }
 

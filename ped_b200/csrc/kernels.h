@@ -96,12 +96,19 @@ void launch_cursor_counts(const unsigned long long* cur, const unsigned long lon
 void launch_sub_hist(const void* keys, int wide, const unsigned long long* seg, const unsigned* tile_prefix,
                      int n_seg, unsigned n_tiles, int k, int a, int b, unsigned* histB, cudaStream_t st);
 // curB[bin * 256 + sub] = next free element of that bucket in `out`
+// limB != null (buckets sized optimistically): limB[bin * 256 + sub] = end of that bucket's room; a run
+// that does not fit is dropped and *overflow set
 void launch_sub_scatter(const void* in, void* out, int wide, const unsigned long long* seg,
                         const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int k, int a, int b,
-                        unsigned long long* curB, cudaStream_t st);
-// buckets (offB[n_buckets + 1]) -> table rows, as launch_count_rows below; ticket = 1 device
-// word, err = device flag raised when a bucket cannot be split any further
-void launch_bucket_count(const void* keys, int wide, const unsigned long long* offB, unsigned n_buckets, int k, int a,
+                        unsigned long long* curB, const unsigned long long* limB, int* overflow, cudaStream_t st);
+// optimistic bucket layout: bin_index[bin] = index of the bin among this rank's bins of the pass (-1: not
+// held here); every bucket gets `cap` elements
+void launch_bucket_layout(const int* bin_index, unsigned n_buckets, unsigned long long cap, unsigned long long* offB,
+                          unsigned long long* limB, cudaStream_t st);
+// buckets [offB[i], endB[i]) -> table rows, as launch_count_rows below (exact sizes: endB = offB + 1);
+// ticket = 1 device word, err = device flag raised when a bucket cannot be split any further
+void launch_bucket_count(const void* keys, int wide, const unsigned long long* offB, const unsigned long long* endB,
+                         unsigned n_buckets, int k, int a,
                          int b, int log_slots, int strand, const uint64_t* corr_key, const uint32_t* corr_cnt,
                          uint64_t n_corr, uint64_t* row_key, uint32_t* row_val, uint64_t cap,
                          unsigned long long* counters, unsigned* ticket, int* err, cudaStream_t st);
@@ -182,7 +189,8 @@ void launch_sub_hist_bits(const void* keys, int wide, const unsigned long long* 
                           int n_seg, unsigned n_tiles, int shiftB, unsigned maskB, unsigned* histB, cudaStream_t st);
 void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned long long* seg,
                              const unsigned* tile_prefix, int n_seg, unsigned n_tiles, int shiftB, unsigned maskB,
-                             unsigned long long* curB, cudaStream_t st);
+                             unsigned long long* curB, const unsigned long long* limB, int* overflow,
+                             cudaStream_t st);
 // buckets of join records (offB[n_buckets + 1]) -> edges; groups that are the first of a 3-nt
 // bucket in either sample (first[128]) are left to the host (F7)
 void launch_join_bucket(const uint64_t* recs, const unsigned long long* offB, unsigned n_buckets, int k, int b,

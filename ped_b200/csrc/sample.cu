@@ -675,64 +675,110 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
         PEDK_CUDA_TRY(cudaMemcpyAsync(d_seg.p + 2 * n_seg, seg_bin.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
         PEDK_CUDA_TRY(cudaMemcpyAsync(tprefix.p, tile_prefix.data(), ((size_t)n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
 
-        // (4) exact bucket sizes, (5) their offsets
+        // (4)-(6) second binning level.  OPTIMISTIC first: the hash spreads a bin evenly over its 256
+        // buckets, so every bucket gets room for the expected number of keys plus a margin and the
+        // keys are scattered at once (no counting pass: k_sub_hist read the whole stream for it).  A
+        // bucket that outgrows its room (one k-mer with very many instances) raises a flag and the
+        // level is done again with exact sizes.  (7) one CTA per bucket: count, rows.  The rows first
+        // land in the level-A buffer (free by then: room for a row per three 4-byte instances); with
+        // one pass they stay there, with several they are collected in the sample's own arrays.
         const size_t n_buckets = (size_t)nbA * NBINS_MAX;
-        DBuf<unsigned> histB(ctx, n_buckets);
-        DBuf<unsigned long long> offB(ctx, n_buckets + 1), curB(ctx, n_buckets);
-        DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
-        {
-            StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_HIST, m * ksz);
-            PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
-            launch_sub_hist(keysA.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, histB.p, st);
-        }
-        {
-            StageScope sc(ctx, PEDK_ST_SORT, 3);
-            exclusive_scan_u32(histB.p, reinterpret_cast<uint64_t*>(offB.p), n_buckets, ctx->scalars + 3, ws.p, st);
-            const unsigned long long total = m;
-            PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
-            PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
-        }
-        // (6) second binning level
-        DBuf<uint8_t> keysB(ctx, m * ksz + 64);  // the count kernel reads it with aligned 16-byte loads
-        {
-            StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
-            launch_sub_scatter(keysA.p, keysB.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, curB.p, st);
-        }
-        if (ctx->trace) {
-            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-            trace(ctx, "  buckets: histogram + scan + scatter");
-        }
-        // (7) one CTA per bucket: count, rows.  The rows first land in the level-A buffer (free
-        // now: room for a row per three 4-byte instances); with one pass they stay there, with
-        // several they are collected in the sample's own arrays.
+        DBuf<unsigned long long> offB(ctx, n_buckets + 1), curB(ctx, n_buckets), limB;
+        DBuf<uint8_t> keysB;
         uint64_t cap = keysA.n / 12;
         uint64_t* tmp_key = reinterpret_cast<uint64_t*>(keysA.p);
         uint32_t* tmp_val = reinterpret_cast<uint32_t*>(tmp_key + cap);
         DBuf<uint64_t> big_key;
         DBuf<uint32_t> big_val;
         uint64_t rows_pass = 0, heads_pass = 0;
-        for (int attempt = 0;; ++attempt) {
-            {
-                StageScope sc(ctx, PEDK_ST_COUNT, 1, 0, 0, PEDK_KC_BUCKET_COUNT, m * ksz);
-                PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), st));
-                launch_bucket_count(keysB.p, wide, offB.p, (unsigned)n_buckets, k, a, b, log_slots, 1, s->ckey.p, s->ccnt.p,
-                                    s->n_corr, tmp_key, tmp_val, cap, ctx->scalars + 8, ctx->tile_ctr, ctx->err_flag, st);
+        int* d_ovfB = reinterpret_cast<int*>(ctx->scalars + 10);
+        bool exact_b = force_exact || env_int("PEDK_BUCKET_B_EXACT", 0, 0, 1) != 0;
+        for (;;) {
+            const unsigned long long* endB = nullptr;
+            PEDK_CUDA_TRY(cudaMemsetAsync(d_ovfB, 0, 8, st));
+            if (!exact_b) {
+                std::vector<int> bin_index((size_t)NBINS_MAX, -1);
+                int nb_local = 0;
+                for (int sg = 0; sg < n_seg; ++sg)
+                    if (bin_index[(size_t)seg_bin[(size_t)sg]] < 0) bin_index[(size_t)seg_bin[(size_t)sg]] = nb_local++;
+                const uint64_t mean = m / ((uint64_t)nb_local * NBINS_MAX) + 1;
+                uint64_t root = 1;
+                while (root * root < mean) ++root;
+                const uint64_t capB = (mean + mean / 16 + 8 * root + 64 + 3) & ~3ull;
+                keysB = DBuf<uint8_t>(ctx, (uint64_t)nb_local * NBINS_MAX * capB * ksz + 64);
+                limB = DBuf<unsigned long long>(ctx, n_buckets);
+                DBuf<int> d_bin_index(ctx, NBINS_MAX);
+                PEDK_CUDA_TRY(cudaMemcpyAsync(d_bin_index.p, bin_index.data(), (size_t)NBINS_MAX * 4, cudaMemcpyHostToDevice, st));
+                {
+                    StageScope sc(ctx, PEDK_ST_SORT, 1);
+                    launch_bucket_layout(d_bin_index.p, (unsigned)n_buckets, capB, offB.p, limB.p, st);
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
+                }
+                {
+                    StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
+                    launch_sub_scatter(keysA.p, keysB.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, curB.p, limB.p,
+                                       d_ovfB, st);
+                }
+                endB = curB.p;  // where every bucket's keys end
+            } else {
+                DBuf<unsigned> histB(ctx, n_buckets);
+                DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
+                {
+                    StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_HIST, m * ksz);
+                    PEDK_CUDA_TRY(cudaMemsetAsync(histB.p, 0, histB.bytes(), st));
+                    launch_sub_hist(keysA.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, histB.p, st);
+                }
+                {
+                    StageScope sc(ctx, PEDK_ST_SORT, 3);
+                    exclusive_scan_u32(histB.p, reinterpret_cast<uint64_t*>(offB.p), n_buckets, ctx->scalars + 3, ws.p, st);
+                    const unsigned long long total = m;
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(offB.p + n_buckets, &total, 8, cudaMemcpyHostToDevice, st));
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(curB.p, offB.p, n_buckets * 8, cudaMemcpyDeviceToDevice, st));
+                }
+                keysB.reset();
+                keysB = DBuf<uint8_t>(ctx, m * ksz + 64);  // the count kernel reads it with aligned 16-byte loads
+                {
+                    StageScope sc(ctx, PEDK_ST_SORT, 1, 0, 0, PEDK_KC_SUB_SCATTER, 2 * m * ksz);
+                    launch_sub_scatter(keysA.p, keysB.p, wide, d_seg.p, tprefix.p, n_seg, n_tiles, k, a, b, curB.p, nullptr,
+                                       nullptr, st);
+                }
+                endB = offB.p + 1;
             }
-            PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 2 * sizeof(unsigned long long),
-                                          cudaMemcpyDeviceToHost, st));
-            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-            ctx->stats.d2h_bytes += 16;
-            trace(ctx, "  buckets: count -> rows");
-            rows_pass = ctx->h_scalars[8];
-            heads_pass = ctx->h_scalars[9];
-            if (rows_pass <= cap) break;
-            if (attempt) throw PedkError(PEDK_E_INTERNAL, "row count changed between two passes");
-            // mostly distinct k-mers (very low coverage): run again into arrays of the exact size
-            cap = rows_pass;
-            big_key = DBuf<uint64_t>(ctx, cap);
-            big_val = DBuf<uint32_t>(ctx, cap);
-            tmp_key = big_key.p;
-            tmp_val = big_val.p;
+            if (ctx->trace) {
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                trace(ctx, exact_b ? "  buckets: histogram + scan + scatter" : "  buckets: scatter (optimistic sizes)");
+            }
+            bool overflowB = false;
+            for (int attempt = 0;; ++attempt) {
+                {
+                    StageScope sc(ctx, PEDK_ST_COUNT, 1, 0, 0, PEDK_KC_BUCKET_COUNT, m * ksz);
+                    PEDK_CUDA_TRY(cudaMemsetAsync(ctx->scalars + 8, 0, 2 * sizeof(unsigned long long), st));
+                    launch_bucket_count(keysB.p, wide, offB.p, endB, (unsigned)n_buckets, k, a, b, log_slots, 1, s->ckey.p,
+                                        s->ccnt.p, s->n_corr, tmp_key, tmp_val, cap, ctx->scalars + 8, ctx->tile_ctr,
+                                        ctx->err_flag, st);
+                }
+                PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 3 * sizeof(unsigned long long),
+                                              cudaMemcpyDeviceToHost, st));
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                ctx->stats.d2h_bytes += 24;
+                trace(ctx, "  buckets: count -> rows");
+                overflowB = !exact_b && (ctx->h_scalars[10] & 0xffffffffull) != 0;
+                if (overflowB) break;  // the buckets were cut short: what was counted is void
+                rows_pass = ctx->h_scalars[8];
+                heads_pass = ctx->h_scalars[9];
+                if (rows_pass <= cap) break;
+                if (attempt) throw PedkError(PEDK_E_INTERNAL, "row count changed between two passes");
+                // mostly distinct k-mers (very low coverage): run again into arrays of the exact size
+                cap = rows_pass;
+                big_key = DBuf<uint64_t>(ctx, cap);
+                big_val = DBuf<uint32_t>(ctx, cap);
+                tmp_key = big_key.p;
+                tmp_val = big_val.p;
+            }
+            if (!overflowB) break;
+            exact_b = true;
+            // (the error flag may have been raised by a bucket that was cut short: it is void too)
+            PEDK_CUDA_TRY(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), st));
         }
         check_err_flag(ctx, "bucket count");
         ctx->stats.kc_bytes[PEDK_KC_BUCKET_COUNT] += rows_pass * 12;
