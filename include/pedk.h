@@ -283,6 +283,9 @@ enum {
     PEDK_N_KC = 12
 };
 int pedk_get_stats(pedk_ctx *ctx, pedk_stats *out);   /* synchronises the stream */
+/* PEDK_GUARD=1 in the environment puts a guard zone behind every device block of the context and checks
+ * it when the block is released: the number of blocks a kernel wrote past the end of (0 = clean). */
+uint64_t pedk_guard_hits(pedk_ctx *ctx);
 int pedk_reset_stats(pedk_ctx *ctx);
 
 /* ---- multi-GPU (one rank per process) ---------------------------------- */

@@ -140,6 +140,7 @@ SIGNATURES = {
     "pedk_lbc_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_join_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
     "pedk_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "pedk_guard_hits": (C.c_uint64, [_P]),
     "pedk_reset_stats": (C.c_int, [_P]),
     "pedk_comm_unique_id": (C.c_int, [_P, _P]),
     "pedk_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
@@ -213,8 +214,11 @@ class Context:
 
     def close(self) -> None:
         if self.h:
+            hits = int(self.lib.pedk_guard_hits(self.h))
             self.lib.pedk_close(self.h)
             self.h = C.c_void_p()
+            if hits:
+                raise PedkError(-8, f"PEDK_GUARD: {hits} device block(s) were written past their end")
 
     def __enter__(self):
         return self

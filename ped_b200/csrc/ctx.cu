@@ -52,7 +52,18 @@ static void release_cached(pedk_ctx* ctx) {
     ctx->free_blocks.clear();
 }
 
+// PEDK_GUARD=1 (tests; compute-sanitizer is not available on every pool): every block gets a guard
+// zone behind the bytes that were asked for, filled with a pattern when the block is handed out and
+// checked when it comes back -- a kernel that wrote past the end of any buffer fails the call loudly.
+constexpr size_t GUARD_BYTES = 512;
+static bool guard_on() {
+    static const bool on = getenv("PEDK_GUARD") && atoi(getenv("PEDK_GUARD")) != 0;
+    return on;
+}
+
 void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
+    const size_t asked = bytes ? bytes : 1;
+    if (guard_on()) bytes = asked + GUARD_BYTES;
     const size_t want = block_size_for(bytes ? bytes : 1);
     // best fit among cached blocks, but never waste more than 1/8 (+2 MiB) of a block
     size_t best = (size_t)-1, best_size = (size_t)-1;
@@ -88,6 +99,10 @@ void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
     ctx->live_blocks[p] = got;
     ctx->cur_bytes += got;
     if (ctx->cur_bytes > ctx->stats.peak_device_bytes) ctx->stats.peak_device_bytes = ctx->cur_bytes;
+    if (guard_on()) {
+        ctx->guard_at[p] = asked;
+        cudaMemsetAsync(static_cast<char*>(p) + asked, 0xA5, GUARD_BYTES, ctx->stream);
+    }
     return p;
 }
 
@@ -95,6 +110,23 @@ void dev_free(pedk_ctx* ctx, void* p, size_t /*bytes*/) {
     if (!p) return;
     auto it = ctx->live_blocks.find(p);
     if (it == ctx->live_blocks.end()) return;
+    if (guard_on()) {
+        auto g = ctx->guard_at.find(p);
+        if (g != ctx->guard_at.end()) {
+            unsigned char h[GUARD_BYTES];
+            memset(h, 0, sizeof h);
+            cudaMemcpyAsync(h, static_cast<char*>(p) + g->second, GUARD_BYTES, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            for (size_t i = 0; i < GUARD_BYTES; ++i)
+                if (h[i] != 0xA5) {
+                    ++ctx->guard_hits;
+                    fprintf(stderr, "[pedk] PEDK_GUARD: a kernel wrote past the end of a %zu-byte device block (guard byte %zu)\n",
+                            g->second, i);
+                    break;
+                }
+            ctx->guard_at.erase(g);
+        }
+    }
     ctx->cur_bytes -= it->second;
     ctx->free_blocks.push_back({p, it->second});
     ctx->live_blocks.erase(it);
@@ -346,6 +378,8 @@ extern "C" int pedk_close(pedk_ctx* ctx) {
     delete ctx;
     return PEDK_OK;
 }
+
+extern "C" uint64_t pedk_guard_hits(pedk_ctx* ctx) { return ctx ? ctx->guard_hits : 0; }
 
 extern "C" int pedk_get_stats(pedk_ctx* ctx, pedk_stats* out) {
     if (!ctx || !out) return PEDK_E_INVAL;

@@ -20,6 +20,8 @@ struct pedk_ctx {
     };
     std::vector<Block> free_blocks;             // cached device blocks (see dev_alloc)
     std::unordered_map<void*, size_t> live_blocks;
+    std::unordered_map<void*, size_t> guard_at;  // PEDK_GUARD: block -> offset of its guard zone
+    uint64_t guard_hits = 0;                     // guard zones found overwritten
     size_t reserved_bytes = 0;
     cudaStream_t copy_stream = nullptr;  // H2D of FASTQ text runs here, under the kernels of the other sample
     cudaEvent_t ev_alloc = nullptr;

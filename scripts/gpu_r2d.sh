@@ -5,6 +5,8 @@ mkdir -p gpurun_out
 timeout 600 scripts/bin/microbench_peer_stores > gpurun_out/r2d_microbench_peer_stores.txt 2>&1; echo "microbench rc=$?"; tail -5 gpurun_out/r2d_microbench_peer_stores.txt
 PEDK_PART_BULK=1 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tiny or adversarial or dup or other_k or overflow or many_instances or corner or c1_40x or mixed or clip or medium" > gpurun_out/r2d_tests_bulk.log 2>&1; echo "bulk parity rc=$?"; tail -3 gpurun_out/r2d_tests_bulk.log
 PEDK_PART_BULK=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/multi_rank_check.py tiny adversarial c1_40x ref30k lowcomplexity > gpurun_out/r2d_check_bulk_n2.log 2>&1; echo "bulk multi check rc=$?"; grep "MULTI_RANK" gpurun_out/r2d_check_bulk_n2.log
+PEDK_GUARD=1 timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/r2d_tests_guard.log 2>&1; echo "guard-zone test run rc=$?"; tail -3 gpurun_out/r2d_tests_guard.log
+PEDK_GUARD=1 PEDK_PART_BULK=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 tests/multi_rank_check.py tiny c1_40x lowcomplexity > gpurun_out/r2d_check_guard_n2.log 2>&1; echo "guard multi check rc=$?"; grep "MULTI_RANK\|PEDK_GUARD" gpurun_out/r2d_check_guard_n2.log | head
 for bulk in 0 1; do
 PEDK_PART_BULK=$bulk timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/r2d_bench_n1_bulk$bulk.log 2>&1; echo "bench n1 bulk=$bulk rc=$?"
 PEDK_PART_BULK=$bulk PEDK_PART_BIG_TILE=2 timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/r2d_bench_n1big_bulk$bulk.log 2>&1; echo "bench n1 big bulk=$bulk rc=$?"
