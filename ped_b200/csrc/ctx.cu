@@ -84,8 +84,28 @@ void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaErrorMemoryAllocation) {
             cudaGetLastError();
-            release_cached(ctx);  // give the cached blocks back and try once more
-            e = cudaMalloc(&p, want);
+            // the device is full.  Before giving the cached blocks back to the driver (a free + malloc
+            // of tens of GB costs tens of ms, every step again): is any idle block large enough?
+            size_t any = (size_t)-1, any_size = (size_t)-1;
+            for (size_t i = 0; i < ctx->free_blocks.size(); ++i) {
+                const size_t sz = ctx->free_blocks[i].size;
+                if (sz >= want && sz < any_size) {
+                    any = i;
+                    any_size = sz;
+                }
+            }
+            if (any != (size_t)-1) {
+                p = ctx->free_blocks[any].p;
+                got = any_size;
+                ctx->free_blocks.erase(ctx->free_blocks.begin() + (long)any);
+                e = cudaSuccess;
+            } else {
+                release_cached(ctx);  // give the cached blocks back and try once more
+                e = cudaMalloc(&p, want);
+                if (e == cudaSuccess) ctx->reserved_bytes += want;
+            }
+        } else if (e == cudaSuccess) {
+            ctx->reserved_bytes += want;
         }
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -94,7 +114,6 @@ void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
                      ctx->cur_bytes, ctx->reserved_bytes, cudaGetErrorString(e));
             throw PedkError(PEDK_E_NOMEM, b);
         }
-        ctx->reserved_bytes += want;
     }
     ctx->live_blocks[p] = got;
     ctx->cur_bytes += got;

@@ -704,7 +704,11 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
                 const uint64_t mean = m / ((uint64_t)nb_local * NBINS_MAX) + 1;
                 uint64_t root = 1;
                 while (root * root < mean) ++root;
-                const uint64_t capB = (mean + mean / 16 + 8 * root + 64 + 3) & ~3ull;
+                // room per bucket: the instances of one k-mer all land in one bucket, so a bucket's size
+                // varies like sqrt(mean x instances per k-mer), not like sqrt(mean): 1/8 + 16 sqrt(mean)
+                // is 8 sigma at 30x coverage.  Deeper coverage overflows now and then and takes the
+                // exact path below.
+                const uint64_t capB = (mean + mean / 8 + 16 * root + 64 + 3) & ~3ull;
                 keysB = DBuf<uint8_t>(ctx, (uint64_t)nb_local * NBINS_MAX * capB * ksz + 64);
                 limB = DBuf<unsigned long long>(ctx, n_buckets);
                 DBuf<int> d_bin_index(ctx, NBINS_MAX);
@@ -720,6 +724,33 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
                                        d_ovfB, st);
                 }
                 endB = curB.p;  // where every bucket's keys end
+                // the verdict has to be in before the count kernel runs: its rows go into the level-A
+                // buffer, which the exact path would have to read again
+                PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 10, d_ovfB, 8, cudaMemcpyDeviceToHost, st));
+                PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                if ((ctx->h_scalars[10] & 0xffffffffull) != 0) {
+                    trace(ctx, "  buckets: optimistic sizes overflowed");
+                    exact_b = true;
+                    continue;
+                }
+                if (ctx->trace > 1) {
+                    // debug: which buckets outgrew their room
+                    std::vector<unsigned long long> hc(n_buckets), hl(n_buckets), ho(n_buckets);
+                    int hf = 0;
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(hc.data(), curB.p, n_buckets * 8, cudaMemcpyDeviceToHost, st));
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(hl.data(), limB.p, n_buckets * 8, cudaMemcpyDeviceToHost, st));
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(ho.data(), offB.p, n_buckets * 8, cudaMemcpyDeviceToHost, st));
+                    PEDK_CUDA_TRY(cudaMemcpyAsync(&hf, d_ovfB, 4, cudaMemcpyDeviceToHost, st));
+                    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+                    unsigned long long over = 0, tot = 0, mx = 0;
+                    for (size_t i = 0; i < n_buckets; ++i) {
+                        if (hc[i] > hl[i]) ++over;
+                        tot += hc[i] - ho[i];
+                        mx = std::max(mx, hc[i] - ho[i]);
+                    }
+                    fprintf(stderr, "[pedk debug] optimistic level B: m=%llu nb_local=%d capB=%llu flag=%d over=%llu total=%llu max=%llu\n",
+                            (unsigned long long)m, nb_local, (unsigned long long)capB, hf, over, tot, mx);
+                }
             } else {
                 DBuf<unsigned> histB(ctx, n_buckets);
                 DBuf<uint64_t> ws(ctx, scan_workspace_words(n_buckets));
@@ -748,7 +779,6 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
                 PEDK_CUDA_TRY(cudaStreamSynchronize(st));
                 trace(ctx, exact_b ? "  buckets: histogram + scan + scatter" : "  buckets: scatter (optimistic sizes)");
             }
-            bool overflowB = false;
             for (int attempt = 0;; ++attempt) {
                 {
                     StageScope sc(ctx, PEDK_ST_COUNT, 1, 0, 0, PEDK_KC_BUCKET_COUNT, m * ksz);
@@ -757,13 +787,11 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
                                         s->ccnt.p, s->n_corr, tmp_key, tmp_val, cap, ctx->scalars + 8, ctx->tile_ctr,
                                         ctx->err_flag, st);
                 }
-                PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 3 * sizeof(unsigned long long),
+                PEDK_CUDA_TRY(cudaMemcpyAsync(ctx->h_scalars + 8, ctx->scalars + 8, 2 * sizeof(unsigned long long),
                                               cudaMemcpyDeviceToHost, st));
                 PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-                ctx->stats.d2h_bytes += 24;
+                ctx->stats.d2h_bytes += 16;
                 trace(ctx, "  buckets: count -> rows");
-                overflowB = !exact_b && (ctx->h_scalars[10] & 0xffffffffull) != 0;
-                if (overflowB) break;  // the buckets were cut short: what was counted is void
                 rows_pass = ctx->h_scalars[8];
                 heads_pass = ctx->h_scalars[9];
                 if (rows_pass <= cap) break;
@@ -775,10 +803,7 @@ void count_bucketed(pedk_sample* s, int k, uint64_t* m_out) {
                 tmp_key = big_key.p;
                 tmp_val = big_val.p;
             }
-            if (!overflowB) break;
-            exact_b = true;
-            // (the error flag may have been raised by a bucket that was cut short: it is void too)
-            PEDK_CUDA_TRY(cudaMemsetAsync(ctx->err_flag, 0, sizeof(int), st));
+            break;
         }
         check_err_flag(ctx, "bucket count");
         ctx->stats.kc_bytes[PEDK_KC_BUCKET_COUNT] += rows_pass * 12;
