@@ -75,6 +75,25 @@ WORKLOADS = {
 }
 
 
+# what ncu shows closest to saturation for each kernel class at configs[1] (profiles/README.md): none of the
+# binning / counting kernels is bound by HBM, which is why their fraction of the HBM roofline is low
+KERNEL_LIMITER = {
+    "part_scatter": "instruction issue (~100 instructions per k-mer: extract, reverse-complement, canonical choice, "
+                    "hash, rank, stage, copy out) + shared-memory pipe; DRAM traffic = algorithmic bytes",
+    "bucket_count": "shared-memory pipe (16-byte group load + atomic per key, random bank conflicts) and instruction issue",
+    "sub_scatter": "shared-memory latency between the three barriers of a tile (short-scoreboard stalls)",
+    "sub_hist": "HBM",
+    "pack": "alu pipe (byte-parallel alphabet tests and 2-bit packing)",
+    "join_table": "shared-memory atomics (CAS + OR per row) and the sweep of the table",
+    "join_scatter": "instruction issue + shared memory",
+    "join_sub": "shared-memory latency, as sub_scatter",
+    "join_count": "alu / latency",
+    "radix_pairs": "instruction issue (stable ranks by ballots)",
+    "radix_keys": "instruction issue (stable ranks by ballots)",
+    "part_count": "alu pipe",
+}
+
+
 def workload(key: str, scale: float, k: int):
     """A BASELINE config scaled by `scale` (1.0 = the full configuration)."""
     w = dict(WORKLOADS[key])
@@ -410,7 +429,8 @@ def main():
                            f"launch over algorithmic bytes = {ratio[top_name]:.3f}) x this run's algorithmic bytes; "
                            f"not measured in this run")
             break
-    roofline = {"bound": "hbm", "kernel": KERNEL_DOC[top_name], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": KERNEL_DOC[top_name], "limiter": KERNEL_LIMITER.get(top_name),
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                 "launches_in_timed_region": top["launches"], "mean_launch_ms": top["ms"] / top["launches"],

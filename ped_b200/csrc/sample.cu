@@ -490,11 +490,13 @@ int choose_count_passes(pedk_ctx* ctx, uint64_t m_rank, size_t ksz, int nbA) {
         const char* cap_env = getenv("PEDK_DEVICE_BUDGET_MB");  // tests: pretend the device is small
         double budget = (double)(free_b + cached) * 0.90;
         if (cap_env && *cap_env) budget = std::min(budget, atof(cap_env) * 1048576.0);
-        // level-A segments (expected + 1/8 + slack per (bin, source)) + buckets + the rows that come out;
-        // a rank receives about what it sends (the hash spreads the k-mers evenly)
+        // per pass: level-A segments (expected + 1/8 + slack per (bin, source)) + buckets (expected + 1/8 +
+        // 16 sqrt); over all passes: the rows that come out (at most one per three instances at the
+        // coverages a comparison makes sense at).  A rank receives about what it sends (the hash
+        // spreads the k-mers evenly).
         auto need = [&](int passes) {
-            const double inst = (double)m_rank * 1.05 / passes;
-            return inst * ksz * (1.125 + 1.0) + (double)nbA / passes * 4096 * ksz + inst * 0.25 * 12;
+            const double inst = (double)m_rank * 1.05;
+            return inst / passes * ksz * (1.125 + 1.2) + (double)nbA / passes * 4096 * ksz + inst * 0.34 * 12;
         };
         while (P < max_pass && need(P) > budget) P <<= 1;
     }
