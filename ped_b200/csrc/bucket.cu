@@ -187,13 +187,6 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
     }
     constexpr uint64_t READS_PER_TILE = (uint64_t)PT_WARPS * RPW;
     const uint64_t n_tiles = (n_reads + READS_PER_TILE - 1) / READS_PER_TILE;
-    // (!BULK) the runs of a tile are copied out while the NEXT tile is extracted and hashed: slice rr of
-    // the previous tile's staging area goes out after read rr of this one.  The stores (NVLink stores on
-    // several ranks: 620 GB/s at best for runs of this length, profiles/r2d_microbench_peer_stores.txt)
-    // then overlap the arithmetic instead of following it -- with one 1024-thread CTA per SM nothing
-    // else would.  The staging area, s_out and sbin are not touched before the scan below.
-    constexpr bool OVERLAP = !BULK && PT_THREADS > 512;  // the 1024-thread tiles of the multi-rank exchange
-    unsigned prev_staged = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (tid < NB) hist[tid] = 0;
         __syncthreads();
@@ -217,14 +210,6 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
                 meta[idx] = 0xffffffffu;
                 // counting in several passes (HBM capacity): only the bins of this pass are kept
                 if (valid[t] && (bin & pass_mask) == pass_id) meta[idx] = (bin << 16) | atomicAdd(&hist[bin], 1u);
-            }
-            if (OVERLAP && prev_staged) {
-                const unsigned lo = (unsigned)(((uint64_t)prev_staged * rr) / RPW);
-                const unsigned hi = (unsigned)(((uint64_t)prev_staged * (rr + 1)) / RPW);
-                for (unsigned i = lo + tid; i < hi; i += PT_THREADS) {
-                    KT* p = s_out[sbin[i]];
-                    if (p) p[i] = stage[i];
-                }
             }
         }
         __syncthreads();
@@ -285,20 +270,12 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
                 }
             }
             __syncthreads();
-            // ---- every bin's run goes out contiguously (to the owner's memory): now, or during the next tile ----
-            prev_staged = (unsigned)total;
-            if (!OVERLAP) {
-                for (unsigned i = tid; i < prev_staged; i += PT_THREADS) {
-                    KT* p = s_out[sbin[i]];
-                    if (p) p[i] = stage[i];
-                }
+            // ---- every bin's run goes out contiguously (to the owner's memory) ----
+            const unsigned n_staged = (unsigned)total;
+            for (unsigned i = tid; i < n_staged; i += PT_THREADS) {
+                KT* p = s_out[sbin[i]];
+                if (p) p[i] = stage[i];
             }
-        }
-    }
-    if (OVERLAP) {
-        for (unsigned i = tid; i < prev_staged; i += PT_THREADS) {
-            KT* p = s_out[sbin[i]];
-            if (p) p[i] = stage[i];
         }
     }
     if (BULK && tid < NB) bulk_wait_all();  // shared memory must outlive the copies that read it
@@ -917,7 +894,7 @@ void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t
                             unsigned long long* cur, const unsigned long long* lim, int* overflow,
                             const PeerPtrs& dst, unsigned pass_mask, unsigned pass_id, cudaStream_t st) {
     // the k = 20 kernel with 32-bit words also comes with long tiles for several ranks
-    const int big = getenv("PEDK_PART_BIG_TILE") ? atoi(getenv("PEDK_PART_BIG_TILE")) : 1;
+    static const int big = getenv("PEDK_PART_BIG_TILE") ? atoi(getenv("PEDK_PART_BIG_TILE")) : 1;
     if (KC == 20 && sizeof(KT) == 4 && (nranks > 1 || big == 2) && big && PT_BIG_OK<KT, NT>::value)
         launch_part_scatter_th<KT, NT, CONTIG, KC, (KC == 20 ? 1024 : 512)>(words, W, L, k, n_reads, a, nranks, cur,
                                                                            lim, overflow, dst, pass_mask, pass_id, st);
