@@ -173,11 +173,12 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
     unsigned long long* d_hist = counts.p;                             // [257]
     unsigned long long* d_all = counts.p + (NB + 1);                   // [R][257]
     unsigned long long* d_first = counts.p + (size_t)(NB + 1) * (PEDK_MAX_RANKS + 1);  // [128]
-    {
-        StageScope sc(ctx, PEDK_ST_ROWSORT, 2, 0, 0, PEDK_KC_JOIN_COUNT, rows_local * 8);
-        PEDK_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)(NB + 1) * 8, st));
-        PEDK_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, 128 * 8, st));
-        for (int i = 0; i < 2; ++i) launch_rows_count(src[i].key, src[i].n, i, k, d_hist, d_first, st);
+    PEDK_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)(NB + 1) * 8, st));
+    PEDK_CUDA_TRY(cudaMemsetAsync(d_first, 0xFF, 128 * 8, st));
+    for (int i = 0; i < 2; ++i) {
+        if (!src[i].n) continue;
+        StageScope sc(ctx, PEDK_ST_ROWSORT, 1, 0, 0, PEDK_KC_JOIN_COUNT, src[i].n * 8);
+        launch_rows_count(src[i].key, src[i].n, i, k, d_hist, d_first, st);
     }
     std::vector<unsigned long long> all((size_t)(NB + 1) * R, 0);
     unsigned char* hstage = static_cast<unsigned char*>(host_stage(ctx, 1 << 16));
@@ -213,9 +214,12 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         } else {
             dst.p[0] = recA.p;
         }
-        StageScope sc(ctx, multi ? PEDK_ST_EXCHANGE : PEDK_ST_ROWSORT, 2, 0, 0, PEDK_KC_JOIN_SCATTER, rows_local * 20);
         if (multi) comm_barrier(ctx);  // nobody stores into a buffer its owner still reads
-        for (int i = 0; i < 2; ++i) launch_rows_scatter(src[i].key, src[i].val, src[i].n, i, k, R, d_cur.p, dst, st);
+        for (int i = 0; i < 2; ++i) {
+            if (!src[i].n) continue;
+            StageScope sc(ctx, multi ? PEDK_ST_EXCHANGE : PEDK_ST_ROWSORT, 1, 0, 0, PEDK_KC_JOIN_SCATTER, src[i].n * 20);
+            launch_rows_scatter(src[i].key, src[i].val, src[i].n, i, k, R, d_cur.p, dst, st);
+        }
         if (multi) comm_barrier(ctx);  // every rank's stores have landed
     }
     std::vector<GroupRec> groups;
