@@ -274,10 +274,6 @@ __global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* 
     const int shiftA = nbitsP - a;
     const uint64_t maskS = (1ull << shiftA) - 1;
     const uint64_t n_tiles = (n + JS_TILE - 1) / JS_TILE;
-    // (!BULK) the runs of a tile go out while the next tile is loaded and hashed (slice j after row j), so
-    // that the stores -- NVLink stores on several ranks -- overlap the arithmetic; the staging area, s_out
-    // and sbin are not touched before the scan below
-    unsigned prev_staged = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (tid < 256) hist[tid] = 0;
         __syncthreads();
@@ -296,10 +292,6 @@ __global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* 
                 rec[j] = ((hp & maskS) << JR_PAYLOAD_BITS) | ((K & 3) << 8) | ((uint64_t)sample << 7) |
                          (c > 127u ? 127u : c);
                 meta[j] = (bin << 16) | atomicAdd(&hist[bin], 1u);
-            }
-            if (!BULK && prev_staged) {
-                const unsigned lo = prev_staged * (unsigned)j / JS_ITEMS, hi = prev_staged * (unsigned)(j + 1) / JS_ITEMS;
-                for (unsigned q = lo + tid; q < hi; q += JS_THREADS) s_out[sbin[q]][q] = stage[q];
             }
         }
         __syncthreads();
@@ -352,11 +344,11 @@ __global__ void __launch_bounds__(JS_THREADS, 2) k_rows_scatter(const uint64_t* 
                 }
             }
             __syncthreads();
-            prev_staged = (unsigned)total;  // copied out during the next tile
+            const unsigned n_staged = (unsigned)total;
+            for (unsigned i = tid; i < n_staged; i += JS_THREADS) s_out[sbin[i]][i] = stage[i];
+            __syncthreads();
         }
     }
-    if (!BULK)
-        for (unsigned q = tid; q < prev_staged; q += JS_THREADS) s_out[sbin[q]][q] = stage[q];
     if (BULK && tid < 256) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
