@@ -894,7 +894,7 @@ void launch_part_scatter_nt(const uint64_t* words, int W, int L, int k, uint64_t
                             unsigned long long* cur, const unsigned long long* lim, int* overflow,
                             const PeerPtrs& dst, unsigned pass_mask, unsigned pass_id, cudaStream_t st) {
     // the k = 20 kernel with 32-bit words also comes with long tiles for several ranks
-    static const int big = getenv("PEDK_PART_BIG_TILE") ? atoi(getenv("PEDK_PART_BIG_TILE")) : 1;
+    const int big = getenv("PEDK_PART_BIG_TILE") ? atoi(getenv("PEDK_PART_BIG_TILE")) : 1;
     if (KC == 20 && sizeof(KT) == 4 && (nranks > 1 || big == 2) && big && PT_BIG_OK<KT, NT>::value)
         launch_part_scatter_th<KT, NT, CONTIG, KC, (KC == 20 ? 1024 : 512)>(words, W, L, k, n_reads, a, nranks, cur,
                                                                            lim, overflow, dst, pass_mask, pass_id, st);
