@@ -192,6 +192,47 @@ __device__ __forceinline__ uint64_t spread32(uint32_t x) {
     return v;
 }
 
+// One warp packs the L bases at src into W 64-bit words (2 bits per base, base 0 in the top bits of word 0),
+// builds the reverse complement and keeps the smaller of the two: lane w returns word w of the canonical
+// read.  *pal: the read equals its reverse complement.  CHECK: *acgt = every base is one of ACGT (upper case);
+// the reads of a sample were filtered before they get here, the windows of the verification were not.
+template <bool CHECK>
+__device__ __forceinline__ uint64_t warp_pack_canonical(const uint8_t* __restrict__ src, int L, int W, unsigned lane,
+                                                        bool* pal, bool* acgt) {
+    // lane w ends up holding word w of the forward read
+    uint64_t mine = 0;
+    unsigned bad = 0;
+    for (int w = 0; w < W; ++w) {
+        int i = 32 * w + (int)lane;
+        uint32_t c = i < L ? src[i] : (uint32_t)'A';
+        uint32_t code = i < L ? base_code(c) : 0u;
+        if (CHECK) bad |= __ballot_sync(0xffffffffu, !(c == 'A' || c == 'C' || c == 'G' || c == 'T'));
+        // ballot bit t <-> base 32w+t; brev puts base 0 at bit 31
+        uint32_t m1 = __brev(__ballot_sync(0xffffffffu, code & 2u));
+        uint32_t m0 = __brev(__ballot_sync(0xffffffffu, code & 1u));
+        uint64_t word = (spread32(m1) << 1) | spread32(m0);
+        if ((int)lane == w) mine = word;
+    }
+    // reverse complement: lane w needs 32 bases starting at L-32w-32
+    int sbase = L - 32 * (int)lane - 32;
+    int wi = sbase >> 5, o = sbase & 31;
+    uint64_t hi = __shfl_sync(0xffffffffu, mine, wi & 31);
+    uint64_t lo = __shfl_sync(0xffffffffu, mine, (wi + 1) & 31);
+    if (wi < 0 || wi >= W) hi = 0;
+    if (wi + 1 < 0 || wi + 1 >= W) lo = 0;
+    uint64_t win = o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+    uint64_t rc = (int)lane < W ? (revcomp_groups64(win) & tail_mask(L, (int)lane)) : 0ull;
+    unsigned diff = __ballot_sync(0xffffffffu, mine != rc);
+    bool use_rc = false;
+    if (diff) {
+        int f = __ffs(diff) - 1;
+        use_rc = __shfl_sync(0xffffffffu, rc < mine ? 1 : 0, f) != 0;
+    }
+    *pal = diff == 0;
+    if (CHECK) *acgt = bad == 0;
+    return use_rc ? rc : mine;
+}
+
 __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ fq, const uint64_t* __restrict__ seq_start,
                                              const uint32_t* __restrict__ chunks,
                                              const uint64_t* __restrict__ chunk_base, uint64_t n_records,
@@ -207,37 +248,51 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ fq, co
         uint64_t s0 = seq_start[r];
         uint64_t slot0 = chunk_base[r];
         for (uint32_t j = 0; j < nch; ++j) {
-            const uint8_t* src = fq + s0 + (uint64_t)j * clip;
-            // lane w ends up holding word w of the forward chunk
-            uint64_t mine = 0;
-            for (int w = 0; w < W; ++w) {
-                int i = 32 * w + (int)lane;
-                uint32_t code = i < L ? base_code(src[i]) : 0u;
-                // ballot bit t <-> base 32w+t; brev puts base 0 at bit 31
-                uint32_t m1 = __brev(__ballot_sync(0xffffffffu, code & 2u));
-                uint32_t m0 = __brev(__ballot_sync(0xffffffffu, code & 1u));
-                uint64_t word = (spread32(m1) << 1) | spread32(m0);
-                if ((int)lane == w) mine = word;
-            }
-            // reverse complement: lane w needs 32 bases starting at L-32w-32
-            int sbase = L - 32 * (int)lane - 32;
-            int wi = sbase >> 5, o = sbase & 31;
-            uint64_t hi = __shfl_sync(0xffffffffu, mine, wi & 31);
-            uint64_t lo = __shfl_sync(0xffffffffu, mine, (wi + 1) & 31);
-            if (wi < 0 || wi >= W) hi = 0;
-            if (wi + 1 < 0 || wi + 1 >= W) lo = 0;
-            uint64_t win = o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
-            uint64_t rc = (int)lane < W ? (revcomp_groups64(win) & tail_mask(L, (int)lane)) : 0ull;
-            unsigned diff = __ballot_sync(0xffffffffu, mine != rc);
-            bool use_rc = false;
-            if (diff) {
-                int f = __ffs(diff) - 1;
-                use_rc = __shfl_sync(0xffffffffu, rc < mine ? 1 : 0, f) != 0;
-            }
+            bool is_pal, unused;
+            uint64_t word = warp_pack_canonical<false>(fq + s0 + (uint64_t)j * clip, L, W, lane, &is_pal, &unused);
             uint64_t slot = slot0 + j;
-            if ((int)lane < W) words[slot * (uint64_t)W + lane] = use_rc ? rc : mine;
-            if (lane == 0) pal[slot] = diff == 0 ? 1 : 0;
+            if ((int)lane < W) words[slot * (uint64_t)W + lane] = word;
+            if (lane == 0) pal[slot] = is_pal ? 1 : 0;
         }
+    }
+}
+
+// f2 (ped.pl:2189-2196, 2601-2620): is the window of L bases at text[start[s] + i] one of the sample's reads?
+// One warp per window; the window is packed and made canonical like a read, hashed like k_dedup hashes it,
+// and looked up in the table k_dedup built over the sample's unique canonical reads (open addressing, the
+// packed words decide).  hits[s] counts the windows of string s that are reads.
+__global__ void __launch_bounds__(256) k_probe_windows(const uint8_t* __restrict__ text,
+                                                      const uint64_t* __restrict__ start,
+                                                      const uint32_t* __restrict__ length, uint64_t n_strings,
+                                                      int L, int W, const uint64_t* __restrict__ words,
+                                                      const uint32_t* __restrict__ table, uint32_t mask,
+                                                      uint32_t* __restrict__ hits) {
+    const unsigned lane = lane_id();
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_windows = n_strings * (uint64_t)L;
+    for (uint64_t p = warp; p < n_windows; p += n_warps) {
+        const uint64_t s = p / (unsigned)L;
+        const uint32_t i = (uint32_t)(p % (unsigned)L);
+        if ((uint64_t)i + (unsigned)L > length[s]) continue;  // substr past the end: a shorter line, never a read
+        bool is_pal, acgt;
+        const uint64_t word = warp_pack_canonical<true>(text + start[s] + i, L, W, lane, &is_pal, &acgt);
+        if (!acgt) continue;
+        uint64_t h = 0x243F6A8885A308D3ull;  // the hash of k_dedup (dedup.cu)
+        for (int w = 0; w < W; ++w) h = mix64(h ^ __shfl_sync(0xffffffffu, word, w));
+        uint32_t slot = (uint32_t)(h >> 20) & mask;
+        bool hit = false;
+        for (;;) {
+            const uint32_t cur = table[slot];
+            if (cur == 0xFFFFFFFFu) break;
+            const uint64_t other = (int)lane < W ? words[(uint64_t)cur * W + lane] : 0ull;
+            if (__ballot_sync(0xffffffffu, (int)lane < W && other != word) == 0) {
+                hit = true;
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+        if (hit && lane == 0) atomicAdd(&hits[s], 1u);
     }
 }
 
@@ -411,6 +466,16 @@ void launch_pack(const uint8_t* fq, const uint64_t* seq_start, const uint32_t* c
     uint64_t blocks = (n_records + 7) / 8;
     unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
     k_pack<<<grid, 256, 0, st>>>(fq, seq_start, chunks, chunk_base, n_records, clip, W, words, pal);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_probe_windows(const uint8_t* text, const uint64_t* start, const uint32_t* length, uint64_t n_strings, int L,
+                          int W, const uint64_t* words, const uint32_t* table, uint32_t capacity, uint32_t* hits,
+                          cudaStream_t st) {
+    if (!n_strings || L <= 0) return;
+    const uint64_t blocks = (n_strings * (uint64_t)L + 7) / 8;
+    const unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_probe_windows<<<grid, 256, 0, st>>>(text, start, length, n_strings, L, W, words, table, capacity - 1, hits);
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 

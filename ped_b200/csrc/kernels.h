@@ -48,6 +48,11 @@ void launch_pack_fixed(const uint8_t* fq, const uint64_t* seq_start, uint64_t n_
 // valid (may be null): slots with valid[i] == 0 are skipped
 void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, const uint8_t* valid,
                   uint8_t* uniq, cudaStream_t st);
+// f2: hits[s] += number of the L-base windows of string s (text[start[s] .. +length[s])) that are reads of the
+// sample whose unique canonical reads are `words` and whose k_dedup table is `table`
+void launch_probe_windows(const uint8_t* text, const uint64_t* start, const uint32_t* length, uint64_t n_strings, int L,
+                          int W, const uint64_t* words, const uint32_t* table, uint32_t capacity, uint32_t* hits,
+                          cudaStream_t st);
 void launch_compact_reads(const uint64_t* words, const uint8_t* pal, const uint8_t* uniq, const uint64_t* pos,
                           int W, uint32_t n, uint64_t* out_words, uint8_t* out_pal, cudaStream_t st);
 

@@ -197,3 +197,38 @@ def test_cnv_restatement_against_the_reference(built):
     ref20 = b"".join(oracle.ref20_uniq_text(fa, t) for t in range(64))
     text = pyref.cnv_text(ref20, oc.table(), ot.table())
     assert (text.count(b"\n"), hashlib.sha256(text).hexdigest()) == (g["cnv_rows"], g["cnv_sha256"])
+
+
+def verification_inputs(fa, control, target, edges: bytes):
+    """What SURVEY row f2 starts from, made with the (pinned) oracle: the position-map lines of all 64
+    tags in `cat` order, the two sort_uniq line sets and the chromosome files."""
+    by_tag = {t: b"" for t in TAGS}
+    for line in edges.splitlines(keepends=True):
+        by_tag[line[:3].decode()] += line
+    map_text = b"".join(oracle.map_kmer_text(by_tag[t], oracle.ref20_uniq_text(fa, i)) for i, t in enumerate(TAGS))
+
+    def lines(o):
+        return {t: o.sort_uniq_text(i).decode().split("\n")[:-1] for i, t in enumerate(TAGS)}
+
+    chromosomes = {n: s.decode() for n, s in oracle.ref_chromosomes(fa).items()}
+    return map_text, lines(target), lines(control), chromosomes
+
+
+@pytest.mark.parametrize("variant", ["control_reads", "control_ref"])
+def test_verification_restatement_against_the_reference(variant, built):
+    """f2: the line-by-line restatement of snpMkT/sortSeq/joinTarget/snpMkC/joinControl/kmerReadCount and of
+    toVcf (oracle/verify_ref.py, ped.pl:2087-2305, 2576-2641, 2388-2500, 1532-1574) over the oracle's edge
+    list, position map and sort_uniq sets reproduces ped.pl's own T.kmer.snp and T.kmer.vcf of a
+    `method=kmer` run with a reference (tests/golden/ref30k_verify.json, scripts/make_golden_verify.py),
+    with sequenced control reads (150 bp) and with the tiled reference as the control (100 bp)."""
+    from oracle import verify_ref
+    from tests.cases import make_cnv_inputs
+
+    with open(os.path.join(GOLDEN, "ref30k_verify.json")) as f:
+        g = json.load(f)[variant]
+    fa, fc, ft = make_cnv_inputs(REF_CASES["ref30k"])
+    oc, ot, edges = oracle.run(fc, ft, 20) if variant == "control_reads" else oracle.run_ref(fa, ft, 20)
+    map_text, t_lines, c_lines, chromosomes = verification_inputs(fa, oc, ot, edges)
+    snp = verify_ref.verify(map_text.decode().splitlines(), t_lines, c_lines, chromosomes)
+    assert snp == g["kmer_snp"]
+    assert verify_ref.to_vcf(snp, "T") == g["kmer_vcf"]
