@@ -139,6 +139,21 @@ int pedk_sample_map_kmer_text(pedk_sample *ref, const char *snp_text, uint64_t s
  * (a k-mer one sample does not have counts 0 there), ordered like `sort -k 1 -n -k 2 -n` -- the text
  * of <target>/<target>.<control>.cnv.  One rank.  Caller frees with pedk_free. */
 int pedk_cnv_text(pedk_sample *ref, pedk_sample *control, pedk_sample *target, char **text, uint64_t *len);
+/* f2, snpMkT + sortSeq + joinTarget + snpMkC + sortSeq + joinControl + kmerReadCount (ped.pl:2087-2305,
+ * 2576-2641, 2388-2500): map_text = the lines of the <tmpdir>/<t>.map.TAG files in tag order
+ * (pedk_sample_map_kmer_text).  For every candidate `chr pos ref alt` of the map the L windows of the
+ * reference around it and of the reference carrying the alternative allele are looked up among the
+ * unique reads of the target (L = its read length) and of the control (its read length); the numbers of
+ * windows found (cw cm tw tm) give the genotype M / H / R / N, and the map lines joined with them are
+ * the text of <target>/<target>.kmer.snp of a run with a reference (20 columns).  target and control
+ * must be ingested with their reads still in HBM; ref went through pedk_sample_ingest_reference (its
+ * chromosomes are the `chrNAME` files ped.pl seeks in).  Orders are bytewise (LC_ALL=C).  One rank.
+ * Caller frees with pedk_free. */
+int pedk_verify_text(pedk_sample *target, pedk_sample *control, pedk_sample *ref, const char *map_text,
+                     uint64_t map_len, char **text, uint64_t *len);
+/* f4, toVcf for method kmer (ped.pl:1532-1574): <target>.kmer.snp -> the text of <target>.kmer.vcf.
+ * Host only (no CUDA call).  Caller frees with pedk_free. */
+int pedk_vcf_text(const char *kmer_snp, uint64_t snp_len, const char *target_name, char **text, uint64_t *len);
 /* S2-S4 = countKmerSub + countKmerMerge (ped.pl:891-932, 862-889): every k-mer
  * of every unique read, brought together (hash bins, buckets) and counted.  4 <= k <= 32 (the reference
  * hard-codes 20, ped.pl:912-913).  Leaves the canonical table in HBM. */
@@ -228,6 +243,14 @@ int pedk_map_kmer(pedk_ctx *ctx, const char *wd, const char *target, const char 
  * <wd>/<target>/<target>.<control>.cnv from the count tables (resident or count files) and the unique
  * k-mer index (resident or ref20_uniq files) */
 int pedk_cnv(pedk_ctx *ctx, const char *wd, const char *target, const char *control, const char *ref, int k);
+/* snpMkT, sortSeq, joinTarget, snpMkC, sortSeq, joinControl, kmerReadCount (ped.pl:380-386) in one call:
+ * reads <tmpdir>/<target>.map.TAG (pedk_map_kmer), the sort_uniq files of target and control (or the
+ * reads still resident from pedk_mk_sort_uniq / pedk_mk_control_read) and <wd>/<ref>/chrNAME, writes
+ * <wd>/<target>/<target>.kmer.snp.  control may equal ref (ped.pl:193). */
+int pedk_verify_kmer(pedk_ctx *ctx, const char *wd, const char *target, const char *control, const char *ref,
+                     const char *tmpdir);
+/* toVcf (ped.pl:387, 1532-1574): <wd>/<target>/<target>.kmer.snp -> <wd>/<target>/<target>.kmer.vcf */
+int pedk_to_vcf(pedk_ctx *ctx, const char *wd, const char *target);
 /* countKmer (ped.pl:784-815): writes <wd>/<subject>/count/<subject>.count.TAG.gz */
 int pedk_count_kmer(pedk_ctx *ctx, const char *wd, const char *subject, int k);
 /* lbcKmer (ped.pl:817-831): writes <wd>/<subject>/lbc/<subject>.lbc.TAG.gz */

@@ -112,6 +112,10 @@ SIGNATURES = {
     "pedk_sample_map_kmer_text": (C.c_int, [_P, C.c_char_p, C.c_uint64, _PP, _U64P]),
     "pedk_cnv_text": (C.c_int, [_P, _P, _P, _PP, _U64P]),
     "pedk_cnv": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "pedk_verify_text": (C.c_int, [_P, _P, _P, C.c_char_p, C.c_uint64, _PP, _U64P]),
+    "pedk_vcf_text": (C.c_int, [C.c_char_p, C.c_uint64, C.c_char_p, _PP, _U64P]),
+    "pedk_verify_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
+    "pedk_to_vcf": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
     "pedk_mk_ref20_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_map_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_sample_table_digest": (C.c_int, [_P, _U64P, _U64P]),
@@ -377,6 +381,18 @@ class Sample:
         finally:
             self.ctx.lib.pedk_free(p)
 
+    def verify_text(self, control: "Sample", target: "Sample", map_text: bytes) -> bytes:
+        """snpMkT ... kmerReadCount (ped.pl:380-386) with this sample as the reference (chromosomes):
+        the map lines of all tags -> `<t>.kmer.snp` of a run with a reference."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.pedk_verify_text(target.h, control.h, self.h, map_text, len(map_text),
+                                                     C.byref(p), C.byref(n)))
+        try:
+            return C.string_at(p, n.value)
+        finally:
+            self.ctx.lib.pedk_free(p)
+
     def count(self, k: int = 20) -> CountInfo:
         """countKmer (ped.pl:784-932)."""
         info = CountInfo()
@@ -496,6 +512,20 @@ def chromosome_file_name(header_line: bytes) -> str:
     if rc:
         raise PedkError(rc, "pedk_chromosome_file_name")
     return buf.value.decode()
+
+
+def vcf_text(kmer_snp: bytes, target_name: str) -> bytes:
+    """toVcf for method kmer (ped.pl:1532-1574): `<t>.kmer.snp` -> `<t>.kmer.vcf` (host-only)."""
+    lib = load_library()
+    p = C.c_void_p()
+    n = C.c_uint64()
+    rc = lib.pedk_vcf_text(kmer_snp, len(kmer_snp), target_name.encode(), C.byref(p), C.byref(n))
+    if rc:
+        raise PedkError(rc, "pedk_vcf_text")
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        lib.pedk_free(p)
 
 
 def fastq_padded_bytes(n: int) -> int:

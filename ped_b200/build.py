@@ -20,7 +20,7 @@ ORACLE_SRC = os.path.join(ROOT, "oracle", "ped_oracle.c")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libped_oracle.so")
 
 CU_SOURCES = ["scan.cu", "ingest.cu", "dedup.cu", "kmer.cu", "bucket.cu", "radix.cu", "edges.cu", "synth.cu", "ctx.cu",
-              "sample.cu", "join.cu", "comm.cu", "files.cu", "reference.cu", "plan.cu", "refindex.cu"]
+              "sample.cu", "join.cu", "comm.cu", "files.cu", "reference.cu", "plan.cu", "refindex.cu", "verify.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
               "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 

@@ -636,6 +636,44 @@ void do_cnv(pedk_ctx* ctx, const std::string& wd, const std::string& target, con
     write_plain_atomic(wd + "/" + target + "/" + target + "." + control + ".cnv", text.data(), text.size());
 }
 
+// snpMkT ... kmerReadCount (ped.pl:380-386): <tmpdir>/<t>.map.TAG + the reads of both samples + <ref>/chrNAME
+// -> <wd>/<target>/<target>.kmer.snp
+void do_verify_kmer(pedk_ctx* ctx, const std::string& wd, const std::string& target, const std::string& control,
+                    const std::string& ref, const std::string& tmpdir) {
+    PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
+    auto with_reads = [&](const std::string& subject) {
+        pedk_sample* s = cached(ctx, wd + "/" + subject);
+        if (!s || !s->ingested || s->reads_released || s->host_only_table) s = sample_from_sort_uniq(ctx, wd, subject);
+        return s;
+    };
+    pedk_sample* t = with_reads(target);
+    pedk_sample* c = control == target ? t : with_reads(control);
+    std::string map;
+    for (int tag = 0; tag < 64; ++tag) map += read_plain(tmpdir + "/" + target + ".map." + tag_name(tag));  // `cat *.map.*`
+    std::map<std::string, std::string> files;
+    std::map<std::string, bool> missing;
+    ChromosomeLookup lookup = [&](const std::string& name) -> const std::string* {
+        auto it = files.find(name);
+        if (it != files.end()) return &it->second;
+        if (missing.count(name)) return nullptr;
+        const std::string p = wd + "/" + ref + "/" + name;
+        struct stat sb;
+        if (name.find('/') != std::string::npos || stat(p.c_str(), &sb) != 0 || !S_ISREG(sb.st_mode)) {
+            missing[name] = true;
+            return nullptr;
+        }
+        return &(files[name] = read_plain(p));
+    };
+    const std::string text = verify_text(t, c, lookup, map.data(), map.size());
+    write_plain_atomic(wd + "/" + target + "/" + target + ".kmer.snp", text.data(), text.size());
+}
+
+void do_to_vcf(const std::string& wd, const std::string& target) {
+    const std::string snp = read_plain(wd + "/" + target + "/" + target + ".kmer.snp");
+    const std::string vcf = vcf_text(snp.data(), snp.size(), target);
+    write_plain_atomic(wd + "/" + target + "/" + target + ".kmer.vcf", vcf.data(), vcf.size());
+}
+
 }  // namespace
 
 namespace pedk {
@@ -676,6 +714,23 @@ extern "C" int pedk_cnv(pedk_ctx* ctx, const char* wd, const char* target, const
     if (!ctx || !wd || !target || !control || !ref) return PEDK_E_INVAL;
     PEDK_API_BEGIN
     do_cnv(ctx, wd, target, control, ref, k);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_verify_kmer(pedk_ctx* ctx, const char* wd, const char* target, const char* control, const char* ref,
+                                const char* tmpdir) {
+    if (!ctx || !wd || !target || !control || !ref || !tmpdir) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_verify_kmer(ctx, wd, target, control, ref, tmpdir);
+    return PEDK_OK;
+    PEDK_API_END(ctx)
+}
+
+extern "C" int pedk_to_vcf(pedk_ctx* ctx, const char* wd, const char* target) {
+    if (!ctx || !wd || !target) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    do_to_vcf(wd, target);
     return PEDK_OK;
     PEDK_API_END(ctx)
 }

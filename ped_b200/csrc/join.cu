@@ -10,8 +10,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "comm.h"
 #include "plan.h"
@@ -19,8 +21,81 @@
 
 using namespace pedk;
 
+// The edge records of a result live in pinned host memory: the device-to-host copy lands where the
+// caller reads them (no second copy, no first-touch page faults per join).  A result outlives joins and
+// may outlive its context, so the buffers are recycled through a small process-wide pool.
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void*, size_t>> idle;
+    void* take(size_t bytes, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = idle.size();
+            for (size_t i = 0; i < idle.size(); ++i)
+                if (idle[i].second >= bytes && (best == idle.size() || idle[i].second < idle[best].second)) best = i;
+            if (best != idle.size()) {
+                void* p = idle[best].first;
+                *cap = idle[best].second;
+                idle.erase(idle.begin() + (long)best);
+                return p;
+            }
+        }
+        size_t want = bytes + bytes / 4;
+        want = (want + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+        void* p = nullptr;
+        PEDK_CUDA_TRY(cudaHostAlloc(&p, want, cudaHostAllocPortable));
+        *cap = want;
+        return p;
+    }
+    void give(void* p, size_t cap) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (idle.size() < 4) {
+                idle.emplace_back(p, cap);
+                return;
+            }
+        }
+        cudaFreeHost(p);
+    }
+};
+PinnedPool& pinned_pool() {
+    static PinnedPool* pool = new PinnedPool();  // never destroyed: results may be freed during process exit
+    return *pool;
+}
+
+struct EdgeArray {
+    pedk_edge* p = nullptr;
+    size_t n = 0, cap_bytes = 0;
+    EdgeArray() = default;
+    EdgeArray(const EdgeArray&) = delete;
+    EdgeArray& operator=(const EdgeArray&) = delete;
+    ~EdgeArray() { pinned_pool().give(p, cap_bytes); }
+    void reserve(size_t count) {
+        if (count * sizeof(pedk_edge) <= cap_bytes) return;
+        size_t cap = 0;
+        pedk_edge* q = static_cast<pedk_edge*>(pinned_pool().take(count * sizeof(pedk_edge), &cap));
+        if (n) memcpy(static_cast<void*>(q), p, n * sizeof(pedk_edge));
+        pinned_pool().give(p, cap_bytes);
+        p = q;
+        cap_bytes = cap;
+    }
+    void push_back(const pedk_edge& e) {
+        if ((n + 1) * sizeof(pedk_edge) > cap_bytes) reserve(n + n / 2 + 64);
+        p[n++] = e;
+    }
+    size_t size() const { return n; }
+    pedk_edge* data() { return p; }
+    const pedk_edge* data() const { return p; }
+    pedk_edge* begin() { return p; }
+    pedk_edge* end() { return p + n; }
+    const pedk_edge& operator[](size_t i) const { return p[i]; }
+};
+}  // namespace
+
 struct pedk_result {
-    std::vector<pedk_edge> edges;                           // unordered until finalised
+    EdgeArray edges;                                        // unordered until finalised
     std::vector<std::pair<uint64_t, std::string>> quirks;   // literal lines of the F7 rows
     std::string text;
     int k = 0;
@@ -228,8 +303,8 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         if (h_first[i] != ~0ull) plist.push_back(h_first[i] >> 2);
     std::sort(plist.begin(), plist.end());
     plist.erase(std::unique(plist.begin(), plist.end()), plist.end());
+    const std::vector<unsigned long long> first(h_first, h_first + 128);
     uint64_t E = 0;
-    unsigned char* stage = nullptr;
     if (m) {
         // ---- (3) second binning level: exact bucket sizes, offsets, scatter ----
         const unsigned TILE = sub_tile_keys();
@@ -296,11 +371,14 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         // EdgeRec and pedk_edge share one layout (quirk = first pad byte = 0): the records go through
         // a pinned staging buffer of the context straight into the result
         static_assert(sizeof(EdgeRec) == sizeof(pedk_edge), "edge record layout");
-        stage = static_cast<unsigned char*>(host_stage(ctx, E * sizeof(EdgeRec) + 2048));
+        res->edges.reserve(E + plist.size() + 64);  // + the first-of-bucket rows the host adds below
+        res->edges.n = E;
         groups.resize(plist.size());
         {
             StageScope sc(ctx, PEDK_ST_COPY, 0);
-            if (E) PEDK_CUDA_TRY(cudaMemcpyAsync(stage, edges.p, E * sizeof(EdgeRec), cudaMemcpyDeviceToHost, st));
+            if (E)
+                PEDK_CUDA_TRY(cudaMemcpyAsync(static_cast<void*>(res->edges.data()), edges.p, E * sizeof(EdgeRec),
+                                              cudaMemcpyDeviceToHost, st));
         }
         // ---- first-of-bucket rows: look the groups up and evaluate their text on the host ----
         if (!plist.empty()) {
@@ -313,15 +391,6 @@ void do_join(pedk_ctx* ctx, pedk_sample* control, pedk_sample* target, pedk_resu
         ctx->stats.d2h_bytes += E * sizeof(EdgeRec) + plist.size() * sizeof(GroupRec);
         trace(ctx, "join: bins + buckets + edges + D2H");
     }
-    // h_first lives in the same pinned buffer host_stage may have re-allocated: take it again
-    std::vector<unsigned long long> first(128);
-    PEDK_CUDA_TRY(cudaMemcpyAsync(first.data(), d_first, 128 * 8, cudaMemcpyDeviceToHost, st));
-    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
-
-    trace(ctx, "  join: first rows back");
-    res->edges.resize(E);
-    if (E) memcpy(static_cast<void*>(res->edges.data()), stage, E * sizeof(pedk_edge));
-    trace(ctx, "  join: edges copied");
     auto& quirks = res->quirks;
     for (const GroupRec& g : groups) {
         bool pc = g.hasc[0] | g.hasc[1] | g.hasc[2] | g.hasc[3];

@@ -1,5 +1,7 @@
 // Device-resident state of one sample (internal).
 #pragma once
+#include <functional>
+#include <string>
 #include <vector>
 
 #include "ctx.h"
@@ -96,4 +98,9 @@ std::string ref20_text(pedk_sample* s, int tag);
 std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len);
 std::string cnv_text(pedk_sample* ref, pedk_sample* control, pedk_sample* target);
 std::string kmer_string(uint64_t v, int k);
+// f2 (verify.cu): the text of a chromosome file ("chr" + name) or null when there is none
+typedef std::function<const std::string*(const std::string&)> ChromosomeLookup;
+std::string verify_text(pedk_sample* target, pedk_sample* control, const ChromosomeLookup& chromosome, const char* map,
+                        uint64_t map_len);
+std::string vcf_text(const char* snp, uint64_t snp_len, const std::string& target);
 }  // namespace pedk

@@ -1,0 +1,506 @@
+// f2: read-level verification and genotype of the mapped candidates, and toVcf.
+//
+// What ped.pl does between the position map and <target>.kmer.snp (ped.pl:380-387):
+//   snpMkT   (2087-2229)  every candidate `chr pos ref alt` -> the L windows of the reference around it
+//                         ("tw") and of the reference with the alternative allele put in ("tm"), L = the
+//                         target's read length; up to ten earlier candidates of the chromosome that fall
+//                         into the window are put in as well
+//   sortSeq, joinTarget (2622-2641, 2601-2620)  the windows that ARE reads of the target (`join` with the
+//                         sort_uniq files)
+//   snpMkC, sortSeq, joinControl (2231-2305, 2576-2599)  the same against the control, with its read length
+//   kmerReadCount (2388-2500)  windows found per candidate and kind -> cw cm tw tm, genotype M/H/R/N,
+//                         `join` with the map lines -> <target>.kmer.snp
+//
+// Here the windows never become text files: the two strings of a candidate (2L-1 reference bases, and the
+// mutant) go to HBM once, one warp per window packs it like a read, makes it canonical and looks it up in
+// the hash table of the sample's de-duplicated reads (`k_probe_windows`, ingest.cu; the table is k_dedup's).
+// sort_uniq holds both strands of every read, so "the window is a line of sort_uniq" is "its canonical form
+// is one of the unique canonical reads".  Everything that is text in ped.pl (split on blanks, zero padding,
+// the order of `sort` and of `sort keys`, `join` on the first field) is kept as text on the host: it is a few
+// hundred bytes per candidate.  Bytewise (C locale) order throughout.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "sample.h"
+
+namespace pedk {
+
+namespace {
+
+typedef std::vector<std::string> Row;
+
+// Perl's split(' ', $_): leading blanks ignored, fields separated by runs of blanks, no trailing empty field
+Row split_blanks(const char* p, size_t n) {
+    Row r;
+    size_t i = 0;
+    while (i < n) {
+        while (i < n && (p[i] == ' ' || p[i] == '\t' || p[i] == '\n' || p[i] == '\r' || p[i] == '\f' || p[i] == '\v')) ++i;
+        size_t a = i;
+        while (i < n && !(p[i] == ' ' || p[i] == '\t' || p[i] == '\n' || p[i] == '\r' || p[i] == '\f' || p[i] == '\v')) ++i;
+        if (i > a) r.emplace_back(p + a, i - a);
+    }
+    return r;
+}
+Row split_blanks(const std::string& s) { return split_blanks(s.data(), s.size()); }
+
+const std::string kEmpty;
+const std::string& field(const Row& r, size_t i) { return i < r.size() ? r[i] : kEmpty; }  // undef prints as ""
+
+bool all_digits(const std::string& s) {
+    if (s.empty()) return false;
+    for (char c : s)
+        if (c < '0' || c > '9') return false;
+    return true;
+}
+
+// numeric value of a string the way `$x += 0` / `$x < $y` see it (the fields here are integers or not numbers)
+long long perl_int(const std::string& s) {
+    size_t i = 0;
+    while (i < s.size() && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n')) ++i;
+    bool neg = false;
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) neg = s[i++] == '-';
+    long long v = 0;
+    while (i < s.size() && s[i] >= '0' && s[i] <= '9') v = v * 10 + (s[i++] - '0');
+    return neg ? -v : v;
+}
+
+std::string pad_chr(const std::string& c) {  // ped.pl:2106-2109
+    if (!all_digits(c)) return c;
+    std::string t = "000" + c;
+    return t.substr(t.size() - 3);
+}
+
+std::string pad_pos(const std::string& p) {  // ped.pl:2110-2111
+    std::string t = "000000000000" + p;
+    return t.substr(t.size() - 11);
+}
+
+std::string strip_zeros(const std::string& c) {  // s/^0+//
+    size_t i = 0;
+    while (i < c.size() && c[i] == '0') ++i;
+    return c.substr(i);
+}
+
+std::vector<std::string> lines_of(const char* p, uint64_t n) {
+    std::vector<std::string> v;
+    uint64_t a = 0;
+    while (a < n) {
+        const char* e = (const char*)memchr(p + a, '\n', n - a);
+        uint64_t b = e ? (uint64_t)(e - p) : n;
+        v.emplace_back(p + a, b - a);
+        a = b + 1;
+    }
+    return v;
+}
+
+struct Candidate {
+    std::string chr, ref, alt;  // chr without leading zeros
+    long long pos = 0;
+};
+
+// snpMkT up to snp.list (ped.pl:2094-2152)
+std::vector<Candidate> candidates_of(const std::vector<std::string>& map_lines) {
+    std::vector<std::string> tmp;
+    tmp.reserve(map_lines.size());
+    for (const std::string& line : map_lines) {
+        Row row = split_blanks(line);
+        const std::string ref = field(row, 4);
+        std::string alt = field(row, 5);
+        if (!ref.empty()) {
+            size_t at = alt.find(ref);  // $alt =~ s/$ref//: ref is a nucleotide here (mapKmerSub prints it only if it is one)
+            if (at != std::string::npos) alt.erase(at, ref.size());
+        }
+        tmp.push_back(pad_chr(field(row, 0)) + " " + pad_pos(field(row, 1)) + " " + ref + " " + alt);
+    }
+    std::sort(tmp.begin(), tmp.end());
+    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    std::vector<Candidate> out;
+    std::string prev;
+    bool first = true;
+    for (const std::string& line : tmp) {
+        Row row = split_blanks(line);
+        const std::string relined = field(row, 0) + " " + field(row, 1) + " " + field(row, 2) + " " + field(row, 3);
+        if (!first && relined == prev) continue;  // `uniq -c`
+        first = false;
+        prev = relined;
+        Row r2 = split_blanks(relined);           // ($count, $chr, $pos, $ref, $alt) = split, the count in front
+        Candidate c;
+        c.chr = strip_zeros(field(r2, 0));
+        c.pos = perl_int(field(r2, 1));
+        c.ref = field(r2, 2);
+        c.alt = field(r2, 3);
+        out.push_back(std::move(c));
+    }
+    return out;
+}
+
+// The two strings of every candidate for read length L (ped.pl:2153-2196 / 2246-2291): index 2c = the
+// reference around the candidate, 2c+1 = the mutant; an empty pair where ped.pl says `next`.
+struct Strings {
+    std::vector<char> text;
+    std::vector<uint64_t> start;
+    std::vector<uint32_t> length;
+};
+
+Strings strings_of(const std::vector<Candidate>& cand, const ChromosomeLookup& chromosome, long long L) {
+    Strings s;
+    s.start.reserve(cand.size() * 2);
+    s.length.reserve(cand.size() * 2);
+    std::string prev_chr;
+    bool have_prev = false;
+    const std::string* seq = nullptr;
+    std::vector<std::string> dat;  // "$pos $ref $alt" of the last candidates of this chromosome (ped.pl:2171-2176)
+    auto push = [&](const std::string& str) {
+        s.start.push_back(s.text.size());
+        s.length.push_back((uint32_t)str.size());
+        s.text.insert(s.text.end(), str.begin(), str.end());
+    };
+    for (const Candidate& c : cand) {
+        if (!have_prev || prev_chr != c.chr) {
+            seq = chromosome("chr" + c.chr);  // open(IN, "$refdir/chr$chr"): a file that is not there reads as nothing
+            dat.clear();
+        }
+        have_prev = true;
+        prev_chr = c.chr;
+        // $count = int(1 + 25/4) = 7 >= 5: always pushed (ped.pl:2158, 2169-2176)
+        dat.push_back(std::to_string(c.pos) + " " + c.ref + " " + c.alt);
+        if (dat.size() > 10) dat.erase(dat.begin());
+        std::string ref_seq, mut_seq;
+        bool skip = c.pos - L < 0 || !seq;
+        if (!skip) {
+            const unsigned long long at = (unsigned long long)(c.pos - L);
+            if (at < seq->size()) ref_seq = seq->substr(at, (size_t)(2 * L - 1));
+            skip = (long long)ref_seq.size() != 2 * L - 1;
+        }
+        if (skip) {
+            push(std::string());
+            push(std::string());
+            continue;
+        }
+        mut_seq = ref_seq.substr(0, (size_t)(L - 1)) + c.alt + ref_seq.substr((size_t)L);
+        for (const std::string& d : dat) {
+            const Row r = split_blanks(d);  // ($tpos, $iref, $ialt) = split
+            const std::string& ialt = field(r, 2);
+            const long long i = perl_int(field(r, 0)) - (c.pos - L) - 1;
+            if (i > 0 && i < 2 * L && i != L - 1) {
+                const size_t ui = (size_t)i;
+                std::string head = mut_seq.substr(0, std::min(ui, mut_seq.size()));
+                std::string tail = ui + 1 <= mut_seq.size() ? mut_seq.substr(ui + 1) : std::string();
+                mut_seq = head + ialt + tail;
+            }
+        }
+        push(ref_seq);
+        push(mut_seq);
+    }
+    return s;
+}
+
+// windows of every string that are reads of the sample -> hits per string
+std::vector<uint32_t> probe(pedk_sample* smp, const Strings& s, int L) {
+    std::vector<uint32_t> hits(s.start.size(), 0);
+    if (s.start.empty() || L <= 0) return hits;
+    const ReadGroup* g = nullptr;
+    for (const ReadGroup& x : smp->groups)
+        if (x.L == L && x.n) g = &x;
+    if (!g) return hits;  // no read of this length: nothing joins
+    pedk_ctx* ctx = smp->ctx;
+    cudaStream_t st = ctx->stream;
+    if (g->n > (1ull << 30)) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^30 unique reads in one length group");
+    uint64_t cap64 = 1024;
+    while (cap64 < 2 * g->n) cap64 <<= 1;
+    DBuf<uint32_t> table(ctx, cap64);
+    DBuf<uint8_t> uniq(ctx, g->n);
+    DBuf<uint8_t> d_text(ctx, s.text.size() + 64);
+    DBuf<uint64_t> d_start(ctx, s.start.size());
+    DBuf<uint32_t> d_len(ctx, s.length.size());
+    DBuf<uint32_t> d_hits(ctx, hits.size());
+    StageScope sc(ctx, PEDK_ST_EDGES, 2);
+    PEDK_CUDA_TRY(cudaMemsetAsync(table.p, 0xFF, table.bytes(), st));
+    launch_dedup(g->words.p, g->W, (uint32_t)g->n, table.p, (uint32_t)cap64, nullptr, uniq.p, st);
+    if (!s.text.empty())
+        PEDK_CUDA_TRY(cudaMemcpyAsync(d_text.p, s.text.data(), s.text.size(), cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_start.p, s.start.data(), s.start.size() * 8, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemcpyAsync(d_len.p, s.length.data(), s.length.size() * 4, cudaMemcpyHostToDevice, st));
+    PEDK_CUDA_TRY(cudaMemsetAsync(d_hits.p, 0, d_hits.bytes(), st));
+    launch_probe_windows(d_text.p, d_start.p, d_len.p, s.start.size(), L, g->W, g->words.p, table.p, (uint32_t)cap64,
+                         d_hits.p, st);
+    PEDK_CUDA_TRY(cudaMemcpyAsync(hits.data(), d_hits.p, hits.size() * 4, cudaMemcpyDeviceToHost, st));
+    PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+    return hits;
+}
+
+char genotype(long long cw, long long cm, long long tw, long long tm) {  // ped.pl:2435-2445
+    if (cw >= 5 && cm <= 1) {
+        if (tm >= 5 && tw <= 1) return 'M';
+        if ((tm + tw) > 0 && (double)tm / (double)(tm + tw) > 0.3 && (double)tm / (double)(tm + tw) < 0.7 && cm <= 1 &&
+            tw >= 5)
+            return 'H';
+        return 'R';
+    }
+    return 'N';
+}
+
+// `join A B` on the first blank-separated field: a merge, whatever the order of the inputs (GNU join does
+// not sort); output `key rest-of-A rest-of-B` with single spaces
+std::vector<std::string> merge_join(const std::vector<std::string>& a, const std::vector<std::string>& b) {
+    std::vector<Row> ka, kb;
+    for (const std::string& x : a) ka.push_back(split_blanks(x));
+    for (const std::string& x : b) kb.push_back(split_blanks(x));
+    std::vector<std::string> out;
+    size_t i = 0, j = 0;
+    while (i < ka.size() && j < kb.size()) {
+        const std::string& x = field(ka[i], 0);
+        const std::string& y = field(kb[j], 0);
+        if (x < y) ++i;
+        else if (y < x) ++j;
+        else {
+            size_t i2 = i, j2 = j;
+            while (i2 < ka.size() && field(ka[i2], 0) == y) ++i2;
+            while (j2 < kb.size() && field(kb[j2], 0) == x) ++j2;
+            for (size_t p = i; p < i2; ++p)
+                for (size_t q = j; q < j2; ++q) {
+                    std::string l = field(ka[p], 0);
+                    for (size_t t = 1; t < ka[p].size(); ++t) l += " " + ka[p][t];
+                    for (size_t t = 1; t < kb[q].size(); ++t) l += " " + kb[q][t];
+                    out.push_back(std::move(l));
+                }
+            i = i2;
+            j = j2;
+        }
+    }
+    return out;
+}
+
+// kmerReadCount (ped.pl:2388-2500)
+std::string read_count(const std::vector<std::string>& map_lines, const std::vector<Candidate>& cand,
+                       const std::vector<uint32_t>& t_hits, const std::vector<uint32_t>& c_hits, long long length,
+                       long long clength) {
+    std::vector<std::string> mp;
+    for (const std::string& line : map_lines) {
+        Row row = split_blanks(line);
+        const long long pos = perl_int(field(row, 1));
+        if (pos < length || pos < clength) continue;
+        std::string l = pad_chr(field(row, 0)) + ":" + pad_pos(field(row, 1));
+        for (size_t i = 2; i <= 14; ++i) l += "\t" + field(row, i);
+        mp.push_back(std::move(l));
+    }
+    std::sort(mp.begin(), mp.end());
+    // %count: one entry per `chr pos ref alt kind` that has at least one window among the reads
+    std::map<std::string, long long> count;
+    static const char* kinds[4] = {"tw", "tm", "cw", "cm"};
+    for (size_t c = 0; c < cand.size(); ++c) {
+        for (int kind = 0; kind < 4; ++kind) {
+            const uint32_t n = (kind < 2 ? t_hits : c_hits)[2 * c + (kind & 1)];
+            if (!n) continue;
+            // the line `join | cut` leaves, split and re-padded (ped.pl:2412-2421)
+            Row row = split_blanks(cand[c].chr + " " + std::to_string(cand[c].pos) + " " + cand[c].ref + " " +
+                                   cand[c].alt + " " + kinds[kind]);
+            while (row.size() < 2) row.emplace_back();
+            row[0] = pad_chr(row[0]);
+            row[1] = pad_pos(row[1]);
+            std::string d = row[0];
+            for (size_t t = 1; t < row.size(); ++t) d += " " + row[t];
+            count[d] += n;
+        }
+    }
+    std::vector<std::string> verify;
+    long long cm = 0, cw = 0, tm = 0, tw = 0;
+    std::string prev;
+    auto flush = [&]() {
+        Row pr = split_blanks(prev);
+        while (pr.size() < 2) pr.emplace_back();
+        return pad_chr(pr[0]) + ":" + pad_pos(pr[1]) + "\t" + std::to_string(cw) + "\t" + std::to_string(cm) + "\t" +
+               std::to_string(tw) + "\t" + std::to_string(tm) + "\t" + genotype(cw, cm, tw, tm);
+    };
+    for (const auto& kv : count) {  // `sort keys`: bytewise
+        Row row = split_blanks(kv.first);
+        while (row.size() < 2) row.emplace_back();
+        row[0] = strip_zeros(row[0]);
+        row[1] = std::to_string(perl_int(row[1]));
+        std::string d;
+        for (size_t t = 0; t + 1 < row.size(); ++t) d += (t ? "\t" : "") + row[t];
+        if (d != prev) {
+            std::string line = flush();
+            if (!prev.empty()) verify.push_back(std::move(line));
+            cm = cw = tm = tw = 0;
+        }
+        const std::string& kind = row.back();
+        if (kind == "cm") cm = kv.second;
+        if (kind == "cw") cw = kv.second;
+        if (kind == "tm") tm = kv.second;
+        if (kind == "tw") tw = kv.second;
+        prev = d;
+    }
+    verify.push_back(flush());  // ped.pl prints the last group without looking at it (2461-2480)
+    std::string out;
+    for (const std::string& line : merge_join(mp, verify)) {
+        Row row = split_blanks(line);
+        const std::string& key = field(row, 0);
+        const size_t colon = key.find(':');
+        const std::string chr = strip_zeros(key.substr(0, colon));
+        std::string rest = colon == std::string::npos ? std::string() : key.substr(colon + 1);
+        const size_t colon2 = rest.find(':');  // split(':', ...) takes the second piece
+        if (colon2 != std::string::npos) rest.resize(colon2);
+        out += chr + "\t" + std::to_string(perl_int(rest));
+        for (size_t i = 1; i <= 18; ++i) out += "\t" + field(row, i);
+        out += "\n";
+    }
+    return out;
+}
+
+long long first_read_length(pedk_sample* s) {  // getLength (ped.pl:3486-3502): the first line of sort_uniq/*.gz
+    uint64_t live = 0;
+    int L = 0;
+    for (const ReadGroup& g : s->groups)
+        if (g.n) {
+            ++live;
+            L = g.L;
+        }
+    if (live == 0) return 0;
+    if (live == 1) return L;
+    ensure_host_reads(s);
+    for (int t = 0; t < 64; ++t)
+        if (!s->h_reads[t].empty()) return (long long)s->h_reads[t][0].size();
+    return 0;
+}
+
+// Perl prints a number with %.15g
+std::string perl_number(double x) {
+    char b[64];
+    snprintf(b, sizeof b, "%.15g", x);
+    return b;
+}
+
+// numeric value of a field for `+` (ped.pl:1560): the fields are counts, or a genotype letter in a shifted row
+double perl_double(const std::string& s) {
+    const char* p = s.c_str();
+    while (*p == ' ' || *p == '\t' || *p == '\n') ++p;
+    const char* q = p;
+    if (*q == '+' || *q == '-') ++q;
+    if (!((*q >= '0' && *q <= '9') || (*q == '.' && q[1] >= '0' && q[1] <= '9'))) return 0.0;  // not "inf"/"nan"/hex
+    return strtod(p, nullptr);
+}
+
+}  // namespace
+
+std::string verify_text(pedk_sample* target, pedk_sample* control, const ChromosomeLookup& chromosome, const char* map,
+                        uint64_t map_len) {
+    if (!target->ingested || !control->ingested || target->reads_released || control->reads_released)
+        throw PedkError(PEDK_E_INVAL, "verification needs the reads of both samples (ingested, not released)");
+    PEDK_CUDA_TRY(cudaSetDevice(target->ctx->device));
+    const long long length = first_read_length(target), clength = first_read_length(control);
+    if (length <= 0 || clength <= 0)
+        throw PedkError(PEDK_E_INVAL, "verification needs reads in both samples (ped.pl dies in read() with a negative length)");
+    const std::vector<std::string> map_lines = lines_of(map, map_len);
+    const std::vector<Candidate> cand = candidates_of(map_lines);
+    std::vector<uint32_t> t_hits, c_hits;
+    {
+        const Strings s = strings_of(cand, chromosome, length);
+        t_hits = probe(target, s, (int)length);
+    }
+    {
+        const Strings s = strings_of(cand, chromosome, clength);
+        c_hits = probe(control, s, (int)clength);
+    }
+    return read_count(map_lines, cand, t_hits, c_hits, length, clength);
+}
+
+// toVcf, method kmer (ped.pl:1532-1574)
+std::string vcf_text(const char* snp, uint64_t snp_len, const std::string& target) {
+    std::string out =
+        "##fileformat=VCFv4.2\n"
+        "##INFO=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+        "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Approximate read depth)\">\n"
+        "##INFO=<ID=AF,Number=.,Type=Float,Description=\"Allele Frequency\">\n"
+        "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+        "##FORMAT=<ID=AD,Number=.,Type=Integer,Description=\"Allelic depths for the reference and alternate alleles in "
+        "the order listed\">\n"
+        "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"Read depth\">\n"
+        "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + target + "\n";
+    std::string output, prev;
+    for (const std::string& line : lines_of(snp, snp_len)) {
+        Row row;  // split('\t', $_): trailing empty fields are dropped
+        size_t a = 0;
+        for (;;) {
+            size_t b = line.find('\t', a);
+            row.push_back(line.substr(a, b == std::string::npos ? std::string::npos : b - a));
+            if (b == std::string::npos) break;
+            a = b + 1;
+        }
+        while (!row.empty() && row.back().empty()) row.pop_back();
+        if (row.empty()) row.emplace_back();
+        if (row[0].size() <= 3 || all_digits(row[0])) row[0] = "chr" + row[0];
+        const double r17 = perl_double(field(row, 17)), r18 = perl_double(field(row, 18));
+        const double dp = r17 + r18;
+        if (dp == 0) continue;
+        const double af = (trunc(1000 * r18 / dp) + 0.0) / 1000;  // int() gives an integer: no negative zero
+        const double p = pow(0.001 * dp, r18);
+        const double qual = p == 0 ? 1000 : (trunc((-10 * log(p) / log(10.0)) * 1000) + 0.0) / 1000;
+        const bool m = line.find('M') != std::string::npos, h = line.find('H') != std::string::npos;
+        if (m || h)
+            output = row[0] + "\t" + field(row, 1) + "\t.\t" + field(row, 4) + "\t" + field(row, 5) + "\t" +
+                     perl_number(qual) + "\t.\tGT=" + (m ? "1/1" : "0/1") + ";AF=" + perl_number(af) + ";DP=" +
+                     field(row, 18) + "\tGT:AD:DP\t" + (m ? "1/1" : "0/1") + ":" + field(row, 17) + "," + field(row, 18) +
+                     ":" + perl_number(dp) + "\n";
+        if (output != prev) out += output;
+        prev = output;
+    }
+    return out;
+}
+
+}  // namespace pedk
+
+using namespace pedk;
+
+static char* dup_text(const std::string& s, uint64_t* len) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (!p) throw std::bad_alloc();
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    *len = s.size();
+    return p;
+}
+
+extern "C" int pedk_verify_text(pedk_sample* target, pedk_sample* control, pedk_sample* ref, const char* map_text,
+                                uint64_t map_len, char** text, uint64_t* len) {
+    if (!target || !control || !ref || (!map_text && map_len) || !text || !len) return PEDK_E_INVAL;
+    PEDK_API_BEGIN
+    // the chromosome files of the reference sample (reference.cu), fetched from HBM when a candidate needs them
+    std::map<std::string, std::string> cache;
+    ChromosomeLookup lookup = [&](const std::string& name) -> const std::string* {
+        auto it = cache.find(name);
+        if (it != cache.end()) return &it->second;
+        int found = -1;
+        for (size_t i = 0; i < ref->chromosomes.size(); ++i)
+            if (ref->chromosomes[i].live && ref->chromosomes[i].name == name) found = (int)i;
+        if (found < 0) return nullptr;
+        const uint64_t n = ref->chromosomes[(size_t)found].length;
+        std::string seq((size_t)n, '\0');
+        int rc = pedk_sample_chromosome(ref, found, nullptr, 0, nullptr, nullptr, n ? &seq[0] : nullptr, n);
+        if (rc) throw PedkError(rc, ref->ctx->err);
+        return &(cache[name] = std::move(seq));
+    };
+    *text = dup_text(verify_text(target, control, lookup, map_text, map_len), len);
+    return PEDK_OK;
+    PEDK_API_END(target->ctx)
+}
+
+extern "C" int pedk_vcf_text(const char* kmer_snp, uint64_t snp_len, const char* target_name, char** text,
+                             uint64_t* len) {
+    if ((!kmer_snp && snp_len) || !target_name || !text || !len) return PEDK_E_INVAL;
+    try {
+        *text = dup_text(vcf_text(kmer_snp, snp_len, target_name), len);
+        return PEDK_OK;
+    } catch (...) {
+        return PEDK_E_NOMEM;
+    }
+}

@@ -122,6 +122,25 @@ map_kmer(wd, target, ref, tmpdir)
     check(aTHX_ pedk_map_kmer(ctx_or_croak(aTHX), wd, target, ref, tmpdir), "map_kmer");
 
 void
+verify_kmer(wd, target, control, ref, tmpdir)
+    const char *wd
+    const char *target
+    const char *control
+    const char *ref
+    const char *tmpdir
+  CODE:
+    /* snpMkT, sortSeq, joinTarget, snpMkC, sortSeq, joinControl, kmerReadCount (ped.pl:380-386) */
+    check(aTHX_ pedk_verify_kmer(ctx_or_croak(aTHX), wd, target, control, ref, tmpdir), "verify_kmer");
+
+void
+to_vcf(wd, target)
+    const char *wd
+    const char *target
+  CODE:
+    /* toVcf, method kmer (ped.pl:387, 1532-1574) */
+    check(aTHX_ pedk_to_vcf(ctx_or_croak(aTHX), wd, target), "to_vcf");
+
+void
 cnv(wd, target, control, ref, k)
     const char *wd
     const char *target

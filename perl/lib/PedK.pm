@@ -8,6 +8,9 @@ package PedK;
 #   PedK::mk_control_read($wd, $ref, $file)        -> ped.pl mkChrFromFile + mkControlRead (1027-1136)
 #   PedK::mk_ref20_uniq($wd, $ref, $file, $k)      -> ped.pl mk20        (1213-1249: mk20mer + mkUniq)
 #   PedK::map_kmer($wd, $t, $ref, $tmpdir)         -> ped.pl mapKmer     (625-685)
+#   PedK::verify_kmer($wd, $t, $c, $ref, $tmpdir)  -> ped.pl snpMkT, sortSeq, joinTarget, snpMkC, sortSeq, joinControl,
+#                                                     kmerReadCount (2087-2305, 2576-2641, 2388-2500)
+#   PedK::to_vcf($wd, $t)                          -> ped.pl toVcf, method kmer (1532-1574)
 #   PedK::cnv($wd, $t, $c, $ref, $k)               -> ped.pl cnvJoin     (934-989)
 # Every sub dies with the library's message on failure; there is no CPU fallback.
 use strict;

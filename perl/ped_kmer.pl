@@ -14,7 +14,9 @@
 # (ped.pl:1017-1025: <wd>/REF/chrNAME, REF/ref20_uniq.TAG.gz and the control reads in
 # REF/sort_uniq/); a later `target=T,control=REF` then compares T with the tiled reference.
 # With `ref=REF` the per-tag edge files go to tmpdir and are mapped to positions
-# (<tmpdir>/<t>.map.TAG, ped.pl:625-685); the read-level stages after that stay ped.pl's.
+# (<tmpdir>/<t>.map.TAG, ped.pl:625-685), the candidates are verified against the reads of both
+# samples and genotyped (<wd>/<t>/<t>.kmer.snp with 20 columns, ped.pl:380-386) and written as VCF
+# (<t>.kmer.vcf, ped.pl:387); `primer` (ped.pl:388) stays ped.pl's.
 # `method=cnv` writes <wd>/<t>/<t>.<c>.cnv (ped.pl:362-366, 934-989).
 #
 use strict;
@@ -109,6 +111,10 @@ if ($method eq "cnv") {
     if ($ref ne "") {
         report("Mapping SNPs between $target and $control");
         PedK::map_kmer($wd, $target, $ref, $tmpdir);
+        report("Verifying SNPs with the reads of $target and $control");   # ped.pl:380-386
+        PedK::verify_kmer($wd, $target, $control, $ref, $tmpdir);
+        report("Converting to VCF format");                                # ped.pl:387
+        PedK::to_vcf($wd, $target);
     }
 }
 my $ms = PedK::stage_ms();

@@ -174,3 +174,51 @@ def make_cnv_inputs(case):
     fc = api.synth_fastq(g, 3000 + c, case["reads"], read_len=case["L"], err_ppm=case["err_ppm"], n_ppm=case["n_ppm"],
                          dup_ppm=case["dup_ppm"])
     return fa, fc, ft
+
+
+def make_verify_inputs(seed: int, L: int = 100, CL: int = 80, chrom_len: int = 5000, coverage: int = 40):
+    """-> (reference FASTA, control FASTQ, target FASTQ) for the read-level verification (SURVEY row f2,
+    ped.pl:2087-2500): three chromosomes ("1", "2", "scX"), a diploid target with homozygous and
+    heterozygous SNPs, SNPs 3 / 25 / 80 bases apart (a window then carries its neighbours, ped.pl:2184-2192),
+    one closer to the start of a chromosome than a read is long and one that close to its end, control reads
+    of another length (CL) drawn from the reference itself."""
+    import random
+    rnd = random.Random(seed)
+    names = ["1", "2", "scX"]
+    ref = {n: [rnd.choice("ACGT") for _ in range(chrom_len)] for n in names}
+
+    def other(b):
+        return rnd.choice([x for x in "ACGT" if x != b])
+
+    hap = [{n: list(s) for n, s in ref.items()}, {n: list(s) for n, s in ref.items()}]
+    for n in names:
+        sites = [(40, "hom"), (chrom_len - 50, "hom"), (700, "hom"), (703, "hom"), (1500, "het"), (1525, "hom"),
+                 (2300, "hom"), (2380, "het"), (3000, "het"), (3600, "hom")]
+        sites += [(p, rnd.choice(["hom", "het"])) for p in rnd.sample(range(3700, chrom_len - 200), 6)]
+        for p, kind in sites:
+            a = other(ref[n][p])
+            hap[0][n][p] = a
+            if kind == "hom":
+                hap[1][n][p] = a
+
+    def reads(genomes, length, cov, tag):
+        out = []
+        i = 0
+        for g in genomes:
+            for n in names:
+                s = "".join(g[n])
+                for _ in range(len(s) * cov // (length * len(genomes))):
+                    a = rnd.randrange(0, len(s) - length + 1)
+                    r = s[a:a + length]
+                    if rnd.random() < 0.5:
+                        r = r[::-1].translate(str.maketrans("ACGT", "TGCA"))
+                    if rnd.random() < 0.05:   # a sequencing error
+                        q = rnd.randrange(length)
+                        r = r[:q] + other(r[q]) + r[q + 1:]
+                    out.append(f"@{tag}{i}\n{r}\n+\n{'I' * length}\n")
+                    i += 1
+        rnd.shuffle(out)
+        return "".join(out).encode()
+
+    fa = "".join(f">{n}\n" + "\n".join("".join(ref[n])[i:i + 60] for i in range(0, chrom_len, 60)) + "\n" for n in names)
+    return fa.encode(), reads([ref], CL, coverage, "c"), reads(hap, L, coverage, "t")

@@ -98,7 +98,39 @@ def test_perl_binding_builds_and_loads(built):
     subprocess.run(["sh", os.path.join(ROOT, "perl", "build.sh")], check=True)
     r = subprocess.run(["perl", "-I" + os.path.join(ROOT, "perl", "lib"), "-MPedK", "-e",
                         "print PedK::abi_version(), ' ', join(',', map { defined &{\"PedK::$_\"} ? 1 : 0 } "
-                        "qw(mk_sort_uniq mk_control_read mk_ref20_uniq count_kmer lbc_kmer join_kmer map_kmer cnv))"],
+                        "qw(mk_sort_uniq mk_control_read mk_ref20_uniq count_kmer lbc_kmer join_kmer map_kmer verify_kmer to_vcf cnv))"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.split()[0] == "1" and r.stdout.split()[1] == "1,1,1,1,1,1,1,1"
+    assert r.stdout.split()[0] == "1" and r.stdout.split()[1] == "1,1,1,1,1,1,1,1,1,1"
+
+
+def test_vcf_writer_is_host_only_and_matches_the_reference(built):
+    """pedk_vcf_text (toVcf, ped.pl:1532-1574) makes no CUDA call, so it runs here: against ped.pl's own
+    T.kmer.vcf (tests/golden/ref30k_verify.json) and, on made-up rows that exercise the quirks (rows whose
+    fields shifted, an M or H anywhere in the line, a line that repeats, depth 0, names longer than three
+    characters), against the line-by-line restatement (oracle/verify_ref.py)."""
+    import json
+    import random
+
+    from oracle import verify_ref
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref30k_verify.json")))
+    for v in ("control_reads", "control_ref"):
+        assert api.vcf_text(g[v]["kmer_snp"].encode(), "T").decode() == g[v]["kmer_vcf"]
+    rnd = random.Random(11)
+    lines = []
+    for i in range(400):
+        chrom = rnd.choice(["1", "12", "scaffoldM", "chrH", "X", "0007", "MT"])
+        f = [chrom, str(rnd.randrange(1, 10 ** 6)), "ACGTACGTACGTACGTACG", "A", "A", rnd.choice(["C", "CT", "G"]),
+             rnd.choice("fr")] + [str(rnd.randrange(0, 60)) for _ in range(8)]
+        f += [str(rnd.randrange(0, 40)), str(rnd.randrange(0, 3)), str(rnd.choice([0, 0, 1, 17, 333])),
+              str(rnd.choice([0, 0, 2, 29, 700])), rnd.choice("MHRN")]
+        if rnd.random() < 0.15:            # an F7 row: a field is missing, the rest moved left, empty fields behind
+            del f[rnd.randrange(7, 15)]
+            f += [""] * 3
+        lines.append("\t".join(f) + "\n")
+        if rnd.random() < 0.1:
+            lines.append(lines[-1])
+    text = "".join(lines)
+    assert api.vcf_text(text.encode(), "sample_1").decode() == verify_ref.to_vcf(text, "sample_1")
+    assert api.vcf_text(b"", "T").decode() == verify_ref.to_vcf("", "T")

@@ -136,8 +136,16 @@ def test_reference_as_control_file_contract(built, tmp_path, gz):
     tmpdir = f"{wd}/T/tmp"
     ctx.check(lib.pedk_join_kmer(ctx.h, wd.encode(), b"T", b"REF", 20, tmpdir.encode(), 1))
     ctx.check(lib.pedk_map_kmer(ctx.h, wd.encode(), b"T", b"REF", tmpdir.encode()))
+    # f2 + toVcf (ped.pl:380-387): snpMkT ... kmerReadCount in one call, then the VCF
+    ctx.check(lib.pedk_verify_kmer(ctx.h, wd.encode(), b"T", b"REF", b"REF", tmpdir.encode()))
+    ctx.check(lib.pedk_to_vcf(ctx.h, wd.encode(), b"T"))
     assert lib.pedk_mk_control_read(ctx.h, wd.encode(), b"REF", b"nosuch.fa") == -4
     ctx.close()
+    gv = json.load(open(os.path.join(GOLDEN, "ref30k_verify.json")))["control_ref"]
+    assert open(f"{wd}/T/T.kmer.snp").read() == gv["kmer_snp"]
+    assert open(f"{wd}/T/T.kmer.vcf").read() == gv["kmer_vcf"]
+    os.unlink(f"{wd}/T/T.kmer.snp")
+    os.unlink(f"{wd}/T/T.kmer.vcf")
     # f1: <ref>/ref20_uniq.TAG.gz and <tmpdir>/<t>.map.TAG as ped.pl leaves them
     g = json.load(open(os.path.join(GOLDEN, "ref30k.json")))
     for i, tag in enumerate(TAGS):
@@ -153,6 +161,12 @@ def test_reference_as_control_file_contract(built, tmp_path, gz):
     ctx = api.Context(0)
     ctx.check(ctx.lib.pedk_map_kmer(ctx.h, wd.encode(), b"T", b"REF", tmpdir.encode()))
     ctx.close()
+    ctx = api.Context(0)   # the verification from the sort_uniq, map and chromosome files alone
+    ctx.check(ctx.lib.pedk_verify_kmer(ctx.h, wd.encode(), b"T", b"REF", b"REF", tmpdir.encode()))
+    ctx.check(ctx.lib.pedk_to_vcf(ctx.h, wd.encode(), b"T"))
+    ctx.close()
+    assert open(f"{wd}/T/T.kmer.snp").read() == gv["kmer_snp"]
+    assert open(f"{wd}/T/T.kmer.vcf").read() == gv["kmer_vcf"]
     for i, tag in enumerate(TAGS):
         assert _zcat(f"{wd}/REF/ref20_uniq.{tag}.gz") == oracle.ref20_uniq_text(fa, i)
         assert open(f"{tmpdir}/T.map.{tag}").read() == g["map"].get(tag, "")
@@ -234,3 +248,7 @@ def test_perl_drop_in_command_line(built, tmp_path):
         assert _zcat(f"{wd2}/REF/ref20_uniq.{tag}.gz") == oracle.ref20_uniq_text(fa, i)
         assert open(f"{wd2}/T/tmp/T.map.{tag}").read() == g["map"].get(tag, "")
     assert "".join(open(f"{wd2}/T/tmp/T.snp.{t}").read() for t in TAGS) == g["kmer_snp"]
+    # ... and the verified, genotyped candidates and their VCF (ped.pl:380-387)
+    gv = json.load(open(os.path.join(GOLDEN, "ref30k_verify.json")))["control_ref"]
+    assert open(f"{wd2}/T/T.kmer.snp").read() == gv["kmer_snp"]
+    assert open(f"{wd2}/T/T.kmer.vcf").read() == gv["kmer_vcf"]

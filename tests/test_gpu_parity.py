@@ -458,3 +458,92 @@ def test_cnv_against_the_reference(ctx):
         e.destroy()
     finally:
         r.destroy(); c.destroy(); t.destroy()
+
+
+def _verify_through_the_library(ctx, fa, fc, ft):
+    """reference + control + target -> edges -> position map -> `<t>.kmer.snp` of a run with a reference,
+    all through the C ABI; fc None: the tiled reference is the control (ped.pl:193)."""
+    r, t = api.Sample(ctx), api.Sample(ctx)
+    c = api.Sample(ctx) if fc is not None else r
+    res = None
+    try:
+        r.add_fastq(fa)
+        r.ingest_reference()
+        r.ref20_uniq(20)
+        t.add_fastq(ft)
+        t.ingest()
+        if fc is not None:
+            c.add_fastq(fc)
+            c.ingest()
+        c.count(20)
+        t.count(20)
+        res = ctx.join(c, t)
+        edges = res.text()
+        map_text = r.map_kmer_text(edges)
+        return edges, map_text, r.verify_text(c, t, map_text)
+    finally:
+        if res is not None:
+            res.destroy()
+        r.destroy(); t.destroy()
+        if c is not r:
+            c.destroy()
+
+
+@pytest.mark.parametrize("variant", ["control_reads", "control_ref"])
+def test_verification_against_the_reference(ctx, variant):
+    """f2: snpMkT, sortSeq, joinTarget, snpMkC, joinControl, kmerReadCount (ped.pl:2087-2305,
+    2576-2641, 2388-2500) and toVcf (1532-1574) against ped.pl's own T.kmer.snp / T.kmer.vcf of a
+    `method=kmer` run with a reference (tests/golden/ref30k_verify.json, scripts/make_golden_verify.py):
+    with sequenced control reads (both samples 150 bp) and with the tiled reference as the control
+    (150 bp target, 100 bp control)."""
+    from tests.cases import make_cnv_inputs
+
+    g = json.load(open(os.path.join(GOLDEN, "ref30k_verify.json")))[variant]
+    fa, fc, ft = make_cnv_inputs(REF_CASES["ref30k"])
+    _, _, snp = _verify_through_the_library(ctx, fa, fc if variant == "control_reads" else None, ft)
+    assert snp.decode() == g["kmer_snp"]
+    assert api.vcf_text(snp, "T").decode() == g["kmer_vcf"]
+
+
+@pytest.mark.parametrize("seed,L,CL", [(1, 100, 80), (2, 100, 100), (3, 64, 97), (4, 150, 33), (5, 33, 150)])
+def test_verification_against_the_restatement(ctx, seed, L, CL):
+    """f2 on a diploid target: heterozygous and homozygous SNPs, SNPs 3 / 25 / 80 bases apart (their windows
+    carry each other, ped.pl:2184-2192), candidates closer to a chromosome end than a read is long, control
+    reads of another length, F7 rows whose fields shift -- against the line-by-line restatement of the
+    Perl (oracle/verify_ref.py, itself pinned to ped.pl's output) over the oracle's map and read sets."""
+    from oracle import verify_ref
+    from tests.cases import make_verify_inputs
+    from tests.test_oracle import verification_inputs
+
+    fa, fc, ft = make_verify_inputs(seed, L=L, CL=CL)
+    edges, map_text, snp = _verify_through_the_library(ctx, fa, fc, ft)
+    oc, ot, oedges = oracle.run(fc, ft, 20)
+    assert edges == oedges
+    omap, t_lines, c_lines, chromosomes = verification_inputs(fa, oc, ot, oedges)
+    assert map_text == omap
+    want = verify_ref.verify(omap.decode().splitlines(), t_lines, c_lines, chromosomes)
+    assert snp.decode() == want
+    kinds = set(line.split("\t")[-1] for line in want.splitlines())
+    assert {"M", "R"} <= kinds
+    assert api.vcf_text(snp, "T").decode() == verify_ref.to_vcf(want, "T")
+
+
+def test_verification_corner_inputs(ctx):
+    """f2: an empty map gives ped.pl's lone last-group line joined with nothing (an empty file); a map whose
+    chromosome has no file, and a sample without reads (ped.pl dies in read(); here an error code)."""
+    from tests.cases import make_verify_inputs
+
+    fa, fc, ft = make_verify_inputs(7, L=50, CL=50, chrom_len=4200, coverage=10)
+    r, c, t, e = api.Sample(ctx), api.Sample(ctx), api.Sample(ctx), api.Sample(ctx)
+    try:
+        r.add_fastq(fa); r.ingest_reference()
+        c.add_fastq(fc); c.ingest()
+        t.add_fastq(ft); t.ingest()
+        e.add_fastq(b""); e.ingest()
+        assert r.verify_text(c, t, b"") == b""
+        line = b"nosuch\t500\tAAAAAAAAAAAAAAAAAAA\tC\tC\tG\tf\t0\t9\t0\t0\t0\t0\t9\t0\n"
+        assert r.verify_text(c, t, line) == b""
+        with pytest.raises(api.PedkError):
+            r.verify_text(e, t, line)
+    finally:
+        r.destroy(); c.destroy(); t.destroy(); e.destroy()
