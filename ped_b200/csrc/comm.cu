@@ -456,12 +456,19 @@ void route_rows(pedk_ctx* ctx, const uint64_t* const* src_key, const uint32_t* c
 // Every rank publishes the IPC handle of one of its device blocks; the others map it once
 // (the caching allocator hands the same block to the same stage on every step, so the
 // mapping is reused) and can then store into it from their own kernels.
+// Peer blocks mapped into this process.  The allocators hand the same blocks out step after step, so
+// the set of live handles is small; a mapping that has not been asked for during the last kIpcKeep
+// requests for its peer is closed (a block its owner no longer uses would otherwise stay mapped --
+// and allocated -- for the life of the context).
+constexpr size_t kIpcKeep = 12;
 struct IpcCache {
     struct Entry {
         cudaIpcMemHandle_t h;
         void* p;
+        uint64_t last_use;
     };
     std::vector<Entry> entries[PEDK_MAX_RANKS];
+    uint64_t clock = 0;
 };
 
 static IpcCache* ipc_cache(pedk_ctx* ctx) {
@@ -486,6 +493,7 @@ void comm_peer_pointers(pedk_ctx* ctx, void* my_block, void** peers) {
     DBuf<unsigned long long> buf(ctx, (size_t)8 * (PEDK_MAX_RANKS + 1));
     cudaIpcMemHandle_t mine;
     PEDK_CUDA_TRY(cudaIpcGetMemHandle(&mine, my_block));
+    dev_mark_exported(ctx, my_block);
     PEDK_CUDA_TRY(cudaMemcpyAsync(buf.p, &mine, 64, cudaMemcpyHostToDevice, st));
     nccl_check(nccl()->AllGather(buf.p, buf.p + 8, 8, ncclUint64, comm_of(ctx), st), "ncclAllGather (ipc handles)");
     std::vector<cudaIpcMemHandle_t> all((size_t)R);
@@ -498,16 +506,29 @@ void comm_peer_pointers(pedk_ctx* ctx, void* my_block, void** peers) {
             continue;
         }
         void* p = nullptr;
+        ++c->clock;
         for (auto& e : c->entries[r])
-            if (memcmp(&e.h, &all[(size_t)r], 64) == 0) p = e.p;
+            if (memcmp(&e.h, &all[(size_t)r], 64) == 0) {
+                p = e.p;
+                e.last_use = c->clock;
+            }
         if (!p) {
+            // every kernel of this rank that stored through an older mapping has finished (the stream was
+            // synchronised above): the least recently used ones can go
+            while (c->entries[r].size() >= kIpcKeep) {
+                size_t old = 0;
+                for (size_t i = 1; i < c->entries[r].size(); ++i)
+                    if (c->entries[r][i].last_use < c->entries[r][old].last_use) old = i;
+                cudaIpcCloseMemHandle(c->entries[r][old].p);
+                c->entries[r].erase(c->entries[r].begin() + (long)old);
+            }
             cudaError_t err = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
             if (err != cudaSuccess) {
                 cudaGetLastError();
                 throw PedkError(PEDK_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(err) +
                                                  " (peer access between the ranks' GPUs is required)");
             }
-            c->entries[r].push_back({all[(size_t)r], p});
+            c->entries[r].push_back({all[(size_t)r], p, c->clock});
         }
         peers[r] = p;
     }

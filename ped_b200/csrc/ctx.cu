@@ -43,14 +43,25 @@ static size_t block_size_for(size_t bytes) {
     return (bytes + g - 1) / g * g;
 }
 
-static void release_cached(pedk_ctx* ctx) {
+// Blocks whose IPC handle went to the peers (comm_peer_pointers) stay with the allocator while the
+// communicator lives: a peer may still have them mapped, and the driver does not return the memory of
+// such a block before every mapping is closed -- freeing it would only lose the block for reuse.
+static void release_cached(pedk_ctx* ctx, bool all = false) {
     cudaStreamSynchronize(ctx->stream);
+    std::vector<pedk_ctx::Block> kept;
     for (auto& b : ctx->free_blocks) {
+        if (!all && ctx->exported_blocks.count(b.p)) {
+            kept.push_back(b);
+            continue;
+        }
         cudaFree(b.p);
+        ctx->exported_blocks.erase(b.p);
         ctx->reserved_bytes -= b.size;
     }
-    ctx->free_blocks.clear();
+    ctx->free_blocks.swap(kept);
 }
+
+void dev_mark_exported(pedk_ctx* ctx, void* p) { ctx->exported_blocks.insert(p); }
 
 // PEDK_GUARD=1 (tests; compute-sanitizer is not available on every pool): every block gets a guard
 // zone behind the bytes that were asked for, filled with a pattern when the block is handed out and
@@ -152,7 +163,7 @@ void dev_free(pedk_ctx* ctx, void* p, size_t /*bytes*/) {
 }
 
 void dev_release_all(pedk_ctx* ctx) {
-    release_cached(ctx);
+    release_cached(ctx, true);
     for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
     ctx->live_blocks.clear();
 }

@@ -4,6 +4,7 @@
 
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -20,6 +21,7 @@ struct pedk_ctx {
     };
     std::vector<Block> free_blocks;             // cached device blocks (see dev_alloc)
     std::unordered_map<void*, size_t> live_blocks;
+    std::unordered_set<void*> exported_blocks;   // blocks peers may have mapped through CUDA IPC (comm.cu)
     std::unordered_map<void*, size_t> guard_at;  // PEDK_GUARD: block -> offset of its guard zone
     uint64_t guard_hits = 0;                     // guard zones found overwritten
     size_t reserved_bytes = 0;
@@ -74,6 +76,7 @@ int ctx_fail(pedk_ctx* ctx, int code, const std::string& msg);
 void* dev_alloc(pedk_ctx* ctx, size_t bytes);
 void dev_free(pedk_ctx* ctx, void* p, size_t bytes);
 void dev_release_all(pedk_ctx* ctx);
+void dev_mark_exported(pedk_ctx* ctx, void* p);  // the block's IPC handle was handed to the peers
 // pinned host buffer of at least `bytes`, owned by the context, valid until the next call
 void* host_stage(pedk_ctx* ctx, size_t bytes);
 
