@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <string>
 
+#include "hostpar.h"
 #include "sample.h"
 
 using namespace pedk;
@@ -337,28 +338,40 @@ std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len) {
         uint64_t key;
     };
     std::vector<Row> rows;
-    const char* p = snp;
-    const char* end = snp + snp_len;
-    while (p < end) {
-        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
-        if (!nl) nl = end;
-        Row r;
-        r.f = awk_split(p, nl);
-        p = nl + 1;
-        // $seq = shift(@row); if (length($row[0]) == 1) { $dat{$seq} = ... }
-        if (r.f.size() < 2 || r.f[1].size() != 1 || (int)r.f[0].size() != k - 1) continue;
-        const char cb = r.f[1][0];
-        if (!is_acgt((unsigned char)cb)) continue;
-        uint64_t v = 0;
-        bool ok = true;
-        for (char c : r.f[0]) {
-            ok = ok && is_acgt((unsigned char)c);
-            v = (v << 2) | base_code((unsigned char)c);
+    {
+        std::vector<std::pair<const char*, const char*>> lines;
+        const char* p = snp;
+        const char* end = snp + snp_len;
+        while (p < end) {
+            const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+            if (!nl) nl = end;
+            lines.emplace_back(p, nl);
+            p = nl + 1;
         }
-        if (!ok) continue;
-        r.key = (v << 2) | base_code((unsigned char)cb);
-        r.f.resize(11);  // undefined fields print as nothing
-        rows.push_back(std::move(r));
+        std::vector<Row> parsed(lines.size());
+        std::vector<uint8_t> keep(lines.size(), 0);
+        parallel_for(lines.size(), [&](size_t lo, size_t hi) {
+            for (size_t li = lo; li < hi; ++li) {
+                Row& r = parsed[li];
+                r.f = awk_split(lines[li].first, lines[li].second);
+                // $seq = shift(@row); if (length($row[0]) == 1) { $dat{$seq} = ... }
+                if (r.f.size() < 2 || r.f[1].size() != 1 || (int)r.f[0].size() != k - 1) continue;
+                const char cb = r.f[1][0];
+                if (!is_acgt((unsigned char)cb)) continue;
+                uint64_t v = 0;
+                bool ok = true;
+                for (char c : r.f[0]) {
+                    ok = ok && is_acgt((unsigned char)c);
+                    v = (v << 2) | base_code((unsigned char)c);
+                }
+                if (!ok) continue;
+                r.key = (v << 2) | base_code((unsigned char)cb);
+                r.f.resize(11);  // undefined fields print as nothing
+                keep[li] = 1;
+            }
+        });
+        for (size_t li = 0; li < parsed.size(); ++li)
+            if (keep[li]) rows.push_back(std::move(parsed[li]));
     }
     std::string out;
     if (rows.empty() || idx.kmer.empty()) return out;
@@ -388,7 +401,12 @@ std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len) {
     std::vector<int> order((size_t)nq);
     for (int i = 0; i < nq; ++i) order[(size_t)i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rows[(size_t)a].key < rows[(size_t)b].key; });
-    for (size_t oi = 0; oi < order.size(); ++oi) {
+    constexpr size_t PARTS = 16;
+    std::vector<std::string> part(PARTS);
+    parallel_for(PARTS, 1, [&](size_t plo, size_t phi) {
+    for (size_t pi = plo; pi < phi; ++pi) {
+    std::string& out = part[pi];
+    for (size_t oi = order.size() * pi / PARTS; oi < order.size() * (pi + 1) / PARTS; ++oi) {
         const int i = order[oi];
         if (oi + 1 < order.size() && (rows[(size_t)order[oi + 1]].key >> 2) == (rows[(size_t)i].key >> 2)) continue;
         const long long h = hit[(size_t)i];
@@ -422,6 +440,9 @@ std::string map_kmer_text(pedk_sample* ref, const char* snp, uint64_t snp_len) {
             out += '\n';
         }
     }
+    }
+    });
+    for (const std::string& x : part) out += x;
     return out;
 }
 

@@ -25,10 +25,14 @@
 
 #include <algorithm>
 #include <functional>
+#include <exception>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
+#include "hostpar.h"
 #include "kernels.h"
 #include "sample.h"
 
@@ -105,23 +109,25 @@ std::vector<std::string> lines_of(const char* p, uint64_t n) {
 struct Candidate {
     std::string chr, ref, alt;  // chr without leading zeros
     long long pos = 0;
+    std::string ialt;           // what `($tpos, $iref, $ialt) = split` of "$pos $ref $alt" gives (ped.pl:2185)
 };
 
 // snpMkT up to snp.list (ped.pl:2094-2152)
 std::vector<Candidate> candidates_of(const std::vector<std::string>& map_lines) {
-    std::vector<std::string> tmp;
-    tmp.reserve(map_lines.size());
-    for (const std::string& line : map_lines) {
-        Row row = split_blanks(line);
-        const std::string ref = field(row, 4);
-        std::string alt = field(row, 5);
-        if (!ref.empty()) {
-            size_t at = alt.find(ref);  // $alt =~ s/$ref//: ref is a nucleotide here (mapKmerSub prints it only if it is one)
-            if (at != std::string::npos) alt.erase(at, ref.size());
+    std::vector<std::string> tmp(map_lines.size());
+    parallel_for(map_lines.size(), [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            Row row = split_blanks(map_lines[i]);
+            const std::string ref = field(row, 4);
+            std::string alt = field(row, 5);
+            if (!ref.empty()) {
+                size_t at = alt.find(ref);  // $alt =~ s/$ref//: ref is a nucleotide here (mapKmerSub prints it only if it is one)
+                if (at != std::string::npos) alt.erase(at, ref.size());
+            }
+            tmp[i] = pad_chr(field(row, 0)) + " " + pad_pos(field(row, 1)) + " " + ref + " " + alt;
         }
-        tmp.push_back(pad_chr(field(row, 0)) + " " + pad_pos(field(row, 1)) + " " + ref + " " + alt);
-    }
-    std::sort(tmp.begin(), tmp.end());
+    });
+    parallel_sort(tmp, std::less<std::string>());
     tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
     std::vector<Candidate> out;
     std::string prev;
@@ -138,6 +144,11 @@ std::vector<Candidate> candidates_of(const std::vector<std::string>& map_lines) 
         c.pos = perl_int(field(r2, 1));
         c.ref = field(r2, 2);
         c.alt = field(r2, 3);
+        // "$pos $ref $alt" split on blanks again: an empty field lets the next one move up
+        const std::string* third[2] = {&c.ref, &c.alt};
+        int seen = 0;
+        for (const std::string* f : third)
+            if (!f->empty() && ++seen == 2) c.ialt = *f;
         out.push_back(std::move(c));
     }
     return out;
@@ -152,55 +163,61 @@ struct Strings {
 };
 
 Strings strings_of(const std::vector<Candidate>& cand, const ChromosomeLookup& chromosome, long long L) {
-    Strings s;
-    s.start.reserve(cand.size() * 2);
-    s.length.reserve(cand.size() * 2);
-    std::string prev_chr;
-    bool have_prev = false;
-    const std::string* seq = nullptr;
-    std::vector<std::string> dat;  // "$pos $ref $alt" of the last candidates of this chromosome (ped.pl:2171-2176)
-    auto push = [&](const std::string& str) {
-        s.start.push_back(s.text.size());
-        s.length.push_back((uint32_t)str.size());
-        s.text.insert(s.text.end(), str.begin(), str.end());
-    };
-    for (const Candidate& c : cand) {
-        if (!have_prev || prev_chr != c.chr) {
-            seq = chromosome("chr" + c.chr);  // open(IN, "$refdir/chr$chr"): a file that is not there reads as nothing
-            dat.clear();
-        }
-        have_prev = true;
-        prev_chr = c.chr;
-        // $count = int(1 + 25/4) = 7 >= 5: always pushed (ped.pl:2158, 2169-2176)
-        dat.push_back(std::to_string(c.pos) + " " + c.ref + " " + c.alt);
-        if (dat.size() > 10) dat.erase(dat.begin());
-        std::string ref_seq, mut_seq;
-        bool skip = c.pos - L < 0 || !seq;
-        if (!skip) {
-            const unsigned long long at = (unsigned long long)(c.pos - L);
-            if (at < seq->size()) ref_seq = seq->substr(at, (size_t)(2 * L - 1));
-            skip = (long long)ref_seq.size() != 2 * L - 1;
-        }
-        if (skip) {
-            push(std::string());
-            push(std::string());
-            continue;
-        }
-        mut_seq = ref_seq.substr(0, (size_t)(L - 1)) + c.alt + ref_seq.substr((size_t)L);
-        for (const std::string& d : dat) {
-            const Row r = split_blanks(d);  // ($tpos, $iref, $ialt) = split
-            const std::string& ialt = field(r, 2);
-            const long long i = perl_int(field(r, 0)) - (c.pos - L) - 1;
-            if (i > 0 && i < 2 * L && i != L - 1) {
-                const size_t ui = (size_t)i;
-                std::string head = mut_seq.substr(0, std::min(ui, mut_seq.size()));
-                std::string tail = ui + 1 <= mut_seq.size() ? mut_seq.substr(ui + 1) : std::string();
-                mut_seq = head + ialt + tail;
+    const size_t n = cand.size();
+    // which chromosome text and which earlier candidates (@dat: the last ten of this chromosome, the
+    // candidate itself included, ped.pl:2169-2176) every candidate sees -- sequential, it is the file order
+    std::vector<const std::string*> seq_of(n, nullptr);
+    std::vector<size_t> dat_from(n, 0);
+    {
+        const std::string* seq = nullptr;
+        size_t chr_first = 0;
+        for (size_t i = 0; i < n; ++i) {
+            if (i == 0 || cand[i - 1].chr != cand[i].chr) {
+                seq = chromosome("chr" + cand[i].chr);  // open(IN, "$refdir/chr$chr"): no such file reads as nothing
+                chr_first = i;
             }
+            seq_of[i] = seq;
+            dat_from[i] = i - chr_first >= 10 ? i - 9 : chr_first;  // $count = int(1 + 25/4) >= 5: always pushed
         }
-        push(ref_seq);
-        push(mut_seq);
     }
+    std::vector<std::string> str(2 * n);
+    parallel_for(n, [&](size_t lo, size_t hi) {
+        for (size_t ci = lo; ci < hi; ++ci) {
+            const Candidate& c = cand[ci];
+            const std::string* seq = seq_of[ci];
+            if (c.pos - L < 0 || !seq) continue;
+            const unsigned long long at = (unsigned long long)(c.pos - L);
+            if (at >= seq->size()) continue;
+            std::string ref_seq = seq->substr(at, (size_t)(2 * L - 1));
+            if ((long long)ref_seq.size() != 2 * L - 1) continue;
+            std::string mut_seq = ref_seq.substr(0, (size_t)(L - 1)) + c.alt + ref_seq.substr((size_t)L);
+            for (size_t d = dat_from[ci]; d <= ci; ++d) {
+                const long long i = cand[d].pos - (c.pos - L) - 1;
+                if (i > 0 && i < 2 * L && i != L - 1) {
+                    const size_t ui = (size_t)i;
+                    std::string head = mut_seq.substr(0, std::min(ui, mut_seq.size()));
+                    std::string tail = ui + 1 <= mut_seq.size() ? mut_seq.substr(ui + 1) : std::string();
+                    mut_seq = head + cand[d].ialt + tail;
+                }
+            }
+            str[2 * ci] = std::move(ref_seq);
+            str[2 * ci + 1] = std::move(mut_seq);
+        }
+    });
+    Strings s;
+    s.start.resize(2 * n);
+    s.length.resize(2 * n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < 2 * n; ++i) {
+        s.start[i] = total;
+        s.length[i] = (uint32_t)str[i].size();
+        total += str[i].size();
+    }
+    s.text.resize(total);
+    parallel_for(2 * n, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i)
+            if (!str[i].empty()) memcpy(s.text.data() + s.start[i], str[i].data(), str[i].size());
+    });
     return s;
 }
 
@@ -249,69 +266,99 @@ char genotype(long long cw, long long cm, long long tw, long long tm) {  // ped.
     return 'N';
 }
 
-// `join A B` on the first blank-separated field: a merge, whatever the order of the inputs (GNU join does
-// not sort); output `key rest-of-A rest-of-B` with single spaces
-std::vector<std::string> merge_join(const std::vector<std::string>& a, const std::vector<std::string>& b) {
-    std::vector<Row> ka, kb;
-    for (const std::string& x : a) ka.push_back(split_blanks(x));
-    for (const std::string& x : b) kb.push_back(split_blanks(x));
-    std::vector<std::string> out;
-    size_t i = 0, j = 0;
-    while (i < ka.size() && j < kb.size()) {
-        const std::string& x = field(ka[i], 0);
-        const std::string& y = field(kb[j], 0);
-        if (x < y) ++i;
-        else if (y < x) ++j;
-        else {
-            size_t i2 = i, j2 = j;
-            while (i2 < ka.size() && field(ka[i2], 0) == y) ++i2;
-            while (j2 < kb.size() && field(kb[j2], 0) == x) ++j2;
-            for (size_t p = i; p < i2; ++p)
-                for (size_t q = j; q < j2; ++q) {
-                    std::string l = field(ka[p], 0);
-                    for (size_t t = 1; t < ka[p].size(); ++t) l += " " + ka[p][t];
-                    for (size_t t = 1; t < kb[q].size(); ++t) l += " " + kb[q][t];
-                    out.push_back(std::move(l));
-                }
-            i = i2;
-            j = j2;
-        }
-    }
-    return out;
+// first blank-separated field of a line, and the non-empty fields behind it
+std::string key_of(const std::string& line) {
+    size_t i = 0, n = line.size();
+    auto blank = [&](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; };
+    while (i < n && blank(line[i])) ++i;
+    size_t a = i;
+    while (i < n && !blank(line[i])) ++i;
+    return line.substr(a, i - a);
 }
 
 // kmerReadCount (ped.pl:2388-2500)
 std::string read_count(const std::vector<std::string>& map_lines, const std::vector<Candidate>& cand,
                        const std::vector<uint32_t>& t_hits, const std::vector<uint32_t>& c_hits, long long length,
                        long long clength) {
-    std::vector<std::string> mp;
-    for (const std::string& line : map_lines) {
-        Row row = split_blanks(line);
-        const long long pos = perl_int(field(row, 1));
-        if (pos < length || pos < clength) continue;
-        std::string l = pad_chr(field(row, 0)) + ":" + pad_pos(field(row, 1));
-        for (size_t i = 2; i <= 14; ++i) l += "\t" + field(row, i);
-        mp.push_back(std::move(l));
-    }
-    std::sort(mp.begin(), mp.end());
-    // %count: one entry per `chr pos ref alt kind` that has at least one window among the reads
-    std::map<std::string, long long> count;
-    static const char* kinds[4] = {"tw", "tm", "cw", "cm"};
-    for (size_t c = 0; c < cand.size(); ++c) {
-        for (int kind = 0; kind < 4; ++kind) {
-            const uint32_t n = (kind < 2 ? t_hits : c_hits)[2 * c + (kind & 1)];
-            if (!n) continue;
-            // the line `join | cut` leaves, split and re-padded (ped.pl:2412-2421)
-            Row row = split_blanks(cand[c].chr + " " + std::to_string(cand[c].pos) + " " + cand[c].ref + " " +
-                                   cand[c].alt + " " + kinds[kind]);
-            while (row.size() < 2) row.emplace_back();
-            row[0] = pad_chr(row[0]);
-            row[1] = pad_pos(row[1]);
-            std::string d = row[0];
-            for (size_t t = 1; t < row.size(); ++t) d += " " + row[t];
-            count[d] += n;
+    // ---- `$tmpdir/$target.map`: the map lines re-keyed `chr:pos`, sorted (ped.pl:2391-2406) ----
+    std::vector<std::string> mp(map_lines.size());
+    std::vector<uint8_t> keep(map_lines.size(), 0);
+    parallel_for(map_lines.size(), [&](size_t lo, size_t hi) {
+        for (size_t li = lo; li < hi; ++li) {
+            Row row = split_blanks(map_lines[li]);
+            const long long pos = perl_int(field(row, 1));
+            if (pos < length || pos < clength) continue;
+            std::string l = pad_chr(field(row, 0)) + ":" + pad_pos(field(row, 1));
+            for (size_t i = 2; i <= 14; ++i) {
+                l += '\t';
+                l += field(row, i);
+            }
+            mp[li] = std::move(l);
+            keep[li] = 1;
         }
+    });
+    {
+        size_t o = 0;
+        for (size_t i = 0; i < mp.size(); ++i)
+            if (keep[i]) {
+                if (o != i) mp[o] = std::move(mp[i]);
+                ++o;
+            }
+        mp.resize(o);
     }
+    parallel_sort(mp, std::less<std::string>());
+    // ---- %count: one entry per `chr pos ref alt kind` that has at least one window among the reads; the key
+    // is the line `join | cut` leaves, split on blanks and re-padded (ped.pl:2410-2421) ----
+    struct Entry {
+        std::string key;
+        Row row;
+        long long n;
+    };
+    static const char* kinds[4] = {"tw", "tm", "cw", "cm"};
+    std::vector<Entry> slot(cand.size() * 4);
+    parallel_for(cand.size(), [&](size_t lo, size_t hi) {
+        for (size_t c = lo; c < hi; ++c)
+            for (int kind = 0; kind < 4; ++kind) {
+                Entry& e = slot[c * 4 + (size_t)kind];
+                e.n = (kind < 2 ? t_hits : c_hits)[2 * c + (size_t)(kind & 1)];
+                if (!e.n) continue;
+                Row row;  // = split of "$chr $pos $ref $alt kind": empty fields vanish
+                if (!cand[c].chr.empty()) row.push_back(cand[c].chr);
+                row.push_back(std::to_string(cand[c].pos));
+                if (!cand[c].ref.empty()) row.push_back(cand[c].ref);
+                if (!cand[c].alt.empty()) row.push_back(cand[c].alt);
+                row.push_back(kinds[kind]);
+                while (row.size() < 2) row.emplace_back();
+                row[0] = pad_chr(row[0]);
+                row[1] = pad_pos(row[1]);
+                e.key = row[0];
+                for (size_t t = 1; t < row.size(); ++t) {
+                    e.key += ' ';
+                    e.key += row[t];
+                }
+                // ... and what the loop over `sort keys` sees when it splits the key again
+                e.row = split_blanks(e.key);
+                while (e.row.size() < 2) e.row.emplace_back();
+            }
+    });
+    std::vector<Entry> count;
+    count.reserve(slot.size());
+    for (Entry& e : slot)
+        if (e.n) count.push_back(std::move(e));
+    std::vector<Entry>().swap(slot);
+    parallel_sort(count, [](const Entry& x, const Entry& y) { return x.key < y.key; });  // `sort keys`
+    {
+        size_t o = 0;  // equal keys are one hash entry
+        for (size_t i = 0; i < count.size(); ++i) {
+            if (o && count[o - 1].key == count[i].key) count[o - 1].n += count[i].n;
+            else {
+                if (o != i) count[o] = std::move(count[i]);
+                ++o;
+            }
+        }
+        count.resize(o);
+    }
+    // ---- `$tmpdir/$target.verify` (ped.pl:2423-2480) ----
     std::vector<std::string> verify;
     long long cm = 0, cw = 0, tm = 0, tw = 0;
     std::string prev;
@@ -321,39 +368,80 @@ std::string read_count(const std::vector<std::string>& map_lines, const std::vec
         return pad_chr(pr[0]) + ":" + pad_pos(pr[1]) + "\t" + std::to_string(cw) + "\t" + std::to_string(cm) + "\t" +
                std::to_string(tw) + "\t" + std::to_string(tm) + "\t" + genotype(cw, cm, tw, tm);
     };
-    for (const auto& kv : count) {  // `sort keys`: bytewise
-        Row row = split_blanks(kv.first);
-        while (row.size() < 2) row.emplace_back();
-        row[0] = strip_zeros(row[0]);
-        row[1] = std::to_string(perl_int(row[1]));
-        std::string d;
-        for (size_t t = 0; t + 1 < row.size(); ++t) d += (t ? "\t" : "") + row[t];
+    for (const Entry& e : count) {
+        std::string d = strip_zeros(e.row[0]);
+        if (e.row.size() > 2) {
+            d += '\t';
+            d += std::to_string(perl_int(e.row[1]));
+        }
+        for (size_t t = 2; t + 1 < e.row.size(); ++t) {
+            d += '\t';
+            d += e.row[t];
+        }
         if (d != prev) {
             std::string line = flush();
             if (!prev.empty()) verify.push_back(std::move(line));
             cm = cw = tm = tw = 0;
         }
-        const std::string& kind = row.back();
-        if (kind == "cm") cm = kv.second;
-        if (kind == "cw") cw = kv.second;
-        if (kind == "tm") tm = kv.second;
-        if (kind == "tw") tw = kv.second;
+        const std::string& kind = e.row.back();
+        if (kind == "cm") cm = e.n;
+        if (kind == "cw") cw = e.n;
+        if (kind == "tm") tm = e.n;
+        if (kind == "tw") tw = e.n;
         prev = d;
     }
     verify.push_back(flush());  // ped.pl prints the last group without looking at it (2461-2480)
-    std::string out;
-    for (const std::string& line : merge_join(mp, verify)) {
-        Row row = split_blanks(line);
-        const std::string& key = field(row, 0);
-        const size_t colon = key.find(':');
-        const std::string chr = strip_zeros(key.substr(0, colon));
-        std::string rest = colon == std::string::npos ? std::string() : key.substr(colon + 1);
-        const size_t colon2 = rest.find(':');  // split(':', ...) takes the second piece
-        if (colon2 != std::string::npos) rest.resize(colon2);
-        out += chr + "\t" + std::to_string(perl_int(rest));
-        for (size_t i = 1; i <= 18; ++i) out += "\t" + field(row, i);
-        out += "\n";
+    // ---- `join map verify` on the first blank-separated field: a merge, whatever the order of the inputs
+    // (GNU join does not sort), every line of a key with every line of the other side ----
+    std::vector<std::string> ka(mp.size()), kb(verify.size());
+    parallel_for(mp.size(), [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) ka[i] = key_of(mp[i]);
+    });
+    for (size_t i = 0; i < verify.size(); ++i) kb[i] = key_of(verify[i]);
+    std::vector<std::pair<uint32_t, uint32_t>> pairs;
+    {
+        size_t i = 0, j = 0;
+        while (i < ka.size() && j < kb.size()) {
+            if (ka[i] < kb[j]) ++i;
+            else if (kb[j] < ka[i]) ++j;
+            else {
+                size_t i2 = i, j2 = j;
+                while (i2 < ka.size() && ka[i2] == kb[j]) ++i2;
+                while (j2 < kb.size() && kb[j2] == ka[i]) ++j2;
+                for (size_t p = i; p < i2; ++p)
+                    for (size_t q = j; q < j2; ++q) pairs.emplace_back((uint32_t)p, (uint32_t)q);
+                i = i2;
+                j = j2;
+            }
+        }
     }
+    // ---- the joined line split on blanks again, `chr pos` from its key, fields 1..18 (ped.pl:2483-2497) ----
+    std::vector<std::string> lines(pairs.size());
+    parallel_for(pairs.size(), [&](size_t lo, size_t hi) {
+        for (size_t x = lo; x < hi; ++x) {
+            Row row = split_blanks(mp[pairs[x].first]);
+            const Row rb = split_blanks(verify[pairs[x].second]);
+            for (size_t t = 1; t < rb.size(); ++t) row.push_back(rb[t]);
+            const std::string& key = field(row, 0);
+            const size_t colon = key.find(':');
+            const std::string chr = strip_zeros(key.substr(0, colon));
+            std::string rest = colon == std::string::npos ? std::string() : key.substr(colon + 1);
+            const size_t colon2 = rest.find(':');  // split(':', ...) takes the second piece
+            if (colon2 != std::string::npos) rest.resize(colon2);
+            std::string l = chr + "\t" + std::to_string(perl_int(rest));
+            for (size_t i = 1; i <= 18; ++i) {
+                l += '\t';
+                l += field(row, i);
+            }
+            l += '\n';
+            lines[x] = std::move(l);
+        }
+    });
+    size_t bytes = 0;
+    for (const std::string& l : lines) bytes += l.size();
+    std::string out;
+    out.reserve(bytes);
+    for (const std::string& l : lines) out += l;
     return out;
 }
 
@@ -400,18 +488,27 @@ std::string verify_text(pedk_sample* target, pedk_sample* control, const Chromos
     const long long length = first_read_length(target), clength = first_read_length(control);
     if (length <= 0 || clength <= 0)
         throw PedkError(PEDK_E_INVAL, "verification needs reads in both samples (ped.pl dies in read() with a negative length)");
+    pedk_ctx* ctx = target->ctx;
+    trace(ctx, "verify: start");
     const std::vector<std::string> map_lines = lines_of(map, map_len);
     const std::vector<Candidate> cand = candidates_of(map_lines);
+    trace(ctx, "verify: candidates");
     std::vector<uint32_t> t_hits, c_hits;
     {
         const Strings s = strings_of(cand, chromosome, length);
+        trace(ctx, "verify: target windows built");
         t_hits = probe(target, s, (int)length);
+        trace(ctx, "verify: target windows looked up");
     }
     {
         const Strings s = strings_of(cand, chromosome, clength);
+        trace(ctx, "verify: control windows built");
         c_hits = probe(control, s, (int)clength);
+        trace(ctx, "verify: control windows looked up");
     }
-    return read_count(map_lines, cand, t_hits, c_hits, length, clength);
+    std::string out = read_count(map_lines, cand, t_hits, c_hits, length, clength);
+    trace(ctx, "verify: counts, genotypes, join");
+    return out;
 }
 
 // toVcf, method kmer (ped.pl:1532-1574)
@@ -426,32 +523,52 @@ std::string vcf_text(const char* snp, uint64_t snp_len, const std::string& targe
         "the order listed\">\n"
         "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"Read depth\">\n"
         "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + target + "\n";
-    std::string output, prev;
-    for (const std::string& line : lines_of(snp, snp_len)) {
-        Row row;  // split('\t', $_): trailing empty fields are dropped
-        size_t a = 0;
-        for (;;) {
-            size_t b = line.find('\t', a);
-            row.push_back(line.substr(a, b == std::string::npos ? std::string::npos : b - a));
-            if (b == std::string::npos) break;
-            a = b + 1;
+    // a line with M or H anywhere in it makes a record, any other line with depth repeats the record before
+    // it, and a record equal to the one printed last is not printed again (ped.pl:1553-1573)
+    const std::vector<std::string> lines = lines_of(snp, snp_len);
+    std::vector<std::string> rec(lines.size());
+    std::vector<uint8_t> kind(lines.size(), 0);  // 0: `next` (depth 0), 1: own record, 2: carries the previous one
+    parallel_for(lines.size(), [&](size_t lo, size_t hi) {
+        for (size_t li = lo; li < hi; ++li) {
+            const std::string& line = lines[li];
+            Row row;  // split('\t', $_): trailing empty fields are dropped
+            size_t a = 0;
+            for (;;) {
+                size_t b = line.find('\t', a);
+                row.push_back(line.substr(a, b == std::string::npos ? std::string::npos : b - a));
+                if (b == std::string::npos) break;
+                a = b + 1;
+            }
+            while (!row.empty() && row.back().empty()) row.pop_back();
+            if (row.empty()) row.emplace_back();
+            if (row[0].size() <= 3 || all_digits(row[0])) row[0] = "chr" + row[0];
+            const double r17 = perl_double(field(row, 17)), r18 = perl_double(field(row, 18));
+            const double dp = r17 + r18;
+            if (dp == 0) continue;
+            const bool m = line.find('M') != std::string::npos, h = line.find('H') != std::string::npos;
+            if (!(m || h)) {
+                kind[li] = 2;
+                continue;
+            }
+            const double af = (trunc(1000 * r18 / dp) + 0.0) / 1000;  // int() gives an integer: no negative zero
+            const double p = pow(0.001 * dp, r18);
+            const double qual = p == 0 ? 1000 : (trunc((-10 * log(p) / log(10.0)) * 1000) + 0.0) / 1000;
+            rec[li] = row[0] + "\t" + field(row, 1) + "\t.\t" + field(row, 4) + "\t" + field(row, 5) + "\t" +
+                      perl_number(qual) + "\t.\tGT=" + (m ? "1/1" : "0/1") + ";AF=" + perl_number(af) + ";DP=" +
+                      field(row, 18) + "\tGT:AD:DP\t" + (m ? "1/1" : "0/1") + ":" + field(row, 17) + "," +
+                      field(row, 18) + ":" + perl_number(dp) + "\n";
+            kind[li] = 1;
         }
-        while (!row.empty() && row.back().empty()) row.pop_back();
-        if (row.empty()) row.emplace_back();
-        if (row[0].size() <= 3 || all_digits(row[0])) row[0] = "chr" + row[0];
-        const double r17 = perl_double(field(row, 17)), r18 = perl_double(field(row, 18));
-        const double dp = r17 + r18;
-        if (dp == 0) continue;
-        const double af = (trunc(1000 * r18 / dp) + 0.0) / 1000;  // int() gives an integer: no negative zero
-        const double p = pow(0.001 * dp, r18);
-        const double qual = p == 0 ? 1000 : (trunc((-10 * log(p) / log(10.0)) * 1000) + 0.0) / 1000;
-        const bool m = line.find('M') != std::string::npos, h = line.find('H') != std::string::npos;
-        if (m || h)
-            output = row[0] + "\t" + field(row, 1) + "\t.\t" + field(row, 4) + "\t" + field(row, 5) + "\t" +
-                     perl_number(qual) + "\t.\tGT=" + (m ? "1/1" : "0/1") + ";AF=" + perl_number(af) + ";DP=" +
-                     field(row, 18) + "\tGT:AD:DP\t" + (m ? "1/1" : "0/1") + ":" + field(row, 17) + "," + field(row, 18) +
-                     ":" + perl_number(dp) + "\n";
-        if (output != prev) out += output;
+    });
+    const std::string* output = nullptr;  // $output
+    const std::string* prev = nullptr;    // $prev
+    static const std::string none;
+    for (size_t li = 0; li < lines.size(); ++li) {
+        if (kind[li] == 0) continue;
+        if (kind[li] == 1) output = &rec[li];
+        const std::string& o = output ? *output : none;
+        const std::string& pv = prev ? *prev : none;
+        if (o != pv) out += o;
         prev = output;
     }
     return out;
