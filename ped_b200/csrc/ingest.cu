@@ -469,6 +469,137 @@ void launch_pack(const uint8_t* fq, const uint64_t* seq_start, const uint32_t* c
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
+// ---- f2, second form: one warp per STRING, its windows as a rolling view of the packed string ----
+//
+// The L windows of a string overlap in all but one base, so the string is packed ONCE (lane w holds word w
+// of the first 2L-1 bases, and word w of their reverse complement) and window i is two funnel shifts of two
+// shuffled words per strand: 64 bits at base offset i of the forward words, and at offset n-L-i of the
+// reverse-complement words.  The smaller of the two is the canonical window.  The read table of this form is
+// its own (k_read_table): the hash is a sum over the words, so every lane hashes its word and five shuffles
+// add them up -- k_dedup's chained hash would put the W words through one lane.
+__device__ __forceinline__ uint64_t word_hash(uint64_t word, int w) {
+    return mix64(word ^ (0x9E3779B97F4A7C15ull * (uint64_t)(w + 1)));
+}
+
+__global__ void __launch_bounds__(256) k_read_table(const uint64_t* __restrict__ words, int W, uint32_t n,
+                                                   uint32_t* __restrict__ table, uint32_t mask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t h = 0;
+    for (int w = 0; w < W; ++w) h += word_hash(words[(uint64_t)i * W + w], w);
+    uint32_t slot = (uint32_t)(mix64(h) >> 20) & mask;
+    // the reads are unique already: the first free slot is this read's
+    while (atomicCAS(&table[slot], 0xFFFFFFFFu, i) != 0xFFFFFFFFu) slot = (slot + 1) & mask;
+}
+
+// 64 bits of a packed string starting at base `at` (0 <= at): lane w gets the bits for its word w
+__device__ __forceinline__ uint64_t rolling_word(uint64_t mine, int at, unsigned lane) {
+    const int q = (at >> 5) + (int)lane, o = at & 31;
+    uint64_t hi = __shfl_sync(0xffffffffu, mine, q & 31);
+    uint64_t lo = __shfl_sync(0xffffffffu, mine, (q + 1) & 31);
+    if (q > 31) hi = 0;
+    if (q + 1 > 31) lo = 0;
+    return o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+}
+
+__global__ void __launch_bounds__(256) k_probe_strings(const uint8_t* __restrict__ text,
+                                                      const uint64_t* __restrict__ start,
+                                                      const uint32_t* __restrict__ length, uint64_t n_strings,
+                                                      int L, int W, const uint64_t* __restrict__ words,
+                                                      const uint32_t* __restrict__ table, uint32_t mask,
+                                                      uint32_t* __restrict__ hits) {
+    const unsigned lane = lane_id();
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t s = warp; s < n_strings; s += n_warps) {
+        const int len = (int)length[s];
+        if (len < L) {  // substr past the end: shorter lines, never a read
+            if (lane == 0) hits[s] = 0;
+            continue;
+        }
+        const int n = len < 2 * L - 1 ? len : 2 * L - 1;  // the windows 0 .. L-1 only see these bases
+        const int last = n - L;                           // last window that is whole
+        const uint8_t* src = text + start[s];
+        // ---- pack: lane w keeps word w of the string and the not-ACGT flags of its 32 bases ----
+        uint64_t fwd = 0;
+        uint32_t bad = 0;
+        const int Wn = (n + 31) >> 5;
+        for (int w = 0; w < Wn; ++w) {
+            const int i = 32 * w + (int)lane;
+            const uint32_t c = i < n ? src[i] : (uint32_t)'A';
+            const uint32_t code = i < n ? base_code(c) : 0u;
+            const uint32_t b = __ballot_sync(0xffffffffu, !(c == 'A' || c == 'C' || c == 'G' || c == 'T'));
+            const uint32_t m1 = __brev(__ballot_sync(0xffffffffu, code & 2u));
+            const uint32_t m0 = __brev(__ballot_sync(0xffffffffu, code & 1u));
+            if ((int)lane == w) {
+                fwd = (spread32(m1) << 1) | spread32(m0);
+                bad = b;  // bit t <-> base 32w + t
+            }
+        }
+        const bool any_bad = __ballot_sync(0xffffffffu, bad != 0) != 0;
+        // ---- its reverse complement: word w = revcomp of the 32 bases that end at n - 32w ----
+        uint64_t rc;
+        {
+            const int sbase = n - 32 * (int)lane - 32;
+            const int wi = sbase >> 5, o = sbase & 31;
+            uint64_t hi = __shfl_sync(0xffffffffu, fwd, wi & 31);
+            uint64_t lo = __shfl_sync(0xffffffffu, fwd, (wi + 1) & 31);
+            if (wi < 0 || wi > 31) hi = 0;
+            if (wi + 1 < 0 || wi + 1 > 31) lo = 0;
+            const uint64_t win = o ? ((hi << (2 * o)) | (lo >> (64 - 2 * o))) : hi;
+            rc = (int)lane < Wn ? (revcomp_groups64(win) & tail_mask(n, (int)lane)) : 0ull;
+        }
+        const uint64_t keep = tail_mask(L, (int)lane);  // 0 for lanes >= W
+        uint32_t found = 0;
+        for (int i = 0; i <= last; ++i) {
+            if (any_bad) {
+                // bases [i, i+L) against this lane's 32: [32 lane, 32 lane + 32)
+                const int a = max(i, 32 * (int)lane), b = min(i + L, 32 * (int)lane + 32);
+                uint32_t m = 0;
+                if (a < b) m = (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u)) << (a - 32 * (int)lane);
+                if (__ballot_sync(0xffffffffu, (bad & m) != 0)) continue;
+            }
+            const uint64_t f = rolling_word(fwd, i, lane) & keep;
+            const uint64_t r = rolling_word(rc, n - L - i, lane) & keep;
+            const unsigned diff = __ballot_sync(0xffffffffu, f != r);
+            bool use_rc = false;
+            if (diff) use_rc = __shfl_sync(0xffffffffu, r < f ? 1 : 0, __ffs(diff) - 1) != 0;
+            const uint64_t word = use_rc ? r : f;
+            uint64_t h = (int)lane < W ? word_hash(word, (int)lane) : 0ull;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+            uint32_t slot = (uint32_t)(mix64(h) >> 20) & mask;
+            for (;;) {
+                const uint32_t cur = table[slot];
+                if (cur == 0xFFFFFFFFu) break;
+                const uint64_t other = (int)lane < W ? words[(uint64_t)cur * W + lane] : 0ull;
+                if (__ballot_sync(0xffffffffu, (int)lane < W && other != word) == 0) {
+                    ++found;
+                    break;
+                }
+                slot = (slot + 1) & mask;
+            }
+        }
+        if (lane == 0) hits[s] = found;
+    }
+}
+
+void launch_read_table(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, cudaStream_t st) {
+    if (!n) return;
+    k_read_table<<<(n + 255) / 256, 256, 0, st>>>(words, W, n, table, capacity - 1);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
+void launch_probe_strings(const uint8_t* text, const uint64_t* start, const uint32_t* length, uint64_t n_strings, int L,
+                          int W, const uint64_t* words, const uint32_t* table, uint32_t capacity, uint32_t* hits,
+                          cudaStream_t st) {
+    if (!n_strings || L <= 0) return;
+    const uint64_t blocks = (n_strings + 7) / 8;
+    const unsigned grid = (unsigned)(blocks < (uint64_t)kNumSMs * 8 ? blocks : (uint64_t)kNumSMs * 8);
+    k_probe_strings<<<grid, 256, 0, st>>>(text, start, length, n_strings, L, W, words, table, capacity - 1, hits);
+    PEDK_CUDA_TRY(cudaGetLastError());
+}
+
 void launch_probe_windows(const uint8_t* text, const uint64_t* start, const uint32_t* length, uint64_t n_strings, int L,
                           int W, const uint64_t* words, const uint32_t* table, uint32_t capacity, uint32_t* hits,
                           cudaStream_t st) {

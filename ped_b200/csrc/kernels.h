@@ -50,6 +50,12 @@ void launch_dedup(const uint64_t* words, int W, uint32_t n, uint32_t* table, uin
                   uint8_t* uniq, cudaStream_t st);
 // f2: hits[s] += number of the L-base windows of string s (text[start[s] .. +length[s])) that are reads of the
 // sample whose unique canonical reads are `words` and whose k_dedup table is `table`
+// the same result from one warp per string (rolling windows over the packed string) and the table of
+// launch_read_table (its own hash); hits[s] is written, not added to
+void launch_read_table(const uint64_t* words, int W, uint32_t n, uint32_t* table, uint32_t capacity, cudaStream_t st);
+void launch_probe_strings(const uint8_t* text, const uint64_t* start, const uint32_t* length, uint64_t n_strings, int L,
+                          int W, const uint64_t* words, const uint32_t* table, uint32_t capacity, uint32_t* hits,
+                          cudaStream_t st);
 void launch_probe_windows(const uint8_t* text, const uint64_t* start, const uint32_t* length, uint64_t n_strings, int L,
                           int W, const uint64_t* words, const uint32_t* table, uint32_t capacity, uint32_t* hits,
                           cudaStream_t st);

@@ -234,22 +234,31 @@ std::vector<uint32_t> probe(pedk_sample* smp, const Strings& s, int L) {
     if (g->n > (1ull << 30)) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^30 unique reads in one length group");
     uint64_t cap64 = 1024;
     while (cap64 < 2 * g->n) cap64 <<= 1;
+    // PEDK_PROBE=windows: the first form of the look-up (one warp per window, packed from its bytes, over
+    // k_dedup's table); default: one warp per string with rolling windows over its own table (ingest.cu)
+    const char* form = getenv("PEDK_PROBE");
+    const bool per_window = form && strcmp(form, "windows") == 0;
     DBuf<uint32_t> table(ctx, cap64);
-    DBuf<uint8_t> uniq(ctx, g->n);
+    DBuf<uint8_t> uniq(ctx, per_window ? g->n : 1);
     DBuf<uint8_t> d_text(ctx, s.text.size() + 64);
     DBuf<uint64_t> d_start(ctx, s.start.size());
     DBuf<uint32_t> d_len(ctx, s.length.size());
     DBuf<uint32_t> d_hits(ctx, hits.size());
     StageScope sc(ctx, PEDK_ST_EDGES, 2);
     PEDK_CUDA_TRY(cudaMemsetAsync(table.p, 0xFF, table.bytes(), st));
-    launch_dedup(g->words.p, g->W, (uint32_t)g->n, table.p, (uint32_t)cap64, nullptr, uniq.p, st);
+    if (per_window) launch_dedup(g->words.p, g->W, (uint32_t)g->n, table.p, (uint32_t)cap64, nullptr, uniq.p, st);
+    else launch_read_table(g->words.p, g->W, (uint32_t)g->n, table.p, (uint32_t)cap64, st);
     if (!s.text.empty())
         PEDK_CUDA_TRY(cudaMemcpyAsync(d_text.p, s.text.data(), s.text.size(), cudaMemcpyHostToDevice, st));
     PEDK_CUDA_TRY(cudaMemcpyAsync(d_start.p, s.start.data(), s.start.size() * 8, cudaMemcpyHostToDevice, st));
     PEDK_CUDA_TRY(cudaMemcpyAsync(d_len.p, s.length.data(), s.length.size() * 4, cudaMemcpyHostToDevice, st));
     PEDK_CUDA_TRY(cudaMemsetAsync(d_hits.p, 0, d_hits.bytes(), st));
-    launch_probe_windows(d_text.p, d_start.p, d_len.p, s.start.size(), L, g->W, g->words.p, table.p, (uint32_t)cap64,
-                         d_hits.p, st);
+    if (per_window)
+        launch_probe_windows(d_text.p, d_start.p, d_len.p, s.start.size(), L, g->W, g->words.p, table.p,
+                             (uint32_t)cap64, d_hits.p, st);
+    else
+        launch_probe_strings(d_text.p, d_start.p, d_len.p, s.start.size(), L, g->W, g->words.p, table.p,
+                             (uint32_t)cap64, d_hits.p, st);
     PEDK_CUDA_TRY(cudaMemcpyAsync(hits.data(), d_hits.p, hits.size() * 4, cudaMemcpyDeviceToHost, st));
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
     return hits;

@@ -505,8 +505,10 @@ def test_verification_against_the_reference(ctx, variant):
     assert api.vcf_text(snp, "T").decode() == g["kmer_vcf"]
 
 
-@pytest.mark.parametrize("seed,L,CL", [(1, 100, 80), (2, 100, 100), (3, 64, 97), (4, 150, 33), (5, 33, 150)])
-def test_verification_against_the_restatement(ctx, seed, L, CL):
+@pytest.mark.parametrize("seed,L,CL", [(1, 100, 80), (2, 100, 100), (3, 64, 97), (4, 150, 33), (5, 33, 150), (6, 31, 32),
+                                       (7, 129, 64), (8, 97, 161)])
+@pytest.mark.parametrize("form", ["strings", "windows"])
+def test_verification_against_the_restatement(ctx, seed, L, CL, form, monkeypatch):
     """f2 on a diploid target: heterozygous and homozygous SNPs, SNPs 3 / 25 / 80 bases apart (their windows
     carry each other, ped.pl:2184-2192), candidates closer to a chromosome end than a read is long, control
     reads of another length, F7 rows whose fields shift -- against the line-by-line restatement of the
@@ -515,6 +517,7 @@ def test_verification_against_the_restatement(ctx, seed, L, CL):
     from tests.cases import make_verify_inputs
     from tests.test_oracle import verification_inputs
 
+    monkeypatch.setenv("PEDK_PROBE", form)   # both forms of the window look-up (ingest.cu)
     fa, fc, ft = make_verify_inputs(seed, L=L, CL=CL)
     edges, map_text, snp = _verify_through_the_library(ctx, fa, fc, ft)
     oc, ot, oedges = oracle.run(fc, ft, 20)
