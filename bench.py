@@ -155,14 +155,19 @@ class ClockSampler:
             return
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
+        # nvidia-smi attaches to every GPU of the box before its first line; that start-up holds driver locks for
+        # tens of ms at a time and used to land inside the warm-up or the timed region (steps of 89 / 93 / 97 /
+        # 106 ms for identical kernel times).  Wait for the first line: from then on it only polls.
+        t_end = time.time() + 20.0
+        while not self.rows and self.proc.poll() is None and time.time() < t_end:
+            time.sleep(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def window(self, t0: float, t1: float) -> None:
-        """Only the samples that arrived inside [t0, t1] (the timed region) count; nvidia-smi is started
-        before the warm-up because it needs a few hundred ms to deliver its first line."""
+        """Only the samples that arrived inside [t0, t1] (the timed region) count."""
         self.t0, self.t1 = t0, t1
 
     def stop(self) -> dict:

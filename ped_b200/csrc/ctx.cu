@@ -1,5 +1,7 @@
 // Context life cycle, stream-ordered device memory, stage timing, the radix
 // sort driver and the raw-kernel test entry points of libpedk.so.
+#include <chrono>
+
 #include "ctx.h"
 
 #include <string.h>
@@ -92,7 +94,12 @@ void* dev_alloc(pedk_ctx* ctx, size_t bytes) {
         got = best_size;
         ctx->free_blocks.erase(ctx->free_blocks.begin() + (long)best);
     } else {
+        const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMalloc(&p, want);
+        if (ctx->trace)
+            fprintf(stderr, "[pedk] cudaMalloc of %zu bytes: %.2f ms (%zu cached blocks)\n", want,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                    ctx->free_blocks.size());
         if (e == cudaErrorMemoryAllocation) {
             cudaGetLastError();
             // the device is full.  Before giving the cached blocks back to the driver (a free + malloc

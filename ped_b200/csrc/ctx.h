@@ -25,6 +25,7 @@ struct pedk_ctx {
     std::unordered_map<void*, size_t> guard_at;  // PEDK_GUARD: block -> offset of its guard zone
     uint64_t guard_hits = 0;                     // guard zones found overwritten
     size_t reserved_bytes = 0;
+    size_t mem_free_seen = 0, mem_reserved_seen = 0;  // last cudaMemGetInfo and reserved_bytes at that moment
     cudaStream_t copy_stream = nullptr;  // H2D of FASTQ text runs here, under the kernels of the other sample
     cudaEvent_t ev_alloc = nullptr;
     std::string err;

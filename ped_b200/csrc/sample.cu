@@ -483,13 +483,6 @@ int choose_count_passes(pedk_ctx* ctx, uint64_t m_rank, size_t ksz, int nbA) {
     if (forced > 0) {
         while (P < forced) P <<= 1;
     } else {
-        size_t free_b = 0, total_b = 0;
-        PEDK_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        // blocks the context's allocator holds but nobody uses count as free
-        const size_t cached = ctx->reserved_bytes > ctx->cur_bytes ? ctx->reserved_bytes - ctx->cur_bytes : 0;
-        const char* cap_env = getenv("PEDK_DEVICE_BUDGET_MB");  // tests: pretend the device is small
-        double budget = (double)(free_b + cached) * 0.90;
-        if (cap_env && *cap_env) budget = std::min(budget, atof(cap_env) * 1048576.0);
         // per pass: level-A segments (expected + 1/8 + slack per (bin, source)) + buckets (expected + 1/8 +
         // 16 sqrt); over all passes: the rows that come out (at most one per three instances at the
         // coverages a comparison makes sense at).  A rank receives about what it sends (the hash
@@ -498,6 +491,25 @@ int choose_count_passes(pedk_ctx* ctx, uint64_t m_rank, size_t ksz, int nbA) {
             const double inst = (double)m_rank * 1.05;
             return inst / passes * ksz * (1.125 + 1.2) + (double)nbA / passes * 4096 * ksz + inst * 0.34 * 12;
         };
+        // blocks the context's allocator holds but nobody uses count as free
+        const size_t cached = ctx->reserved_bytes > ctx->cur_bytes ? ctx->reserved_bytes - ctx->cur_bytes : 0;
+        const char* cap_env = getenv("PEDK_DEVICE_BUDGET_MB");  // tests: pretend the device is small
+        // cudaMemGetInfo takes the driver's global lock: next to a monitoring tool that polls the device
+        // (nvidia-smi every 100 ms in bench.py) it was seen to take anything from 0.1 to 70 ms, per sample,
+        // inside the step.  Ask once, then follow what this context's own allocator took since; ask again
+        // only when one pass would need more than half of what that estimate leaves.
+        double free_est = (double)ctx->mem_free_seen + ((double)ctx->mem_reserved_seen - (double)ctx->reserved_bytes);
+        const bool ask = !ctx->mem_free_seen || (cap_env && *cap_env) || free_est <= 0 ||
+                         need(1) * 2.0 > (free_est + (double)cached) * 0.90;
+        if (ask) {
+            size_t free_b = 0, total_b = 0;
+            PEDK_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            ctx->mem_free_seen = free_b;
+            ctx->mem_reserved_seen = ctx->reserved_bytes;
+            free_est = (double)free_b;
+        }
+        double budget = (free_est + (double)cached) * 0.90;
+        if (cap_env && *cap_env) budget = std::min(budget, atof(cap_env) * 1048576.0);
         while (P < max_pass && need(P) > budget) P <<= 1;
     }
     return P > max_pass ? max_pass : P;
