@@ -16,6 +16,7 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <unordered_map>
 #include <vector>
 
 #include "comm.h"
@@ -469,6 +470,7 @@ struct IpcCache {
     };
     std::vector<Entry> entries[PEDK_MAX_RANKS];
     uint64_t clock = 0;
+    std::unordered_map<void*, cudaIpcMemHandle_t> own;  // handles of this rank's exported blocks
 };
 
 static IpcCache* ipc_cache(pedk_ctx* ctx) {
@@ -491,9 +493,18 @@ void comm_peer_pointers(pedk_ctx* ctx, void* my_block, void** peers) {
     cudaStream_t st = ctx->stream;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     DBuf<unsigned long long> buf(ctx, (size_t)8 * (PEDK_MAX_RANKS + 1));
+    // the handle of a block is asked for once (a driver call under the global lock, like cudaMemGetInfo);
+    // an exported block stays with the allocator until the context closes, so the handle stays valid
     cudaIpcMemHandle_t mine;
-    PEDK_CUDA_TRY(cudaIpcGetMemHandle(&mine, my_block));
-    dev_mark_exported(ctx, my_block);
+    IpcCache* hc = ipc_cache(ctx);
+    auto own = hc->own.find(my_block);
+    if (own == hc->own.end()) {
+        PEDK_CUDA_TRY(cudaIpcGetMemHandle(&mine, my_block));
+        hc->own[my_block] = mine;
+        dev_mark_exported(ctx, my_block);
+    } else {
+        mine = own->second;
+    }
     PEDK_CUDA_TRY(cudaMemcpyAsync(buf.p, &mine, 64, cudaMemcpyHostToDevice, st));
     nccl_check(nccl()->AllGather(buf.p, buf.p + 8, 8, ncclUint64, comm_of(ctx), st), "ncclAllGather (ipc handles)");
     std::vector<cudaIpcMemHandle_t> all((size_t)R);
