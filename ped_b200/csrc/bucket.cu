@@ -283,15 +283,22 @@ __global__ void __launch_bounds__(PT_THREADS, PT_THREADS > 512 ? 1 : 2)
 
 // ------------------------------------------------------------------ level B
 // keys per tile of the level-B passes (a tile lies inside one segment of a level-A bin) and the CTA
-// shape of the scatter: 512 threads x 16 keys (two CTAs per SM: 64 registers) or 256 x 16 (four
-// CTAs per SM: the same threads per SM, but twice as many independent barrier domains -- the
-// kernel is bound by shared-memory latency between its barriers, not by issue slots or HBM)
-constexpr int SS_ITEMS = 16;
+// shape of the scatter (threads x keys per thread).  The kernel is bound by shared-memory latency
+// between its barriers, not by issue slots or HBM.  Measured at configs[1], 32-bit keys: 256 x 16 (four
+// CTAs per SM, 64 registers) 14.9 ms/step, 512 x 16 14.8, 512 x 8 (32 registers, 2048 threads per SM)
+// 14.2, 256 x 8 (tiles of 2048 keys: runs too short) 22.6; 64-bit keys (72 bytes of spills at 32
+// registers): 256 x 16 3.7, 512 x 8 3.95.  Default: 512 x 8 for 32-bit keys, 256 x 16 for 64-bit keys --
+// both are tiles of 4096 keys.  PEDK_SUB_THREADS / PEDK_SUB_ITEMS force a shape for both.
 constexpr int SH_THREADS = 256;
 constexpr int SH_GROUP_KEYS = 65536;  // keys per CTA of the histogram kernel
+bool sub_scatter_forced() { return getenv("PEDK_SUB_THREADS") || getenv("PEDK_SUB_ITEMS"); }
 int sub_scatter_threads() {
     const int t = getenv("PEDK_SUB_THREADS") ? atoi(getenv("PEDK_SUB_THREADS")) : 256;
     return t >= 512 ? 512 : 256;
+}
+int sub_scatter_items() {
+    const int t = getenv("PEDK_SUB_ITEMS") ? atoi(getenv("PEDK_SUB_ITEMS")) : 16;
+    return t == 8 ? 8 : 16;
 }
 
 // A level-A bin arrives as one or more SEGMENTS (one per source rank, or one per bin when the
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(SH_THREADS) k_sub_hist(const KT* __restrict__ 
 // One tile of a level-A bin -> its 2^b sub-bins.  WHOLE: the tile holds SUB_TILE keys (all but
 // the last tile of a bin), so no index is tested.  A thread keeps its 16 keys and their ranks
 // (two 16-bit ranks per register; the sub-bin is recomputed from the key) between the phases.
-template <typename KT, bool WHOLE, int SS_THREADS>
+template <typename KT, bool WHOLE, int SS_THREADS, int SS_ITEMS>
 __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, unsigned n, KT* __restrict__ out,
                                                  unsigned long long* __restrict__ cur,
                                                  const unsigned long long* __restrict__ lim, int* __restrict__ overflow,
@@ -408,8 +415,8 @@ __device__ __forceinline__ void sub_scatter_tile(const KT* __restrict__ src, uns
     }
 }
 
-template <typename KT, int SS_THREADS>
-__global__ void __launch_bounds__(SS_THREADS, 1024 / SS_THREADS) k_sub_scatter(const KT* __restrict__ in, KT* __restrict__ out,
+template <typename KT, int SS_THREADS, int SS_ITEMS>
+__global__ void __launch_bounds__(SS_THREADS, 16384 / (SS_THREADS * SS_ITEMS)) k_sub_scatter(const KT* __restrict__ in, KT* __restrict__ out,
                                                               const unsigned long long* __restrict__ seg,
                                                               const unsigned* __restrict__ tile_prefix, int n_bins,
                                                               unsigned n_tiles, int shiftB, unsigned maskB,
@@ -433,11 +440,11 @@ __global__ void __launch_bounds__(SS_THREADS, 1024 / SS_THREADS) k_sub_scatter(c
     if (tid < NB) hist[tid] = 0;
     __syncthreads();
     if (n == SUB_TILE)
-        sub_scatter_tile<KT, true, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB,
+        sub_scatter_tile<KT, true, SS_THREADS, SS_ITEMS>(in + start, n, out, curB + (size_t)bin * NB,
                                                limB ? limB + (size_t)bin * NB : nullptr, overflow, shiftB, maskB, stage,
                                                hist, off, s_out);
     else
-        sub_scatter_tile<KT, false, SS_THREADS>(in + start, n, out, curB + (size_t)bin * NB,
+        sub_scatter_tile<KT, false, SS_THREADS, SS_ITEMS>(in + start, n, out, curB + (size_t)bin * NB,
                                                 limB ? limB + (size_t)bin * NB : nullptr, overflow, shiftB, maskB, stage,
                                                 hist, off, s_out);
 }
@@ -987,7 +994,7 @@ void launch_part_scatter(const uint64_t* words, int W, int L, int k, uint64_t n_
     PEDK_CUDA_TRY(cudaGetLastError());
 }
 
-unsigned sub_tile_keys() { return (unsigned)(sub_scatter_threads() * SS_ITEMS); }
+unsigned sub_tile_keys() { return (unsigned)(sub_scatter_threads() * sub_scatter_items()); }
 
 namespace {
 __global__ void k_cursor_counts(const unsigned long long* __restrict__ cur, const unsigned long long* __restrict__ lim,
@@ -1039,22 +1046,29 @@ void launch_sub_scatter_bits(const void* in, void* out, int wide, const unsigned
     const unsigned long long* offA = seg;
     const int n_bins = n_seg;
     if (!n_tiles) return;
-    const int threads = sub_scatter_threads();
-    const size_t smem = (size_t)threads * SS_ITEMS * (wide ? sizeof(uint64_t) : sizeof(uint32_t));
-#define PEDK_SS(KT, TH)                                                                                          \
-    do {                                                                                                         \
-        ensure_dyn_smem(k_sub_scatter<KT, TH>, smem);                                                            \
-        k_sub_scatter<KT, TH><<<n_tiles, TH, smem, st>>>(static_cast<const KT*>(in), static_cast<KT*>(out), offA, \
-                                                         tile_prefix, n_bins, n_tiles, shiftB, maskB, curB, limB, \
-                                                         overflow);                                              \
-    } while (0)
-    if (wide) {
-        if (threads == 512) PEDK_SS(uint64_t, 512);
-        else PEDK_SS(uint64_t, 256);
-    } else {
-        if (threads == 512) PEDK_SS(uint32_t, 512);
-        else PEDK_SS(uint32_t, 256);
+    int threads = sub_scatter_threads(), items = sub_scatter_items();
+    if (!sub_scatter_forced() && !wide) {
+        threads = 512;  // the same 4096-key tile with twice the threads
+        items = 8;
     }
+    const size_t smem = (size_t)threads * items * (wide ? sizeof(uint64_t) : sizeof(uint32_t));
+#define PEDK_SS(KT, TH, IT)                                                                                        \
+    do {                                                                                                           \
+        ensure_dyn_smem(k_sub_scatter<KT, TH, IT>, smem);                                                          \
+        k_sub_scatter<KT, TH, IT><<<n_tiles, TH, smem, st>>>(static_cast<const KT*>(in), static_cast<KT*>(out),    \
+                                                             offA, tile_prefix, n_bins, n_tiles, shiftB, maskB,    \
+                                                             curB, limB, overflow);                               \
+    } while (0)
+#define PEDK_SS_SHAPE(KT)                                  \
+    do {                                                   \
+        if (threads == 512 && items == 8) PEDK_SS(KT, 512, 8);  \
+        else if (threads == 512) PEDK_SS(KT, 512, 16);     \
+        else if (items == 8) PEDK_SS(KT, 256, 8);          \
+        else PEDK_SS(KT, 256, 16);                         \
+    } while (0)
+    if (wide) PEDK_SS_SHAPE(uint64_t);
+    else PEDK_SS_SHAPE(uint32_t);
+#undef PEDK_SS_SHAPE
 #undef PEDK_SS
     PEDK_CUDA_TRY(cudaGetLastError());
 }

@@ -227,7 +227,8 @@ def test_full_size_properties(ctx, k, G, N):
                                  {"PEDK_COUNT_PASSES": "4"}, {"PEDK_COUNT_PASSES": "2", "PEDK_BUCKET_EXACT": "1"},
                                  {"PEDK_DEVICE_BUDGET_MB": "8"}, {"PEDK_BC_THREADS": "1024"},
                                  {"PEDK_SUB_THREADS": "512"}, {"PEDK_BUCKET_B_EXACT": "1"}, {"PEDK_PART_BULK": "1"},
-                                 {"PEDK_PART_BIG_TILE": "2"}])
+                                 {"PEDK_PART_BIG_TILE": "2"}, {"PEDK_SUB_ITEMS": "8"}, {"PEDK_SUB_ITEMS": "16"},
+                                 {"PEDK_SUB_ITEMS": "8", "PEDK_SUB_THREADS": "512"}])
 @pytest.mark.parametrize("k", [20, 31])
 def test_bucket_table_overflow_and_legacy_path(ctx, env, k):
     """The per-bucket hash table is forced to overflow (1024 slots, buckets 128x larger) so that
