@@ -147,8 +147,10 @@ int pedk_cnv_text(pedk_sample *ref, pedk_sample *control, pedk_sample *target, c
  * windows found (cw cm tw tm) give the genotype M / H / R / N, and the map lines joined with them are
  * the text of <target>/<target>.kmer.snp of a run with a reference (20 columns).  target and control
  * must be ingested with their reads still in HBM; ref went through pedk_sample_ingest_reference (its
- * chromosomes are the `chrNAME` files ped.pl seeks in).  Orders are bytewise (LC_ALL=C).  One rank.
- * Caller frees with pedk_free. */
+ * chromosomes are the `chrNAME` files ped.pl seeks in).  Orders are bytewise (LC_ALL=C).  On several
+ * ranks the call is collective: every rank passes the WHOLE map (all ranks' lines) and its own share of
+ * the two samples, looks every window up among its reads, and the counters are summed over the ranks;
+ * every rank gets the whole text.  Caller frees with pedk_free. */
 int pedk_verify_text(pedk_sample *target, pedk_sample *control, pedk_sample *ref, const char *map_text,
                      uint64_t map_len, char **text, uint64_t *len);
 /* f4, toVcf for method kmer (ped.pl:1532-1574): <target>.kmer.snp -> the text of <target>.kmer.vcf.

@@ -301,6 +301,12 @@ void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n) {
     nccl_check(nccl()->AllReduce(dev, dev, n, ncclUint64, ncclSum, comm_of(ctx), ctx->stream), "ncclAllReduce");
 }
 
+void comm_allreduce_sum_u32(pedk_ctx* ctx, uint32_t* dev, size_t n) {
+    if (ctx->nranks <= 1 || !n) return;
+    StageScope sc(ctx, PEDK_ST_EXCHANGE, 0);
+    nccl_check(nccl()->AllReduce(dev, dev, n, ncclUint32, ncclSum, comm_of(ctx), ctx->stream), "ncclAllReduce (u32)");
+}
+
 void comm_allreduce_min(pedk_ctx* ctx, unsigned long long* dev, size_t n) {
     if (ctx->nranks <= 1 || !n) return;
     StageScope sc(ctx, PEDK_ST_EXCHANGE, 0);

@@ -23,6 +23,7 @@ void comm_destroy(pedk_ctx* ctx);
 void comm_ipc_destroy(pedk_ctx* ctx);
 // in-place sum over ranks of n u64 words in device memory (no-op on one rank)
 void comm_allreduce_sum(pedk_ctx* ctx, unsigned long long* dev, size_t n);
+void comm_allreduce_sum_u32(pedk_ctx* ctx, uint32_t* dev, size_t n);
 void comm_allreduce_min(pedk_ctx* ctx, unsigned long long* dev, size_t n);
 void comm_allreduce_max(pedk_ctx* ctx, unsigned long long* dev, size_t n);
 // Elements to allocate for a block of `elems` 8-byte words that peers map through CUDA IPC: IPC

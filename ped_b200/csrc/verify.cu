@@ -32,6 +32,7 @@
 #include <thread>
 #include <vector>
 
+#include "comm.h"
 #include "hostpar.h"
 #include "kernels.h"
 #include "sample.h"
@@ -228,9 +229,21 @@ std::vector<uint32_t> probe(pedk_sample* smp, const Strings& s, int L) {
     const ReadGroup* g = nullptr;
     for (const ReadGroup& x : smp->groups)
         if (x.L == L && x.n) g = &x;
-    if (!g) return hits;  // no read of this length: nothing joins
     pedk_ctx* ctx = smp->ctx;
     cudaStream_t st = ctx->stream;
+    if (!g) {
+        // no read of this length here: nothing joins.  On several ranks the reads of a sample are spread
+        // over the ranks by their hash and every rank looks ALL windows up among its own: a window is a
+        // read of the sample iff it is one on exactly one rank, so the counters add up (collective)
+        if (ctx->nranks > 1) {
+            DBuf<uint32_t> d_zero(ctx, hits.size());
+            PEDK_CUDA_TRY(cudaMemsetAsync(d_zero.p, 0, d_zero.bytes(), st));
+            comm_allreduce_sum_u32(ctx, d_zero.p, hits.size());
+            PEDK_CUDA_TRY(cudaMemcpyAsync(hits.data(), d_zero.p, hits.size() * 4, cudaMemcpyDeviceToHost, st));
+            PEDK_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        return hits;
+    }
     if (g->n > (1ull << 30)) throw PedkError(PEDK_E_UNSUPPORTED, "more than 2^30 unique reads in one length group");
     uint64_t cap64 = 1024;
     while (cap64 < 2 * g->n) cap64 <<= 1;
@@ -259,6 +272,7 @@ std::vector<uint32_t> probe(pedk_sample* smp, const Strings& s, int L) {
     else
         launch_probe_strings(d_text.p, d_start.p, d_len.p, s.start.size(), L, g->W, g->words.p, table.p,
                              (uint32_t)cap64, d_hits.p, st);
+    comm_allreduce_sum_u32(ctx, d_hits.p, hits.size());  // several ranks: see above
     PEDK_CUDA_TRY(cudaMemcpyAsync(hits.data(), d_hits.p, hits.size() * 4, cudaMemcpyDeviceToHost, st));
     PEDK_CUDA_TRY(cudaStreamSynchronize(st));
     return hits;
@@ -494,7 +508,19 @@ std::string verify_text(pedk_sample* target, pedk_sample* control, const Chromos
     if (!target->ingested || !control->ingested || target->reads_released || control->reads_released)
         throw PedkError(PEDK_E_INVAL, "verification needs the reads of both samples (ingested, not released)");
     PEDK_CUDA_TRY(cudaSetDevice(target->ctx->device));
-    const long long length = first_read_length(target), clength = first_read_length(control);
+    long long length = first_read_length(target), clength = first_read_length(control);
+    if (target->ctx->nranks > 1) {
+        // a rank may hold no read of a (small) sample; the samples of a multi-rank job have one read length
+        // (mixed lengths are refused at ingest), so the largest value over the ranks is everybody's
+        pedk_ctx* cx = target->ctx;
+        unsigned long long v[2] = {(unsigned long long)length, (unsigned long long)clength};
+        PEDK_CUDA_TRY(cudaMemcpyAsync(cx->scalars + 12, v, sizeof v, cudaMemcpyHostToDevice, cx->stream));
+        comm_allreduce_max(cx, cx->scalars + 12, 2);
+        PEDK_CUDA_TRY(cudaMemcpyAsync(v, cx->scalars + 12, sizeof v, cudaMemcpyDeviceToHost, cx->stream));
+        PEDK_CUDA_TRY(cudaStreamSynchronize(cx->stream));
+        length = (long long)v[0];
+        clength = (long long)v[1];
+    }
     if (length <= 0 || clength <= 0)
         throw PedkError(PEDK_E_INVAL, "verification needs reads in both samples (ped.pl dies in read() with a negative length)");
     pedk_ctx* ctx = target->ctx;

@@ -71,10 +71,17 @@ def main():
         parts = [None] * world
         dist.all_gather_object(parts, dict(text=r.text(), ck=ck, cc=cc, tk=tk, tc=tc, cd=c.table_digest(),
                                            td=t.table_digest(), cu=int(ci.unique_reads), tu=int(ti.unique_reads)))
+        lines = [ln for p in parts for ln in p["text"].split(b"\n") if ln]
+        text = b"".join(ln + b"\n" for ln in sorted(lines))  # a line starts with its (k-1)-mer: sorted = key order
+        verified = None
+        if is_ref:
+            # rows f1 + f2 on several ranks: every rank indexes the (whole) reference, maps the merged edge
+            # list, and looks every window up among ITS share of the reads; the counters are summed over ranks
+            c.ref20_uniq(20)
+            map_text = c.map_kmer_text(text)
+            verified = c.verify_text(c, t, map_text)
         if rank == 0:
             oc, ot, osnp = oracle.run_ref(fc, ft, 20) if is_ref else oracle.run(fc, ft, 20, clip)
-            lines = [ln for p in parts for ln in p["text"].split(b"\n") if ln]
-            text = b"".join(ln + b"\n" for ln in sorted(lines))  # a line starts with its (k-1)-mer: sorted = key order
             for key, cnt, o in (("ck", "cc", oc), ("tk", "tc", ot)):
                 km = np.concatenate([p[key] for p in parts])
                 ct = np.concatenate([p[cnt] for p in parts])
@@ -91,6 +98,15 @@ def main():
             good = text == osnp
             print(f"[{name}] edges {text.count(b'%c' % 10)} vs oracle {osnp.count(b'%c' % 10)}: {'ok' if good else 'MISMATCH'}")
             ok &= good
+            if verified is not None:
+                import json
+                gpath = os.path.join(ROOT, "tests", "golden", name + "_verify.json")
+                if os.path.exists(gpath):
+                    want = json.load(open(gpath))["control_ref"]["kmer_snp"]
+                    good = verified.decode() == want
+                    print(f"[{name}] verified candidates {verified.count(b'%c' % 10)} lines vs ped.pl's "
+                          f"{want.count(chr(10))}: {'ok' if good else 'MISMATCH'}")
+                    ok &= good
         r.destroy(); c.destroy(); t.destroy()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
