@@ -137,7 +137,8 @@ int pedk_sample_map_kmer_text(pedk_sample *ref, const char *snp_text, uint64_t s
 /* f3, cnvJoin + cnvJoinSub (ped.pl:934-989): the full outer join of the two count tables, for the
  * k-mers of the unique k-mer index of `ref`: lines `chr\tpos\tstrand\ttarget_count\tcontrol_count`
  * (a k-mer one sample does not have counts 0 there), ordered like `sort -k 1 -n -k 2 -n` -- the text
- * of <target>/<target>.<control>.cnv.  One rank.  Caller frees with pedk_free. */
+ * of <target>/<target>.<control>.cnv.  Collective on several ranks (the counts found in every rank's key
+ * range of the rows are summed; every rank gets the whole text).  Caller frees with pedk_free. */
 int pedk_cnv_text(pedk_sample *ref, pedk_sample *control, pedk_sample *target, char **text, uint64_t *len);
 /* f2, snpMkT + sortSeq + joinTarget + snpMkC + sortSeq + joinControl + kmerReadCount (ped.pl:2087-2305,
  * 2576-2641, 2388-2500): map_text = the lines of the <tmpdir>/<t>.map.TAG files in tag order

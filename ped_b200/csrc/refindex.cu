@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <string>
 
+#include "comm.h"
 #include "hostpar.h"
 #include "sample.h"
 
@@ -472,7 +473,6 @@ std::string cnv_text(pedk_sample* ref, pedk_sample* control, pedk_sample* target
     if (!idx.built) throw PedkError(PEDK_E_INVAL, "pedk_cnv_text: no unique k-mer index (pedk_sample_ref20_uniq first)");
     if (!control->k || control->k != target->k || control->k != idx.k)
         throw PedkError(PEDK_E_INVAL, "pedk_cnv_text: the samples and the index must use the same k");
-    if (ctx->nranks > 1) throw PedkError(PEDK_E_UNSUPPORTED, "pedk_cnv_text runs on one rank");
     PEDK_CUDA_TRY(cudaSetDevice(ctx->device));
     const uint64_t U = idx.kmer.size();
     std::string out;
@@ -484,15 +484,24 @@ std::string cnv_text(pedk_sample* ref, pedk_sample* control, pedk_sample* target
     }
     RowTable rows;  // both tables in one array sorted by k-mer
     build_rows(ctx, control, target, &rows);
+    // On several ranks every rank holds the rows of a key range (build_rows routes them) and the whole
+    // index: it looks all index k-mers up among its rows, finds each in at most one rank's range, and
+    // the two count arrays are summed over the ranks (collective; every rank gets the whole text).
     std::vector<uint32_t> ht(U, 0), hc(U, 0);
-    if (rows.n) {
+    const bool multi = ctx->nranks > 1;
+    if (rows.n || multi) {
         DBuf<uint32_t> d_t(ctx, U), d_c(ctx, U);
-        {
+        if (rows.n) {
             StageScope sc(ctx, PEDK_ST_EDGES, 1);
             k_cnv_lookup<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(idx.d_kmer.p, U, rows.key.p, rows.val.p, rows.n,
                                                                       d_t.p, d_c.p);
             PEDK_CUDA_TRY(cudaGetLastError());
+        } else {
+            PEDK_CUDA_TRY(cudaMemsetAsync(d_t.p, 0, U * 4, st));
+            PEDK_CUDA_TRY(cudaMemsetAsync(d_c.p, 0, U * 4, st));
         }
+        comm_allreduce_sum_u32(ctx, d_t.p, U);
+        comm_allreduce_sum_u32(ctx, d_c.p, U);
         PEDK_CUDA_TRY(cudaMemcpyAsync(ht.data(), d_t.p, U * 4, cudaMemcpyDeviceToHost, st));
         PEDK_CUDA_TRY(cudaMemcpyAsync(hc.data(), d_c.p, U * 4, cudaMemcpyDeviceToHost, st));
         PEDK_CUDA_TRY(cudaStreamSynchronize(st));

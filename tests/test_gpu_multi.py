@@ -16,7 +16,7 @@ def test_two_ranks_reproduce_the_oracle(built):
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi_rank_check.py"), "tiny",
-           "adversarial", "clip50", "c1_40x", "ref30k", "lowcomplexity"]
+           "adversarial", "clip50", "c1_40x", "ref30k", "lowcomplexity", "ref30k_cnv"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "MULTI_RANK_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
