@@ -130,27 +130,31 @@ std::vector<Candidate> candidates_of(const std::vector<std::string>& map_lines) 
     });
     parallel_sort(tmp, std::less<std::string>());
     tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    // every line re-split and re-joined (snp.tmp -> snp.list, ped.pl:2145-2150), then `uniq -c`
+    std::vector<std::string> relined(tmp.size());
+    std::vector<Candidate> parsed(tmp.size());
+    parallel_for(tmp.size(), [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            Row row = split_blanks(tmp[i]);
+            relined[i] = field(row, 0) + " " + field(row, 1) + " " + field(row, 2) + " " + field(row, 3);
+            Row r2 = split_blanks(relined[i]);  // ($count, $chr, $pos, $ref, $alt) = split, the count in front
+            Candidate& c = parsed[i];
+            c.chr = strip_zeros(field(r2, 0));
+            c.pos = perl_int(field(r2, 1));
+            c.ref = field(r2, 2);
+            c.alt = field(r2, 3);
+            // "$pos $ref $alt" split on blanks again: an empty field lets the next one move up
+            const std::string* third[2] = {&c.ref, &c.alt};
+            int seen = 0;
+            for (const std::string* f : third)
+                if (!f->empty() && ++seen == 2) c.ialt = *f;
+        }
+    });
     std::vector<Candidate> out;
-    std::string prev;
-    bool first = true;
-    for (const std::string& line : tmp) {
-        Row row = split_blanks(line);
-        const std::string relined = field(row, 0) + " " + field(row, 1) + " " + field(row, 2) + " " + field(row, 3);
-        if (!first && relined == prev) continue;  // `uniq -c`
-        first = false;
-        prev = relined;
-        Row r2 = split_blanks(relined);           // ($count, $chr, $pos, $ref, $alt) = split, the count in front
-        Candidate c;
-        c.chr = strip_zeros(field(r2, 0));
-        c.pos = perl_int(field(r2, 1));
-        c.ref = field(r2, 2);
-        c.alt = field(r2, 3);
-        // "$pos $ref $alt" split on blanks again: an empty field lets the next one move up
-        const std::string* third[2] = {&c.ref, &c.alt};
-        int seen = 0;
-        for (const std::string* f : third)
-            if (!f->empty() && ++seen == 2) c.ialt = *f;
-        out.push_back(std::move(c));
+    out.reserve(tmp.size());
+    for (size_t i = 0; i < tmp.size(); ++i) {
+        if (i && relined[i] == relined[i - 1]) continue;  // `uniq -c`
+        out.push_back(std::move(parsed[i]));
     }
     return out;
 }
@@ -335,6 +339,7 @@ std::string read_count(const std::vector<std::string>& map_lines, const std::vec
     struct Entry {
         std::string key;
         Row row;
+        std::string group;  // the loop over `sort keys` compares this: the fields but the last, tab-joined
         long long n;
     };
     static const char* kinds[4] = {"tw", "tm", "cw", "cm"};
@@ -362,6 +367,15 @@ std::string read_count(const std::vector<std::string>& map_lines, const std::vec
                 // ... and what the loop over `sort keys` sees when it splits the key again
                 e.row = split_blanks(e.key);
                 while (e.row.size() < 2) e.row.emplace_back();
+                e.group = strip_zeros(e.row[0]);  // $row[0] =~ s/^0+//g; $row[1] += 0; join("\t", @row[0 .. $#row - 1])
+                if (e.row.size() > 2) {
+                    e.group += '\t';
+                    e.group += std::to_string(perl_int(e.row[1]));
+                }
+                for (size_t t = 2; t + 1 < e.row.size(); ++t) {
+                    e.group += '\t';
+                    e.group += e.row[t];
+                }
             }
     });
     std::vector<Entry> count;
@@ -382,45 +396,48 @@ std::string read_count(const std::vector<std::string>& map_lines, const std::vec
         count.resize(o);
     }
     // ---- `$tmpdir/$target.verify` (ped.pl:2423-2480) ----
-    std::vector<std::string> verify;
-    long long cm = 0, cw = 0, tm = 0, tw = 0;
-    std::string prev;
-    auto flush = [&]() {
-        Row pr = split_blanks(prev);
-        while (pr.size() < 2) pr.emplace_back();
-        return pad_chr(pr[0]) + ":" + pad_pos(pr[1]) + "\t" + std::to_string(cw) + "\t" + std::to_string(cm) + "\t" +
-               std::to_string(tw) + "\t" + std::to_string(tm) + "\t" + genotype(cw, cm, tw, tm);
+    struct Group {
+        const std::string* key;  // the group's fields, tab-joined (null: the empty $prev of the first flush)
+        long long cw, cm, tw, tm;
     };
-    for (const Entry& e : count) {
-        std::string d = strip_zeros(e.row[0]);
-        if (e.row.size() > 2) {
-            d += '\t';
-            d += std::to_string(perl_int(e.row[1]));
+    std::vector<Group> groups;
+    {
+        long long cm = 0, cw = 0, tm = 0, tw = 0;
+        const std::string* prev = nullptr;
+        for (const Entry& e : count) {
+            if (!prev || e.group != *prev) {
+                if (prev && !prev->empty()) groups.push_back(Group{prev, cw, cm, tw, tm});
+                cm = cw = tm = tw = 0;
+            }
+            const std::string& kind = e.row.back();
+            if (kind == "cm") cm = e.n;
+            if (kind == "cw") cw = e.n;
+            if (kind == "tm") tm = e.n;
+            if (kind == "tw") tw = e.n;
+            prev = &e.group;
         }
-        for (size_t t = 2; t + 1 < e.row.size(); ++t) {
-            d += '\t';
-            d += e.row[t];
-        }
-        if (d != prev) {
-            std::string line = flush();
-            if (!prev.empty()) verify.push_back(std::move(line));
-            cm = cw = tm = tw = 0;
-        }
-        const std::string& kind = e.row.back();
-        if (kind == "cm") cm = e.n;
-        if (kind == "cw") cw = e.n;
-        if (kind == "tm") tm = e.n;
-        if (kind == "tw") tw = e.n;
-        prev = d;
+        groups.push_back(Group{prev, cw, cm, tw, tm});  // ped.pl prints the last group without looking at it (2461-2480)
     }
-    verify.push_back(flush());  // ped.pl prints the last group without looking at it (2461-2480)
+    std::vector<std::string> verify(groups.size());
+    parallel_for(groups.size(), [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const Group& g = groups[i];
+            Row pr = g.key ? split_blanks(*g.key) : Row();
+            while (pr.size() < 2) pr.emplace_back();
+            verify[i] = pad_chr(pr[0]) + ":" + pad_pos(pr[1]) + "\t" + std::to_string(g.cw) + "\t" +
+                        std::to_string(g.cm) + "\t" + std::to_string(g.tw) + "\t" + std::to_string(g.tm) + "\t" +
+                        genotype(g.cw, g.cm, g.tw, g.tm);
+        }
+    });
     // ---- `join map verify` on the first blank-separated field: a merge, whatever the order of the inputs
     // (GNU join does not sort), every line of a key with every line of the other side ----
     std::vector<std::string> ka(mp.size()), kb(verify.size());
     parallel_for(mp.size(), [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) ka[i] = key_of(mp[i]);
     });
-    for (size_t i = 0; i < verify.size(); ++i) kb[i] = key_of(verify[i]);
+    parallel_for(verify.size(), [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) kb[i] = key_of(verify[i]);
+    });
     std::vector<std::pair<uint32_t, uint32_t>> pairs;
     {
         size_t i = 0, j = 0;
