@@ -154,6 +154,18 @@ int pedk_cnv_text(pedk_sample *ref, pedk_sample *control, pedk_sample *target, c
  * every rank gets the whole text.  Caller frees with pedk_free. */
 int pedk_verify_text(pedk_sample *target, pedk_sample *control, pedk_sample *ref, const char *map_text,
                      uint64_t map_len, char **text, uint64_t *len);
+/* The two host-only halves of pedk_verify_text (no CUDA call; for tests and for hosts that bring their own
+ * look-up): (1) one line per candidate of the map, `chr pos ref alt \t reference string \t mutant string`
+ * (ped.pl:2153-2192 for a read length; both strings empty where ped.pl says `next`), the chromosome texts given
+ * as n_chr (file name, sequence, length) triples; (2) the <target>.kmer.snp text from the numbers of windows
+ * found, hits[2c] = reference string of candidate c, hits[2c+1] = its mutant string, candidates in the order of (1)
+ * (kmerReadCount, ped.pl:2388-2500).  Caller frees with pedk_free. */
+int pedk_verify_strings_text(const char *map_text, uint64_t map_len, const char *const *chr_names,
+                             const char *const *chr_seqs, const uint64_t *chr_lens, int n_chr, int read_length,
+                             char **text, uint64_t *len);
+int pedk_verify_counts_text(const char *map_text, uint64_t map_len, const uint32_t *target_hits,
+                            const uint32_t *control_hits, uint64_t n_strings, int length, int clength, char **text,
+                            uint64_t *len);
 /* f4, toVcf for method kmer (ped.pl:1532-1574): <target>.kmer.snp -> the text of <target>.kmer.vcf.
  * Host only (no CUDA call).  Caller frees with pedk_free. */
 int pedk_vcf_text(const char *kmer_snp, uint64_t snp_len, const char *target_name, char **text, uint64_t *len);

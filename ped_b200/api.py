@@ -114,6 +114,9 @@ SIGNATURES = {
     "pedk_cnv": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
     "pedk_verify_text": (C.c_int, [_P, _P, _P, C.c_char_p, C.c_uint64, _PP, _U64P]),
     "pedk_vcf_text": (C.c_int, [C.c_char_p, C.c_uint64, C.c_char_p, _PP, _U64P]),
+    "pedk_verify_strings_text": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _U64P,
+                                           C.c_int, C.c_int, _PP, _U64P]),
+    "pedk_verify_counts_text": (C.c_int, [C.c_char_p, C.c_uint64, _P, _P, C.c_uint64, C.c_int, C.c_int, _PP, _U64P]),
     "pedk_verify_kmer": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
     "pedk_to_vcf": (C.c_int, [_P, C.c_char_p, C.c_char_p]),
     "pedk_mk_ref20_uniq": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
@@ -524,6 +527,46 @@ def vcf_text(kmer_snp: bytes, target_name: str) -> bytes:
         raise PedkError(rc, "pedk_vcf_text")
     try:
         return C.string_at(p, n.value)
+    finally:
+        lib.pedk_free(p)
+
+
+def verify_strings(map_text: bytes, chromosomes: dict, read_length: int):
+    """Host-only: [(candidate "chr pos ref alt", reference string, mutant string)] of a position map for one
+    read length (snpMkT / snpMkC up to the windows, ped.pl:2087-2192).  chromosomes: file name -> bytes."""
+    lib = load_library()
+    names = list(chromosomes)
+    n = len(names)
+    c_names = (C.c_char_p * max(1, n))(*[x.encode() if isinstance(x, str) else x for x in names])
+    c_seqs = (C.c_char_p * max(1, n))(*[chromosomes[x] for x in names])
+    c_lens = (C.c_uint64 * max(1, n))(*[len(chromosomes[x]) for x in names])
+    p = C.c_void_p()
+    ln = C.c_uint64()
+    rc = lib.pedk_verify_strings_text(map_text, len(map_text), c_names, c_seqs, c_lens, n, read_length, C.byref(p),
+                                      C.byref(ln))
+    if rc:
+        raise PedkError(rc, "pedk_verify_strings_text")
+    try:
+        text = C.string_at(p, ln.value)
+    finally:
+        lib.pedk_free(p)
+    return [tuple(x.split(b"\t")) for x in text.split(b"\n")[:-1]]
+
+
+def verify_counts_text(map_text: bytes, target_hits, control_hits, length: int, clength: int) -> bytes:
+    """Host-only: kmerReadCount (ped.pl:2388-2500) from the numbers of windows found per string (uint32 arrays,
+    two per candidate in the order of verify_strings) -> `<t>.kmer.snp` of a run with a reference."""
+    lib = load_library()
+    th = np.ascontiguousarray(target_hits, dtype=np.uint32)
+    ch = np.ascontiguousarray(control_hits, dtype=np.uint32)
+    p = C.c_void_p()
+    ln = C.c_uint64()
+    rc = lib.pedk_verify_counts_text(map_text, len(map_text), _ptr(th), _ptr(ch), len(th), length, clength, C.byref(p),
+                                     C.byref(ln))
+    if rc:
+        raise PedkError(rc, "pedk_verify_counts_text")
+    try:
+        return C.string_at(p, ln.value)
     finally:
         lib.pedk_free(p)
 

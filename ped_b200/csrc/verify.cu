@@ -663,6 +663,62 @@ extern "C" int pedk_verify_text(pedk_sample* target, pedk_sample* control, pedk_
     PEDK_API_END(target->ctx)
 }
 
+// Host-only halves of the verification (no CUDA call), so that the text logic around the look-up kernel can
+// be checked without a device: the strings whose windows are looked up, and the text made from the counters.
+namespace {
+ChromosomeLookup lookup_in(const std::map<std::string, std::string>& files) {
+    return [&files](const std::string& name) -> const std::string* {
+        auto it = files.find(name);
+        return it == files.end() ? nullptr : &it->second;
+    };
+}
+std::map<std::string, std::string> files_of(const char* const* names, const char* const* seqs, const uint64_t* lens,
+                                            int n) {
+    std::map<std::string, std::string> m;
+    for (int i = 0; i < n; ++i) m[names[i]] = std::string(seqs[i], (size_t)lens[i]);
+    return m;
+}
+}  // namespace
+
+extern "C" int pedk_verify_strings_text(const char* map_text, uint64_t map_len, const char* const* chr_names,
+                                        const char* const* chr_seqs, const uint64_t* chr_lens, int n_chr,
+                                        int read_length, char** text, uint64_t* len) {
+    if ((!map_text && map_len) || !text || !len || n_chr < 0 || read_length <= 0) return PEDK_E_INVAL;
+    try {
+        const std::map<std::string, std::string> files = files_of(chr_names, chr_seqs, chr_lens, n_chr);
+        const std::vector<Candidate> cand = candidates_of(lines_of(map_text, map_len));
+        const Strings s = strings_of(cand, lookup_in(files), read_length);
+        std::string out;
+        for (size_t c = 0; c < cand.size(); ++c) {
+            out += cand[c].chr + " " + std::to_string(cand[c].pos) + " " + cand[c].ref + " " + cand[c].alt + "\t";
+            out.append(s.text.data() + s.start[2 * c], s.length[2 * c]);
+            out += '\t';
+            out.append(s.text.data() + s.start[2 * c + 1], s.length[2 * c + 1]);
+            out += '\n';
+        }
+        *text = dup_text(out, len);
+        return PEDK_OK;
+    } catch (...) {
+        return PEDK_E_INTERNAL;
+    }
+}
+
+extern "C" int pedk_verify_counts_text(const char* map_text, uint64_t map_len, const uint32_t* target_hits,
+                                       const uint32_t* control_hits, uint64_t n_strings, int length, int clength,
+                                       char** text, uint64_t* len) {
+    if ((!map_text && map_len) || !text || !len || (n_strings && (!target_hits || !control_hits))) return PEDK_E_INVAL;
+    try {
+        const std::vector<std::string> map_lines = lines_of(map_text, map_len);
+        const std::vector<Candidate> cand = candidates_of(map_lines);
+        if (n_strings != 2 * cand.size()) return PEDK_E_INVAL;
+        const std::vector<uint32_t> th(target_hits, target_hits + n_strings), ch(control_hits, control_hits + n_strings);
+        *text = dup_text(read_count(map_lines, cand, th, ch, length, clength), len);
+        return PEDK_OK;
+    } catch (...) {
+        return PEDK_E_INTERNAL;
+    }
+}
+
 extern "C" int pedk_vcf_text(const char* kmer_snp, uint64_t snp_len, const char* target_name, char** text,
                              uint64_t* len) {
     if ((!kmer_snp && snp_len) || !target_name || !text || !len) return PEDK_E_INVAL;
